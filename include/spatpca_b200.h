@@ -1,0 +1,226 @@
+/*
+ * spatpca_b200 -- C ABI of the B200-native cross-validated regularized-PCA engine.
+ *
+ * This is the drop-in boundary for the hot path of the R package SpatPCA
+ * (reference: src/RcppSpatPCA.cpp, bound to R through src/RcppExports.cpp:16-85
+ * and R/RcppExports.R:14-68).  Every entry point below names the reference
+ * interface it replaces.  The Rcpp glue that re-exports the reference's four
+ * `.Call` symbols on top of this ABI is in r-package/src/rcpp_glue.cpp; the
+ * ctypes binding used by the tests is spatpca_b200/_lib.py.
+ *
+ * Conventions
+ *   - every pointer is a HOST pointer to caller-owned memory unless its name
+ *     ends in `_dev`;
+ *   - every matrix is column-major FP64 with leading dimension = its row count,
+ *     exactly as R / Armadillo hand them over (src/RcppSpatPCA.cpp:552-558);
+ *   - every function returns SPB_OK (0) or a negative status; no C++ exception
+ *     crosses the ABI.  `spb_last_error()` returns a thread-local message for
+ *     the last failing call on the calling thread (the text the glue passes to
+ *     Rcpp::stop, mirroring END_RCPP at src/RcppExports.cpp:23,36,57,71);
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with SPB_ERR_NO_DEVICE.
+ */
+#ifndef SPATPCA_B200_H
+#define SPATPCA_B200_H
+
+#if defined(SPB_BUILDING) && defined(__GNUC__)
+#define SPB_API __attribute__((visibility("default")))
+#else
+#define SPB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPB_ABI_VERSION 1
+
+/* status codes */
+#define SPB_OK                 0
+#define SPB_ERR_INVALID_ARG   -1   /* bad size / NULL pointer / unsupported d or K            */
+#define SPB_ERR_NO_DEVICE     -2   /* no usable CUDA device                                   */
+#define SPB_ERR_CUDA          -3   /* CUDA / cuBLAS / cuSOLVER runtime failure                */
+#define SPB_ERR_NOT_POSDEF    -4   /* inv_sympd(): matrix is singular or not positive definite */
+#define SPB_ERR_SINGULAR      -5   /* inv()/solve(): matrix is singular                        */
+#define SPB_ERR_POLAR         -6   /* Stiefel projection met a rank-deficient p x K iterate    */
+#define SPB_ERR_SVD           -7   /* SVD / symmetric eigensolver failed to converge           */
+#define SPB_ERR_INTERNAL      -8
+
+#define SPB_MAX_K             32   /* largest number of eigenfunctions the kernels are built for */
+
+/* ------------------------------------------------------------------------ */
+/* library / device                                                          */
+/* ------------------------------------------------------------------------ */
+SPB_API int          spb_abi_version(void);
+SPB_API const char*  spb_last_error(void);
+SPB_API int          spb_device_count(void);           /* < 0 on error */
+SPB_API int          spb_set_device(int ordinal);      /* device used by subsequent calls of this thread */
+
+/* ------------------------------------------------------------------------ */
+/* thinPlateSplineMatrix(location)                                           */
+/*   reference: src/RcppSpatPCA.cpp:58-76, stub R/RcppExports.R:14-16,       */
+/*              symbol _SpatPCA_thinPlateSplineMatrix (src/RcppExports.cpp:16)*/
+/*   location : p x d, d in {1,2,3};  omega_out : p x p (NOT symmetrized,    */
+/*   like the reference's return value)                                      */
+/* ------------------------------------------------------------------------ */
+SPB_API int spb_tps_matrix(const double* location, int p, int d, double* omega_out);
+
+/* ------------------------------------------------------------------------ */
+/* eigenFunction(new_location, original_location, Phi)                       */
+/*   reference: src/RcppSpatPCA.cpp:94-147, stub R/RcppExports.R:33-35,      */
+/*              symbol _SpatPCA_eigenFunction (src/RcppExports.cpp:27)       */
+/*   out : p_new x K                                                         */
+/* ------------------------------------------------------------------------ */
+SPB_API int spb_eigen_function(const double* new_location, int p_new,
+                       const double* original_location, int p, int d,
+                       const double* Phi, int K, double* out);
+
+/* ------------------------------------------------------------------------ */
+/* spatialPrediction(phir, Yr, gamma, predicted_eignefunction)               */
+/*   reference: src/RcppSpatPCA.cpp:715-770, stub R/RcppExports.R:66-68,     */
+/*              symbol _SpatPCA_spatialPrediction (src/RcppExports.cpp:61)   */
+/*   prediction : n x p_new; estimated_covariance : p x p_new;               */
+/*   eigenvalue : K; error : 1.  Any output pointer may be NULL.             */
+/* ------------------------------------------------------------------------ */
+SPB_API int spb_spatial_prediction(const double* phi, int p, int K,
+                           const double* Y, int n, double gamma,
+                           const double* predicted_phi, int p_new,
+                           double* prediction, double* estimated_covariance,
+                           double* eigenvalue, double* error);
+
+/* ------------------------------------------------------------------------ */
+/* spatpcaCV(sxyr, Yr, M, K, tau1r, tau2r, gammar, nkr, maxit, tol, l2r)     */
+/*   reference: src/RcppSpatPCA.cpp:543-701, stub R/RcppExports.R:51-53,     */
+/*              symbol _SpatPCA_spatpcaCV (src/RcppExports.cpp:40)           */
+/* ------------------------------------------------------------------------ */
+typedef struct spb_cv_stats {
+  int       n_admm_calls;     /* spatpcaCore2/2p/3 calls made                          */
+  long long admm_iters;       /* ADMM iterations summed over those calls               */
+  int       n_inverses;       /* p x p SPD inverses (inv_sympd call sites)             */
+  double    ms_total;         /* wall time of the call (host clock)                    */
+  double    ms_h2d;           /* host->device copies                                   */
+  double    ms_d2h;           /* device->host copies of results                        */
+  double    ms_omega;         /* thin-plate-spline matrix (device time)                */
+  double    ms_prologue;      /* fold gathers, SVD starts, Gram matrices               */
+  double    ms_inverse;       /* assembly + Cholesky inverse + mirror                  */
+  double    ms_admm;          /* persistent ADMM kernel                                */
+  double    ms_cv_loss;       /* hold-out reconstruction losses                        */
+  double    ms_gamma;         /* stage-3 eigen step + covariance losses                */
+  long long bytes_h2d;
+  long long bytes_d2h;
+  int       gpu_launches;     /* kernels of this library launched (library calls not counted) */
+} spb_cv_stats;
+
+/*
+ * sxy   : p x d locations (already scaled by the caller, R/SpatPCA.R:183)
+ * Y     : n x p data
+ * nk    : n fold ids in 1..M, as doubles (R/SpatPCA.R:184)
+ * outputs (all caller-allocated):
+ *   cv_score_tau1  : n_tau1  values if n_tau1 > 1, else 1 value (0)   (:600, :649)
+ *   cv_score_tau2  : n_tau2  values if n_tau2 > 1, else 1 value (0)   (:668, :679)
+ *   cv_score_gamma : n_gamma values                                    (:692)
+ *   estimated_eigenfn : p x K                                          (:697)
+ *   selected       : 3 values {selected_tau1, selected_tau2, selected_gamma}
+ *   stats          : may be NULL
+ */
+SPB_API int spb_cv(const double* sxy, int p, int d,
+           const double* Y, int n, int M, int K,
+           const double* tau1, int n_tau1,
+           const double* tau2, int n_tau2,
+           const double* gamma, int n_gamma,
+           const double* nk, int maxit, double tol,
+           const double* l2, int n_l2,
+           double* cv_score_tau1, double* cv_score_tau2, double* cv_score_gamma,
+           double* estimated_eigenfn, double* selected, spb_cv_stats* stats);
+
+/* ------------------------------------------------------------------------ */
+/* Engine handle: the same computation as spb_cv, cut at the reference's     */
+/* natural seams (per fold inside each stage, src/RcppSpatPCA.cpp:315, 385,  */
+/* 460 -- the old parallelFor axis) so that folds can be placed on different */
+/* GPUs / processes.  The caller gathers the per-fold score rows, takes the  */
+/* argmin (spb_select_index) and hands the index to the next stage.          */
+/* spb_cv() is exactly: create, upload, prepare, then every fold and the     */
+/* full-data fit of each stage in order on one device.                       */
+/* ------------------------------------------------------------------------ */
+typedef struct spb_engine spb_engine;
+
+SPB_API int spb_engine_create(spb_engine** out, int p, int d, int n, int M, int K,
+                      const double* tau1, int n_tau1,
+                      const double* tau2, int n_tau2,
+                      const double* gamma, int n_gamma,
+                      int maxit, double tol,
+                      const double* l2, int n_l2);
+SPB_API int spb_engine_destroy(spb_engine* e);
+
+/* host -> device copy of the inputs (the only H2D traffic of a run) */
+SPB_API int spb_engine_upload(spb_engine* e, const double* sxy, const double* Y, const double* nk);
+/* optional: inject thinPlateSplineMatrix(sxy) (p x p, host) instead of building it */
+SPB_API int spb_engine_set_omega(spb_engine* e, const double* omega);
+/* Omega (if any tau is non-zero) and the full-data SVD start (:561-575).   */
+SPB_API int spb_engine_prepare(spb_engine* e);
+/* copy the engine's Omega (without the extra 1e-8 I of :574) to the host   */
+SPB_API int spb_engine_get_omega(spb_engine* e, double* omega_out);
+
+/* stage 1 (:592-650).  fold k in 0..M-1; cv_row receives n_tau1 values when
+ * n_tau1 > 1 (row k of `cv`, :327-331), otherwise it is not written.       */
+SPB_API int spb_engine_stage1_fold(spb_engine* e, int k, double* cv_row);
+SPB_API int spb_engine_stage1_full(spb_engine* e, int index1);
+/* stage 2 (:652-680).  cv_row receives n_tau2 values when n_tau2 > 1.      */
+SPB_API int spb_engine_stage2_fold(spb_engine* e, int k, int index1, double* cv_row);
+SPB_API int spb_engine_stage2_full(spb_engine* e, int index1, int index2);
+/* stage 3 (:682-692, worker :459-525).  cv_row receives n_gamma values.    */
+SPB_API int spb_engine_stage3_fold(spb_engine* e, int k, int index1, int index2, double* cv_row);
+
+/* estimated_eigenfn (p x K) of the full-data fit, device -> host */
+SPB_API int spb_engine_get_eigenfn(spb_engine* e, double* eigenfn_out);
+SPB_API int spb_engine_get_stats(spb_engine* e, spb_cv_stats* stats);
+/* per-call ADMM log: 4 ints per call {kind, fold, grid index, iterations};
+ * kind: 2 = Core2, 20 = Core2p, 3 = Core3; fold -1 = full data.
+ * Returns the number of calls logged (writes at most `cap` of them).       */
+SPB_API int spb_engine_call_log(spb_engine* e, int* log4, int cap);
+/* release the per-fold p x p matrices early (optional)                     */
+SPB_API int spb_engine_release_fold(spb_engine* e, int k);
+
+/* `index_min(sum(cv, 0))` and `sum(cv, 0) / M` over an M x n_grid column-major
+ * score matrix, with Armadillo's accumulation order (:595-600, 657-668,
+ * 685-692).  score_out (n_grid values) may be NULL.  Host-only helper.     */
+SPB_API int spb_select_index(const double* cv, int M, int n_grid, double* score_out);
+
+/* ------------------------------------------------------------------------ */
+/* Kernel-level entry points (parity tests, benchmarks).                     */
+/* ------------------------------------------------------------------------ */
+/* inv_sympd(symmatu(scale * (tau1 * Omega - G) + rho * I))   (:165, :397)   */
+SPB_API int spb_inv_sympd(const double* omega, const double* G, int p,
+                  double tau1, double rho, double scale, double* out);
+/* spatpcaCore2 (:150-185) with the inverse supplied; Phi is output only.    */
+SPB_API int spb_admm_core2(const double* tempinv, int p, int K, double rho, int maxit, double tol,
+                   double* Phi, double* C, double* Lambda2, int* iters);
+/* spatpcaCore3 (:224-270)                                                   */
+SPB_API int spb_admm_core3(const double* tempinv, int p, int K, double tau2, double rho,
+                   int maxit, double tol,
+                   double* Phi, double* R, double* C, double* Lambda1, double* Lambda2,
+                   int* iters);
+/* pow(norm(Yva * (I - Phi Phi'), "fro"), 2)   (:327, :331, :400)            */
+SPB_API int spb_cv_loss(const double* Yva, int n_va, int p, const double* Phi, int K, double* loss);
+/* stage-3 losses of one fold for all gammas (:489-523)                      */
+SPB_API int spb_gamma_loss(const double* Phi, int p, int K,
+                   const double* Ytr, int n_tr, const double* Yva, int n_va,
+                   const double* gamma, int n_gamma, double* out);
+
+/* ------------------------------------------------------------------------ */
+/* Device-resident benchmark hooks (bench.py).                               */
+/* ------------------------------------------------------------------------ */
+/* Runs `iters` forced Core3 iterations on a synthetic SPD p x p matrix that
+ * lives in device memory and returns the average device time per iteration
+ * (CUDA events on the launching stream) -- the roofline probe of the
+ * persistent ADMM kernel.  mode: 2 = Core2 update, 3 = Core3 update.        */
+SPB_API int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_per_iter);
+/* FP64 GEMM peak of this device measured with cuBLAS DGEMM m^3 (TFLOP/s)    */
+SPB_API int spb_bench_dgemm(int m, int repeats, double* tflops);
+/* average device time of one inv_sympd at size p (assembly + potrf + potri + mirror) */
+SPB_API int spb_bench_inverse(int p, int repeats, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPATPCA_B200_H */

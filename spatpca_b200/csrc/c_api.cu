@@ -1,0 +1,555 @@
+// extern "C" boundary (include/spatpca_b200.h).  No exception leaves this file.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "engine.cuh"
+
+namespace spb {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+}  // namespace spb
+
+using namespace spb;
+
+struct spb_engine {
+  Engine* impl;
+};
+
+namespace {
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return SPB_OK;
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    set_last_error("out of host memory");
+    return SPB_ERR_INTERNAL;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return SPB_ERR_INTERNAL;
+  } catch (...) {
+    set_last_error("unknown failure");
+    return SPB_ERR_INTERNAL;
+  }
+}
+
+// p x p host (ld = p) <-> device (ld = padded)
+void upload_square(const double* host, int p, double* dev, size_t ld, cudaStream_t s) {
+  SPB_CUDA(cudaMemsetAsync(dev, 0, sizeof(double) * ld * p, s));
+  SPB_CUDA(cudaMemcpy2DAsync(dev, ld * sizeof(double), host, (size_t)p * sizeof(double),
+                             (size_t)p * sizeof(double), p, cudaMemcpyHostToDevice, s));
+}
+void download_square(double* host, int p, const double* dev, size_t ld, cudaStream_t s) {
+  SPB_CUDA(cudaMemcpy2DAsync(host, (size_t)p * sizeof(double), dev, ld * sizeof(double),
+                             (size_t)p * sizeof(double), p, cudaMemcpyDeviceToHost, s));
+}
+
+int select_index_impl(const double* cv, int M, int n_grid, double* score_out) {
+  // index_min(sum(cv, 0)) with Armadillo's accumulation order; first minimum wins (:596, 658, 686)
+  int best = 0;
+  double best_v = 0.0;
+  for (int j = 0; j < n_grid; ++j) {
+    double sm = arma_accumulate(cv + (size_t)j * M, M);
+    if (score_out) score_out[j] = sm / (double)M;
+    if (j == 0 || sm < best_v) { best_v = sm; best = j; }
+  }
+  return best;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spb_abi_version(void) { return SPB_ABI_VERSION; }
+
+const char* spb_last_error(void) { return g_last_error.c_str(); }
+
+int spb_device_count(void) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_last_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return SPB_ERR_NO_DEVICE;
+  }
+  return c;
+}
+
+int spb_set_device(int ordinal) {
+  return guarded([&] {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess || c <= 0) {
+      cudaGetLastError();
+      throw Error(SPB_ERR_NO_DEVICE, "no CUDA device available (spatpca_b200 has no CPU fallback)");
+    }
+    SPB_REQUIRE(ordinal >= 0 && ordinal < c, "device ordinal out of range");
+    SPB_CUDA(cudaSetDevice(ordinal));
+  });
+}
+
+int spb_select_index(const double* cv, int M, int n_grid, double* score_out) {
+  if (!cv || M < 1 || n_grid < 1) {
+    set_last_error("spb_select_index: invalid argument");
+    return SPB_ERR_INVALID_ARG;
+  }
+  return select_index_impl(cv, M, n_grid, score_out);
+}
+
+// ---------------------------------------------------------------------------------------------
+int spb_tps_matrix(const double* location, int p, int d, double* omega_out) {
+  return guarded([&] {
+    SPB_REQUIRE(location && omega_out, "NULL argument");
+    SPB_REQUIRE(p >= 1, "p must be positive");
+    SPB_REQUIRE(d >= 1 && d <= 3, "Dimension of locations must be less than 4.");
+    DeviceCtx& ctx = DeviceCtx::get();
+    const size_t ld = padded_ld(p);
+    DevBuf<double> x((size_t)p * d), om(ld * (size_t)p);
+    SPB_CUDA(cudaMemcpyAsync(x.get(), location, sizeof(double) * p * d, cudaMemcpyHostToDevice, ctx.stream));
+    Engine::build_omega_raw(ctx, x.get(), p, d, om.get(), ld);
+    download_square(omega_out, p, om.get(), ld, ctx.stream);
+    ctx.sync_and_check();
+  });
+}
+
+int spb_eigen_function(const double* new_location, int p_new, const double* original_location, int p,
+                       int d, const double* Phi, int K, double* out) {
+  return guarded([&] {
+    // eigenFunction (:94-147): solve the (un-ridged) bordered TPS system for the spline
+    // coefficients of each eigenfunction, then evaluate at the new sites.
+    SPB_REQUIRE(new_location && original_location && Phi && out, "NULL argument");
+    SPB_REQUIRE(p >= 1 && p_new >= 1 && K >= 1, "sizes must be positive");
+    SPB_REQUIRE(d >= 1 && d <= 3, "Dimension of locations must be less than 4.");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    const int q = p + d + 1;
+    const size_t ldq = padded_ld(q);
+    DevBuf<double> xo((size_t)p * d), xn((size_t)p_new * d), L(ldq * (size_t)q), rhs(ldq * (size_t)K),
+        res((size_t)p_new * K);
+    SPB_CUDA(cudaMemcpyAsync(xo.get(), original_location, sizeof(double) * p * d, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(xn.get(), new_location, sizeof(double) * p_new * d, cudaMemcpyHostToDevice, s));
+    launch_tps_fill(xo.get(), p, d, L.get(), ldq, 0.0, true, s);                      // :100-103
+    SPB_CUDA(cudaMemsetAsync(rhs.get(), 0, sizeof(double) * ldq * K, s));
+    SPB_CUDA(cudaMemcpy2DAsync(rhs.get(), ldq * sizeof(double), Phi, (size_t)p * sizeof(double),
+                               (size_t)p * sizeof(double), K, cudaMemcpyHostToDevice, s));   // :105-106
+    int lwork = 0;
+    SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(ctx.solver, q, q, L.get(), (int)ldq, &lwork));
+    ctx.ipiv.ensure(q);
+    double* work = ctx.work((size_t)lwork);
+    SPB_CUSOLVER(cusolverDnDgetrf(ctx.solver, q, q, L.get(), (int)ldq, work, ctx.ipiv.get(), ctx.info.get()));
+    launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_SINGULAR, s);
+    SPB_CUSOLVER(cusolverDnDgetrs(ctx.solver, CUBLAS_OP_N, q, K, L.get(), (int)ldq, ctx.ipiv.get(), rhs.get(),
+                                  (int)ldq, ctx.info.get()));                           // :108
+    launch_tps_eval(xn.get(), p_new, xo.get(), p, d, rhs.get(), ldq, K, res.get(), s); // :113-145
+    SPB_CUDA(cudaMemcpyAsync(out, res.get(), sizeof(double) * (size_t)p_new * K, cudaMemcpyDeviceToHost, s));
+    ctx.sync_and_check();
+  });
+}
+
+int spb_spatial_prediction(const double* phi, int p, int K, const double* Y, int n, double gamma,
+                           const double* predicted_phi, int p_new, double* prediction,
+                           double* estimated_covariance, double* eigenvalue, double* error) {
+  return guarded([&] {
+    // spatialPrediction (:715-770).  phi' cov phi and trace(cov) come from Y phi and ||Y||_F^2,
+    // so the p x p covariance of :728 is never formed.
+    SPB_REQUIRE(phi && Y && predicted_phi, "NULL argument");
+    SPB_REQUIRE(p >= 1 && K >= 1 && n >= 1 && p_new >= 1, "sizes must be positive");
+    SPB_REQUIRE(K <= SPB_MAX_K, "K must be in 1..SPB_MAX_K");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    DevBuf<double> dphi((size_t)p * K), dY((size_t)n * p), dpp((size_t)p_new * K), W((size_t)n * K),
+        scr(yphi_scratch_doubles(n, p, K) + 512), H((size_t)K * K), ss(1);
+    SPB_CUDA(cudaMemcpyAsync(dphi.get(), phi, sizeof(double) * (size_t)p * K, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(dY.get(), Y, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(dpp.get(), predicted_phi, sizeof(double) * (size_t)p_new * K, cudaMemcpyHostToDevice, s));
+    launch_yphi(dY.get(), n, p, dphi.get(), K, W.get(), scr.get(), s);
+    launch_small_gram(W.get(), n, K, 1.0 / (double)n, H.get(), s);                  // phi' cov phi (:729)
+    launch_sumsq(dY.get(), (size_t)n * p, scr.get(), ss.get(), s);                  // trace(cov) * n (:731)
+    std::vector<double> Hh((size_t)K * K);
+    double ssq = 0.0;
+    SPB_CUDA(cudaMemcpyAsync(Hh.data(), H.get(), sizeof(double) * K * K, cudaMemcpyDeviceToHost, s));
+    SPB_CUDA(cudaMemcpyAsync(&ssq, ss.get(), sizeof(double), cudaMemcpyDeviceToHost, s));
+    ctx.sync_and_check();
+    const double tv = ssq / (double)n;
+    std::vector<double> evals, evecs;
+    host_jacobi_eigh(K, Hh, evals, evecs);
+    const double total = arma_accumulate(evals.data(), K);
+    std::vector<double> dvals(K), Qd((size_t)K * K);
+    for (int c = 0; c < K; ++c) {
+      dvals[c] = evals[K - 1 - c];
+      for (int i = 0; i < K; ++i) Qd[(size_t)c * K + i] = evecs[(size_t)(K - 1 - c) * K + i];
+    }
+    const double err = water_filling(dvals, total, tv, gamma, p, K);               // :734-760
+    std::vector<double> ev(K), Qs((size_t)K * K);
+    for (int k = 0; k < K; ++k) {
+      ev[k] = std::max(dvals[k] - (err + gamma), 0.0);                              // :762
+      const double ratio = ev[k] / (ev[k] + err);                                   // :763-764
+      for (int i = 0; i < K; ++i) Qs[(size_t)k * K + i] = Qd[(size_t)k * K + i] * ratio;
+    }
+    if (eigenvalue) std::memcpy(eigenvalue, ev.data(), sizeof(double) * K);
+    if (error) *error = err;
+    if (prediction || estimated_covariance) {
+      DevBuf<double> Qdev((size_t)K * K), Qsdev((size_t)K * K), A1((size_t)p * K), A2((size_t)p_new * K),
+          cov((size_t)p * p_new);
+      SPB_CUDA(cudaMemcpyAsync(Qdev.get(), Qd.data(), sizeof(double) * K * K, cudaMemcpyHostToDevice, s));
+      SPB_CUDA(cudaMemcpyAsync(Qsdev.get(), Qs.data(), sizeof(double) * K * K, cudaMemcpyHostToDevice, s));
+      launch_small_rmul(dphi.get(), p, K, Qsdev.get(), A1.get(), s);                // phi Q diag(ratio)
+      launch_small_rmul(dpp.get(), p_new, K, Qdev.get(), A2.get(), s);              // predicted_phi Q
+      const double one = 1.0, zero = 0.0;
+      SPB_CUBLAS(cublasDgemm(ctx.blas, CUBLAS_OP_N, CUBLAS_OP_T, p, p_new, K, &one, A1.get(), p, A2.get(), p_new,
+                             &zero, cov.get(), p));                                 // :764
+      if (estimated_covariance)
+        SPB_CUDA(cudaMemcpyAsync(estimated_covariance, cov.get(), sizeof(double) * (size_t)p * p_new,
+                                 cudaMemcpyDeviceToHost, s));
+      if (prediction) {
+        DevBuf<double> pred((size_t)n * p_new);
+        SPB_CUBLAS(cublasDgemm(ctx.blas, CUBLAS_OP_N, CUBLAS_OP_N, n, p_new, p, &one, dY.get(), n, cov.get(), p,
+                               &zero, pred.get(), n));                              // :765
+        SPB_CUDA(cudaMemcpyAsync(prediction, pred.get(), sizeof(double) * (size_t)n * p_new,
+                                 cudaMemcpyDeviceToHost, s));
+        ctx.sync_and_check();
+      }
+      ctx.sync_and_check();
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+int spb_engine_create(spb_engine** out, int p, int d, int n, int M, int K, const double* tau1, int n_tau1,
+                      const double* tau2, int n_tau2, const double* gamma, int n_gamma, int maxit,
+                      double tol, const double* l2, int n_l2) {
+  return guarded([&] {
+    SPB_REQUIRE(out != nullptr, "NULL handle pointer");
+    *out = nullptr;
+    Engine* e = new Engine(p, d, n, M, K, tau1, n_tau1, tau2, n_tau2, gamma, n_gamma, maxit, tol, l2, n_l2);
+    *out = new spb_engine{e};
+  });
+}
+
+int spb_engine_destroy(spb_engine* e) {
+  return guarded([&] {
+    if (e) {
+      delete e->impl;
+      delete e;
+    }
+  });
+}
+
+#define SPB_ENGINE_CALL(body)                                   \
+  return guarded([&] {                                           \
+    SPB_REQUIRE(e != nullptr && e->impl != nullptr, "NULL engine"); \
+    body;                                                        \
+  })
+
+int spb_engine_upload(spb_engine* e, const double* sxy, const double* Y, const double* nk) {
+  SPB_ENGINE_CALL(e->impl->upload(sxy, Y, nk));
+}
+int spb_engine_set_omega(spb_engine* e, const double* omega) { SPB_ENGINE_CALL(e->impl->set_omega(omega)); }
+int spb_engine_prepare(spb_engine* e) { SPB_ENGINE_CALL(e->impl->prepare()); }
+int spb_engine_get_omega(spb_engine* e, double* omega_out) { SPB_ENGINE_CALL(e->impl->get_omega(omega_out)); }
+int spb_engine_stage1_fold(spb_engine* e, int k, double* cv_row) { SPB_ENGINE_CALL(e->impl->stage1_fold(k, cv_row)); }
+int spb_engine_stage1_full(spb_engine* e, int index1) { SPB_ENGINE_CALL(e->impl->stage1_full(index1)); }
+int spb_engine_stage2_fold(spb_engine* e, int k, int index1, double* cv_row) {
+  SPB_ENGINE_CALL(e->impl->stage2_fold(k, index1, cv_row));
+}
+int spb_engine_stage2_full(spb_engine* e, int index1, int index2) {
+  SPB_ENGINE_CALL(e->impl->stage2_full(index1, index2));
+}
+int spb_engine_stage3_fold(spb_engine* e, int k, int index1, int index2, double* cv_row) {
+  SPB_ENGINE_CALL(e->impl->stage3_fold(k, index1, index2, cv_row));
+}
+int spb_engine_get_eigenfn(spb_engine* e, double* out) { SPB_ENGINE_CALL(e->impl->get_eigenfn(out)); }
+int spb_engine_get_stats(spb_engine* e, spb_cv_stats* st) { SPB_ENGINE_CALL(e->impl->get_stats(st)); }
+int spb_engine_release_fold(spb_engine* e, int k) { SPB_ENGINE_CALL(e->impl->release_fold(k)); }
+
+int spb_engine_call_log(spb_engine* e, int* log4, int cap) {
+  int n = 0;
+  int rc = guarded([&] {
+    SPB_REQUIRE(e != nullptr && e->impl != nullptr, "NULL engine");
+    n = e->impl->call_log(log4, cap);
+  });
+  return rc == SPB_OK ? n : rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+int spb_cv(const double* sxy, int p, int d, const double* Y, int n, int M, int K, const double* tau1,
+           int n_tau1, const double* tau2, int n_tau2, const double* gamma, int n_gamma, const double* nk,
+           int maxit, double tol, const double* l2, int n_l2, double* cv_score_tau1, double* cv_score_tau2,
+           double* cv_score_gamma, double* estimated_eigenfn, double* selected, spb_cv_stats* stats) {
+  return guarded([&] {
+    SPB_REQUIRE(cv_score_tau1 && cv_score_tau2 && cv_score_gamma && estimated_eigenfn && selected,
+                "NULL output");
+    Engine eng(p, d, n, M, K, tau1, n_tau1, tau2, n_tau2, gamma, n_gamma, maxit, tol, l2, n_l2);
+    eng.upload(sxy, Y, nk);
+    eng.prepare();
+    // stage 1 (:592-650)
+    int index1 = 0, index2 = 0, index3 = 0;
+    std::vector<double> cv1((size_t)M * n_tau1, 0.0);
+    {
+      std::vector<double> row(n_tau1);
+      for (int k = 0; k < M; ++k) {
+        eng.stage1_fold(k, row.data());
+        if (n_tau1 > 1)
+          for (int i = 0; i < n_tau1; ++i) cv1[(size_t)i * M + k] = row[i];
+      }
+    }
+    if (n_tau1 > 1) index1 = select_index_impl(cv1.data(), M, n_tau1, cv_score_tau1);
+    else cv_score_tau1[0] = 0.0;                                              // :649
+    eng.stage1_full(index1);
+    selected[0] = eng.selected_tau1(index1);
+    // stage 2 (:652-680)
+    if (n_tau2 > 1) {
+      std::vector<double> cv2((size_t)M * n_tau2, 0.0), row(n_tau2);
+      for (int k = 0; k < M; ++k) {
+        eng.stage2_fold(k, index1, row.data());
+        for (int i = 0; i < n_tau2; ++i) cv2[(size_t)i * M + k] = row[i];
+      }
+      index2 = select_index_impl(cv2.data(), M, n_tau2, cv_score_tau2);
+      selected[1] = tau2[index2];
+    } else {
+      cv_score_tau2[0] = 0.0;                                                 // :679
+      selected[1] = tau2[0];                                                  // :671
+    }
+    eng.stage2_full(index1, index2);
+    // stage 3 (:682-692)
+    {
+      std::vector<double> cv3((size_t)M * n_gamma, 0.0), row(n_gamma);
+      for (int k = 0; k < M; ++k) {
+        eng.stage3_fold(k, index1, index2, row.data());
+        for (int i = 0; i < n_gamma; ++i) cv3[(size_t)i * M + k] = row[i];
+      }
+      index3 = select_index_impl(cv3.data(), M, n_gamma, cv_score_gamma);
+      selected[2] = (n_gamma > 1) ? gamma[index3] : gamma[0];                 // :684-691
+    }
+    eng.get_eigenfn(estimated_eigenfn);
+    eng.get_stats(stats);
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel-level entry points
+// ---------------------------------------------------------------------------------------------
+int spb_inv_sympd(const double* omega, const double* G, int p, double tau1, double rho, double scale,
+                  double* out) {
+  return guarded([&] {
+    SPB_REQUIRE(omega && G && out && p >= 1, "invalid argument");
+    DeviceCtx& ctx = DeviceCtx::get();
+    const size_t ld = padded_ld(p);
+    DevBuf<double> om(ld * (size_t)p), g(ld * (size_t)p), w(ld * (size_t)p);
+    upload_square(omega, p, om.get(), ld, ctx.stream);
+    upload_square(G, p, g.get(), ld, ctx.stream);
+    launch_symmatu_inplace(om.get(), p, ld, 0.0, ctx.stream);
+    Engine::spd_inverse(ctx, om.get(), ld, g.get(), ld, p, tau1, rho, scale, w.get(), ld);
+    download_square(out, p, w.get(), ld, ctx.stream);
+    ctx.sync_and_check();
+  });
+}
+
+static void run_admm_host(int mode, const double* tempinv, int p, int K, double tau2, double rho, int maxit,
+                          double tol, double* Phi, double* R, double* C, double* L1, double* L2, int* iters) {
+  SPB_REQUIRE(tempinv && Phi && C && L2 && p >= 1, "invalid argument");
+  SPB_REQUIRE(K >= 1 && K <= SPB_MAX_K && K <= p, "K must be in 1..min(SPB_MAX_K, p)");
+  if (mode == 3) SPB_REQUIRE(R && L1, "invalid argument");
+  DeviceCtx& ctx = DeviceCtx::get();
+  cudaStream_t s = ctx.stream;
+  const size_t ld = padded_ld(p), pk = (size_t)p * K;
+  DevBuf<double> A(ld * (size_t)p), err(1);
+  DevBuf<int> stat(4);
+  DevBuf<char> ws(admm_workspace_bytes(p, K));
+  ChainState st;
+  st.alloc(pk);
+  upload_square(tempinv, p, A.get(), ld, s);
+  SPB_CUDA(cudaMemsetAsync(st.Phi.get(), 0, sizeof(double) * pk, s));
+  SPB_CUDA(cudaMemcpyAsync(st.C.get(), C, sizeof(double) * pk, cudaMemcpyHostToDevice, s));
+  SPB_CUDA(cudaMemcpyAsync(st.L2.get(), L2, sizeof(double) * pk, cudaMemcpyHostToDevice, s));
+  if (mode == 3) {
+    SPB_CUDA(cudaMemcpyAsync(st.R.get(), R, sizeof(double) * pk, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(st.L1.get(), L1, sizeof(double) * pk, cudaMemcpyHostToDevice, s));
+  }
+  SPB_CUDA(cudaMemsetAsync(stat.get(), 0, 4 * sizeof(int), s));
+  AdmmCall c;
+  c.Ainv = A.get(); c.ld = ld; c.p = p; c.K = K; c.mode = mode; c.rho = rho; c.tau2 = tau2;
+  c.maxit = maxit; c.tol = tol;
+  c.Phi = st.Phi.get(); c.R = st.R.get(); c.C = st.C.get(); c.L1 = st.L1.get(); c.L2 = st.L2.get();
+  c.stat_slot = stat.get(); c.err_slot = err.get();
+  if (maxit > 0) launch_admm(c, ws.get(), s);
+  int sth[4] = {0, 0, 0, 0};
+  SPB_CUDA(cudaMemcpyAsync(sth, stat.get(), sizeof(sth), cudaMemcpyDeviceToHost, s));
+  if (maxit > 0) SPB_CUDA(cudaMemcpyAsync(Phi, st.Phi.get(), sizeof(double) * pk, cudaMemcpyDeviceToHost, s));
+  SPB_CUDA(cudaMemcpyAsync(C, st.C.get(), sizeof(double) * pk, cudaMemcpyDeviceToHost, s));
+  SPB_CUDA(cudaMemcpyAsync(L2, st.L2.get(), sizeof(double) * pk, cudaMemcpyDeviceToHost, s));
+  if (mode == 3) {
+    SPB_CUDA(cudaMemcpyAsync(R, st.R.get(), sizeof(double) * pk, cudaMemcpyDeviceToHost, s));
+    SPB_CUDA(cudaMemcpyAsync(L1, st.L1.get(), sizeof(double) * pk, cudaMemcpyDeviceToHost, s));
+  }
+  ctx.sync_and_check();
+  if (iters) *iters = sth[0];
+  if (sth[1] != 0)
+    throw Error(SPB_ERR_POLAR, "svd_econ(): the p x K iterate is rank deficient, Stiefel projection undefined");
+}
+
+int spb_admm_core2(const double* tempinv, int p, int K, double rho, int maxit, double tol, double* Phi,
+                   double* C, double* Lambda2, int* iters) {
+  return guarded([&] {
+    run_admm_host(2, tempinv, p, K, 0.0, rho, maxit, tol, Phi, nullptr, C, nullptr, Lambda2, iters);
+  });
+}
+
+int spb_admm_core3(const double* tempinv, int p, int K, double tau2, double rho, int maxit, double tol,
+                   double* Phi, double* R, double* C, double* Lambda1, double* Lambda2, int* iters) {
+  return guarded([&] {
+    run_admm_host(3, tempinv, p, K, tau2, rho, maxit, tol, Phi, R, C, Lambda1, Lambda2, iters);
+  });
+}
+
+int spb_cv_loss(const double* Yva, int n_va, int p, const double* Phi, int K, double* loss) {
+  return guarded([&] {
+    SPB_REQUIRE(Yva && Phi && loss && n_va >= 1 && p >= 1 && K >= 1, "invalid argument");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    DevBuf<double> dY((size_t)n_va * p), dP((size_t)p * K), W((size_t)n_va * K),
+        scr(yphi_scratch_doubles(n_va, p, K) + 16), out(1);
+    SPB_CUDA(cudaMemcpyAsync(dY.get(), Yva, sizeof(double) * (size_t)n_va * p, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(dP.get(), Phi, sizeof(double) * (size_t)p * K, cudaMemcpyHostToDevice, s));
+    Engine::cv_loss(ctx, dY.get(), n_va, p, dP.get(), K, W.get(), scr.get(), out.get());
+    SPB_CUDA(cudaMemcpyAsync(loss, out.get(), sizeof(double), cudaMemcpyDeviceToHost, s));
+    ctx.sync_and_check();
+  });
+}
+
+int spb_gamma_loss(const double* Phi, int p, int K, const double* Ytr, int n_tr, const double* Yva, int n_va,
+                   const double* gamma, int n_gamma, double* out) {
+  return guarded([&] {
+    SPB_REQUIRE(Phi && Ytr && Yva && gamma && out, "NULL argument");
+    SPB_REQUIRE(p >= 1 && K >= 1 && K <= SPB_MAX_K && n_tr >= 1 && n_va >= 1 && n_gamma >= 1, "invalid size");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    DevBuf<double> dP((size_t)p * K), dtr((size_t)n_tr * p), dva((size_t)n_va * p), scr(512), ss(1);
+    SPB_CUDA(cudaMemcpyAsync(dP.get(), Phi, sizeof(double) * (size_t)p * K, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(dtr.get(), Ytr, sizeof(double) * (size_t)n_tr * p, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(dva.get(), Yva, sizeof(double) * (size_t)n_va * p, cudaMemcpyHostToDevice, s));
+    launch_sumsq(dtr.get(), (size_t)n_tr * p, scr.get(), ss.get(), s);
+    double ssq = 0.0;
+    SPB_CUDA(cudaMemcpyAsync(&ssq, ss.get(), sizeof(double), cudaMemcpyDeviceToHost, s));
+    ctx.sync_and_check();
+    std::vector<double> g(gamma, gamma + n_gamma);
+    Engine::gamma_losses(ctx, dP.get(), p, K, dtr.get(), n_tr, ssq / (double)n_tr, dva.get(), n_va, g, out);
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident benchmark hooks
+// ---------------------------------------------------------------------------------------------
+int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_per_iter) {
+  return guarded([&] {
+    SPB_REQUIRE(p >= 1 && K >= 1 && K <= SPB_MAX_K && K <= p && iters >= 1 && repeats >= 1 && ms_per_iter,
+                "invalid argument");
+    SPB_REQUIRE(mode == 2 || mode == 3, "mode must be 2 or 3");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    const size_t ld = padded_ld(p), pk = (size_t)p * K;
+    DevBuf<double> A(ld * (size_t)p), err(1);
+    DevBuf<int> stat(4);
+    DevBuf<char> ws(admm_workspace_bytes(p, K));
+    ChainState st;
+    st.alloc(pk);
+    // a well-posed synthetic chain: Ainv = I, C = R = first K unit vectors, duals = 0, rho = 1
+    SPB_CUDA(cudaMemsetAsync(A.get(), 0, sizeof(double) * ld * p, s));
+    launch_set_identity(A.get(), p, p, ld, s);
+    cudaEvent_t e0, e1;
+    SPB_CUDA(cudaEventCreate(&e0));
+    SPB_CUDA(cudaEventCreate(&e1));
+    double best = 1e300;
+    for (int r = 0; r < repeats + 1; ++r) {
+      launch_set_identity(st.C.get(), p, K, p, s);
+      launch_set_identity(st.R.get(), p, K, p, s);
+      SPB_CUDA(cudaMemsetAsync(st.L1.get(), 0, sizeof(double) * pk, s));
+      SPB_CUDA(cudaMemsetAsync(st.L2.get(), 0, sizeof(double) * pk, s));
+      AdmmCall c;
+      c.Ainv = A.get(); c.ld = ld; c.p = p; c.K = K; c.mode = mode; c.rho = 1.0; c.tau2 = 1e-3;
+      c.maxit = iters; c.tol = -1.0;          // never satisfied: every call runs `iters` iterations
+      c.Phi = st.Phi.get(); c.R = st.R.get(); c.C = st.C.get(); c.L1 = st.L1.get(); c.L2 = st.L2.get();
+      c.stat_slot = stat.get(); c.err_slot = err.get();
+      SPB_CUDA(cudaEventRecord(e0, s));
+      launch_admm(c, ws.get(), s);
+      SPB_CUDA(cudaEventRecord(e1, s));
+      SPB_CUDA(cudaStreamSynchronize(s));
+      int sth[4];
+      SPB_CUDA(cudaMemcpy(sth, stat.get(), sizeof(sth), cudaMemcpyDeviceToHost));
+      if (sth[0] != iters || sth[1] != 0) throw Error(SPB_ERR_INTERNAL, "bench chain did not run all iterations");
+      float ms = 0.f;
+      SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (r > 0) best = std::min(best, (double)ms / iters);   // r == 0 is the warm-up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_iter = best;
+  });
+}
+
+int spb_bench_dgemm(int m, int repeats, double* tflops) {
+  return guarded([&] {
+    SPB_REQUIRE(m >= 1 && repeats >= 1 && tflops, "invalid argument");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    const size_t mm = (size_t)m * m;
+    DevBuf<double> A(mm), B(mm), C(mm);
+    launch_set_identity(A.get(), m, m, m, s);
+    launch_set_identity(B.get(), m, m, m, s);
+    const double one = 1.0, zero = 0.0;
+    cudaEvent_t e0, e1;
+    SPB_CUDA(cudaEventCreate(&e0));
+    SPB_CUDA(cudaEventCreate(&e1));
+    double best = 1e300;
+    for (int r = 0; r < repeats + 1; ++r) {
+      SPB_CUDA(cudaEventRecord(e0, s));
+      SPB_CUBLAS(cublasDgemm(ctx.blas, CUBLAS_OP_N, CUBLAS_OP_N, m, m, m, &one, A.get(), m, B.get(), m, &zero,
+                             C.get(), m));
+      SPB_CUDA(cudaEventRecord(e1, s));
+      SPB_CUDA(cudaStreamSynchronize(s));
+      float ms = 0.f;
+      SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (r > 0) best = std::min(best, (double)ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = 2.0 * (double)m * m * m / (best * 1e-3) / 1e12;
+  });
+}
+
+int spb_bench_inverse(int p, int repeats, double* ms_out) {
+  return guarded([&] {
+    SPB_REQUIRE(p >= 1 && repeats >= 1 && ms_out, "invalid argument");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    const size_t ld = padded_ld(p);
+    DevBuf<double> om(ld * (size_t)p), g(ld * (size_t)p), w(ld * (size_t)p);
+    SPB_CUDA(cudaMemsetAsync(om.get(), 0, sizeof(double) * ld * p, s));
+    SPB_CUDA(cudaMemsetAsync(g.get(), 0, sizeof(double) * ld * p, s));
+    launch_set_identity(om.get(), p, p, ld, s);
+    cudaEvent_t e0, e1;
+    SPB_CUDA(cudaEventCreate(&e0));
+    SPB_CUDA(cudaEventCreate(&e1));
+    double best = 1e300;
+    for (int r = 0; r < repeats + 1; ++r) {
+      SPB_CUDA(cudaEventRecord(e0, s));
+      Engine::spd_inverse(ctx, om.get(), ld, g.get(), ld, p, 0.5, 10.0, 2.0, w.get(), ld);
+      SPB_CUDA(cudaEventRecord(e1, s));
+      ctx.sync_and_check();
+      float ms = 0.f;
+      SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (r > 0) best = std::min(best, (double)ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_out = best;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Shared host/device helpers for the spatpca_b200 engine.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/spatpca_b200.h"
+
+namespace spb {
+
+// Internal exception carrying an ABI status; translated at the extern "C" boundary.
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+void set_last_error(const std::string& s);
+
+#define SPB_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      throw ::spb::Error(SPB_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(_e) + \
+                                           " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+#define SPB_CUBLAS(expr)                                                                 \
+  do {                                                                                   \
+    cublasStatus_t _s = (expr);                                                          \
+    if (_s != CUBLAS_STATUS_SUCCESS)                                                     \
+      throw ::spb::Error(SPB_ERR_CUDA, std::string("cuBLAS error ") + std::to_string((int)_s) + \
+                                           " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+#define SPB_CUSOLVER(expr)                                                               \
+  do {                                                                                   \
+    cusolverStatus_t _s = (expr);                                                        \
+    if (_s != CUSOLVER_STATUS_SUCCESS)                                                   \
+      throw ::spb::Error(SPB_ERR_CUDA, std::string("cuSOLVER error ") + std::to_string((int)_s) + \
+                                           " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+#define SPB_REQUIRE(cond, msg)                                                           \
+  do {                                                                                   \
+    if (!(cond)) throw ::spb::Error(SPB_ERR_INVALID_ARG, std::string(msg));              \
+  } while (0)
+
+inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Leading dimension used for every p x p device matrix: columns start 128-byte
+// aligned so that 16-byte vector loads and bulk copies never straddle a column.
+inline size_t padded_ld(size_t rows) { return round_up(rows, 16); }
+
+// RAII device buffer of doubles (or bytes).
+template <typename T>
+struct DevBuf {
+  T* ptr = nullptr;
+  size_t count = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : ptr(o.ptr), count(o.count) { o.ptr = nullptr; o.count = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); ptr = o.ptr; count = o.count; o.ptr = nullptr; o.count = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    if (n == 0) return;
+    cudaError_t e = cudaMalloc((void**)&ptr, n * sizeof(T));
+    if (e != cudaSuccess) {
+      ptr = nullptr;
+      throw Error(SPB_ERR_CUDA, std::string("cudaMalloc of ") + std::to_string(n * sizeof(T)) +
+                                    " bytes failed: " + cudaGetErrorString(e));
+    }
+    count = n;
+  }
+  void ensure(size_t n) { if (n > count) alloc(n); }
+  void release() { if (ptr) { cudaFree(ptr); ptr = nullptr; count = 0; } }
+  T* get() const { return ptr; }
+  operator T*() const { return ptr; }
+};
+
+// Kernel-launch counter (claimed in bench.py as `gpu_launches`): only launches of
+// this library's own kernels are counted, never cuBLAS / cuSOLVER internals.
+extern thread_local long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
+}  // namespace spb

@@ -1,0 +1,798 @@
+// Engine implementation.  Control flow follows the *semantics* of the reference's
+// spatpcaCV (src/RcppSpatPCA.cpp:543-701) including its quirks, but is
+// organised per (stage, fold) so that folds can live on different devices; the data path is
+// device-resident from upload() to get_eigenfn().
+#include "engine.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <numeric>
+
+namespace spb {
+
+thread_local long long g_launch_count = 0;
+
+// ---------------------------------------------------------------------------------------
+// DeviceCtx
+// ---------------------------------------------------------------------------------------
+DeviceCtx& DeviceCtx::get() {
+  static thread_local std::map<int, std::unique_ptr<DeviceCtx>> ctxs;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    throw Error(SPB_ERR_NO_DEVICE,
+                "no CUDA device available (spatpca_b200 has no CPU fallback)");
+  }
+  int dev = 0;
+  SPB_CUDA(cudaGetDevice(&dev));
+  auto it = ctxs.find(dev);
+  if (it != ctxs.end()) return *it->second;
+  std::unique_ptr<DeviceCtx> c(new DeviceCtx());
+  c->device = dev;
+  SPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  SPB_CUBLAS(cublasCreate(&c->blas));
+  SPB_CUBLAS(cublasSetStream(c->blas, c->stream));
+  SPB_CUBLAS(cublasSetPointerMode(c->blas, CUBLAS_POINTER_MODE_HOST));
+  SPB_CUSOLVER(cusolverDnCreate(&c->solver));
+  SPB_CUSOLVER(cusolverDnSetStream(c->solver, c->stream));
+  c->info.alloc(4);
+  c->flag.alloc(1);
+  SPB_CUDA(cudaMemsetAsync(c->flag.get(), 0, sizeof(int), c->stream));
+  DeviceCtx& ref = *c;
+  ctxs[dev] = std::move(c);
+  return ref;
+}
+
+DeviceCtx::~DeviceCtx() {
+  if (solver) cusolverDnDestroy(solver);
+  if (blas) cublasDestroy(blas);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+void DeviceCtx::sync_and_check() {
+  SPB_CUDA(cudaStreamSynchronize(stream));
+  int f = 0;
+  SPB_CUDA(cudaMemcpy(&f, flag.get(), sizeof(int), cudaMemcpyDeviceToHost));
+  if (f != 0) {
+    SPB_CUDA(cudaMemset(flag.get(), 0, sizeof(int)));
+    switch (f) {
+      case SPB_ERR_NOT_POSDEF:
+        throw Error(f, "inv_sympd(): matrix is singular or not positive definite");
+      case SPB_ERR_SINGULAR:
+        throw Error(f, "inv(): matrix is singular");
+      case SPB_ERR_SVD:
+        throw Error(f, "svd(): decomposition failed");
+      default:
+        throw Error(f, "device-side failure");
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// PhaseClock
+// ---------------------------------------------------------------------------------------
+cudaEvent_t PhaseClock::grab() {
+  if (used_ == pool_.size()) {
+    cudaEvent_t e;
+    SPB_CUDA(cudaEventCreate(&e));
+    pool_.push_back(e);
+  }
+  return pool_[used_++];
+}
+void PhaseClock::begin(Phase ph, cudaStream_t s) {
+  if (open_ >= 0) return;   // nested spans are attributed to the outer phase
+  Span sp; sp.ph = ph; sp.a = grab(); sp.b = grab();
+  SPB_CUDA(cudaEventRecord(sp.a, s));
+  spans_.push_back(sp);
+  open_ = (int)spans_.size() - 1;
+}
+void PhaseClock::end(cudaStream_t s) {
+  if (open_ < 0) return;
+  SPB_CUDA(cudaEventRecord(spans_[open_].b, s));
+  open_ = -1;
+}
+void PhaseClock::collect(double ms[PH_COUNT]) {
+  for (auto& sp : spans_) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) acc_[sp.ph] += t;
+  }
+  spans_.clear();
+  used_ = 0;
+  for (int i = 0; i < PH_COUNT; ++i) ms[i] = acc_[i];
+}
+void PhaseClock::reset() {
+  spans_.clear(); used_ = 0; open_ = -1;
+  for (int i = 0; i < PH_COUNT; ++i) acc_[i] = 0;
+}
+PhaseClock::~PhaseClock() { for (auto e : pool_) cudaEventDestroy(e); }
+
+struct Scoped {
+  PhaseClock& c; cudaStream_t s;
+  Scoped(PhaseClock& c_, Phase ph, cudaStream_t s_) : c(c_), s(s_) { c.begin(ph, s); }
+  ~Scoped() { try { c.end(s); } catch (...) {} }
+};
+
+// ---------------------------------------------------------------------------------------
+// small host math
+// ---------------------------------------------------------------------------------------
+double arma_accumulate(const double* x, int n) {
+  // Armadillo arrayops::accumulate: two interleaved accumulators (used by sum(cv, 0), accu()).
+  double a1 = 0.0, a2 = 0.0;
+  int i = 0, j = 1;
+  for (; j < n; j += 2, i += 2) { a1 += x[i]; a2 += x[i + 1]; }
+  if ((j - 1) < n) a1 += x[i];
+  return a1 + a2;
+}
+
+void host_jacobi_eigh(int K, std::vector<double>& A, std::vector<double>& evals,
+                      std::vector<double>& evecs) {
+  // cyclic Jacobi on the upper triangle's symmetric completion; eigenvalues ascending.
+  std::vector<double> V((size_t)K * K, 0.0);
+  for (int i = 0; i < K; ++i) V[(size_t)i * K + i] = 1.0;
+  for (int a = 0; a < K; ++a)
+    for (int b = a + 1; b < K; ++b) A[(size_t)a * K + b] = A[(size_t)b * K + a] = A[(size_t)b * K + a];
+  // (col-major: element (a, b) at A[b*K + a]; upper triangle is the source, as dsyevd 'U')
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    bool rotated = false;
+    for (int pp = 0; pp < K - 1; ++pp) {
+      for (int qq = pp + 1; qq < K; ++qq) {
+        double apq = A[(size_t)qq * K + pp], app = A[(size_t)pp * K + pp], aqq = A[(size_t)qq * K + qq];
+        if (apq == 0.0 || std::fabs(apq) <= 1e-17 * std::sqrt(std::fabs(app * aqq))) continue;
+        rotated = true;
+        double theta = (aqq - app) / (2.0 * apq);
+        double t = 1.0 / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        if (theta < 0) t = -t;
+        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c, tau = s / (1.0 + c);
+        for (int i = 0; i < K; ++i) {
+          if (i != pp && i != qq) {
+            double aip = A[(size_t)pp * K + i], aiq = A[(size_t)qq * K + i];
+            double nip = aip - s * (aiq + tau * aip), niq = aiq + s * (aip - tau * aiq);
+            A[(size_t)pp * K + i] = A[(size_t)i * K + pp] = nip;
+            A[(size_t)qq * K + i] = A[(size_t)i * K + qq] = niq;
+          }
+          double vip = V[(size_t)pp * K + i], viq = V[(size_t)qq * K + i];
+          V[(size_t)pp * K + i] = vip - s * (viq + tau * vip);
+          V[(size_t)qq * K + i] = viq + s * (vip - tau * viq);
+        }
+        A[(size_t)pp * K + pp] = app - t * apq;
+        A[(size_t)qq * K + qq] = aqq + t * apq;
+        A[(size_t)qq * K + pp] = A[(size_t)pp * K + qq] = 0.0;
+      }
+    }
+    if (!rotated) break;
+  }
+  std::vector<int> order(K);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int a, int b) { return A[(size_t)a * K + a] < A[(size_t)b * K + b]; });
+  evals.resize(K);
+  evecs.assign((size_t)K * K, 0.0);
+  for (int c = 0; c < K; ++c) {
+    evals[c] = A[(size_t)order[c] * K + order[c]];
+    for (int i = 0; i < K; ++i) evecs[(size_t)c * K + i] = V[(size_t)order[c] * K + i];
+  }
+}
+
+double water_filling(const std::vector<double>& d, double total, double tv, double g, int p, int K) {
+  // noise level of reference :499-519 / :743-760; d = descending eigenvalues of Phi' S Phi
+  int tempL = K;
+  double error;
+  if (d[0] > g) {
+    error = (tv - total + K * g) / (p - tempL);
+    double temp = d[tempL - 1];
+    while (temp - g < error) {
+      if (tempL == 1) {
+        error = (tv - d[0] + g) / (p - 1);
+        break;
+      }
+      total -= d[tempL - 1];
+      tempL--;
+      error = (tv - total + tempL * g) / (p - tempL);
+      temp = d[tempL - 1];
+    }
+    if (d[0] - g < error) error = tv / p;
+  } else {
+    error = tv / p;
+  }
+  return error;
+}
+
+// ---------------------------------------------------------------------------------------
+// static building blocks
+// ---------------------------------------------------------------------------------------
+void Engine::build_omega_raw(DeviceCtx& ctx, const double* x_dev, int p, int d, double* omega_dev,
+                             size_t ld) {
+  // thinPlateSplineMatrix (:58-76): Lp = top-left block of inv(L + 1e-8 I) by LU with partial
+  // pivoting (the reference's dgetrf/dgetri class; here getrf + getrs on [I_p; 0]); Omega = Lp'(E Lp).
+  const int q = p + d + 1;
+  const size_t ldq = padded_ld(q);
+  DevBuf<double> L(ldq * (size_t)q), Bm(ldq * (size_t)p), T1(ld * (size_t)p);
+  cudaStream_t s = ctx.stream;
+  launch_tps_fill(x_dev, p, d, L.get(), ldq, 1e-8, true, s);
+  launch_set_identity(Bm.get(), q, p, ldq, s);
+  int lwork = 0;
+  SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(ctx.solver, q, q, L.get(), (int)ldq, &lwork));
+  ctx.ipiv.ensure(q);
+  double* work = ctx.work((size_t)lwork);
+  SPB_CUSOLVER(cusolverDnDgetrf(ctx.solver, q, q, L.get(), (int)ldq, work, ctx.ipiv.get(), ctx.info.get()));
+  launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_SINGULAR, s);
+  SPB_CUSOLVER(cusolverDnDgetrs(ctx.solver, CUBLAS_OP_N, q, p, L.get(), (int)ldq, ctx.ipiv.get(), Bm.get(),
+                                (int)ldq, ctx.info.get()));
+  // E (p x p, zero diagonal) regenerated into L's storage
+  launch_tps_fill(x_dev, p, d, L.get(), ldq, 0.0, false, s);
+  const double one = 1.0, zero = 0.0;
+  SPB_CUBLAS(cublasDgemm(ctx.blas, CUBLAS_OP_N, CUBLAS_OP_N, p, p, p, &one, L.get(), (int)ldq, Bm.get(),
+                         (int)ldq, &zero, T1.get(), (int)ld));
+  SPB_CUBLAS(cublasDgemm(ctx.blas, CUBLAS_OP_T, CUBLAS_OP_N, p, p, p, &one, Bm.get(), (int)ldq, T1.get(),
+                         (int)ld, &zero, omega_dev, (int)ld));
+  ctx.sync_and_check();     // temporaries are freed on return
+}
+
+void Engine::spd_inverse(DeviceCtx& ctx, const double* omega_u, size_t ldo, const double* G, size_t ldg,
+                         int p, double tau1, double rho, double scale, double* out, size_t ldout) {
+  // inv_sympd(symmatu(scale*(tau1*Omega - G) + rho*I)) (:164-165, :397): upper-triangle assembly,
+  // Cholesky factor + inverse from the factor (dpotrf/dpotri class), then mirror to full storage
+  // for the matrix-stream kernel.
+  cudaStream_t s = ctx.stream;
+  launch_assemble_upper(omega_u, ldo, G, ldg, p, tau1, scale, rho, out, ldout, s);
+  int lw1 = 0, lw2 = 0;
+  SPB_CUSOLVER(cusolverDnDpotrf_bufferSize(ctx.solver, CUBLAS_FILL_MODE_UPPER, p, out, (int)ldout, &lw1));
+  SPB_CUSOLVER(cusolverDnDpotri_bufferSize(ctx.solver, CUBLAS_FILL_MODE_UPPER, p, out, (int)ldout, &lw2));
+  int lw = std::max(lw1, lw2);
+  double* work = ctx.work((size_t)lw);
+  SPB_CUSOLVER(cusolverDnDpotrf(ctx.solver, CUBLAS_FILL_MODE_UPPER, p, out, (int)ldout, work, lw, ctx.info.get()));
+  launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_NOT_POSDEF, s);
+  SPB_CUSOLVER(cusolverDnDpotri(ctx.solver, CUBLAS_FILL_MODE_UPPER, p, out, (int)ldout, work, lw, ctx.info.get()));
+  launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_NOT_POSDEF, s);
+  launch_symmatu_inplace(out, p, ldout, 0.0, s);
+}
+
+void Engine::gram_upper(DeviceCtx& ctx, const double* Ymat, int m, int p, double* G, size_t ldg) {
+  const double one = 1.0, zero = 0.0;
+  SPB_CUBLAS(cublasDsyrk(ctx.blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, p, m, &one, Ymat, m, &zero, G, (int)ldg));
+}
+
+void Engine::svd_right(DeviceCtx& ctx, const double* Ymat, int m, int p, int K, std::vector<double>& sv,
+                       double* Phi_dev) {
+  // svd_econ(U, s, V, Y, "right") (:321, :563): singular values and right singular vectors.
+  // cuSOLVER's gesvd needs rows >= cols, so the tall orientation is factorised.
+  cudaStream_t s = ctx.stream;
+  const int r = std::min(m, p);
+  SPB_REQUIRE(K <= r, "K must not exceed min(rows of the training block, p)");
+  DevBuf<double> S((size_t)r);
+  sv.assign(r, 0.0);
+  if (p >= m) {
+    // A = Y' (p x m); its left singular vectors are Y's right singular vectors
+    DevBuf<double> A((size_t)p * m), U((size_t)p * m);
+    launch_transpose(Ymat, m, p, A.get(), s);
+    int lwork = 0;
+    SPB_CUSOLVER(cusolverDnDgesvd_bufferSize(ctx.solver, p, m, &lwork));
+    double* work = ctx.work((size_t)lwork);
+    SPB_CUSOLVER(cusolverDnDgesvd(ctx.solver, 'S', 'N', p, m, A.get(), p, S.get(), U.get(), p, nullptr, 1,
+                                  work, lwork, nullptr, ctx.info.get()));
+    launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_SVD, s);
+    SPB_CUDA(cudaMemcpyAsync(Phi_dev, U.get(), sizeof(double) * (size_t)p * K, cudaMemcpyDeviceToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(sv.data(), S.get(), sizeof(double) * r, cudaMemcpyDeviceToHost, s));
+    ctx.sync_and_check();
+  } else {
+    DevBuf<double> A((size_t)m * p), VT((size_t)p * p), V((size_t)p * p);
+    SPB_CUDA(cudaMemcpyAsync(A.get(), Ymat, sizeof(double) * (size_t)m * p, cudaMemcpyDeviceToDevice, s));
+    int lwork = 0;
+    SPB_CUSOLVER(cusolverDnDgesvd_bufferSize(ctx.solver, m, p, &lwork));
+    double* work = ctx.work((size_t)lwork);
+    SPB_CUSOLVER(cusolverDnDgesvd(ctx.solver, 'N', 'S', m, p, A.get(), m, S.get(), nullptr, 1, VT.get(), p,
+                                  work, lwork, nullptr, ctx.info.get()));
+    launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_SVD, s);
+    launch_transpose(VT.get(), p, p, V.get(), s);
+    SPB_CUDA(cudaMemcpyAsync(Phi_dev, V.get(), sizeof(double) * (size_t)p * K, cudaMemcpyDeviceToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(sv.data(), S.get(), sizeof(double) * r, cudaMemcpyDeviceToHost, s));
+    ctx.sync_and_check();
+  }
+}
+
+void Engine::cv_loss(DeviceCtx& ctx, const double* Yva, int m, int p, const double* Phi, int K, double* W,
+                     double* scratch, double* out_dev) {
+  launch_yphi(Yva, m, p, Phi, K, W, scratch, ctx.stream);
+  launch_residual_sumsq(Yva, m, p, Phi, K, W, scratch, out_dev, ctx.stream);
+}
+
+void Engine::gamma_losses(DeviceCtx& ctx, const double* Phi, int p, int K, const double* Ytr, int n_tr,
+                          double tv, const double* Yva, int n_va, const std::vector<double>& gamma,
+                          double* out_host) {
+  // stage-3 body for one fold (:489-523).  K x K eigen step and water-filling run on the host
+  // (O(K^3)); everything that touches p runs on the device.
+  cudaStream_t s = ctx.stream;
+  const int ng = (int)gamma.size();
+  DevBuf<double> W((size_t)n_tr * K), scr(yphi_scratch_doubles(n_tr, p, K)), H((size_t)K * K);
+  launch_yphi(Ytr, n_tr, p, Phi, K, W.get(), scr.get(), s);
+  launch_small_gram(W.get(), n_tr, K, 1.0 / (double)n_tr, H.get(), s);
+  std::vector<double> Hh((size_t)K * K);
+  SPB_CUDA(cudaMemcpyAsync(Hh.data(), H.get(), sizeof(double) * K * K, cudaMemcpyDeviceToHost, s));
+  ctx.sync_and_check();
+  std::vector<double> evals, evecs;
+  host_jacobi_eigh(K, Hh, evals, evecs);                 // ascending, like eig_sym (:492)
+  const double total = arma_accumulate(evals.data(), K); // accu(transformed_eigenvalues) (:493)
+  std::vector<double> dvals(K), Qd((size_t)K * K);
+  for (int c = 0; c < K; ++c) {                          // descending order (:494-495)
+    dvals[c] = evals[K - 1 - c];
+    for (int i = 0; i < K; ++i) Qd[(size_t)c * K + i] = evecs[(size_t)(K - 1 - c) * K + i];
+  }
+  std::vector<double> errs(ng), lams((size_t)ng * K);
+  for (int g = 0; g < ng; ++g) {
+    errs[g] = water_filling(dvals, total, tv, gamma[g], p, K);
+    for (int k = 0; k < K; ++k) lams[(size_t)g * K + k] = std::max(dvals[k] - (errs[g] + gamma[g]), 0.0);  // :520
+  }
+  DevBuf<double> Qdev((size_t)K * K), B((size_t)p * K), lam_dev((size_t)ng * K), err_dev((size_t)ng),
+      out_dev((size_t)ng), gscr(gamma_scratch_doubles(p));
+  SPB_CUDA(cudaMemcpyAsync(Qdev.get(), Qd.data(), sizeof(double) * K * K, cudaMemcpyHostToDevice, s));
+  SPB_CUDA(cudaMemcpyAsync(lam_dev.get(), lams.data(), sizeof(double) * ng * K, cudaMemcpyHostToDevice, s));
+  SPB_CUDA(cudaMemcpyAsync(err_dev.get(), errs.data(), sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+  launch_small_rmul(Phi, p, K, Qdev.get(), B.get(), s);
+  for (int g0 = 0; g0 < ng; g0 += kGammaBatch) {
+    const int nb = std::min(kGammaBatch, ng - g0);
+    launch_gamma_loss(Yva, n_va, p, B.get(), K, lam_dev.get() + (size_t)g0 * K, err_dev.get() + g0, nb,
+                      gscr.get(), out_dev.get() + g0, s);
+  }
+  SPB_CUDA(cudaMemcpyAsync(out_host, out_dev.get(), sizeof(double) * ng, cudaMemcpyDeviceToHost, s));
+  ctx.sync_and_check();
+}
+
+// ---------------------------------------------------------------------------------------
+// Engine
+// ---------------------------------------------------------------------------------------
+Engine::Engine(int p, int d, int n, int M, int K, const double* tau1, int n1, const double* tau2, int n2,
+               const double* gamma, int n3, int maxit, double tol, const double* l2, int nl2)
+    : p_(p), d_(d), n_(n), M_(M), K_(K), maxit_(maxit), tol_(tol), ctx_(DeviceCtx::get()) {
+  SPB_REQUIRE(p >= 1 && n >= 1, "p and n must be positive");
+  SPB_REQUIRE(d >= 1 && d <= 3, "Dimension of locations must be less than 4.");
+  SPB_REQUIRE(M >= 1, "M must be positive");
+  SPB_REQUIRE(K >= 1 && K <= SPB_MAX_K, "K must be in 1..SPB_MAX_K");
+  SPB_REQUIRE(K <= p && K <= n, "K must not exceed min(n, p)");
+  SPB_REQUIRE(n1 >= 1 && n2 >= 1 && n3 >= 1, "tuning grids must not be empty");
+  SPB_REQUIRE(tau1 && tau2 && gamma, "NULL tuning grid");
+  SPB_REQUIRE(maxit >= 0, "maxit must be non-negative");
+  tau1_.assign(tau1, tau1 + n1);
+  tau2_.assign(tau2, tau2 + n2);
+  gamma_.assign(gamma, gamma + n3);
+  if (l2 && nl2 > 0) l2_.assign(l2, l2 + nl2);
+  any_tau_ = (*std::max_element(tau1_.begin(), tau1_.end()) != 0.0) ||
+             (*std::max_element(tau2_.begin(), tau2_.end()) != 0.0);
+  ld_ = padded_ld((size_t)p);
+  folds_.resize(M);
+  const size_t pk = (size_t)p * K;
+  full_.alloc(pk);
+  chain_.alloc(pk);
+  admm_ws_.alloc(admm_workspace_bytes(p, K));
+  int max_m = n;
+  lossW_.alloc((size_t)max_m * K);
+  loss_scratch_.alloc(yphi_scratch_doubles(max_m, p, K) + 512);
+  int max_grid = std::max({n1, n2, n3, 1});
+  loss_out_.alloc((size_t)max_grid + 1);
+  slot_cap_ = (n1 + 2 * n2 + nl2 + 8) * (M + 2);
+  stat_slots_.alloc((size_t)slot_cap_ * 4);
+  err_slots_.alloc((size_t)slot_cap_);
+  std::memset(&stats_, 0, sizeof(stats_));
+  launches_at_start_ = g_launch_count;
+  t_created = std::chrono::steady_clock::now();
+}
+
+Engine::~Engine() {}
+
+double Engine::selected_tau1(int index1) const {
+  if (tau1_.size() > 1) return tau1_[index1];
+  return *std::max_element(tau1_.begin(), tau1_.end());
+}
+
+void Engine::copy_pk(double* dst, const double* src) {
+  SPB_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)p_ * K_, cudaMemcpyDeviceToDevice, ctx_.stream));
+}
+void Engine::zero_pk(double* dst) {
+  SPB_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)p_ * K_, ctx_.stream));
+}
+
+void Engine::upload(const double* sxy, const double* Y, const double* nk) {
+  SPB_REQUIRE(sxy && Y && nk, "NULL input");
+  auto t0 = std::chrono::steady_clock::now();
+  dY_.alloc((size_t)n_ * p_);
+  dX_.alloc((size_t)p_ * d_);
+  SPB_CUDA(cudaMemcpyAsync(dY_.get(), Y, sizeof(double) * (size_t)n_ * p_, cudaMemcpyHostToDevice, ctx_.stream));
+  SPB_CUDA(cudaMemcpyAsync(dX_.get(), sxy, sizeof(double) * (size_t)p_ * d_, cudaMemcpyHostToDevice, ctx_.stream));
+  nk_.assign(nk, nk + n_);
+  for (int k = 0; k < M_; ++k) {
+    FoldData& f = folds_[k];
+    f = FoldData();
+    for (int r = 0; r < n_; ++r) {
+      if (nk_[r] == (double)(k + 1)) f.rows_va.push_back(r); else f.rows_tr.push_back(r);   // :318-319
+    }
+    f.n_tr = (int)f.rows_tr.size();
+    f.n_va = (int)f.rows_va.size();
+    SPB_REQUIRE(f.n_tr >= 1, "a fold has no training rows");
+    SPB_REQUIRE(K_ <= std::min(f.n_tr, p_), "K must not exceed min(training rows, p)");
+  }
+  SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
+  stats_.bytes_h2d += (long long)sizeof(double) * ((size_t)n_ * p_ + (size_t)p_ * d_ + n_);
+  stats_.ms_h2d += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  omega_ready_ = omega_injected_;
+  full_ready_ = false;
+  gram_owner_ = -2;
+}
+
+void Engine::set_omega(const double* omega_host) {
+  SPB_REQUIRE(omega_host, "NULL omega");
+  omega_u_.alloc(ld_ * (size_t)p_);
+  omega_diag_raw_.alloc(p_);
+  SPB_CUDA(cudaMemsetAsync(omega_u_.get(), 0, sizeof(double) * ld_ * p_, ctx_.stream));
+  SPB_CUDA(cudaMemcpy2DAsync(omega_u_.get(), ld_ * sizeof(double), omega_host, (size_t)p_ * sizeof(double),
+                             (size_t)p_ * sizeof(double), p_, cudaMemcpyHostToDevice, ctx_.stream));
+  SPB_CUDA(cudaMemcpy2DAsync(omega_diag_raw_.get(), sizeof(double), omega_u_.get(), (ld_ + 1) * sizeof(double),
+                             sizeof(double), p_, cudaMemcpyDeviceToDevice, ctx_.stream));
+  launch_symmatu_inplace(omega_u_.get(), p_, ld_, 1e-8, ctx_.stream);     // symmatu + the ridge of :574
+  SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
+  omega_ready_ = true;
+  omega_injected_ = true;
+}
+
+void Engine::init_lambda(const double* Phi, const std::vector<double>& sv, double rho, double* L2) {
+  // Phi * diagmat(rho - 1 / (rho - 2 * pow(sv, 2)))  (:326, :567, :617, :642)
+  double coef[SPB_MAX_K];
+  for (int k = 0; k < K_; ++k) {
+    volatile double sq = sv[k] * sv[k];
+    volatile double den = rho - 2.0 * sq;
+    volatile double inv = 1.0 / den;
+    coef[k] = rho - inv;
+  }
+  launch_lambda_init_host(Phi, p_, K_, coef, L2, ctx_.stream);
+}
+
+void Engine::prepare() {
+  SPB_REQUIRE(dY_.get() != nullptr, "upload() must be called before prepare()");
+  cudaStream_t s = ctx_.stream;
+  if (!full_ready_) {
+    Scoped sc(clock_, PH_PROLOGUE, s);
+    svd_right(ctx_, dY_.get(), n_, p_, K_, sv_full_, full_.Phi.get());       // :563
+    rho_full_ = 10.0 * (sv_full_[0] * sv_full_[0]);                           // :564
+    copy_pk(full_.C.get(), full_.Phi.get());                                  // :566
+    init_lambda(full_.Phi.get(), sv_full_, rho_full_, full_.L2.get());        // :567
+    full_ready_ = true;
+  }
+  const bool need_omega = any_tau_ || tau1_.size() > 1 || tau2_.size() > 1;
+  if (need_omega && !omega_ready_) {
+    Scoped sc(clock_, PH_OMEGA, s);
+    omega_u_.alloc(ld_ * (size_t)p_);
+    omega_diag_raw_.alloc(p_);
+    if (any_tau_) {
+      SPB_CUDA(cudaMemsetAsync(omega_u_.get(), 0, sizeof(double) * ld_ * p_, s));
+      build_omega_raw(ctx_, dX_.get(), p_, d_, omega_u_.get(), ld_);          // :574
+      SPB_CUDA(cudaMemcpy2DAsync(omega_diag_raw_.get(), sizeof(double), omega_u_.get(),
+                                 (ld_ + 1) * sizeof(double), sizeof(double), p_, cudaMemcpyDeviceToDevice, s));
+      launch_symmatu_inplace(omega_u_.get(), p_, ld_, 1e-8, s);
+    } else {
+      // all taus are zero but a grid has several entries: Omega = I (:578); tau * Omega vanishes.
+      launch_set_identity(omega_u_.get(), p_, p_, ld_, s);
+    }
+    omega_ready_ = true;
+  }
+  work_.ensure(ld_ * (size_t)p_);
+  gram_.ensure(ld_ * (size_t)p_);
+}
+
+void Engine::get_omega(double* out) {
+  SPB_REQUIRE(omega_ready_ && any_tau_, "no thin-plate-spline matrix has been built");
+  SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
+  SPB_CUDA(cudaMemcpy2D(out, (size_t)p_ * sizeof(double), omega_u_.get(), ld_ * sizeof(double),
+                        (size_t)p_ * sizeof(double), p_, cudaMemcpyDeviceToHost));
+  std::vector<double> dg(p_);
+  SPB_CUDA(cudaMemcpy(dg.data(), omega_diag_raw_.get(), sizeof(double) * p_, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < p_; ++i) out[(size_t)i * p_ + i] = dg[i];
+}
+
+void Engine::fold_prepare(int k) {
+  FoldData& f = folds_[k];
+  if (f.prepared) return;
+  Scoped sc(clock_, PH_PROLOGUE, ctx_.stream);
+  cudaStream_t s = ctx_.stream;
+  DevBuf<int> rows((size_t)n_);
+  f.Ytr.alloc((size_t)f.n_tr * p_);
+  SPB_CUDA(cudaMemcpyAsync(rows.get(), f.rows_tr.data(), sizeof(int) * f.n_tr, cudaMemcpyHostToDevice, s));
+  launch_gather_rows(dY_.get(), n_, p_, rows.get(), f.n_tr, f.Ytr.get(), s);
+  SPB_CUDA(cudaStreamSynchronize(s));
+  if (f.n_va > 0) {
+    f.Yva.alloc((size_t)f.n_va * p_);
+    SPB_CUDA(cudaMemcpyAsync(rows.get(), f.rows_va.data(), sizeof(int) * f.n_va, cudaMemcpyHostToDevice, s));
+    launch_gather_rows(dY_.get(), n_, p_, rows.get(), f.n_va, f.Yva.get(), s);
+  }
+  f.Phi0.alloc((size_t)p_ * K_);
+  f.L20.alloc((size_t)p_ * K_);
+  svd_right(ctx_, f.Ytr.get(), f.n_tr, p_, K_, f.sv, f.Phi0.get());           // :321
+  f.rho = 10.0 * (f.sv[0] * f.sv[0]);                                         // :322
+  // trace(Ytr'Ytr) / n_tr (:489, :491)
+  launch_sumsq(f.Ytr.get(), (size_t)f.n_tr * p_, loss_scratch_.get(), loss_out_.get(), s);
+  double ss = 0.0;
+  SPB_CUDA(cudaMemcpyAsync(&ss, loss_out_.get(), sizeof(double), cudaMemcpyDeviceToHost, s));
+  SPB_CUDA(cudaStreamSynchronize(s));
+  f.tv = ss / (double)f.n_tr;
+  f.prepared = true;
+}
+
+void Engine::ensure_gram(int k) {
+  if (gram_owner_ == k) return;
+  Scoped sc(clock_, PH_PROLOGUE, ctx_.stream);
+  gram_.ensure(ld_ * (size_t)p_);
+  if (k < 0) gram_upper(ctx_, dY_.get(), n_, p_, gram_.get(), ld_);           // :561
+  else gram_upper(ctx_, folds_[k].Ytr.get(), folds_[k].n_tr, p_, gram_.get(), ld_);   // :328
+  gram_owner_ = k;
+}
+
+void Engine::run_core2(int kind, int fold, int idx, double tau1, double rho, ChainState& st) {
+  // spatpcaCore2 / spatpcaCore2p (:150-222): the inverse is rebuilt on every call (:165)
+  ensure_gram(fold);
+  {
+    Scoped sc(clock_, PH_INVERSE, ctx_.stream);
+    work_.ensure(ld_ * (size_t)p_);
+    spd_inverse(ctx_, omega_u_.get(), ld_, gram_.get(), ld_, p_, tau1, rho, 2.0, work_.get(), ld_);
+    stats_.n_inverses++;
+  }
+  if (next_slot_ >= slot_cap_) flush();
+  AdmmCall c;
+  c.Ainv = work_.get(); c.ld = ld_; c.p = p_; c.K = K_; c.mode = 2; c.rho = rho; c.tau2 = 0.0;
+  c.maxit = maxit_; c.tol = tol_;
+  c.Phi = st.Phi.get(); c.R = nullptr; c.C = st.C.get(); c.L1 = nullptr; c.L2 = st.L2.get();
+  c.stat_slot = stat_slots_.get() + (size_t)next_slot_ * 4;
+  c.err_slot = err_slots_.get() + next_slot_;
+  {
+    Scoped sc(clock_, PH_ADMM, ctx_.stream);
+    SPB_CUDA(cudaMemsetAsync(c.stat_slot, 0, 4 * sizeof(int), ctx_.stream));
+    if (maxit_ > 0) launch_admm(c, admm_ws_.get(), ctx_.stream);
+  }
+  pending_.push_back({kind, fold, idx, next_slot_});
+  next_slot_++;
+}
+
+void Engine::run_core3(int kind, int fold, int idx, const double* tinv, double tau2, double rho,
+                       ChainState& st) {
+  if (next_slot_ >= slot_cap_) flush();
+  AdmmCall c;
+  c.Ainv = tinv; c.ld = ld_; c.p = p_; c.K = K_; c.mode = 3; c.rho = rho; c.tau2 = tau2;
+  c.maxit = maxit_; c.tol = tol_;
+  c.Phi = st.Phi.get(); c.R = st.R.get(); c.C = st.C.get(); c.L1 = st.L1.get(); c.L2 = st.L2.get();
+  c.stat_slot = stat_slots_.get() + (size_t)next_slot_ * 4;
+  c.err_slot = err_slots_.get() + next_slot_;
+  {
+    Scoped sc(clock_, PH_ADMM, ctx_.stream);
+    SPB_CUDA(cudaMemsetAsync(c.stat_slot, 0, 4 * sizeof(int), ctx_.stream));
+    if (maxit_ > 0) launch_admm(c, admm_ws_.get(), ctx_.stream);
+  }
+  pending_.push_back({kind, fold, idx, next_slot_});
+  next_slot_++;
+}
+
+void Engine::launch_loss(const FoldData& f, const double* Phi, double* out_dev) {
+  Scoped sc(clock_, PH_CVLOSS, ctx_.stream);
+  if (f.n_va == 0) {
+    SPB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), ctx_.stream));
+    return;
+  }
+  cv_loss(ctx_, f.Yva.get(), f.n_va, p_, Phi, K_, lossW_.get(), loss_scratch_.get(), out_dev);
+}
+
+void Engine::flush() {
+  ctx_.sync_and_check();
+  if (next_slot_ > 0) {
+    std::vector<int> st((size_t)next_slot_ * 4);
+    SPB_CUDA(cudaMemcpy(st.data(), stat_slots_.get(), sizeof(int) * st.size(), cudaMemcpyDeviceToHost));
+    bool polar_failed = false;
+    for (auto& r : pending_) {
+      int iters = st[(size_t)r.slot * 4 + 0];
+      if (st[(size_t)r.slot * 4 + 1] != 0) polar_failed = true;
+      log_.push_back(r.kind); log_.push_back(r.fold); log_.push_back(r.idx); log_.push_back(iters);
+    }
+    pending_.clear();
+    next_slot_ = 0;
+    if (polar_failed)
+      throw Error(SPB_ERR_POLAR, "svd_econ(): the p x K iterate is rank deficient, Stiefel projection undefined");
+  }
+}
+
+// ---- stage 1 (:592-650) -----------------------------------------------------------------
+void Engine::stage1_fold(int k, double* cv_row) {
+  SPB_REQUIRE(k >= 0 && k < M_, "fold index out of range");
+  SPB_REQUIRE(full_ready_, "prepare() must be called first");
+  fold_prepare(k);
+  FoldData& f = folds_[k];
+  const int n1 = (int)tau1_.size();
+  const double max_tau2 = *std::max_element(tau2_.begin(), tau2_.end());
+  if (n1 > 1) {                                                               // worker :312-334
+    init_lambda(f.Phi0.get(), f.sv, f.rho, f.L20.get());
+    copy_pk(chain_.Phi.get(), f.Phi0.get());
+    copy_pk(chain_.C.get(), f.Phi0.get());
+    copy_pk(chain_.L2.get(), f.L20.get());
+    launch_loss(f, f.Phi0.get(), loss_out_.get() + 0);                        // :327 (tau1[0] scored as PCA)
+    for (int i = 1; i < n1; ++i) {                                            // warm-started path :329-332
+      run_core2(2, k, i, tau1_[i], f.rho, chain_);
+      launch_loss(f, chain_.Phi.get(), loss_out_.get() + i);
+    }
+    flush();
+    SPB_REQUIRE(cv_row != nullptr, "cv_row is NULL");
+    SPB_CUDA(cudaMemcpy(cv_row, loss_out_.get(), sizeof(double) * n1, cudaMemcpyDeviceToHost));
+    stats_.bytes_d2h += (long long)sizeof(double) * n1;
+    return;
+  }
+  const double sel = tau1_[0];
+  if (sel != 0.0 && max_tau2 == 0.0) {                                        // :604-623
+    init_lambda(f.Phi0.get(), f.sv, f.rho, f.L20.get());
+    copy_pk(chain_.Phi.get(), f.Phi0.get());
+    copy_pk(chain_.C.get(), f.Phi0.get());
+    copy_pk(chain_.L2.get(), f.L20.get());
+    run_core2(2, k, 0, sel, f.rho, chain_);
+    copy_pk(f.Phi0.get(), chain_.Phi.get());                                  // Phi_cv.slice(k) (:619)
+    copy_pk(f.L20.get(), chain_.L2.get());                                    // Lambd2_cv.slice(k) (:620)
+    // (:621 also forms tempinv_cv here; nothing reads it unless stage 2 runs, which recomputes it)
+  } else if (sel == 0.0 && max_tau2 == 0.0) {                                 // :624-629, :576-590
+    // Phi_cv.slice(k) = fold PCA start (already in Phi0); Lambd2_cv is never read on this path.
+    SPB_CUDA(cudaMemsetAsync(f.L20.get(), 0, sizeof(double) * (size_t)p_ * K_, ctx_.stream));
+  } else {                                                                    // :630-648
+    init_lambda(f.Phi0.get(), sv_full_, f.rho, f.L20.get());                  // quirk :642: FULL-data singular values
+    if (sel != 0.0) {
+      copy_pk(chain_.Phi.get(), f.Phi0.get());
+      copy_pk(chain_.C.get(), f.Phi0.get());
+      copy_pk(chain_.L2.get(), f.L20.get());
+      run_core2(2, k, 0, sel, f.rho, chain_);
+      copy_pk(f.Phi0.get(), chain_.Phi.get());
+      copy_pk(f.L20.get(), chain_.L2.get());
+    }
+  }
+  flush();
+}
+
+void Engine::stage1_full(int index1) {
+  SPB_REQUIRE(full_ready_, "prepare() must be called first");
+  const int n1 = (int)tau1_.size();
+  const double max_tau2 = *std::max_element(tau2_.begin(), tau2_.end());
+  if (n1 > 1) {
+    SPB_REQUIRE(index1 >= 0 && index1 < n1, "index1 out of range");
+    if (index1 > 0) run_core2(20, -1, index1, tau1_[index1], rho_full_, full_);    // :598-599
+  } else {
+    const double sel = tau1_[0];
+    if (sel != 0.0 && max_tau2 == 0.0) run_core2(20, -1, 0, sel, rho_full_, full_); // :605
+  }
+  flush();
+}
+
+// ---- stage 2 (:652-680) -----------------------------------------------------------------
+void Engine::stage2_fold(int k, int index1, double* cv_row) {
+  SPB_REQUIRE(k >= 0 && k < M_, "fold index out of range");
+  const int n2 = (int)tau2_.size();
+  if (n2 <= 1) return;
+  FoldData& f = folds_[k];
+  SPB_REQUIRE(f.prepared, "stage1_fold(k) must run before stage2_fold(k)");
+  const double sel1 = selected_tau1(index1);
+  copy_pk(chain_.Phi.get(), f.Phi0.get());                                    // :389
+  copy_pk(chain_.C.get(), f.Phi0.get());
+  zero_pk(chain_.L1.get());                                                   // :390
+  copy_pk(chain_.L2.get(), f.L20.get());                                      // :391
+  if (sel1 != 0.0) run_core2(2, k, 0, sel1, f.rho, chain_);                   // :392-393
+  copy_pk(chain_.R.get(), chain_.Phi.get());                                  // :394
+  copy_pk(f.Phi0.get(), chain_.Phi.get());                                    // :395
+  copy_pk(f.L20.get(), chain_.L2.get());                                      // :396
+  ensure_gram(k);
+  {
+    Scoped sc(clock_, PH_INVERSE, ctx_.stream);
+    f.tinv.ensure(ld_ * (size_t)p_);
+    spd_inverse(ctx_, omega_u_.get(), ld_, gram_.get(), ld_, p_, sel1, f.rho, 1.0, f.tinv.get(), ld_);   // :397
+    stats_.n_inverses++;
+  }
+  for (int i = 0; i < n2; ++i) {                                              // :398-401
+    run_core3(3, k, i, f.tinv.get(), tau2_[i], f.rho, chain_);
+    launch_loss(f, chain_.Phi.get(), loss_out_.get() + i);
+  }
+  flush();
+  SPB_REQUIRE(cv_row != nullptr, "cv_row is NULL");
+  SPB_CUDA(cudaMemcpy(cv_row, loss_out_.get(), sizeof(double) * n2, cudaMemcpyDeviceToHost));
+  stats_.bytes_d2h += (long long)sizeof(double) * n2;
+}
+
+void Engine::stage2_full(int index1, int index2) {
+  const int n2 = (int)tau2_.size();
+  const double sel1 = selected_tau1(index1);
+  const std::vector<double>* path = nullptr;
+  int upto = 0;
+  if (n2 > 1) {
+    SPB_REQUIRE(index2 >= 0 && index2 < n2, "index2 out of range");
+    path = &tau2_; upto = index2 + 1;                                         // :665-666
+  } else if (tau2_[0] > 0.0) {
+    path = &l2_; upto = (int)l2_.size();                                      // :672-678
+  }
+  if (!path) return;
+  ensure_gram(-1);
+  {
+    Scoped sc(clock_, PH_INVERSE, ctx_.stream);
+    work_.ensure(ld_ * (size_t)p_);
+    spd_inverse(ctx_, omega_u_.get(), ld_, gram_.get(), ld_, p_, sel1, rho_full_, 1.0, work_.get(), ld_);  // :661, :673
+    stats_.n_inverses++;
+  }
+  copy_pk(full_.R.get(), full_.Phi.get());                                    // :662
+  zero_pk(full_.L1.get());                                                    // :663
+  for (int i = 0; i < upto; ++i) run_core3(3, -1, i, work_.get(), (*path)[i], rho_full_, full_);
+  flush();
+}
+
+// ---- stage 3 (:682-692, worker :459-525) ---------------------------------------------------
+void Engine::stage3_fold(int k, int index1, int index2, double* cv_row) {
+  SPB_REQUIRE(k >= 0 && k < M_, "fold index out of range");
+  SPB_REQUIRE(cv_row != nullptr, "cv_row is NULL");
+  FoldData& f = folds_[k];
+  SPB_REQUIRE(f.prepared, "stage1_fold(k) must run before stage3_fold(k)");
+  const int n2 = (int)tau2_.size();
+  const double sel1 = selected_tau1(index1);
+  const double max_tau2 = *std::max_element(tau2_.begin(), tau2_.end());
+  copy_pk(chain_.Phi.get(), f.Phi0.get());                                    // :469
+  copy_pk(chain_.C.get(), f.Phi0.get());
+  copy_pk(chain_.L2.get(), f.L20.get());                                      // :471
+  if (max_tau2 != 0.0 || sel1 != 0.0) {                                       // :473
+    if (n2 == 1) {
+      run_core2(2, k, 0, sel1, f.rho, chain_);                                // :475
+    } else {
+      SPB_REQUIRE(f.tinv.get() != nullptr, "stage2_fold(k) must run before stage3_fold(k)");
+      copy_pk(chain_.R.get(), chain_.Phi.get());                              // :478
+      zero_pk(chain_.L1.get());                                               // :479
+      for (int i = 0; i <= index2; ++i)                                       // :480-482
+        run_core3(3, k, i, f.tinv.get(), tau2_[i], f.rho, chain_);
+    }
+  }
+  flush();
+  {
+    Scoped sc(clock_, PH_GAMMA, ctx_.stream);
+    gamma_losses(ctx_, chain_.Phi.get(), p_, K_, f.Ytr.get(), f.n_tr, f.tv, f.Yva.get(), f.n_va, gamma_, cv_row);
+  }
+  stats_.bytes_d2h += (long long)sizeof(double) * gamma_.size();
+}
+
+void Engine::get_eigenfn(double* out) {
+  SPB_REQUIRE(out != nullptr, "NULL output");
+  auto t0 = std::chrono::steady_clock::now();
+  flush();
+  SPB_CUDA(cudaMemcpy(out, full_.Phi.get(), sizeof(double) * (size_t)p_ * K_, cudaMemcpyDeviceToHost));
+  stats_.bytes_d2h += (long long)sizeof(double) * p_ * K_;
+  stats_.ms_d2h += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+void Engine::get_stats(spb_cv_stats* st) {
+  flush();
+  double ms[PH_COUNT];
+  clock_.collect(ms);
+  stats_.ms_omega = ms[PH_OMEGA];
+  stats_.ms_prologue = ms[PH_PROLOGUE];
+  stats_.ms_inverse = ms[PH_INVERSE];
+  stats_.ms_admm = ms[PH_ADMM];
+  stats_.ms_cv_loss = ms[PH_CVLOSS];
+  stats_.ms_gamma = ms[PH_GAMMA];
+  stats_.n_admm_calls = (int)(log_.size() / 4);
+  long long it = 0;
+  for (size_t i = 0; i < log_.size(); i += 4) it += log_[i + 3];
+  stats_.admm_iters = it;
+  stats_.gpu_launches = (int)(g_launch_count - launches_at_start_);
+  stats_.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_created).count();
+  if (st) *st = stats_;
+}
+
+int Engine::call_log(int* log4, int cap) {
+  flush();
+  int ncalls = (int)(log_.size() / 4);
+  if (log4) {
+    int ncopy = std::min(ncalls, cap);
+    std::memcpy(log4, log_.data(), sizeof(int) * 4 * (size_t)ncopy);
+  }
+  return ncalls;
+}
+
+void Engine::release_fold(int k) {
+  SPB_REQUIRE(k >= 0 && k < M_, "fold index out of range");
+  SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
+  folds_[k].tinv.release();
+}
+
+}  // namespace spb

@@ -1,0 +1,171 @@
+// Host-side engine: owns device memory, the stream and the cuBLAS/cuSOLVER handles, and
+// sequences the stages of spatpcaCV (reference src/RcppSpatPCA.cpp:543-701).
+#pragma once
+
+#include <chrono>
+#include <memory>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace spb {
+
+enum Phase { PH_OMEGA = 0, PH_PROLOGUE, PH_INVERSE, PH_ADMM, PH_CVLOSS, PH_GAMMA, PH_COUNT };
+
+// Per-thread, per-device CUDA context (stream + library handles + solver workspaces).
+struct DeviceCtx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cublasHandle_t blas = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+  DevBuf<double> solver_work;     // cuSOLVER workspace (grown on demand)
+  DevBuf<int> info;               // devInfo
+  DevBuf<int> flag;               // sticky error flag
+  DevBuf<int> ipiv;
+
+  static DeviceCtx& get();        // context of the calling thread's current device
+  void sync_and_check();          // stream sync + translate the sticky flag into an Error
+  double* work(size_t doubles) { solver_work.ensure(doubles); return solver_work.get(); }
+  ~DeviceCtx();
+};
+
+// Event-based phase timing on the launching stream (no synchronisation until collect()).
+class PhaseClock {
+ public:
+  void begin(Phase ph, cudaStream_t s);
+  void end(cudaStream_t s);
+  void collect(double ms[PH_COUNT]);     // stream must be idle
+  void reset();
+  ~PhaseClock();
+ private:
+  cudaEvent_t grab();
+  std::vector<cudaEvent_t> pool_;
+  size_t used_ = 0;
+  struct Span { Phase ph; cudaEvent_t a, b; };
+  std::vector<Span> spans_;
+  int open_ = -1;
+  double acc_[PH_COUNT] = {0, 0, 0, 0, 0, 0};
+};
+
+struct ChainState {              // ADMM iterate of one chain (p x K each)
+  DevBuf<double> Phi, R, C, L1, L2;
+  void alloc(size_t n) { Phi.alloc(n); R.alloc(n); C.alloc(n); L1.alloc(n); L2.alloc(n); }
+};
+
+struct FoldData {
+  bool prepared = false;
+  int n_tr = 0, n_va = 0;
+  std::vector<int> rows_tr, rows_va;
+  DevBuf<double> Ytr, Yva;        // n_tr x p, n_va x p
+  DevBuf<double> Phi0, L20;       // Phi_cv / Lambd2_cv slices of the reference (:569)
+  DevBuf<double> tinv;            // tempinv_cv slice (p x p), allocated in stage 2
+  std::vector<double> sv;         // singular values of Ytr
+  double rho = 0.0;
+  double tv = 0.0;                // trace(Ytr'Ytr) / n_tr
+};
+
+struct CallRec { int kind, fold, idx, slot; };
+
+class Engine {
+ public:
+  Engine(int p, int d, int n, int M, int K, const double* tau1, int n1, const double* tau2, int n2,
+         const double* gamma, int n3, int maxit, double tol, const double* l2, int nl2);
+  ~Engine();
+
+  void upload(const double* sxy, const double* Y, const double* nk);
+  void set_omega(const double* omega_host);
+  void prepare();
+  void get_omega(double* out);
+
+  void stage1_fold(int k, double* cv_row);
+  void stage1_full(int index1);
+  void stage2_fold(int k, int index1, double* cv_row);
+  void stage2_full(int index1, int index2);
+  void stage3_fold(int k, int index1, int index2, double* cv_row);
+  void get_eigenfn(double* out);
+  void get_stats(spb_cv_stats* st);
+  int call_log(int* log4, int cap);
+  void release_fold(int k);
+
+  int p() const { return p_; }
+  int K() const { return K_; }
+  int M() const { return M_; }
+  int n_tau1() const { return (int)tau1_.size(); }
+  int n_tau2() const { return (int)tau2_.size(); }
+  int n_gamma() const { return (int)gamma_.size(); }
+  double tau1_at(int i) const { return tau1_[i]; }
+  double tau2_at(int i) const { return tau2_[i]; }
+  double gamma_at(int i) const { return gamma_[i]; }
+  double selected_tau1(int index1) const;
+  std::chrono::steady_clock::time_point t_created;
+
+  // building blocks shared with the kernel-level C entry points
+  static void build_omega_raw(DeviceCtx& ctx, const double* x_dev, int p, int d, double* omega_dev,
+                              size_t ld);
+  static void spd_inverse(DeviceCtx& ctx, const double* omega_u, size_t ldo, const double* G,
+                          size_t ldg, int p, double tau1, double rho, double scale, double* out,
+                          size_t ldout);
+  static void gram_upper(DeviceCtx& ctx, const double* Ymat, int m, int p, double* G, size_t ldg);
+  // SVD-right start: singular values (host) and the first K right singular vectors (device)
+  static void svd_right(DeviceCtx& ctx, const double* Ymat, int m, int p, int K,
+                        std::vector<double>& sv, double* Phi_dev);
+  static void cv_loss(DeviceCtx& ctx, const double* Yva, int m, int p, const double* Phi, int K,
+                      double* W, double* scratch, double* out_dev);
+  // all-gamma covariance losses of one fold; `out_host` receives n_gamma values
+  static void gamma_losses(DeviceCtx& ctx, const double* Phi, int p, int K, const double* Ytr, int n_tr,
+                           double tv, const double* Yva, int n_va, const std::vector<double>& gamma,
+                           double* out_host);
+
+ private:
+  void fold_prepare(int k);
+  void ensure_gram(int k);                      // k = -1: full data
+  void init_lambda(const double* Phi, const std::vector<double>& sv, double rho, double* L2);
+  void run_core2(int kind, int fold, int idx, double tau1, double rho, ChainState& st);
+  void run_core3(int kind, int fold, int idx, const double* tinv, double tau2, double rho, ChainState& st);
+  void launch_loss(const FoldData& f, const double* Phi, double* out_dev);
+  void flush();                                  // sync, check, move call stats to the host log
+  void copy_pk(double* dst, const double* src);
+  void zero_pk(double* dst);
+
+  int p_, d_, n_, M_, K_, maxit_;
+  double tol_;
+  std::vector<double> tau1_, tau2_, gamma_, l2_;
+  bool any_tau_ = false;
+  size_t ld_ = 0;                                // leading dimension of every p x p matrix
+  DeviceCtx& ctx_;
+
+  DevBuf<double> dY_, dX_;
+  std::vector<double> nk_;
+  DevBuf<double> omega_u_;                       // symmatu(Omega) + 1e-8 I
+  DevBuf<double> omega_diag_raw_;                // diagonal before the ridge (for get_omega)
+  bool omega_ready_ = false, omega_injected_ = false;
+  DevBuf<double> gram_;                          // upper triangle of Ytr'Ytr of `gram_owner_`
+  int gram_owner_ = -2;
+  DevBuf<double> work_;                          // assembled matrix -> inverse
+  std::vector<FoldData> folds_;
+  // full-data fit (:563-567)
+  std::vector<double> sv_full_;
+  double rho_full_ = 0.0;
+  ChainState full_, chain_;
+  bool full_ready_ = false;
+
+  DevBuf<char> admm_ws_;
+  DevBuf<double> lossW_, loss_scratch_, loss_out_;
+  DevBuf<int> stat_slots_;
+  DevBuf<double> err_slots_;
+  int next_slot_ = 0, slot_cap_ = 0;
+  std::vector<CallRec> pending_;
+  std::vector<int> log_;                         // 4 ints per call
+
+  PhaseClock clock_;
+  spb_cv_stats stats_;
+  long long launches_at_start_ = 0;
+};
+
+// small host helpers (host_math.cpp-like, defined in engine.cu)
+void host_jacobi_eigh(int K, std::vector<double>& A /*K x K col-major, destroyed*/,
+                      std::vector<double>& evals, std::vector<double>& evecs);
+double arma_accumulate(const double* x, int n);
+double water_filling(const std::vector<double>& d, double total, double tv, double g, int p, int K);
+
+}  // namespace spb

@@ -1,0 +1,87 @@
+// Launchers of the hand-written sm_100a kernels (definitions in *_kernels.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace spb {
+
+// ---- thin-plate-spline / matrix assembly (tps_kernels.cu) -------------------
+// Bordered TPS system [[E + ridge I, T], [T', ridge I]], T = [1 X], q = p + d + 1
+// (reference: struct thinPlateSpline, src/RcppSpatPCA.cpp:12-45 + symmatu :67 + ridge :69).
+// border = false writes only the p x p kernel block E (diag = ridge).
+void launch_tps_fill(const double* x_dev, int p, int d, double* L, size_t ld, double ridge,
+                     bool border, cudaStream_t s);
+// In-place A <- symmatu(A) + diag_add * I for the leading n x n block (tile-pair transpose).
+void launch_symmatu_inplace(double* A, int n, size_t ld, double diag_add, cudaStream_t s);
+// Upper triangle of  scale * (tau1 * Omega_u - G) + rho * I  (reference :164-165, :397),
+// same operation order as the reference, no FMA contraction.  G may alias out.
+void launch_assemble_upper(const double* omega_u, size_t ldo, const double* G, size_t ldg,
+                           int p, double tau1, double scale, double rho,
+                           double* out, size_t ldout, cudaStream_t s);
+// out (m x ncol) <- rows `rows[0..m)` of Y (n x ncol)
+void launch_gather_rows(const double* Y, int n, int ncol, const int* rows, int m, double* out,
+                        cudaStream_t s);
+// out (cols x rows, ld = cols) <- transpose of in (rows x cols, ld = rows)
+void launch_transpose(const double* in, int rows, int cols, double* out, cudaStream_t s);
+// identity columns: B (q x ncol, ld) <- [I_ncol; 0]
+void launch_set_identity(double* B, int q, int ncol, size_t ld, cudaStream_t s);
+// out[0] <- sum of squares of x[0..n)   (deterministic two-level tree)
+void launch_sumsq(const double* x, size_t n, double* scratch, double* out, cudaStream_t s);
+// Lambda2 = Phi * diag(coef_k), coef_k = rho - 1 / (rho - 2 sv_k^2) computed by the host in the
+// reference's operation order (reference :326, :567)
+void launch_lambda_init_host(const double* Phi, int p, int K, const double* coef_host, double* Lambda2,
+                             cudaStream_t s);
+// dst[i] = alpha * src[i]
+void launch_scale_copy(const double* src, double alpha, double* dst, size_t n, cudaStream_t s);
+// sticky device-side status: if (*info != 0) *flag = code (first failure wins)
+void launch_check_info(const int* info, int* flag, int code, cudaStream_t s);
+// B = Phi * Q  (p x K times K x K, Q on device)
+void launch_small_rmul(const double* Phi, int p, int K, const double* Q_dev, double* out, cudaStream_t s);
+
+// ---- persistent ADMM kernel (admm_kernels.cu) --------------------------------
+struct AdmmWorkspace;   // partial-sum buffers, sized by (p, K)
+
+struct AdmmCall {
+  const double* Ainv;   // p x p symmetric inverse, full storage
+  size_t ld;
+  int p, K;
+  int mode;             // 2 = spatpcaCore2 / 2p update, 3 = spatpcaCore3 update
+  double rho, tau2;
+  int maxit;
+  double tol;
+  double *Phi, *R, *C, *L1, *L2;   // p x K, ld = p.  R/L1 unused in mode 2
+  int* stat_slot;       // device: {iterations, status, sweeps}
+  double* err_slot;     // device: last max error
+};
+
+size_t admm_workspace_bytes(int p, int K);
+// `ws` must hold admm_workspace_bytes(p, K) bytes.  Asynchronous on `s`.
+void launch_admm(const AdmmCall& c, void* ws, cudaStream_t s);
+// deterministic segment count used by phase 1 (exposed for DESIGN/bench reporting)
+int admm_num_segments(int p, int K);
+
+// ---- losses (loss_kernels.cu) --------------------------------------------------
+// W (m x K) <- Ymat (m x p) * Phi (p x K); scratch must hold cvloss_scratch_doubles(m, p, K)
+size_t yphi_scratch_doubles(int m, int p, int K);
+void launch_yphi(const double* Ymat, int m, int p, const double* Phi, int K, double* W,
+                 double* scratch, cudaStream_t s);
+// out[0] <- || Yva - W Phi' ||_F^2   with W = Yva Phi precomputed
+void launch_residual_sumsq(const double* Yva, int m, int p, const double* Phi, int K,
+                           const double* W, double* scratch, double* out, cudaStream_t s);
+// H (K x K) <- W' W * alpha
+void launch_small_gram(const double* W, int m, int K, double alpha, double* H, cudaStream_t s);
+// stage-3 covariance losses for up to SPB_GAMMA_BATCH gammas per launch:
+// out[g] = || Yva'Yva / m - B diag(lam_g) B' - err_g I ||_F^2
+constexpr int kGammaBatch = 16;
+size_t gamma_scratch_doubles(int p);
+void launch_gamma_loss(const double* Yva, int m, int p, const double* B, int K,
+                       const double* lam_dev /* ng x K, row g contiguous */,
+                       const double* err_dev /* ng */, int ng, double* scratch, double* out,
+                       cudaStream_t s);
+
+// ---- eigenFunction evaluation (tps_kernels.cu) ----------------------------------
+// out (p_new x K) = kernel(new, orig) * para[0:p] + affine part (reference :113-145)
+void launch_tps_eval(const double* xnew, int pnew, const double* xorig, int p, int d,
+                     const double* para, size_t ldpara, int K, double* out, cudaStream_t s);
+
+}  // namespace spb

@@ -1,0 +1,332 @@
+// Hold-out losses of the cross-validation (sm_100a).
+//
+//  * cv loss   ||Yva (I - Phi Phi')||_F^2  (reference src/RcppSpatPCA.cpp:327, 331, 400) is
+//    evaluated as ||Yva - (Yva Phi) Phi'||_F^2: two coalesced passes over the m x p hold-out
+//    block (8 m p bytes each) instead of a p x p projector and an m x p x p product.
+//  * gamma loss ||S_va - Sigma_hat - err I||_F^2 (:520-522) is evaluated tile by tile from the
+//    low-rank factors (Yva: m x p, B = Phi Q: p x K) without ever forming a p x p matrix:
+//    2 p^2 (m + K n_gamma) flop over 8 p (m + K) bytes -- FP64-pipe-bound, 64 x 64 tiles,
+//    4 x 4 register blocking, only tiles on or above the diagonal (x2 weight off-diagonal).
+// All reductions are fixed-shape (block tree, then per-block partials summed in block order).
+#include "kernels.cuh"
+
+namespace spb {
+
+namespace {
+
+constexpr int kT = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- W = Ymat * Phi -------------------------------------------------------------------
+// Block b handles columns j in [b*JB, (b+1)*JB).  Thread (r-lane, js): rows r, r+64, ...;
+// columns js, js+4, ... of the block.  Partial W per block, then an ordered sum over blocks.
+constexpr int kJB = 128;        // columns (locations) per block
+constexpr int kRL = 64;         // row lanes
+constexpr int kJS = kT / kRL;   // column splits
+
+__global__ void __launch_bounds__(kT)
+yphi_partial_kernel(const double* __restrict__ Ym, int m, int p, const double* __restrict__ Phi, int K,
+                    double* __restrict__ wpart) {
+  extern __shared__ double sh[];            // Phi block: kJB x K
+  double* phis = sh;
+  double* red = sh + kJB * K;               // kJS x (kRL) staging for the js reduction
+  const int tid = threadIdx.x;
+  const int j0 = blockIdx.x * kJB;
+  const int nj = min(kJB, p - j0);
+  for (int idx = tid; idx < nj * K; idx += kT) {
+    const int jj = idx % nj, k = idx / nj;
+    phis[jj * K + k] = Phi[(size_t)k * p + j0 + jj];
+  }
+  __syncthreads();
+  const int rl = tid % kRL, js = tid / kRL;
+  double* out = wpart + (size_t)blockIdx.x * m * K;
+  for (int r0 = 0; r0 < m; r0 += kRL) {
+    const int r = r0 + rl;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      double acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+      if (r < m) {
+        for (int jj = js; jj < nj; jj += kJS) {
+          const double y = Ym[(size_t)(j0 + jj) * m + r];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k0 + k < K) acc[k] = fma(y, phis[jj * K + k0 + k], acc[k]);
+        }
+      }
+      // reduce over js (fixed order) through shared memory
+      for (int k = 0; k < 8 && k0 + k < K; ++k) {
+        __syncthreads();
+        red[js * kRL + rl] = acc[k];
+        __syncthreads();
+        if (js == 0 && r < m) {
+          double t = 0.0;
+#pragma unroll
+          for (int q = 0; q < kJS; ++q) t += red[q * kRL + rl];
+          out[(size_t)(k0 + k) * m + r] = t;
+        }
+      }
+    }
+  }
+}
+
+__global__ void ordered_sum_kernel(const double* __restrict__ part, int nblocks, size_t n,
+                                   double* __restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  double t = 0.0;
+  for (int b = 0; b < nblocks; ++b) t += part[(size_t)b * n + idx];
+  out[idx] = t;
+}
+
+// ---- || Yva - W Phi' ||_F^2 ----------------------------------------------------------
+__global__ void __launch_bounds__(kT)
+residual_partial_kernel(const double* __restrict__ Ym, int m, int p, const double* __restrict__ Phi,
+                        int K, const double* __restrict__ W, double* __restrict__ lpart) {
+  extern __shared__ double sh[];
+  double* phis = sh;                      // kJB x K
+  __shared__ double wred[kT / 32];
+  const int tid = threadIdx.x;
+  const int j0 = blockIdx.x * kJB;
+  const int nj = min(kJB, p - j0);
+  for (int idx = tid; idx < nj * K; idx += kT) {
+    const int jj = idx % nj, k = idx / nj;
+    phis[jj * K + k] = Phi[(size_t)k * p + j0 + jj];
+  }
+  __syncthreads();
+  double acc = 0.0;
+  const size_t total = (size_t)nj * m;
+  for (size_t e = tid; e < total; e += kT) {
+    const int jj = (int)(e / m), r = (int)(e - (size_t)jj * m);
+    double fit = 0.0;
+    for (int k = 0; k < K; ++k) fit = fma(__ldg(W + (size_t)k * m + r), phis[jj * K + k], fit);
+    const double d = Ym[(size_t)(j0 + jj) * m + r] - fit;
+    acc = fma(d, d, acc);
+  }
+  acc = warp_sum(acc);
+  if ((tid & 31) == 0) wred[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kT / 32; ++w) t += wred[w];
+    lpart[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kT)
+final_sum_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
+  __shared__ double wred[kT / 32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += kT) acc += part[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kT / 32; ++w) t += wred[w];
+    out[0] = t;
+  }
+}
+
+// ---- H = alpha * W' W  (K x K, one block) -------------------------------------------------
+__global__ void __launch_bounds__(kT)
+small_gram_kernel(const double* __restrict__ W, int m, int K, double alpha, double* __restrict__ H) {
+  __shared__ double wred[kT / 32];
+  for (int a = 0; a < K; ++a) {
+    for (int b = a; b < K; ++b) {
+      double acc = 0.0;
+      for (int r = threadIdx.x; r < m; r += kT) acc = fma(W[(size_t)a * m + r], W[(size_t)b * m + r], acc);
+      acc = warp_sum(acc);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kT / 32; ++w) t += wred[w];
+        t *= alpha;
+        H[(size_t)b * K + a] = t;
+        H[(size_t)a * K + b] = t;
+      }
+    }
+  }
+}
+
+// ---- stage-3 covariance loss ----------------------------------------------------------------
+constexpr int kGT = 64;     // tile edge
+constexpr int kGR = 32;     // hold-out rows staged per step
+
+template <int NG>
+__global__ void __launch_bounds__(kT)
+gamma_loss_kernel(const double* __restrict__ Yva, int m, int p, const double* __restrict__ B, int K,
+                  const double* __restrict__ lam, const double* __restrict__ errv, int ng,
+                  int ntile, double* __restrict__ part) {
+  // linear tile index -> (bi <= bj)
+  int bi = 0, rem = blockIdx.x;
+  while (rem >= ntile - bi) { rem -= ntile - bi; ++bi; }
+  const int bj = bi + rem;
+  const int i0 = bi * kGT, j0 = bj * kGT;
+  const int tid = threadIdx.x;
+  const int ti = tid & 15, tj = tid >> 4;          // 16 x 16 threads, 4 x 4 outputs each
+
+  __shared__ double ya[kGR][kGT + 4];
+  __shared__ double yb[kGR][kGT + 4];
+  extern __shared__ double dsh[];                  // Bi: kGT x K, Bj: kGT x K, lam: ng x K, err: ng
+  double* Bi = dsh;
+  double* Bj = Bi + kGT * K;
+  double* lams = Bj + kGT * K;
+  double* errs = lams + NG * K;
+  __shared__ double wred[kT / 32][NG];
+
+  for (int idx = tid; idx < kGT * K; idx += kT) {
+    const int ii = idx % kGT, k = idx / kGT;
+    Bi[ii * K + k] = (i0 + ii < p) ? B[(size_t)k * p + i0 + ii] : 0.0;
+    Bj[ii * K + k] = (j0 + ii < p) ? B[(size_t)k * p + j0 + ii] : 0.0;
+  }
+  for (int idx = tid; idx < NG * K; idx += kT) lams[idx] = (idx < ng * K) ? lam[idx] : 0.0;
+  for (int idx = tid; idx < NG; idx += kT) errs[idx] = (idx < ng) ? errv[idx] : 0.0;
+
+  double s[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) s[a][b] = 0.0;
+
+  for (int r0 = 0; r0 < m; r0 += kGR) {
+    __syncthreads();
+    for (int idx = tid; idx < kGR * kGT; idx += kT) {
+      const int rr = idx % kGR, cc = idx / kGR;
+      const int r = r0 + rr;
+      ya[rr][cc] = (r < m && i0 + cc < p) ? Yva[(size_t)(i0 + cc) * m + r] : 0.0;
+      yb[rr][cc] = (r < m && j0 + cc < p) ? Yva[(size_t)(j0 + cc) * m + r] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = 0; rr < kGR; ++rr) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = ya[rr][ti * 4 + a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = yb[rr][tj * 4 + b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) s[a][b] = fma(av[a], bv[b], s[a][b]);
+    }
+  }
+  __syncthreads();
+  const double dm = (double)m;
+  double acc[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) acc[g] = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int gi = i0 + ti * 4 + a, gj = j0 + tj * 4 + b;
+      if (gi < p && gj < p) {
+        const double sv = s[a][b] / dm;              // S_va = Yva'Yva / n_va (:490)
+        const double* bi_row = Bi + (ti * 4 + a) * K;
+        const double* bj_row = Bj + (tj * 4 + b) * K;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          if (g < ng) {
+            double sig = 0.0;
+            for (int k = 0; k < K; ++k) sig = fma(bi_row[k] * lams[g * K + k], bj_row[k], sig);
+            double dlt = sv - sig;
+            if (gi == gj) dlt -= errs[g];
+            acc[g] = fma(dlt, dlt, acc[g]);
+          }
+        }
+      }
+    }
+  }
+  const double wgt = (bi == bj) ? 1.0 : 2.0;         // symmetric residual: count (bj, bi) too
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    double v = warp_sum(acc[g]);
+    if ((tid & 31) == 0) wred[tid >> 5][g] = v;
+  }
+  __syncthreads();
+  if (tid < NG) {
+    double t = 0.0;
+    for (int w = 0; w < kT / 32; ++w) t += wred[w][tid];
+    part[(size_t)tid * gridDim.x + blockIdx.x] = wgt * t;
+  }
+}
+
+// out[g] = ordered sum over tiles of part[g][tile]
+__global__ void __launch_bounds__(kT)
+gamma_final_kernel(const double* __restrict__ part, int ntiles, int ng, double* __restrict__ out) {
+  __shared__ double chunk[kT];
+  const int g = blockIdx.x;
+  if (g >= ng) return;
+  // fixed shape: thread t sums tiles t, t+256, ...; then thread 0 sums the 256 partials in order
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < ntiles; i += kT) acc += part[(size_t)g * ntiles + i];
+  chunk[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kT; ++i) t += chunk[i];
+    out[g] = t;
+  }
+}
+
+}  // namespace
+
+size_t yphi_scratch_doubles(int m, int p, int K) {
+  return (size_t)ceil_div(p, kJB) * m * K + (size_t)ceil_div(p, kJB);
+}
+
+void launch_yphi(const double* Ymat, int m, int p, const double* Phi, int K, double* W,
+                 double* scratch, cudaStream_t s) {
+  if (m == 0) return;
+  const int nb = ceil_div(p, kJB);
+  size_t smem = ((size_t)kJB * K + (size_t)kJS * kRL) * sizeof(double);
+  yphi_partial_kernel<<<nb, kT, smem, s>>>(Ymat, m, p, Phi, K, scratch);
+  size_t n = (size_t)m * K;
+  ordered_sum_kernel<<<ceil_div(n, 256), 256, 0, s>>>(scratch, nb, n, W);
+  count_launch(2);
+  SPB_CUDA(cudaGetLastError());
+}
+
+void launch_residual_sumsq(const double* Yva, int m, int p, const double* Phi, int K,
+                           const double* W, double* scratch, double* out, cudaStream_t s) {
+  const int nb = ceil_div(p, kJB);
+  size_t smem = (size_t)kJB * K * sizeof(double);
+  residual_partial_kernel<<<nb, kT, smem, s>>>(Yva, m, p, Phi, K, W, scratch);
+  final_sum_kernel<<<1, kT, 0, s>>>(scratch, nb, out);
+  count_launch(2);
+  SPB_CUDA(cudaGetLastError());
+}
+
+void launch_small_gram(const double* W, int m, int K, double alpha, double* H, cudaStream_t s) {
+  small_gram_kernel<<<1, kT, 0, s>>>(W, m, K, alpha, H);
+  count_launch();
+  SPB_CUDA(cudaGetLastError());
+}
+
+size_t gamma_scratch_doubles(int p) {
+  size_t nt = ceil_div(p, kGT);
+  return (size_t)kGammaBatch * (nt * (nt + 1) / 2);
+}
+
+void launch_gamma_loss(const double* Yva, int m, int p, const double* B, int K, const double* lam_dev,
+                       const double* err_dev, int ng, double* scratch, double* out, cudaStream_t s) {
+  SPB_REQUIRE(ng >= 1 && ng <= kGammaBatch, "gamma batch too large");
+  const int nt = ceil_div(p, kGT);
+  const int ntiles = nt * (nt + 1) / 2;
+  size_t smem = ((size_t)2 * kGT * K + (size_t)kGammaBatch * K + kGammaBatch) * sizeof(double);
+  gamma_loss_kernel<kGammaBatch><<<ntiles, kT, smem, s>>>(Yva, m, p, B, K, lam_dev, err_dev, ng, nt,
+                                                          scratch);
+  gamma_final_kernel<<<ng, kT, 0, s>>>(scratch, ntiles, ng, out);
+  count_launch(2);
+  SPB_CUDA(cudaGetLastError());
+}
+
+}  // namespace spb

@@ -1,0 +1,260 @@
+"""The four `.Call` entry points of the reference (R/RcppExports.R:14-68) over the
+C ABI, with the reference's names and argument meaning, plus the engine handle
+used to place folds on different GPUs.  Pure marshalling: all computing happens
+in libspatpca_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import CvStats, check, fmat, fvec, ptr
+
+
+def thinPlateSplineMatrix(location) -> np.ndarray:
+    """`thinPlateSplineMatrix(location)` -- src/RcppSpatPCA.cpp:58-76."""
+    lib = _lib.load()
+    x = fmat(location)
+    p, d = x.shape
+    out = np.empty((p, p), order="F")
+    check(lib.spb_tps_matrix(ptr(x), p, d, ptr(out)))
+    return out
+
+
+def eigenFunction(new_location, original_location, Phi) -> np.ndarray:
+    """`eigenFunction(new_location, original_location, Phi)` -- src/RcppSpatPCA.cpp:94-147."""
+    lib = _lib.load()
+    xo = fmat(original_location)
+    xn = fmat(new_location, ncol=xo.shape[1])
+    phi = fmat(Phi)
+    if xn.shape[1] != xo.shape[1]:
+        raise ValueError("Inconsistent dimension of locations")
+    if phi.shape[0] != xo.shape[0]:
+        raise ValueError("Phi must have one row per original location")
+    out = np.empty((xn.shape[0], phi.shape[1]), order="F")
+    check(lib.spb_eigen_function(ptr(xn), xn.shape[0], ptr(xo), xo.shape[0], xo.shape[1], ptr(phi),
+                                 phi.shape[1], ptr(out)))
+    return out
+
+
+def spatialPrediction(phir, Yr, gamma, predicted_eignefunction) -> dict:
+    """`spatialPrediction(phir, Yr, gamma, predicted_eignefunction)` -- src/RcppSpatPCA.cpp:715-770."""
+    lib = _lib.load()
+    phi = fmat(phir)
+    Y = fmat(Yr)
+    pp = fmat(predicted_eignefunction, ncol=phi.shape[1])
+    p, K = phi.shape
+    n = Y.shape[0]
+    if Y.shape[1] != p or pp.shape[1] != K:
+        raise ValueError("inconsistent shapes")
+    p2 = pp.shape[0]
+    pred = np.empty((n, p2), order="F")
+    cov = np.empty((p, p2), order="F")
+    ev = np.empty(K)
+    err = np.empty(1)
+    check(lib.spb_spatial_prediction(ptr(phi), p, K, ptr(Y), n, float(gamma), ptr(pp), p2, ptr(pred),
+                                     ptr(cov), ptr(ev), ptr(err)))
+    return {"prediction": pred, "estimated_covariance": cov, "eigenvalue": ev, "error": float(err[0])}
+
+
+def spatpcaCV(sxyr, Yr, M, K, tau1r, tau2r, gammar, nkr, maxit, tol, l2r, return_stats=False) -> dict:
+    """`spatpcaCV(...)` -- src/RcppSpatPCA.cpp:543-701; returns the reference's 7-entry list."""
+    lib = _lib.load()
+    Y = fmat(Yr)
+    n, p = Y.shape
+    x = fmat(sxyr)
+    if x.shape[0] != p:
+        raise ValueError("The number of rows of x should be equal to the number of columns of Y.")
+    t1, t2, g, nk, l2 = fvec(tau1r), fvec(tau2r), fvec(gammar), fvec(nkr), fvec(l2r)
+    if len(nk) != n:
+        raise ValueError("nk must have one fold id per row of Y")
+    s1 = np.zeros(max(len(t1), 1))
+    s2 = np.zeros(max(len(t2), 1))
+    s3 = np.zeros(len(g))
+    eig = np.empty((p, int(K)), order="F")
+    sel = np.zeros(3)
+    stats = CvStats()
+    check(lib.spb_cv(ptr(x), p, x.shape[1], ptr(Y), n, int(M), int(K), ptr(t1), len(t1), ptr(t2), len(t2),
+                     ptr(g), len(g), ptr(nk), int(maxit), float(tol), ptr(l2), len(l2),
+                     ptr(s1), ptr(s2), ptr(s3), ptr(eig), ptr(sel), C.byref(stats)))
+    out = {
+        "cv_score_tau1": s1 if len(t1) > 1 else np.zeros(1),
+        "cv_score_tau2": s2 if len(t2) > 1 else np.zeros(1),
+        "cv_score_gamma": s3,
+        "estimated_eigenfn": eig,
+        "selected_tau1": float(sel[0]),
+        "selected_tau2": float(sel[1]),
+        "selected_gamma": float(sel[2]),
+    }
+    if return_stats:
+        out["stats"] = stats.as_dict()
+    return out
+
+
+def select_index(cv: np.ndarray):
+    """`index_min(sum(cv, 0))`, `sum(cv, 0) / M` with Armadillo's accumulation order."""
+    lib = _lib.load()
+    cv = fmat(cv)
+    M, ng = cv.shape
+    score = np.empty(ng)
+    idx = check(lib.spb_select_index(ptr(cv), M, ng, ptr(score)))
+    return idx, score
+
+
+class Engine:
+    """Handle API (include/spatpca_b200.h): one engine per GPU / process; folds are the
+    independent units (src/RcppSpatPCA.cpp:315, 385, 460)."""
+
+    def __init__(self, p, d, n, M, K, tau1, tau2, gamma, maxit, tol, l2):
+        self._lib = _lib.load()
+        self.p, self.d, self.n, self.M, self.K = int(p), int(d), int(n), int(M), int(K)
+        self.tau1, self.tau2, self.gamma, self.l2 = fvec(tau1), fvec(tau2), fvec(gamma), fvec(l2)
+        self._h = C.c_void_p()
+        check(self._lib.spb_engine_create(C.byref(self._h), self.p, self.d, self.n, self.M, self.K,
+                                          ptr(self.tau1), len(self.tau1), ptr(self.tau2), len(self.tau2),
+                                          ptr(self.gamma), len(self.gamma), int(maxit), float(tol),
+                                          ptr(self.l2), len(self.l2)))
+
+    def close(self):
+        if self._h:
+            self._lib.spb_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, sxy, Y, nk):
+        x, Yf, nkf = fmat(sxy), fmat(Y), fvec(nk)
+        assert Yf.shape == (self.n, self.p) and x.shape == (self.p, self.d) and len(nkf) == self.n
+        check(self._lib.spb_engine_upload(self._h, ptr(x), ptr(Yf), ptr(nkf)))
+
+    def set_omega(self, omega):
+        om = fmat(omega)
+        assert om.shape == (self.p, self.p)
+        check(self._lib.spb_engine_set_omega(self._h, ptr(om)))
+
+    def prepare(self):
+        check(self._lib.spb_engine_prepare(self._h))
+
+    def get_omega(self):
+        out = np.empty((self.p, self.p), order="F")
+        check(self._lib.spb_engine_get_omega(self._h, ptr(out)))
+        return out
+
+    def stage1_fold(self, k):
+        row = np.zeros(max(len(self.tau1), 1))
+        check(self._lib.spb_engine_stage1_fold(self._h, int(k), ptr(row)))
+        return row
+
+    def stage1_full(self, index1):
+        check(self._lib.spb_engine_stage1_full(self._h, int(index1)))
+
+    def stage2_fold(self, k, index1):
+        row = np.zeros(max(len(self.tau2), 1))
+        check(self._lib.spb_engine_stage2_fold(self._h, int(k), int(index1), ptr(row)))
+        return row
+
+    def stage2_full(self, index1, index2):
+        check(self._lib.spb_engine_stage2_full(self._h, int(index1), int(index2)))
+
+    def stage3_fold(self, k, index1, index2):
+        row = np.zeros(len(self.gamma))
+        check(self._lib.spb_engine_stage3_fold(self._h, int(k), int(index1), int(index2), ptr(row)))
+        return row
+
+    def get_eigenfn(self):
+        out = np.empty((self.p, self.K), order="F")
+        check(self._lib.spb_engine_get_eigenfn(self._h, ptr(out)))
+        return out
+
+    def stats(self) -> dict:
+        st = CvStats()
+        check(self._lib.spb_engine_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def call_log(self):
+        n = check(self._lib.spb_engine_call_log(self._h, None, 0))
+        buf = np.zeros((max(n, 1), 4), dtype=np.int32)
+        check(self._lib.spb_engine_call_log(self._h, buf.ctypes.data_as(C.POINTER(C.c_int)), n))
+        return [tuple(int(v) for v in buf[i]) for i in range(n)]
+
+    def release_fold(self, k):
+        check(self._lib.spb_engine_release_fold(self._h, int(k)))
+
+
+# ---- kernel-level entry points (parity tests, benchmarks) ----------------------------------
+def inv_sympd(omega, G, tau1, rho, scale):
+    lib = _lib.load()
+    om, g = fmat(omega), fmat(G)
+    p = om.shape[0]
+    out = np.empty((p, p), order="F")
+    check(lib.spb_inv_sympd(ptr(om), ptr(g), p, float(tau1), float(rho), float(scale), ptr(out)))
+    return out
+
+
+def admm_core2(tempinv, C_, Lambda2, rho, maxit, tol):
+    lib = _lib.load()
+    A = fmat(tempinv)
+    Cm, L2 = fmat(C_).copy(order="F"), fmat(Lambda2).copy(order="F")
+    p, K = Cm.shape
+    Phi = np.zeros((p, K), order="F")
+    it = C.c_int(0)
+    check(lib.spb_admm_core2(ptr(A), p, K, float(rho), int(maxit), float(tol), ptr(Phi), ptr(Cm), ptr(L2),
+                             C.byref(it)))
+    return Phi, Cm, L2, it.value
+
+
+def admm_core3(tempinv, R, C_, Lambda1, Lambda2, tau2, rho, maxit, tol):
+    lib = _lib.load()
+    A = fmat(tempinv)
+    Rm, Cm = fmat(R).copy(order="F"), fmat(C_).copy(order="F")
+    L1, L2 = fmat(Lambda1).copy(order="F"), fmat(Lambda2).copy(order="F")
+    p, K = Cm.shape
+    Phi = np.zeros((p, K), order="F")
+    it = C.c_int(0)
+    check(lib.spb_admm_core3(ptr(A), p, K, float(tau2), float(rho), int(maxit), float(tol), ptr(Phi), ptr(Rm),
+                             ptr(Cm), ptr(L1), ptr(L2), C.byref(it)))
+    return Phi, Rm, Cm, L1, L2, it.value
+
+
+def cv_loss(Yva, Phi):
+    lib = _lib.load()
+    Y, P = fmat(Yva), fmat(Phi)
+    out = np.zeros(1)
+    check(lib.spb_cv_loss(ptr(Y), Y.shape[0], Y.shape[1], ptr(P), P.shape[1], ptr(out)))
+    return float(out[0])
+
+
+def gamma_loss(Phi, Ytr, Yva, gamma):
+    lib = _lib.load()
+    P, tr, va, g = fmat(Phi), fmat(Ytr), fmat(Yva), fvec(gamma)
+    out = np.zeros(len(g))
+    check(lib.spb_gamma_loss(ptr(P), P.shape[0], P.shape[1], ptr(tr), tr.shape[0], ptr(va), va.shape[0],
+                             ptr(g), len(g), ptr(out)))
+    return out
+
+
+def bench_admm(p, K, mode, iters, repeats=3):
+    lib = _lib.load()
+    out = np.zeros(1)
+    check(lib.spb_bench_admm(int(p), int(K), int(mode), int(iters), int(repeats), ptr(out)))
+    return float(out[0])
+
+
+def bench_dgemm(m, repeats=3):
+    lib = _lib.load()
+    out = np.zeros(1)
+    check(lib.spb_bench_dgemm(int(m), int(repeats), ptr(out)))
+    return float(out[0])
+
+
+def bench_inverse(p, repeats=2):
+    lib = _lib.load()
+    out = np.zeros(1)
+    check(lib.spb_bench_inverse(int(p), int(repeats), ptr(out)))
+    return float(out[0])

@@ -1,0 +1,363 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerances are the ones BASELINE.json's north_star states:
+  eigenfunctions up to column sign, max-abs error <= 1e-8 relative;
+  CV losses <= 1e-9 relative; identical selections; identical per-call iteration counts.
+"""
+import numpy as np
+import pytest
+
+from oracle import r_api
+from oracle import spatpca_ref as ref
+from oracle.r_rng import RRng, r_seq_len
+
+from ref_cases import case_1d, case_3d, tps_locations
+from synth import make_case
+
+pytestmark = pytest.mark.gpu
+
+EIG_RTOL = 1e-8
+CV_RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import spatpca_b200 as sp
+    from spatpca_b200 import _lib
+    _lib.check(_lib.load().spb_set_device(0))
+    return sp
+
+
+def eig_err(A, B):
+    sgn = np.sign(np.sum(A * B, axis=0))
+    sgn[sgn == 0] = 1
+    return np.max(np.abs(A * sgn - B)) / np.max(np.abs(B))
+
+
+def assert_cv_parity(got, want, eig_rtol=EIG_RTOL, cv_rtol=CV_RTOL):
+    for key in ("selected_tau1", "selected_tau2", "selected_gamma"):
+        assert got[key] == want[key], (key, got[key], want[key])
+    for key in ("cv_score_tau1", "cv_score_tau2", "cv_score_gamma"):
+        np.testing.assert_allclose(got[key], want[key], rtol=cv_rtol, atol=0, err_msg=key)
+    assert eig_err(got["estimated_eigenfn"], want["estimated_eigenfn"]) <= eig_rtol
+
+
+# ---------------------------------------------------------------------------------------------
+# reference goldens through the GPU path (tests/testthat/*.R)
+# ---------------------------------------------------------------------------------------------
+def test_tps_matrix_goldens(sp):                       # test-RcppExports.R:10-15
+    l2d, l3d = tps_locations()
+    assert abs(np.linalg.norm(sp.thinPlateSplineMatrix(l2d)) - 0.362588) <= 1e-6
+    assert abs(np.linalg.norm(sp.thinPlateSplineMatrix(l3d)) - 8.191034) <= 1e-6
+
+
+def test_eigen_function_golden(sp):                    # test-RcppExports.R:18-23
+    l2d, _ = tps_locations()
+    v = sp.eigenFunction(np.array([[0.1, 0.2]]), l2d, np.array([[1.0], [0], [0], [0]]))
+    assert abs(v[0, 0] - 0.2352884) <= 1e-6
+
+
+@pytest.fixture(scope="module")
+def seq_1d(sp):
+    """test-SpatPCA.R:13-88 on one shared R-RNG stream, through the GPU engine."""
+    rng, x, Y = case_1d()
+    out = {"x": x, "Y": Y}
+    out["cv_1D"] = sp.spatpca(x, Y, rng=rng, num_cores=1)
+    out["multi_tau2"] = sp.spatpca(x, Y, K=1, tau2=[0, 1], rng=rng)
+    out["multi_gamma"] = sp.spatpca(x, Y, K=1, gamma=[0, 1], rng=rng)
+    out["fixed_both"] = sp.spatpca(x, Y, K=1, tau1=10, tau2=100, rng=rng)
+    out["zero_multi_gamma"] = sp.spatpca(x, Y, K=1, tau1=0, tau2=0, gamma=[0, 0.5, 1], rng=rng)
+    out["fixed_tau1"] = sp.spatpca(x, Y, K=1, tau1=10, rng=rng)
+    out["zero_zero_K5"] = sp.spatpca(x, Y, K=5, tau1=0, tau2=0, rng=rng)
+    return out
+
+
+def test_selected_tuning_parameters(seq_1d):           # test-SpatPCA.R:97-122
+    s = seq_1d
+    tol = 1e-6
+    assert abs(s["cv_1D"].selected_tau1 - 0.00046416) <= tol
+    assert abs(s["cv_1D"].selected_tau2) <= tol
+    assert abs(s["cv_1D"].selected_gamma - 0.44503397) <= 1.0001 * tol
+    assert s["cv_1D"].selected_K is None
+    assert s["cv_1D"].eigenfn.shape == (10, 2)
+    assert s["multi_tau2"].selected_K == 1
+    assert abs(s["multi_tau2"].selected_tau1 - 0.002154435) <= tol
+    assert s["multi_tau2"].selected_tau2 == 1
+    assert s["multi_gamma"].selected_gamma == 0
+    assert s["fixed_both"].selected_tau1 == 10 and s["fixed_both"].selected_tau2 == 100
+    assert s["zero_multi_gamma"].selected_gamma == 0
+    assert s["fixed_tau1"].selected_tau1 == 10
+    assert np.sum(s["fixed_tau1"].cv_score_tau1) == 0
+
+
+def test_spatial_prediction_eigenvalues(sp, seq_1d):   # test-SpatPCA.R:52-88, 123-127
+    f, z = seq_1d["fixed_tau1"], seq_1d["zero_zero_K5"]
+    assert sp.spatialPrediction(f.eigenfn, f.detrended_Y, 1000, f.eigenfn)["eigenvalue"].sum() == 0
+    assert sp.spatialPrediction(z.eigenfn, z.detrended_Y, 10, z.eigenfn)["eigenvalue"].sum() == 0
+    assert abs(sp.spatialPrediction(z.eigenfn, z.detrended_Y, 0.5, z.eigenfn)["eigenvalue"].sum()
+               - 9.397599) <= 1e-6
+    assert sp.spatialPrediction(f.eigenfn, f.detrended_Y, 5, f.eigenfn)["eigenvalue"].sum() - 0.1066821 <= 1e-6
+
+
+def test_predict_shapes(sp, seq_1d):                   # test-SpatPCA.R:138-146
+    xn = r_seq_len(6, 7, 4).reshape(-1, 1)
+    assert sp.predict(seq_1d["cv_1D"], xn).shape[1] == 4
+    assert sp.predictEigenfunction(seq_1d["cv_1D"], xn).shape[0] == 4
+
+
+def test_k_selection_aux(sp):                          # test-SpatPCA.R:150-165
+    _, x, Y = case_1d()
+    rng = RRng(1234)
+    M = 3
+    split = rng.sample(np.resize(np.arange(1, M + 1), 100))
+    tau2 = sp.setTau2(None, M)
+    r = sp.spatpcaCVWithSelectedK(x, Y, M, sp.setTau1(None, M), tau2, [1.0], split, 10, 1e-4, sp.setL2(tau2))
+    assert r["selected_K"] == 1
+    assert r["cv_result"]["selected_gamma"] == 1
+    assert r["cv_result"]["selected_tau1"] == 1
+    assert r["cv_result"]["selected_tau2"] == 0
+
+
+def test_3d_case(sp):                                  # test-SpatPCA.R:169-187
+    rng, d, Y = case_3d()
+    cv = sp.spatpca(d, Y, rng=rng)
+    assert cv.eigenfn.shape == (64, 2)
+    pred = sp.eigenFunction(np.zeros((1, 3)), d, cv.eigenfn)
+    # the reference pins the sign LAPACK's SVD happened to pick; parity is up to column sign
+    want = np.array([0.232199, 0.007501031])
+    assert np.sum(np.abs(np.abs(pred[0]) - np.abs(want))) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel-level parity against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,p", [(1, 37), (2, 100), (3, 125), (2, 900)])
+def test_tps_matrix_vs_oracle(sp, d, p):
+    rng = np.random.default_rng(d * 100 + p)
+    x = rng.uniform(-3, 3, size=(p, d))
+    got = sp.thinPlateSplineMatrix(x)
+    want = ref.thin_plate_spline_matrix(x)
+    # the bordered system has cond ~1e6..1e9: two backward-stable LU solvers agree to ~cond * eps
+    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) <= 1e-7
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_eigen_function_vs_oracle(sp, d):
+    rng = np.random.default_rng(40 + d)
+    xo = rng.uniform(-2, 2, size=(80, d))
+    xn = np.vstack([rng.uniform(-2, 2, size=(17, d)), xo[:3]])     # includes coincident sites (r = 0 guard)
+    Phi = rng.normal(size=(80, 3))
+    got = sp.eigenFunction(xn, xo, Phi)
+    want = ref.eigen_function(xn, xo, Phi)
+    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) <= 1e-8
+
+
+def _spd_problem(p, K, seed, n=40):
+    rng = np.random.default_rng(seed)
+    Yt = rng.normal(size=(n, p))
+    G = Yt.T @ Yt
+    x = rng.uniform(0, 1, size=(p, 2))
+    Om = ref.thin_plate_spline_matrix(x)
+    Om[np.diag_indices(p)] += 1e-8
+    s, rho, Phi0, L20 = ref.pca_init(Yt, K)
+    return Yt, G, Om, rho, Phi0, L20
+
+
+@pytest.mark.parametrize("p,K", [(50, 1), (300, 3), (1000, 5), (513, 8), (700, 12)])
+def test_inverse_and_core2_vs_oracle(sp, p, K):
+    from spatpca_b200 import engine as eng
+    Yt, G, Om, rho, Phi0, L20 = _spd_problem(p, K, 3 * p + K)
+    tau1 = 0.01
+    A = 2.0 * (tau1 * Om - G)
+    A[np.diag_indices(p)] += rho
+    want_inv = ref.arma_inv_sympd_symmatu(A)
+    got_inv = eng.inv_sympd(Om, G, tau1, rho, 2.0)
+    assert np.max(np.abs(got_inv - want_inv)) / np.max(np.abs(want_inv)) <= 1e-10
+    tr = ref.Trace()
+    wPhi, wC, wL2 = ref.core2(G, None, Phi0, L20, Om, tau1, rho, 100, 1e-4, tr)
+    gPhi, gC, gL2, it = eng.admm_core2(want_inv, Phi0, L20, rho, 100, 1e-4)
+    assert it == tr.calls[0][3]
+    for g, w in ((gPhi, wPhi), (gC, wC), (gL2, wL2)):
+        assert np.max(np.abs(g - w)) / np.max(np.abs(w)) <= 1e-10
+
+
+@pytest.mark.parametrize("p,K,tau2", [(60, 2, 0.0), (300, 3, 5.0), (1000, 5, 50.0), (513, 8, 1.0)])
+def test_core3_vs_oracle(sp, p, K, tau2):
+    from spatpca_b200 import engine as eng
+    Yt, G, Om, rho, Phi0, L20 = _spd_problem(p, K, 7 * p + K)
+    tinv = ref.core3_tempinv(Om, G, 0.01, rho)
+    R0 = Phi0.copy()
+    L10 = np.zeros_like(Phi0)
+    tr = ref.Trace()
+    want = ref.core3(tinv, Phi0, R0, Phi0, L10, L20, tau2, rho, 100, 1e-4, tr)
+    got = eng.admm_core3(tinv, R0, Phi0, L10, L20, tau2, rho, 100, 1e-4)
+    assert got[5] == tr.calls[0][3]
+    for g, w in zip(got[:5], want):
+        scale = max(np.max(np.abs(w)), 1e-300)
+        assert np.max(np.abs(g - w)) / scale <= 1e-10
+
+
+def test_core3_forced_iterations(sp):
+    """thr = 0: exactly maxit iterations, still matching the oracle iterate by iterate."""
+    from spatpca_b200 import engine as eng
+    Yt, G, Om, rho, Phi0, L20 = _spd_problem(400, 4, 99)
+    tinv = ref.core3_tempinv(Om, G, 0.1, rho)
+    tr = ref.Trace()
+    want = ref.core3(tinv, Phi0, Phi0.copy(), Phi0, np.zeros_like(Phi0), L20, 2.0, rho, 25, 0.0, tr)
+    got = eng.admm_core3(tinv, Phi0.copy(), Phi0, np.zeros_like(Phi0), L20, 2.0, rho, 25, 0.0)
+    assert got[5] == 25 == tr.calls[0][3]
+    assert np.max(np.abs(got[0] - want[0])) / np.max(np.abs(want[0])) <= 1e-10
+
+
+@pytest.mark.parametrize("m,p,K", [(1, 10, 1), (20, 50, 2), (40, 1000, 5), (100, 333, 8), (7, 4097, 3)])
+def test_cv_loss_vs_oracle(sp, m, p, K):
+    from spatpca_b200 import engine as eng
+    rng = np.random.default_rng(m + p + K)
+    Yva = rng.normal(size=(m, p))
+    Phi = np.linalg.qr(rng.normal(size=(p, K)))[0] * (1 + 0.01 * rng.normal(size=(1, K)))
+    want = float(np.linalg.norm(Yva @ (np.eye(p) - Phi @ Phi.T)) ** 2)    # the reference's literal form (:327)
+    got = eng.cv_loss(Yva, Phi)
+    assert abs(got - want) / want <= 1e-12
+
+
+@pytest.mark.parametrize("p,K,ng", [(10, 1, 3), (130, 3, 11), (600, 5, 11), (257, 4, 20)])
+def test_gamma_loss_vs_oracle(sp, p, K, ng):
+    from spatpca_b200 import engine as eng
+    rng = np.random.default_rng(p + K)
+    n_tr, n_va = 64, 16
+    load = np.linalg.qr(rng.normal(size=(p, K)))[0]
+    Z = rng.normal(size=(n_tr + n_va, K)) * np.linspace(6, 2, K)
+    Yall = Z @ load.T + rng.normal(size=(n_tr + n_va, p))
+    Ytr, Yva = Yall[:n_tr], Yall[n_tr:]
+    Phi = load + 0.01 * rng.normal(size=(p, K))
+    gam = np.concatenate([[0.0], np.exp(np.linspace(np.log(1e-3), np.log(40.0), ng - 1))])
+    want = ref.gamma_losses(Phi, Ytr, Yva, gam)
+    got = eng.gamma_loss(Phi, Ytr, Yva, gam)
+    np.testing.assert_allclose(got, want, rtol=1e-11)
+
+
+# ---------------------------------------------------------------------------------------------
+# end-to-end spatpcaCV parity on synthetic fields (reduced sizes)
+# ---------------------------------------------------------------------------------------------
+def run_both(sp, case, **kw):
+    args = (case["x"], case["Y"], case["M"], case["K"], case["tau1"], case["tau2"], case["gamma"],
+            case["nk"], kw.get("maxit", 100), kw.get("tol", 1e-4), case["l2"])
+    got = sp.spatpcaCV(*args, return_stats=True)
+    tr = ref.Trace()
+    want = ref.spatpca_cv(*args, trace=tr)
+    return got, want, tr
+
+
+def test_cv_1d_demo_config(sp):
+    """BASELINE config 1: 1-D demo, p=50, n=100, default grids (R/SpatPCA.R:94-98)."""
+    rng = RRng(1234)
+    x = r_seq_len(-5, 5, 50).reshape(-1, 1)
+    phi = np.exp(-x ** 2)
+    phi /= np.linalg.norm(phi)
+    Y = np.outer(rng.rnorm(100, sd=3.0), phi[:, 0]) + rng.rnorm(100 * 50).reshape(50, 100).T
+    nk = rng.sample(np.resize(np.arange(1, 6), 100)).astype(float)
+    sx = r_api.scale_location(x)
+    case = dict(x=sx, Y=Y, M=5, K=2, tau1=r_api.set_tau1(None, 5), tau2=np.array([0.0]),
+                gamma=r_api.set_gamma(None, Y[nk != 1]), nk=nk, l2=np.array([1.0]))
+    got, want, _ = run_both(sp, case)
+    assert_cv_parity(got, want)
+
+
+@pytest.mark.parametrize("name", ["grid2d_small", "irregular2d_small", "grid3d_small"])
+def test_cv_synthetic_vs_oracle(sp, name):
+    case = make_case(name)
+    got, want, tr = run_both(sp, case)
+    assert_cv_parity(got, want)
+    assert got["stats"]["n_admm_calls"] == len(tr.calls)
+    assert got["stats"]["admm_iters"] == tr.admm_iters
+
+
+def test_cv_call_log_matches_oracle(sp):
+    """Per-call ADMM iteration counts must be identical (trap 1)."""
+    case = make_case("irregular2d_small")
+    e = sp.Engine(case["x"].shape[0], case["x"].shape[1], case["Y"].shape[0], case["M"], case["K"],
+                  case["tau1"], case["tau2"], case["gamma"], 100, 1e-4, case["l2"])
+    e.upload(case["x"], case["Y"], case["nk"])
+    e.prepare()
+    M = case["M"]
+    cv1 = np.array([e.stage1_fold(k) for k in range(M)])
+    i1, _ = sp.select_index(cv1)
+    e.stage1_full(i1)
+    cv2 = np.array([e.stage2_fold(k, i1) for k in range(M)])
+    i2, _ = sp.select_index(cv2)
+    e.stage2_full(i1, i2)
+    cv3 = np.array([e.stage3_fold(k, i1, i2) for k in range(M)])
+    log = e.call_log()
+    tr = ref.Trace()
+    want = ref.spatpca_cv(case["x"], case["Y"], M, case["K"], case["tau1"], case["tau2"], case["gamma"],
+                          case["nk"], 100, 1e-4, case["l2"], trace=tr)
+    # the engine runs fold work stage by stage in the same order as the reference's workers
+    got_seq = [(3 if k == 3 else 2, f, i, it) for (k, f, i, it) in log]
+    want_seq = [(3 if "core3" in c[0] else 2, c[1], c[2], c[3]) for c in tr.calls]
+    assert sorted(got_seq) == sorted(want_seq)
+    np.testing.assert_allclose(cv1, want["aux"]["cv1"], rtol=CV_RTOL)
+    np.testing.assert_allclose(cv2, want["aux"]["cv2"], rtol=CV_RTOL)
+    np.testing.assert_allclose(cv3, want["aux"]["cv3"], rtol=CV_RTOL)
+    e.close()
+
+
+def test_cv_with_injected_omega(sp):
+    """ADMM parity separated from the ill-conditioned bordered inverse: both sides get the same Omega."""
+    case = make_case("irregular2d_small")
+    om = ref.thin_plate_spline_matrix(case["x"])
+    e = sp.Engine(case["x"].shape[0], case["x"].shape[1], case["Y"].shape[0], case["M"], case["K"],
+                  case["tau1"], case["tau2"], case["gamma"], 100, 1e-4, case["l2"])
+    e.set_omega(om)
+    e.upload(case["x"], case["Y"], case["nk"])
+    e.prepare()
+    M = case["M"]
+    cv1 = np.array([e.stage1_fold(k) for k in range(M)])
+    i1, s1 = sp.select_index(cv1)
+    e.stage1_full(i1)
+    cv2 = np.array([e.stage2_fold(k, i1) for k in range(M)])
+    i2, s2 = sp.select_index(cv2)
+    e.stage2_full(i1, i2)
+    phi = e.get_eigenfn()
+    want = ref.spatpca_cv(case["x"], case["Y"], M, case["K"], case["tau1"], case["tau2"], case["gamma"],
+                          case["nk"], 100, 1e-4, case["l2"], omega=om)
+    np.testing.assert_allclose(s1, want["cv_score_tau1"], rtol=1e-11)
+    np.testing.assert_allclose(s2, want["cv_score_tau2"], rtol=1e-11)
+    assert eig_err(phi, want["estimated_eigenfn"]) <= 1e-10
+    e.close()
+
+
+def test_cv_branches(sp):
+    """Every branch of spatpcaCV :592-692 on one small input (mirrors test-SpatPCA.R:14-51)."""
+    case = make_case("grid2d_small")
+    base = dict(case)
+    variants = [
+        dict(tau1=[0.0], tau2=[0.0], gamma=[0.0, 0.5, 1.0]),
+        dict(tau1=[10.0], tau2=[0.0], gamma=case["gamma"]),
+        dict(tau1=[10.0], tau2=[100.0], gamma=[0.0, 1.0]),
+        dict(tau1=[0.0], tau2=[0.0, 1.0, 10.0], gamma=case["gamma"]),
+        dict(tau1=[0.5], tau2=[0.0, 1.0, 10.0], gamma=[2.0]),
+        dict(tau1=case["tau1"], tau2=[3.0], gamma=case["gamma"]),
+        dict(tau1=[0.0], tau2=[5.0], gamma=case["gamma"]),
+    ]
+    for v in variants:
+        c = dict(base)
+        c.update({k: np.asarray(val, dtype=float) for k, val in v.items()})
+        c["l2"] = r_api.set_l2(c["tau2"])
+        got, want, _ = run_both(sp, c)
+        assert_cv_parity(got, want)
+
+
+def test_error_paths(sp):
+    from spatpca_b200 import SpatpcaError
+    with pytest.raises(SpatpcaError):
+        sp.thinPlateSplineMatrix(np.zeros((5, 4)))              # d > 3
+    x = np.random.default_rng(0).uniform(size=(20, 2))
+    Y = np.random.default_rng(1).normal(size=(10, 20))
+    with pytest.raises(SpatpcaError):                            # K larger than the training block
+        sp.spatpcaCV(x, Y, 5, 9, [0, 1.0], [0.0], [0.0], np.resize(np.arange(1, 6), 10), 10, 1e-4, [1.0])
+    # duplicate 2-D sites: 0 * log(0) = NaN in the reference too (:29); the LU then fails or yields NaN
+    xd = np.vstack([x, x[:1]])
+    try:
+        om = sp.thinPlateSplineMatrix(xd)
+        assert not np.all(np.isfinite(om))
+    except SpatpcaError:
+        pass
