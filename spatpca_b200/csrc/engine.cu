@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -239,6 +240,17 @@ void Engine::spd_inverse(DeviceCtx& ctx, const double* omega_u, size_t ldo, cons
   // for the matrix-stream kernel.
   cudaStream_t s = ctx.stream;
   launch_assemble_upper(omega_u, ldo, G, ldg, p, tau1, scale, rho, out, ldout, s);
+  static const bool use_cusolver = [] {
+    const char* e = std::getenv("SPB_INVERSE");
+    return e != nullptr && std::string(e) == "cusolver";
+  }();
+  if (!use_cusolver) {
+    // GEMM-rate recursive Schur-complement inverse (spd_inverse.cu); result is in full storage
+    ctx.inv_work.ensure(spd_inverse_workspace_doubles(p));
+    spd_inverse_recursive(ctx, out, p, ldout, ctx.inv_work.get());
+    return;
+  }
+  // cross-check path: the reference's own algorithm class, dpotrf + dpotri, then mirror
   int lw1 = 0, lw2 = 0;
   SPB_CUSOLVER(cusolverDnDpotrf_bufferSize(ctx.solver, CUBLAS_FILL_MODE_UPPER, p, out, (int)ldout, &lw1));
   SPB_CUSOLVER(cusolverDnDpotri_bufferSize(ctx.solver, CUBLAS_FILL_MODE_UPPER, p, out, (int)ldout, &lw2));
@@ -258,40 +270,64 @@ void Engine::gram_upper(DeviceCtx& ctx, const double* Ymat, int m, int p, double
 
 void Engine::svd_right(DeviceCtx& ctx, const double* Ymat, int m, int p, int K, std::vector<double>& sv,
                        double* Phi_dev) {
-  // svd_econ(U, s, V, Y, "right") (:321, :563): singular values and right singular vectors.
-  // cuSOLVER's gesvd needs rows >= cols, so the tall orientation is factorised.
+  // svd_econ(U, s, V, Y, "right") (:321, :563): singular values and right singular vectors of the
+  // m x p block.  The long side is removed by a Householder QR first (what LAPACK's dgesvd does
+  // for very rectangular inputs), the r x r triangular factor (r = min(m, p)) goes through
+  // cuSOLVER's one-sided Jacobi SVD, and the K leading vectors are mapped back with Q.
+  // (cusolverDnDgesvd on the full block took > 100 ms per fold at p = 900: profiles/r01_notes.)
   cudaStream_t s = ctx.stream;
   const int r = std::min(m, p);
   SPB_REQUIRE(K <= r, "K must not exceed min(rows of the training block, p)");
-  DevBuf<double> S((size_t)r);
-  sv.assign(r, 0.0);
-  if (p >= m) {
-    // A = Y' (p x m); its left singular vectors are Y's right singular vectors
-    DevBuf<double> A((size_t)p * m), U((size_t)p * m);
-    launch_transpose(Ymat, m, p, A.get(), s);
-    int lwork = 0;
-    SPB_CUSOLVER(cusolverDnDgesvd_bufferSize(ctx.solver, p, m, &lwork));
-    double* work = ctx.work((size_t)lwork);
-    SPB_CUSOLVER(cusolverDnDgesvd(ctx.solver, 'S', 'N', p, m, A.get(), p, S.get(), U.get(), p, nullptr, 1,
-                                  work, lwork, nullptr, ctx.info.get()));
+  const bool wide = (p >= m);                  // wide: factorise Y' (p x m); else Y (m x p)
+  const int rows = wide ? p : m;
+  DevBuf<double> A((size_t)rows * r), tau((size_t)r), Rm((size_t)r * r), S((size_t)r), U((size_t)r * r),
+      V((size_t)r * r);
+  if (wide) launch_transpose(Ymat, m, p, A.get(), s);
+  else SPB_CUDA(cudaMemcpyAsync(A.get(), Ymat, sizeof(double) * (size_t)m * p, cudaMemcpyDeviceToDevice, s));
+  int lq = 0, lo = 0, lj = 0;
+  SPB_CUSOLVER(cusolverDnDgeqrf_bufferSize(ctx.solver, rows, r, A.get(), rows, &lq));
+  double* work = ctx.work((size_t)lq);
+  SPB_CUSOLVER(cusolverDnDgeqrf(ctx.solver, rows, r, A.get(), rows, tau.get(), work, lq, ctx.info.get()));
+  launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_SVD, s);
+  launch_copy_upper(A.get(), (size_t)rows, r, Rm.get(), (size_t)r, s);           // R, zero below the diagonal
+  gesvdjInfo_t gi = nullptr;
+  SPB_CUSOLVER(cusolverDnCreateGesvdjInfo(&gi));
+  try {
+    SPB_CUSOLVER(cusolverDnXgesvdjSetMaxSweeps(gi, 100));
+    SPB_CUSOLVER(cusolverDnXgesvdjSetSortEig(gi, 1));
+    SPB_CUSOLVER(cusolverDnDgesvdj_bufferSize(ctx.solver, CUSOLVER_EIG_MODE_VECTOR, 1, r, r, Rm.get(), r, S.get(),
+                                              U.get(), r, V.get(), r, &lj, gi));
+    work = ctx.work((size_t)lj);
+    SPB_CUSOLVER(cusolverDnDgesvdj(ctx.solver, CUSOLVER_EIG_MODE_VECTOR, 1, r, r, Rm.get(), r, S.get(), U.get(), r,
+                                   V.get(), r, work, lj, ctx.info.get(), gi));
     launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_SVD, s);
-    SPB_CUDA(cudaMemcpyAsync(Phi_dev, U.get(), sizeof(double) * (size_t)p * K, cudaMemcpyDeviceToDevice, s));
-    SPB_CUDA(cudaMemcpyAsync(sv.data(), S.get(), sizeof(double) * r, cudaMemcpyDeviceToHost, s));
-    ctx.sync_and_check();
-  } else {
-    DevBuf<double> A((size_t)m * p), VT((size_t)p * p), V((size_t)p * p);
-    SPB_CUDA(cudaMemcpyAsync(A.get(), Ymat, sizeof(double) * (size_t)m * p, cudaMemcpyDeviceToDevice, s));
-    int lwork = 0;
-    SPB_CUSOLVER(cusolverDnDgesvd_bufferSize(ctx.solver, m, p, &lwork));
-    double* work = ctx.work((size_t)lwork);
-    SPB_CUSOLVER(cusolverDnDgesvd(ctx.solver, 'N', 'S', m, p, A.get(), m, S.get(), nullptr, 1, VT.get(), p,
-                                  work, lwork, nullptr, ctx.info.get()));
-    launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_SVD, s);
-    launch_transpose(VT.get(), p, p, V.get(), s);
-    SPB_CUDA(cudaMemcpyAsync(Phi_dev, V.get(), sizeof(double) * (size_t)p * K, cudaMemcpyDeviceToDevice, s));
-    SPB_CUDA(cudaMemcpyAsync(sv.data(), S.get(), sizeof(double) * r, cudaMemcpyDeviceToHost, s));
-    ctx.sync_and_check();
+    sv.assign(r, 0.0);
+    if (wide) {
+      // Y' = Q R = Q U_R S V_R'  =>  right singular vectors of Y are Q U_R
+      DevBuf<double> Z((size_t)p * K);
+      SPB_CUDA(cudaMemsetAsync(Z.get(), 0, sizeof(double) * (size_t)p * K, s));
+      SPB_CUDA(cudaMemcpy2DAsync(Z.get(), (size_t)p * sizeof(double), U.get(), (size_t)r * sizeof(double),
+                                 (size_t)r * sizeof(double), K, cudaMemcpyDeviceToDevice, s));
+      SPB_CUSOLVER(cusolverDnDormqr_bufferSize(ctx.solver, CUBLAS_SIDE_LEFT, CUBLAS_OP_N, p, K, r, A.get(), rows,
+                                               tau.get(), Z.get(), p, &lo));
+      work = ctx.work((size_t)lo);
+      SPB_CUSOLVER(cusolverDnDormqr(ctx.solver, CUBLAS_SIDE_LEFT, CUBLAS_OP_N, p, K, r, A.get(), rows, tau.get(),
+                                    Z.get(), p, work, lo, ctx.info.get()));
+      launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_SVD, s);
+      SPB_CUDA(cudaMemcpyAsync(Phi_dev, Z.get(), sizeof(double) * (size_t)p * K, cudaMemcpyDeviceToDevice, s));
+      SPB_CUDA(cudaMemcpyAsync(sv.data(), S.get(), sizeof(double) * r, cudaMemcpyDeviceToHost, s));
+      ctx.sync_and_check();
+    } else {
+      // Y = Q R = Q U_R S V_R'  =>  right singular vectors of Y are V_R (r = p)
+      SPB_CUDA(cudaMemcpyAsync(Phi_dev, V.get(), sizeof(double) * (size_t)p * K, cudaMemcpyDeviceToDevice, s));
+      SPB_CUDA(cudaMemcpyAsync(sv.data(), S.get(), sizeof(double) * r, cudaMemcpyDeviceToHost, s));
+      ctx.sync_and_check();
+    }
+  } catch (...) {
+    cusolverDnDestroyGesvdjInfo(gi);
+    throw;
   }
+  cusolverDnDestroyGesvdjInfo(gi);
 }
 
 void Engine::cv_loss(DeviceCtx& ctx, const double* Yva, int m, int p, const double* Phi, int K, double* W,

@@ -22,6 +22,7 @@ struct DeviceCtx {
   DevBuf<int> info;               // devInfo
   DevBuf<int> flag;               // sticky error flag
   DevBuf<int> ipiv;
+  DevBuf<double> inv_work;        // workspace of the recursive SPD inverse
 
   static DeviceCtx& get();        // context of the calling thread's current device
   void sync_and_check();          // stream sync + translate the sticky flag into an Error
@@ -161,6 +162,10 @@ class Engine {
   spb_cv_stats stats_;
   long long launches_at_start_ = 0;
 };
+
+// recursive GEMM-rate SPD inverse (spd_inverse.cu): A (upper valid) -> A^-1 (full storage)
+size_t spd_inverse_workspace_doubles(int n);
+void spd_inverse_recursive(DeviceCtx& ctx, double* A, int n, size_t ld, double* workspace);
 
 // small host helpers (host_math.cpp-like, defined in engine.cu)
 void host_jacobi_eigh(int K, std::vector<double>& A /*K x K col-major, destroyed*/,

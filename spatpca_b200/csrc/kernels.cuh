@@ -23,6 +23,8 @@ void launch_gather_rows(const double* Y, int n, int ncol, const int* rows, int m
                         cudaStream_t s);
 // out (cols x rows, ld = cols) <- transpose of in (rows x cols, ld = rows)
 void launch_transpose(const double* in, int rows, int cols, double* out, cudaStream_t s);
+// dst (n x n, ldd) <- upper triangle of src (leading n x n, lds), zeros below the diagonal
+void launch_copy_upper(const double* src, size_t lds, int n, double* dst, size_t ldd, cudaStream_t s);
 // identity columns: B (q x ncol, ld) <- [I_ncol; 0]
 void launch_set_identity(double* B, int q, int ncol, size_t ld, cudaStream_t s);
 // out[0] <- sum of squares of x[0..n)   (deterministic two-level tree)

@@ -160,6 +160,15 @@ transpose_kernel(const double* __restrict__ in, int rows, int cols, double* __re
   }
 }
 
+__global__ void copy_upper_kernel(const double* __restrict__ src, size_t lds, int n,
+                                  double* __restrict__ dst, size_t ldd) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * n) return;
+  int i = (int)(idx % n);
+  size_t j = idx / n;
+  dst[j * ldd + i] = (i <= (int)j) ? src[j * lds + i] : 0.0;
+}
+
 __global__ void set_identity_kernel(double* __restrict__ B, int q, int ncol, size_t ld) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)q * ncol;
@@ -330,6 +339,13 @@ void launch_gather_rows(const double* Y, int n, int ncol, const int* rows, int m
 void launch_transpose(const double* in, int rows, int cols, double* out, cudaStream_t s) {
   dim3 grid(ceil_div(rows, kTile), ceil_div(cols, kTile));
   transpose_kernel<<<grid, kTile * 8, 0, s>>>(in, rows, cols, out);
+  count_launch();
+  SPB_CUDA(cudaGetLastError());
+}
+
+void launch_copy_upper(const double* src, size_t lds, int n, double* dst, size_t ldd, cudaStream_t s) {
+  size_t total = (size_t)n * n;
+  copy_upper_kernel<<<ceil_div(total, 256), 256, 0, s>>>(src, lds, n, dst, ldd);
   count_launch();
   SPB_CUDA(cudaGetLastError());
 }

@@ -148,7 +148,11 @@ def test_eigen_function_vs_oracle(sp, d):
     Phi = rng.normal(size=(80, 3))
     got = sp.eigenFunction(xn, xo, Phi)
     want = ref.eigen_function(xn, xo, Phi)
-    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) <= 1e-8
+    # two backward-stable LU solves of the un-ridged bordered system agree to ~cond * eps
+    # (cond ~ 1e11 for 80 random 1-D sites, 1e5 in 2-D, 4e3 in 3-D)
+    cond = np.linalg.cond(ref.tps_bordered(xo))
+    tol = max(1e-8, 10 * cond * np.finfo(float).eps)
+    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) <= tol
 
 
 def _spd_problem(p, K, seed, n=40):
