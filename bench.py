@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the spatpcaCV hot path (BASELINE.json: spatpcaCV wall time and ADMM iterations/s at
+p = 10 000, n = 200, K = 5, 1-8 B200 vs host CPU).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+
+One "step" is one complete spatpcaCV job (Omega, 62 SPD inverses, every ADMM call, all CV losses,
+selection of tau1 / tau2 / gamma, final fit) on the synthetic field of SURVEY.md section 8d.
+`value` is ADMM iterations per second of the whole job with the inputs already resident in HBM;
+`e2e` is the same through the reference-facing C-ABI call `spb_cv` with host buffers (H2D and D2H
+copies inside the timed region).  Under torchrun (N > 1) the folds of the same job are sharded over
+the ranks ("strong" scaling) and timing is the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "spatpcaCV ADMM iterations/s (whole CV job: Omega + SPD inverses + ADMM + CV losses)"
+UNIT = "iters/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            pk = json.load(f)
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_workload(name):
+    from spatpca_b200.synth import make_case
+    c = make_case(name)
+    cfg = {
+        "workload": f"{name}: 2-D irregular locations p={c['x'].shape[0]}, n={c['Y'].shape[0]}, K={c['K']}, "
+                    f"M={c['M']}-fold CV, tau1 x tau2 x gamma = {len(c['tau1'])} x {len(c['tau2'])} x {len(c['gamma'])}, "
+                    "maxit=100, thr=1e-4 (SURVEY.md section 8d generator, seed 2024)",
+        "p": int(c["x"].shape[0]), "n": int(c["Y"].shape[0]), "K": int(c["K"]), "M": int(c["M"]),
+        "n_tau1": len(c["tau1"]), "n_tau2": len(c["tau2"]), "n_gamma": len(c["gamma"]),
+        "l2_policy": "inputs (800 MB p x p operands) exceed the 126 MB L2; no reuse across steps",
+    }
+    return c, cfg
+
+
+def run_job_resident(sp, case, coll=None):
+    """One spatpcaCV job with the inputs already in HBM: returns (seconds, result, stats)."""
+    import torch
+    from spatpca_b200 import distributed as D
+    eng = case["_engine"]
+    M = case["M"]
+    torch.cuda.synchronize()
+    if coll is not None and coll.world > 1:
+        coll.barrier()
+    t0 = time.perf_counter()
+    eng.prepare()
+    if coll is None:
+        coll = D.Collective()
+    res = D.run_sharded(eng, sp.select_index, coll, M, len(case["tau1"]), len(case["tau2"]), len(case["gamma"]),
+                        case["tau1"], case["tau2"], case["gamma"])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return dt, res
+
+
+def new_engine(sp, case):
+    e = sp.Engine(case["x"].shape[0], case["x"].shape[1], case["Y"].shape[0], case["M"], case["K"],
+                  case["tau1"], case["tau2"], case["gamma"], 100, 1e-4, case["l2"])
+    e.upload(case["x"], case["Y"], case["nk"])
+    return e
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference's path) -- bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(case, omega, tau1_idx=(0, 5), fold=0):
+    """Stage-1 work of one fold restricted to two tau1 values: SVD start, Gram matrix, one
+    inv_sympd + its ADMM iterations (spatpcaCore2), two hold-out losses.  Returns (seconds, iters)."""
+    from oracle import spatpca_ref as ref
+    Y, nk, K = case["Y"], case["nk"], case["K"]
+    tr = ref.Trace()
+    t0 = time.perf_counter()
+    Ytr, Yva = Y[nk != (fold + 1)], Y[nk == (fold + 1)]
+    _, rho, Phi0, L20 = ref.pca_init(Ytr, K)
+    G = np.asfortranarray(Ytr.T @ Ytr)
+    loss0 = ref.cv_loss(Yva, Phi0)
+    Phi, C, L2 = Phi0, Phi0, L20
+    losses = [loss0]
+    for i in tau1_idx[1:]:
+        Phi, C, L2 = ref.core2(G, Phi, C, L2, omega, case["tau1"][i], rho, 100, 1e-4, tr)
+        losses.append(ref.cv_loss(Yva, Phi))
+    dt = time.perf_counter() - t0
+    return dt, tr.admm_iters, tr
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        nums = [d.get("num_threads", 1) for d in threadpool_info() if d.get("user_api") == "blas"]
+        if nums:
+            return int(max(nums))
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def reference_arm(args, rank, world):
+    """`--impl reference`: the reference's CPU path (the oracle port; the reference itself needs R +
+    RcppArmadillo, absent here) on the host cores, on a bounded sample of the same workload."""
+    if rank != 0:
+        return 0
+    from oracle import spatpca_ref as ref
+    case, cfg = make_workload(args.config)
+    p = cfg["p"]
+    t0 = time.perf_counter()
+    om = ref.thin_plate_spline_matrix(case["x"])          # untimed set-up of the sample (reported)
+    om[np.diag_indices(p)] += 1e-8
+    t_omega = time.perf_counter() - t0
+    for _ in range(args.warmup):
+        cpu_sample(case, om)
+    times, iters = [], 0
+    for _ in range(args.steps):
+        dt, it, _ = cpu_sample(case, om)
+        times.append(dt)
+        iters = it
+    mean_t = float(np.mean(times))
+    value = iters / mean_t
+    cores = cpu_threads()
+    sample = ("fold 0 of stage 1 restricted to tau1[{0,5}]: SVD start + Gram matrix + 1 inv_sympd + its "
+              f"{iters} ADMM iterations + 2 hold-out losses at p={p}; Omega built once on the CPU before the "
+              f"timed steps ({t_omega:.1f} s, untimed)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_t * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "omega_s": t_omega},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="C4")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import torch
+    import spatpca_b200 as sp
+    from spatpca_b200 import _lib, engine as eng_mod
+    from spatpca_b200 import distributed as D
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (spatpca_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    _lib.check(_lib.load().spb_set_device(local_rank))
+    coll = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        coll = D.TorchCollective(torch.device("cuda", local_rank))
+
+    case, cfg = make_workload(args.config)
+    cfg["parallelism"] = f"folds sharded over {world} rank(s); full-data fit on rank {D.full_fit_owner(case['M'], world)}"
+    p, K = cfg["p"], cfg["K"]
+    hbm_peak, peak_src = load_peaks()
+
+    # ---- device-resident runs: `value` ----
+    case["_engine"] = new_engine(sp, case)
+    for _ in range(args.warmup):
+        case["_engine"].close()
+        case["_engine"] = new_engine(sp, case)
+        run_job_resident(sp, case, coll)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    times, stats, res = [], None, None
+    for _ in range(args.steps):
+        case["_engine"].close()
+        case["_engine"] = new_engine(sp, case)          # upload outside the timed region
+        dt, res = run_job_resident(sp, case, coll)
+        times.append(dt)
+        stats = case["_engine"].stats()
+    clocks = sampler.stop() if rank == 0 else None
+    t_local = float(np.mean(times))
+    iters_local = int(stats["admm_iters"])
+    launches_local = int(stats["gpu_launches"])
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([t_local], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_job = float(t.item())
+        c = torch.tensor([iters_local, launches_local], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        iters_job, launches_job = int(c[0].item()), int(c[1].item())
+    else:
+        t_job, iters_job, launches_job = t_local, iters_local, launches_local
+    value = iters_job / t_job
+
+    # ---- end to end through the C ABI with host buffers: `e2e` (single-GPU entry point) ----
+    e2e = None
+    if world == 1:
+        args_cv = (case["x"], case["Y"], case["M"], case["K"], case["tau1"], case["tau2"], case["gamma"], case["nk"],
+                   100, 1e-4, case["l2"])
+        sp.spatpcaCV(*args_cv)                                      # warm-up
+        t_e2e, st_e2e = [], None
+        for _ in range(args.steps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r2 = sp.spatpcaCV(*args_cv, return_stats=True)
+            t_e2e.append(time.perf_counter() - t0)
+            st_e2e = r2["stats"]
+        e2e = {"value": st_e2e["admm_iters"] / float(np.mean(t_e2e)), "unit": UNIT,
+               "h2d_bytes_per_step": int(st_e2e["bytes_h2d"]), "d2h_bytes_per_step": int(st_e2e["bytes_d2h"]),
+               "ms_per_step": float(np.mean(t_e2e)) * 1e3,
+               "selected": [r2["selected_tau1"], r2["selected_tau2"], r2["selected_gamma"]]}
+    else:
+        # N > 1: the public multi-GPU call is the sharded runner itself; its timed region already
+        # contains the NCCL gathers and the D2H reads of every score row; add the H2D upload.
+        t_up = []
+        for _ in range(args.steps):
+            case["_engine"].close()
+            if coll is not None:
+                coll.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            case["_engine"] = new_engine(sp, case)
+            dt, _ = run_job_resident(sp, case, coll)
+            torch.cuda.synchronize()
+            t_up.append(time.perf_counter() - t0)
+        import torch.distributed as dist
+        t = torch.tensor([float(np.mean(t_up))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        st = case["_engine"].stats()
+        e2e = {"value": iters_job / float(t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(st["bytes_h2d"]) * world, "d2h_bytes_per_step": int(st["bytes_d2h"]),
+               "ms_per_step": float(t.item()) * 1e3}
+
+    if rank != 0:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant own kernel: the persistent ADMM kernel (HBM-bound) ----
+    roof_iters = 10
+    ms_iter = eng_mod.bench_admm(p, K, 3, roof_iters, 3)
+    alg_bytes_iter = 8.0 * p * p + 72.0 * p * K                     # SURVEY.md section 8d, U-iter (Core3)
+    achieved = alg_bytes_iter / (ms_iter * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_admm_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("p") == p and tj.get("K") == K:
+            traffic = tj["dram_bytes_per_iteration"] * roof_iters
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": traffic, "kernel": "admm_persistent_kernel<K> (one launch = %d Core3 iterations)" % roof_iters,
+                "algorithmic_bytes_per_launch": alg_bytes_iter * roof_iters, "ms_per_launch": ms_iter * roof_iters,
+                "peak_source": peak_src}
+    # second bound: the p^3 SPD inverse against the FP64 GEMM rate measured in the same run
+    dgemm_tf = eng_mod.bench_dgemm(8192, 2)
+    inv_ms = eng_mod.bench_inverse(p, 2)
+    fp64 = {"dgemm_8192_tflops": dgemm_tf, "inverse_ms": inv_ms, "inverse_tflops_p3": (float(p) ** 3) / (inv_ms * 1e-3) / 1e12,
+            "inverse_frac_of_dgemm": (float(p) ** 3) / (inv_ms * 1e-3) / 1e12 / dgemm_tf}
+
+    # ---- CPU baseline on a bounded sample (oracle port, host cores) ----
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import spatpca_ref as ref                     # checker / baseline only
+        om = case["_engine"].get_omega()                           # sample input: Omega taken from the GPU run
+        om[np.diag_indices(p)] += 1e-8
+        dt, it, _ = cpu_sample(case, om)
+        n_inv_job = int(stats["n_inverses"])
+        cpu = {"value": it / dt, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+               "sample": ("fold 0 of stage 1 restricted to tau1[{0,5}] with Omega supplied: SVD start + Gram + 1 inv_sympd + "
+                          f"{it} ADMM iterations + 2 losses at p={p} ({dt:.1f} s); the full job has {n_inv_job} inverses"),
+               "sample_s": dt, "est_full_job_s": dt * n_inv_job}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_job * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg,
+        "wall_s": t_job, "admm_iters": iters_job, "admm_calls": int(stats["n_admm_calls"]),
+        "selected": [res["selected_tau1"], res["selected_tau2"], res["selected_gamma"]],
+        "phases_ms_rank0": {k: stats[k] for k in ("ms_omega", "ms_prologue", "ms_inverse", "ms_admm", "ms_cv_loss", "ms_gamma")},
+        "roofline": roofline, "fp64": fp64, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_job,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

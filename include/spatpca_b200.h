@@ -55,6 +55,9 @@ SPB_API int          spb_abi_version(void);
 SPB_API const char*  spb_last_error(void);
 SPB_API int          spb_device_count(void);           /* < 0 on error */
 SPB_API int          spb_set_device(int ordinal);      /* device used by subsequent calls of this thread */
+/* The library keeps released device buffers for reuse (cudaMalloc/cudaFree synchronise the device);
+ * this returns them to the driver. */
+SPB_API int          spb_trim_memory(void);
 
 /* ------------------------------------------------------------------------ */
 /* thinPlateSplineMatrix(location)                                           */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "spb_last_error": (C.c_char_p, []),
     "spb_device_count": (C.c_int, []),
     "spb_set_device": (C.c_int, [C.c_int]),
+    "spb_trim_memory": (C.c_int, []),
     "spb_tps_matrix": (C.c_int, [_dp, C.c_int, C.c_int, _dp]),
     "spb_eigen_function": (C.c_int, [_dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
     "spb_spatial_prediction": (C.c_int, [_dp, C.c_int, C.c_int, _dp, C.c_int, C.c_double, _dp, C.c_int,

@@ -94,6 +94,13 @@ int spb_set_device(int ordinal) {
   });
 }
 
+int spb_trim_memory(void) {
+  return guarded([&] {
+    cudaDeviceSynchronize();
+    cached_trim();
+  });
+}
+
 int spb_select_index(const double* cv, int M, int n_grid, double* score_out) {
   if (!cv || M < 1 || n_grid < 1) {
     set_last_error("spb_select_index: invalid argument");

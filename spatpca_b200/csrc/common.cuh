@@ -59,7 +59,15 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 // aligned so that 16-byte vector loads and bulk copies never straddle a column.
 inline size_t padded_ld(size_t rows) { return round_up(rows, 16); }
 
-// RAII device buffer of doubles (or bytes).
+// Size-bucketed caching allocator.  cudaMalloc / cudaFree synchronise the device and were seen to
+// stall for 10-500 ms inside a multi-second job (profiles/r01_notes.md), so released buffers are
+// kept per device and handed back on the next request of the same size; spb_trim_memory() (or a
+// failed cudaMalloc) returns the cache to the driver.
+void* cached_alloc(size_t bytes);
+void cached_free(void* ptr, size_t bytes);
+void cached_trim();
+
+// RAII device buffer.
 template <typename T>
 struct DevBuf {
   T* ptr = nullptr;
@@ -77,16 +85,11 @@ struct DevBuf {
   void alloc(size_t n) {
     release();
     if (n == 0) return;
-    cudaError_t e = cudaMalloc((void**)&ptr, n * sizeof(T));
-    if (e != cudaSuccess) {
-      ptr = nullptr;
-      throw Error(SPB_ERR_CUDA, std::string("cudaMalloc of ") + std::to_string(n * sizeof(T)) +
-                                    " bytes failed: " + cudaGetErrorString(e));
-    }
+    ptr = static_cast<T*>(cached_alloc(n * sizeof(T)));
     count = n;
   }
   void ensure(size_t n) { if (n > count) alloc(n); }
-  void release() { if (ptr) { cudaFree(ptr); ptr = nullptr; count = 0; } }
+  void release() { if (ptr) { cached_free(ptr, count * sizeof(T)); ptr = nullptr; count = 0; } }
   T* get() const { return ptr; }
   operator T*() const { return ptr; }
 };

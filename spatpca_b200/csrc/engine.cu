@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 #include <map>
 #include <mutex>
 #include <numeric>
@@ -15,6 +16,87 @@
 namespace spb {
 
 thread_local long long g_launch_count = 0;
+
+// SPB_TRACE=1: host-side timeline of the prologue (stream-synchronised), for performance debugging
+static bool trace_on() {
+  static const bool on = [] { const char* e = std::getenv("SPB_TRACE"); return e && e[0] == '1'; }();
+  return on;
+}
+static void trace(DeviceCtx& ctx, const char* label) {
+  if (!trace_on()) return;
+  static auto last = std::chrono::steady_clock::now();
+  cudaStreamSynchronize(ctx.stream);
+  auto now = std::chrono::steady_clock::now();
+  fprintf(stderr, "[spb trace] %-28s +%8.3f ms\n", label, std::chrono::duration<double, std::milli>(now - last).count());
+  last = now;
+}
+
+// ---------------------------------------------------------------------------------------
+// caching allocator
+// ---------------------------------------------------------------------------------------
+namespace {
+struct MemCache {
+  std::mutex mu;
+  std::map<std::pair<int, size_t>, std::vector<void*>> free_lists;   // (device, bytes) -> buffers
+};
+MemCache& mem_cache() {
+  static MemCache* c = new MemCache();   // leaked on purpose: outlives every static destructor
+  return *c;
+}
+size_t bucket(size_t bytes) { return (bytes + 511) / 512 * 512; }
+}  // namespace
+
+void cached_trim() {
+  MemCache& c = mem_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& kv : c.free_lists) {
+    if (kv.second.empty()) continue;
+    cudaSetDevice(kv.first.first);
+    for (void* p : kv.second) cudaFree(p);
+    kv.second.clear();
+  }
+  cudaSetDevice(cur);
+}
+
+void* cached_alloc(size_t bytes) {
+  const size_t b = bucket(bytes);
+  int dev = 0;
+  SPB_CUDA(cudaGetDevice(&dev));
+  MemCache& c = mem_cache();
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.free_lists.find({dev, b});
+    if (it != c.free_lists.end() && !it->second.empty()) {
+      void* p = it->second.back();
+      it->second.pop_back();
+      return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, b);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cached_trim();
+    e = cudaMalloc(&p, b);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw Error(SPB_ERR_CUDA, std::string("cudaMalloc of ") + std::to_string(b) + " bytes failed: " +
+                                  cudaGetErrorString(e));
+  }
+  return p;
+}
+
+void cached_free(void* ptr, size_t bytes) {
+  if (!ptr) return;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+  MemCache& c = mem_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  c.free_lists[{dev, bucket(bytes)}].push_back(ptr);
+}
 
 // ---------------------------------------------------------------------------------------
 // DeviceCtx
@@ -280,6 +362,7 @@ void Engine::svd_right(DeviceCtx& ctx, const double* Ymat, int m, int p, int K, 
   SPB_REQUIRE(K <= r, "K must not exceed min(rows of the training block, p)");
   const bool wide = (p >= m);                  // wide: factorise Y' (p x m); else Y (m x p)
   const int rows = wide ? p : m;
+  trace(ctx, "svd: enter");
   DevBuf<double> A((size_t)rows * r), tau((size_t)r), Rm((size_t)r * r), S((size_t)r), U((size_t)r * r),
       V((size_t)r * r);
   if (wide) launch_transpose(Ymat, m, p, A.get(), s);
@@ -289,6 +372,7 @@ void Engine::svd_right(DeviceCtx& ctx, const double* Ymat, int m, int p, int K, 
   double* work = ctx.work((size_t)lq);
   SPB_CUSOLVER(cusolverDnDgeqrf(ctx.solver, rows, r, A.get(), rows, tau.get(), work, lq, ctx.info.get()));
   launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_SVD, s);
+  trace(ctx, "svd: alloc+transpose+geqrf");
   launch_copy_upper(A.get(), (size_t)rows, r, Rm.get(), (size_t)r, s);           // R, zero below the diagonal
   gesvdjInfo_t gi = nullptr;
   SPB_CUSOLVER(cusolverDnCreateGesvdjInfo(&gi));
@@ -301,6 +385,7 @@ void Engine::svd_right(DeviceCtx& ctx, const double* Ymat, int m, int p, int K, 
     SPB_CUSOLVER(cusolverDnDgesvdj(ctx.solver, CUSOLVER_EIG_MODE_VECTOR, 1, r, r, Rm.get(), r, S.get(), U.get(), r,
                                    V.get(), r, work, lj, ctx.info.get(), gi));
     launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_SVD, s);
+    trace(ctx, "svd: gesvdj");
     sv.assign(r, 0.0);
     if (wide) {
       // Y' = Q R = Q U_R S V_R'  =>  right singular vectors of Y are Q U_R
@@ -317,6 +402,7 @@ void Engine::svd_right(DeviceCtx& ctx, const double* Ymat, int m, int p, int K, 
       SPB_CUDA(cudaMemcpyAsync(Phi_dev, Z.get(), sizeof(double) * (size_t)p * K, cudaMemcpyDeviceToDevice, s));
       SPB_CUDA(cudaMemcpyAsync(sv.data(), S.get(), sizeof(double) * r, cudaMemcpyDeviceToHost, s));
       ctx.sync_and_check();
+      trace(ctx, "svd: ormqr+copy");
     } else {
       // Y = Q R = Q U_R S V_R'  =>  right singular vectors of Y are V_R (r = p)
       SPB_CUDA(cudaMemcpyAsync(Phi_dev, V.get(), sizeof(double) * (size_t)p * K, cudaMemcpyDeviceToDevice, s));
@@ -486,6 +572,7 @@ void Engine::init_lambda(const double* Phi, const std::vector<double>& sv, doubl
 
 void Engine::prepare() {
   SPB_REQUIRE(dY_.get() != nullptr, "upload() must be called before prepare()");
+  trace(ctx_, "prepare: enter");
   cudaStream_t s = ctx_.stream;
   if (!full_ready_) {
     Scoped sc(clock_, PH_PROLOGUE, s);
@@ -514,6 +601,7 @@ void Engine::prepare() {
   }
   work_.ensure(ld_ * (size_t)p_);
   gram_.ensure(ld_ * (size_t)p_);
+  trace(ctx_, "prepare: done");
 }
 
 void Engine::get_omega(double* out) {
@@ -529,6 +617,7 @@ void Engine::get_omega(double* out) {
 void Engine::fold_prepare(int k) {
   FoldData& f = folds_[k];
   if (f.prepared) return;
+  trace(ctx_, "fold_prepare: enter");
   Scoped sc(clock_, PH_PROLOGUE, ctx_.stream);
   cudaStream_t s = ctx_.stream;
   DevBuf<int> rows((size_t)n_);
@@ -552,6 +641,7 @@ void Engine::fold_prepare(int k) {
   SPB_CUDA(cudaStreamSynchronize(s));
   f.tv = ss / (double)f.n_tr;
   f.prepared = true;
+  trace(ctx_, "fold_prepare: done");
 }
 
 void Engine::ensure_gram(int k) {

@@ -1,0 +1,135 @@
+"""Fold-sharded spatpcaCV: one process per GPU, `torch.distributed` for the plumbing.
+
+The reference's only parallel axis is the fold loop of each stage (the old parallelFor of
+src/RcppSpatPCA.cpp:315, 385, 460) plus the independent full-data fit (:598-599, 661-666).
+Folds are dealt round-robin to ranks; the full-data fit goes to the least-loaded rank.  The
+three stages are separated by an argmin over fold-summed scores (:595-597, 657-659, 684-687),
+so the only collective is an all-gather of M x |grid| doubles per stage, and one broadcast of
+the p x K result.  There is no collective on the data path.
+
+Selections are bitwise independent of the number of ranks: a fold's scores do not depend on
+where the fold ran, and rows are summed in fold order k = 0..M-1 with the reference's
+accumulation order (`spb_select_index`).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def fold_owner(k: int, world: int) -> int:
+    return k % world
+
+
+def full_fit_owner(M: int, world: int) -> int:
+    """Rank with the fewest folds (ties: the highest such rank, which finishes its folds first)."""
+    loads = [len([k for k in range(M) if fold_owner(k, world) == r]) for r in range(world)]
+    best = min(loads)
+    return max(r for r in range(world) if loads[r] == best)
+
+
+class Collective:
+    """Minimal collective interface; `TorchCollective` wraps torch.distributed (nccl or gloo)."""
+
+    rank = 0
+    world = 1
+
+    def all_gather_rows(self, rows: np.ndarray) -> np.ndarray:      # (n_local, width) -> (world, n_max, width)
+        return rows[None]
+
+    def broadcast(self, arr: np.ndarray, src: int) -> np.ndarray:
+        return arr
+
+    def barrier(self):
+        pass
+
+
+class TorchCollective(Collective):
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device if device is not None else torch.device("cpu")
+
+    def all_gather_rows(self, rows: np.ndarray) -> np.ndarray:
+        t = self.torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float64)).to(self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return np.stack([o.cpu().numpy() for o in out])
+
+    def broadcast(self, arr: np.ndarray, src: int) -> np.ndarray:
+        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
+        self.dist.broadcast(t, src=src)
+        return t.cpu().numpy()
+
+    def barrier(self):
+        self.dist.barrier()
+
+
+def _gather_stage(coll: Collective, local: dict, M: int, width: int) -> np.ndarray:
+    """All-gather the per-fold score rows; returns the M x width matrix in fold order."""
+    per_rank = (M + coll.world - 1) // coll.world
+    buf = np.zeros((per_rank, width))
+    mine = sorted(local)
+    for slot, k in enumerate(mine):
+        buf[slot, :] = local[k]
+    allr = coll.all_gather_rows(buf)
+    cv = np.zeros((M, width))
+    for r in range(coll.world):
+        ks = [k for k in range(M) if fold_owner(k, coll.world) == r]
+        for slot, k in enumerate(ks):
+            cv[k, :] = allr[r, slot, :]
+    return cv
+
+
+def run_sharded(engine, select_index, coll: Collective, M: int, n_tau1: int, n_tau2: int, n_gamma: int,
+                tau1, tau2, gamma):
+    """The stage sequence of spatpcaCV (:592-692) over a fold-sharded set of engines.
+
+    `engine` is this rank's engine (already uploaded and prepared); `select_index(cv)` returns
+    (argmin index, mean scores) like `spb_select_index`.  Returns the reference's result dict on
+    every rank."""
+    rank, world = coll.rank, coll.world
+    mine = [k for k in range(M) if fold_owner(k, world) == rank]
+    full_rank = full_fit_owner(M, world)
+
+    # ---- stage 1 ----
+    rows = {k: engine.stage1_fold(k) for k in mine}
+    index1 = 0
+    if n_tau1 > 1:
+        cv1 = _gather_stage(coll, rows, M, n_tau1)
+        index1, score1 = select_index(cv1)
+        sel_tau1 = float(tau1[index1])
+    else:
+        score1 = np.zeros(1)
+        sel_tau1 = float(np.max(tau1))
+    if rank == full_rank:
+        engine.stage1_full(index1)
+
+    # ---- stage 2 ----
+    index2 = 0
+    if n_tau2 > 1:
+        rows = {k: engine.stage2_fold(k, index1) for k in mine}
+        cv2 = _gather_stage(coll, rows, M, n_tau2)
+        index2, score2 = select_index(cv2)
+        sel_tau2 = float(tau2[index2])
+    else:
+        score2 = np.zeros(1)
+        sel_tau2 = float(np.max(tau2))
+    if rank == full_rank:
+        engine.stage2_full(index1, index2)
+
+    # ---- stage 3 ----
+    rows = {k: engine.stage3_fold(k, index1, index2) for k in mine}
+    cv3 = _gather_stage(coll, rows, M, n_gamma)
+    index3, score3 = select_index(cv3)
+    sel_gamma = float(gamma[index3]) if n_gamma > 1 else float(np.max(gamma))
+
+    eig = engine.get_eigenfn() if rank == full_rank else np.zeros((engine.p, engine.K))
+    eig = coll.broadcast(np.ascontiguousarray(eig), full_rank)
+    return {
+        "cv_score_tau1": score1, "cv_score_tau2": score2, "cv_score_gamma": score3,
+        "estimated_eigenfn": np.asfortranarray(eig),
+        "selected_tau1": sel_tau1, "selected_tau2": sel_tau2, "selected_gamma": sel_gamma,
+        "index": (index1, index2, index3),
+    }
