@@ -37,13 +37,11 @@ def setCores(num_cores=None):
     """R/helper.R:10-32 -- a validator only; the worker pool is replaced by GPU batching."""
     if num_cores is None:
         return None
-    if isinstance(num_cores, (str, bytes)) or not np.isscalar(num_cores) and not hasattr(num_cores, "__len__"):
-        raise ValueError(f"Please enter valid type - but got {type(num_cores).__name__}")
-    if hasattr(num_cores, "__len__"):
+    if isinstance(num_cores, (list, tuple, np.ndarray)):
         if len(num_cores) != 1:
             raise ValueError("Please supply a single numeric value for num_cores.")
         num_cores = num_cores[0]
-    if not isinstance(num_cores, (int, float, np.integer, np.floating)):
+    if isinstance(num_cores, bool) or not isinstance(num_cores, (int, float, np.integer, np.floating)):
         raise ValueError(f"Please enter valid type - but got {type(num_cores).__name__}")
     default_number = os.cpu_count() or 1
     if num_cores > default_number:

@@ -3,21 +3,27 @@
 // src/RcppSpatPCA.cpp:150-270) including the stopping rule, so the host never
 // synchronises inside the iteration loop.
 //
-// Per iteration (three grid-wide barriers):
-//   phase 1  Phi_partial = Ainv[:, cols] * X[cols, :]      -- the p x p matrix stream.
+// Per iteration (two grid-wide barriers):
+//   stream   Phi_partial = Ainv[:, cols] * X[cols, :]      -- the p x p matrix stream.
 //            HBM-bound: 8 p^2 bytes, 2 p^2 K flop (K/4 flop/B).  The (row tile x column)
 //            space is cut into S equal segments ("stream-K") so that every CTA streams the
 //            same number of bytes; a thread owns RPT consecutive rows, loads them with one
 //            16-byte non-allocating load per column (a warp reads 512 contiguous bytes), and
 //            keeps RPT x K accumulators in registers; X rows are broadcast from shared memory.
-//   phase 2  Phi = sum of partials (fixed order); T = Phi + Lambda2 / rho; per-row-block
-//            partial Gram matrices of T.
-//   phase 3  G = T'T (fixed order) -> K x K Jacobi eigen (one warp) -> P = G^{-1/2};
-//            C = T P (polar factor = U V' of the reference's svd_econ), R = soft threshold,
-//            dual updates, the four squared error norms, and X for the next iteration --
-//            one fused, coalesced pass over the five p x K arrays.
-// Every reduction has a fixed shape that depends only on (p, K), never on the grid size or
-// on atomics, so results are bitwise reproducible across launches and devices.
+//   reduce   the CTA that delivers the LAST partial of a row tile (atomic ticket) sums the
+//            tile's partials in fixed slot order -> Phi, forms T = Phi + Lambda2 / rho and the
+//            tile's partial Gram matrix.  The CTA that finishes the last tile sums the tile
+//            Grams in tile order, runs the K x K Jacobi eigen-solve in one warp and publishes
+//            P = (T'T)^(-1/2).  Who does the work is decided at run time; what is computed,
+//            and in which order, is not -- so the result is bitwise reproducible.
+//   barrier
+//   update   C = T P (polar factor = U V' of the reference's svd_econ), R = soft threshold,
+//            dual updates, the squared error norms and X for the next iteration: one fused,
+//            coalesced pass over the five p x K arrays.  The CTA that delivers the last norm
+//            partial sums them in row-block order and publishes the stopping decision.
+//   barrier
+// Every reduction has a fixed shape that depends only on (p, K), never on the grid size or on
+// floating-point atomics.
 #include <cooperative_groups.h>
 
 #include <map>
@@ -33,7 +39,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kSegTarget = 296;      // 2 CTAs x 148 SMs (B200); fixed so results do not depend on the device
-constexpr int kMinSegCols = 16;
+constexpr int kMinSegCols = 64;
 constexpr int kRowBlock = kThreads;  // phases 2/3: one row per thread
 constexpr int kXsBytes = 56 * 1024;  // shared-memory window for X rows in phase 1
 
@@ -52,11 +58,25 @@ struct Params {
   double rho, thr, tol, scale;
   double *Phi, *R, *C, *L1, *L2;
   double *X, *part, *gpart, *npart;
+  double* ctrl;        // [0] = max error, [1] = status, [2] = sweeps, [8 ..] = P (K x K)
+  int* counters;       // [0] = tiles done, [1] = row blocks done, [2 ..] = per-tile piece tickets
   int* stat;
   double* err;
   int nrt, S, nrb, xcap;
   long long U;
+  unsigned long long* dbg;   // optional: globaltimer stamps of CTA 0 (8 per iteration), or nullptr
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define SPB_STAMP(slot)                                                         \
+  do {                                                                          \
+    if (P.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && it < 16)     \
+      P.dbg[it * 8 + (slot)] = gtimer();                                        \
+  } while (0)
 
 __device__ __forceinline__ double2 ld_stream2(const double* ptr) {
   double2 v;
@@ -105,147 +125,16 @@ __device__ __forceinline__ double make_x(int mode, double rho, double r, double 
   return __dsub_rn(__dmul_rn(rho, __dadd_rn(r, c)), __dadd_rn(l1, l2));
 }
 
-// ---- phase 1: matrix stream --------------------------------------------------------
-template <int KP>
-__device__ __forceinline__ void phase1(const Params& P, double* xs) {
-  using C = Cfg<KP>;
-  constexpr int RPT = C::RPT, TR = C::TR, KX = C::KX;
-  const int tid = threadIdx.x;
-  const int p = P.p, K = P.K;
-  for (int s = blockIdx.x; s < P.S; s += gridDim.x) {
-    const long long u0 = seg_begin(s, P.U, P.S), u1 = seg_begin(s + 1, P.U, P.S);
-    const int t0 = (int)(u0 / p);
-    for (int w = 0; w < 2; ++w) {
-      const int t = t0 + w;
-      const long long a = max(u0, (long long)t * p), b = min(u1, (long long)(t + 1) * p);
-      if (a >= b) continue;
-      const int c0 = (int)(a - (long long)t * p), c1 = (int)(b - (long long)t * p);
-      const int r0 = t * TR + RPT * tid;
-      double acc[RPT][KP];
-#pragma unroll
-      for (int r = 0; r < RPT; ++r)
-#pragma unroll
-        for (int k = 0; k < KP; ++k) acc[r][k] = 0.0;
+// per-tile segment bookkeeping, built once per launch in shared memory
+struct TileInfo { int s_lo, s_hi, first_w; };
 
-      for (int cb = c0; cb < c1; cb += P.xcap) {
-        const int ncols = min(c1 - cb, P.xcap);
-        __syncthreads();                       // previous window fully consumed
-        for (int idx = tid; idx < ncols * KX; idx += kThreads) {
-          const int jj = idx / KX, k = idx - jj * KX;
-          xs[idx] = (k < K) ? __ldcg(P.X + (size_t)k * p + cb + jj) : 0.0;
-        }
-        __syncthreads();
-        if (r0 < p) {
-          const double* ap = P.A + (size_t)cb * P.ld + r0;
-          int jj = 0;
-          constexpr int UN = 8;
-          for (; jj + UN <= ncols; jj += UN) {
-            if (RPT == 2) {
-              double2 av[UN];
-#pragma unroll
-              for (int u = 0; u < UN; ++u) av[u] = ld_stream2(ap + (size_t)(jj + u) * P.ld);
-#pragma unroll
-              for (int u = 0; u < UN; ++u) {
-                const double* xv = xs + (jj + u) * KX;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) {
-                  const double x = xv[k];
-                  acc[0][k] = fma(av[u].x, x, acc[0][k]);
-                  acc[RPT - 1][k] = fma(av[u].y, x, acc[RPT - 1][k]);
-                }
-              }
-            } else {
-              double av[UN];
-#pragma unroll
-              for (int u = 0; u < UN; ++u) av[u] = ld_stream1(ap + (size_t)(jj + u) * P.ld);
-#pragma unroll
-              for (int u = 0; u < UN; ++u) {
-                const double* xv = xs + (jj + u) * KX;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) acc[0][k] = fma(av[u], xv[k], acc[0][k]);
-              }
-            }
-          }
-          for (; jj < ncols; ++jj) {
-            const double* xv = xs + jj * KX;
-            if (RPT == 2) {
-              const double2 a2 = ld_stream2(ap + (size_t)jj * P.ld);
-#pragma unroll
-              for (int k = 0; k < KP; ++k) {
-                const double x = xv[k];
-                acc[0][k] = fma(a2.x, x, acc[0][k]);
-                acc[RPT - 1][k] = fma(a2.y, x, acc[RPT - 1][k]);
-              }
-            } else {
-              const double a1 = ld_stream1(ap + (size_t)jj * P.ld);
-#pragma unroll
-              for (int k = 0; k < KP; ++k) acc[0][k] = fma(a1, xv[k], acc[0][k]);
-            }
-          }
-        }
-      }
-      // partial slot of (segment, piece): [k][row in tile]
-      double* slot = P.part + ((size_t)(2 * s + w) * KP) * TR;
-      if (r0 < p) {
-#pragma unroll
-        for (int k = 0; k < KP; ++k) {
-          if (k < K) {
-            if (RPT == 2) {
-              double2 o; o.x = acc[0][k]; o.y = acc[RPT - 1][k];
-              __stcg(reinterpret_cast<double2*>(slot + (size_t)k * TR + RPT * tid), o);
-            } else {
-              __stcg(slot + (size_t)k * TR + tid, acc[0][k]);
-            }
-          }
-        }
-      }
-    }
-  }
-}
-
-// ---- phase 2: reduce partials, Gram partials -----------------------------------------
-template <int KP>
-__device__ __forceinline__ void phase2(const Params& P, double* red) {
-  using C = Cfg<KP>;
-  constexpr int TR = C::TR, KG = C::KG;
-  const int tid = threadIdx.x;
-  const int p = P.p, K = P.K;
-  for (int rb = blockIdx.x; rb < P.nrb; rb += gridDim.x) {
-    const int i = rb * kRowBlock + tid;
-    double g[KG];
-#pragma unroll
-    for (int q = 0; q < KG; ++q) g[q] = 0.0;
-    if (i < p) {
-      const int t = i / TR, li = i - t * TR;
-      const int s_lo = seg_of((long long)t * p, P.U, P.S);
-      const int s_hi = seg_of((long long)(t + 1) * p - 1, P.U, P.S);
-      double phi[KP];
-#pragma unroll
-      for (int k = 0; k < KP; ++k) phi[k] = 0.0;
-      for (int s = s_lo; s <= s_hi; ++s) {
-        const int w = ((int)(seg_begin(s, P.U, P.S) / p) == t) ? 0 : 1;
-        const double* slot = P.part + ((size_t)(2 * s + w) * KP) * TR + li;
-#pragma unroll
-        for (int k = 0; k < KP; ++k)
-          if (k < K) phi[k] += __ldcg(slot + (size_t)k * TR);
-      }
-      double tt[KP];
-#pragma unroll
-      for (int k = 0; k < KP; ++k) {
-        tt[k] = 0.0;
-        if (k < K) {
-          const double ph = __dmul_rn(P.scale, phi[k]);          // 0.5 * (...) in Core3 (:247)
-          P.Phi[(size_t)k * p + i] = ph;
-          tt[k] = __dadd_rn(ph, __ddiv_rn(__ldcg(P.L2 + (size_t)k * p + i), P.rho));   // :169, :251
-        }
-      }
-      int q = 0;
-#pragma unroll
-      for (int a = 0; a < KP; ++a)
-#pragma unroll
-        for (int b = a; b < KP; ++b) g[q++] = tt[a] * tt[b];
-    }
-    block_reduce_store<KG>(g, red, P.gpart + (size_t)rb * KG);
+__device__ __forceinline__ void build_tile_table(const Params& P, TileInfo* tiles) {
+  for (int t = threadIdx.x; t < P.nrt; t += kThreads) {
+    TileInfo ti;
+    ti.s_lo = seg_of((long long)t * P.p, P.U, P.S);
+    ti.s_hi = seg_of((long long)(t + 1) * P.p - 1, P.U, P.S);
+    ti.first_w = (seg_begin(ti.s_lo, P.U, P.S) < (long long)t * P.p) ? 1 : 0;   // first piece started in tile t-1
+    tiles[t] = ti;
   }
 }
 
@@ -265,7 +154,7 @@ __device__ int jacobi_inv_sqrt_warp(double* Am, double* Vm, double* Pm, int K, i
         const double apq = Am[pp * K + qq];
         const double app = Am[pp * K + pp];
         const double aqq = Am[qq * K + qq];
-        if (apq == 0.0 || fabs(apq) <= 1e-16 * sqrt(fabs(app * aqq))) continue;
+        if (apq == 0.0 || apq * apq <= 1e-32 * fabs(app * aqq)) continue;
         rotated = true;
         const double theta = (aqq - app) / (2.0 * apq);
         double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
@@ -303,51 +192,284 @@ __device__ int jacobi_inv_sqrt_warp(double* Am, double* Vm, double* Pm, int K, i
     if (!rotated) break;
   }
   *sweeps_out = sweeps;
-  int bad = 0;
-  double lmax = 0.0;
-  for (int k = 0; k < K; ++k) lmax = fmax(lmax, Am[k * K + k]);
-  for (int k = 0; k < K; ++k) {
-    const double l = Am[k * K + k];
-    if (!(l > 1e-28 * lmax) || !isfinite(l)) bad = 1;
-  }
-  // P = V diag(lam^-1/2) V'
+  // eigenvalues -> lam^-1/2 (one lane each), positivity check, P = V diag(lam^-1/2) V'
+  double lam = 1.0;
+  if (lane < K) lam = Am[lane * K + lane];
+  double lmax = lam;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  const int mybad = (lane < K) && (!(lam > 1e-28 * lmax) || !isfinite(lam));
+  const int bad = __any_sync(0xffffffffu, mybad) ? 1 : 0;
+  __syncwarp();
+  if (lane < K) Am[lane] = 1.0 / sqrt(lam);       // row 0 of Am reused as scratch
+  __syncwarp();
   for (int idx = lane; idx < K * K; idx += 32) {
     const int a = idx / K, b = idx - a * K;
     double acc = 0.0;
-    for (int k = 0; k < K; ++k) acc = fma(Vm[a * K + k] / sqrt(Am[k * K + k]), Vm[b * K + k], acc);
+    for (int k = 0; k < K; ++k) acc = fma(Vm[a * K + k] * Am[k], Vm[b * K + k], acc);
     Pm[idx] = acc;
   }
   __syncwarp();
   return bad;
 }
 
-// ---- phase 3: polar factor, soft threshold, dual updates, norms, next X ------------------
+
+// ---- reduce of one row tile: partials -> Phi, T, Gram partial ------------------------------
+// Thread tid owns rows RPT*tid .. RPT*tid+RPT-1 of the tile (the stream's ownership), so one
+// 16-byte load fetches both rows of a slot column; loads of kBatch slots are in flight together
+// and the additions run in slot order.
 template <int KP>
-__device__ __forceinline__ int phase3(const Params& P, double* red, double* jA, double* jV, double* jP,
-                                      int* sh_flag) {
+__device__ __forceinline__ void reduce_tile(const Params& P, int t, const TileInfo& ti, double* red) {
+  using C = Cfg<KP>;
+  constexpr int RPT = C::RPT, TR = C::TR, KG = C::KG;
+  constexpr int kBatch = (KP <= 4) ? 8 : ((KP <= 8) ? 4 : 2);
+  const int tid = threadIdx.x;
+  const int p = P.p, K = P.K;
+  const int li = RPT * tid;
+  const int i0 = t * TR + li;
+  double phi[RPT][KP];
+#pragma unroll
+  for (int r = 0; r < RPT; ++r)
+#pragma unroll
+    for (int k = 0; k < KP; ++k) phi[r][k] = 0.0;
+  if (i0 < p) {
+    for (int s = ti.s_lo; s <= ti.s_hi; s += kBatch) {
+      double v[kBatch][KP][RPT];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int su = s + u;
+        const bool live = (su <= ti.s_hi);
+        const int w = (su == ti.s_lo) ? ti.first_w : 0;
+        const double* slot = P.part + ((size_t)(2 * (live ? su : ti.s_lo) + w) * KP) * TR + li;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          if (live && k < K) {
+            if (RPT == 2) {
+              const double2 x = __ldcg(reinterpret_cast<const double2*>(slot + (size_t)k * TR));
+              v[u][k][0] = x.x; v[u][k][RPT - 1] = x.y;
+            } else {
+              v[u][k][0] = __ldcg(slot + (size_t)k * TR);
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) v[u][k][r] = 0.0;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u)
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) phi[r][k] += v[u][k][r];     // adding +0.0 for dead slots is exact
+    }
+  }
+  double g[KG];
+#pragma unroll
+  for (int q = 0; q < KG; ++q) g[q] = 0.0;
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int i = i0 + r;
+    if (i < p) {
+      double tt[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        tt[k] = 0.0;
+        if (k < K) {
+          const double ph = __dmul_rn(P.scale, phi[r][k]);       // 0.5 * (...) in Core3 (:247)
+          P.Phi[(size_t)k * p + i] = ph;
+          tt[k] = __dadd_rn(ph, __ddiv_rn(__ldcg(P.L2 + (size_t)k * p + i), P.rho));   // :169, :251
+        }
+      }
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < KP; ++a)
+#pragma unroll
+        for (int b = a; b < KP; ++b) { g[q] = fma(tt[a], tt[b], g[q]); ++q; }
+    }
+  }
+  block_reduce_store<KG>(g, red, P.gpart + (size_t)t * KG);
+}
+
+// ---- Gram reduce + Jacobi by the CTA that finished the last tile ------------------------------
+template <int KP>
+__device__ __forceinline__ void finish_polar(const Params& P, double* jA, double* jV, double* jP) {
   using C = Cfg<KP>;
   constexpr int KG = C::KG;
   const int tid = threadIdx.x;
-  const int p = P.p, K = P.K;
-  // G = sum over row blocks, fixed order; scatter to the symmetric K x K matrix
-  for (int q = tid; q < KG; q += kThreads) {
+  const int K = P.K;
+  if (P.dbg != nullptr && tid == 0) P.dbg[120] = gtimer();
+  // fixed-shape reduction over tiles: lane j of a 16-lane group sums tiles j, j+16, ... in order,
+  // then a xor-shuffle tree combines the 16 lanes (the shape depends only on nrt)
+  for (int q0 = 0; q0 < KG; q0 += kThreads / 16) {
+    const int q = q0 + (tid >> 4), j = tid & 15;
     double t = 0.0;
-    for (int rb = 0; rb < P.nrb; ++rb) t += __ldcg(P.gpart + (size_t)rb * KG + q);
-    // unpack q -> (a, b), a <= b, in the KP-packed order used by phase 2
-    int a = 0, rem = q;
-    while (rem >= KP - a) { rem -= KP - a; ++a; }
-    const int b = a + rem;
-    if (a < K && b < K) { jA[a * K + b] = t; jA[b * K + a] = t; }
+    if (q < KG)
+      for (int tb = j; tb < P.nrt; tb += 16) t += __ldcg(P.gpart + (size_t)tb * KG + q);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (q < KG && j == 0) {
+      int a = 0, rem = q;                          // unpack q -> (a, b), a <= b, KP-packed order
+      while (rem >= KP - a) { rem -= KP - a; ++a; }
+      const int b = a + rem;
+      if (a < K && b < K) { jA[a * K + b] = t; jA[b * K + a] = t; }
+    }
   }
   __syncthreads();
+  if (P.dbg != nullptr && tid == 0) P.dbg[121] = gtimer();
   if (tid < 32) {
     int sweeps = 0;
-    int bad = jacobi_inv_sqrt_warp(jA, jV, jP, K, &sweeps);
-    if (tid == 0) { sh_flag[0] = bad; sh_flag[1] = sweeps; }
+    const int bad = jacobi_inv_sqrt_warp(jA, jV, jP, K, &sweeps);
+    if (P.dbg != nullptr && tid == 0) { P.dbg[122] = gtimer(); P.dbg[125] = (unsigned long long)sweeps; }
+    for (int idx = tid; idx < K * K; idx += 32) __stcg(P.ctrl + 8 + idx, jP[idx]);
+    if (tid == 0) { __stcg(P.ctrl + 1, (double)bad); __stcg(P.ctrl + 2, (double)sweeps); }
   }
   __syncthreads();
-  const int bad = sh_flag[0];
+}
 
+// ---- stream: matrix-stream partials, then ticketed tile / polar reduction ---------------------
+template <int KP>
+__device__ __forceinline__ void stream_phase(const Params& P, double* xs, double* red, const TileInfo* tiles,
+                                             double* jA, double* jV, double* jP, int* sh_i, bool rev) {
+  using C = Cfg<KP>;
+  constexpr int RPT = C::RPT, TR = C::TR, KX = C::KX;
+  const int tid = threadIdx.x;
+  const int p = P.p, K = P.K;
+  for (int s = blockIdx.x; s < P.S; s += gridDim.x) {
+    const long long u0 = seg_begin(s, P.U, P.S), u1 = seg_begin(s + 1, P.U, P.S);
+    const int t0 = (int)(u0 / p);
+    for (int w = 0; w < 2; ++w) {
+      const int t = t0 + w;
+      const long long a = max(u0, (long long)t * p), b = min(u1, (long long)(t + 1) * p);
+      if (a >= b) continue;
+      const int c0 = (int)(a - (long long)t * p), c1 = (int)(b - (long long)t * p);
+      const int r0 = t * TR + RPT * tid;
+      double acc[RPT][KP];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[r][k] = 0.0;
+
+      // Boustrophedon: odd iterations walk the segment's columns backwards, so the ~100 MB of the
+      // matrix that the previous iteration left in the 126 MB L2 (its tail) is what this iteration
+      // reads first.  The order inside a segment depends only on the iteration parity, so results
+      // stay bitwise reproducible.
+      const int nwin = (c1 - c0 + P.xcap - 1) / P.xcap;
+      for (int wi = 0; wi < nwin; ++wi) {
+        const int cb = c0 + (rev ? (nwin - 1 - wi) : wi) * P.xcap;
+        const int ncols = min(c1 - cb, P.xcap);
+        __syncthreads();                       // previous window fully consumed
+        for (int idx = tid; idx < ncols * KX; idx += kThreads) {
+          const int jj = idx / KX, k = idx - jj * KX;
+          xs[idx] = (k < K) ? __ldcg(P.X + (size_t)k * p + cb + jj) : 0.0;
+        }
+        __syncthreads();
+        if (r0 < p) {
+          const long long cs = rev ? -(long long)P.ld : (long long)P.ld;
+          const int xstep = rev ? -KX : KX;
+          const double* ap = P.A + (size_t)(rev ? cb + ncols - 1 : cb) * P.ld + r0;
+          const double* xp = xs + (rev ? (ncols - 1) * KX : 0);
+          int jj = 0;
+          constexpr int UN = 8;
+          for (; jj + UN <= ncols; jj += UN) {
+            if (RPT == 2) {
+              double2 av[UN];
+#pragma unroll
+              for (int u = 0; u < UN; ++u) av[u] = ld_stream2(ap + (long long)(jj + u) * cs);
+#pragma unroll
+              for (int u = 0; u < UN; ++u) {
+                const double* xv = xp + (jj + u) * xstep;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                  const double x = xv[k];
+                  acc[0][k] = fma(av[u].x, x, acc[0][k]);
+                  acc[RPT - 1][k] = fma(av[u].y, x, acc[RPT - 1][k]);
+                }
+              }
+            } else {
+              double av[UN];
+#pragma unroll
+              for (int u = 0; u < UN; ++u) av[u] = ld_stream1(ap + (long long)(jj + u) * cs);
+#pragma unroll
+              for (int u = 0; u < UN; ++u) {
+                const double* xv = xp + (jj + u) * xstep;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) acc[0][k] = fma(av[u], xv[k], acc[0][k]);
+              }
+            }
+          }
+          for (; jj < ncols; ++jj) {
+            const double* xv = xp + jj * xstep;
+            if (RPT == 2) {
+              const double2 a2 = ld_stream2(ap + (long long)jj * cs);
+#pragma unroll
+              for (int k = 0; k < KP; ++k) {
+                const double x = xv[k];
+                acc[0][k] = fma(a2.x, x, acc[0][k]);
+                acc[RPT - 1][k] = fma(a2.y, x, acc[RPT - 1][k]);
+              }
+            } else {
+              const double a1 = ld_stream1(ap + (long long)jj * cs);
+#pragma unroll
+              for (int k = 0; k < KP; ++k) acc[0][k] = fma(a1, xv[k], acc[0][k]);
+            }
+          }
+        }
+      }
+      // partial slot of (segment, piece): [k][row in tile]; thread tid holds rows RPT*tid .. +RPT-1
+      double* slot = P.part + ((size_t)(2 * s + w) * KP) * TR;
+      if (r0 < p) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          if (k < K) {
+            if (RPT == 2) {
+              double2 o; o.x = acc[0][k]; o.y = acc[RPT - 1][k];
+              __stcg(reinterpret_cast<double2*>(slot + (size_t)k * TR + RPT * tid), o);
+            } else {
+              __stcg(slot + (size_t)k * TR + tid, acc[0][k]);
+            }
+          }
+        }
+      }
+      // ticket: the CTA that delivers the last piece of tile t reduces the tile
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const int npieces = tiles[t].s_hi - tiles[t].s_lo + 1;
+        const int old = atomicAdd(P.counters + 2 + t, 1);
+        sh_i[0] = (old == npieces - 1) ? 1 : 0;
+      }
+      __syncthreads();
+      if (sh_i[0]) {
+        __threadfence();
+        if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[123] = gtimer();
+        reduce_tile<KP>(P, t, tiles[t], red);
+        if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[124] = gtimer();
+        if (tid == 0) {
+          P.counters[2 + t] = 0;                       // re-arm for the next iteration
+          __threadfence();
+          const int old = atomicAdd(P.counters + 0, 1);
+          sh_i[1] = (old == P.nrt - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (sh_i[1]) {
+          __threadfence();
+          if (tid == 0) P.counters[0] = 0;
+          finish_polar<KP>(P, jA, jV, jP);
+        }
+      }
+    }
+  }
+}
+
+// ---- update: polar factor applied, soft threshold, dual updates, norms, next X ------------------
+template <int KP>
+__device__ __forceinline__ void update_phase(const Params& P, double* red, double* jP, double* sh_d, int* sh_i) {
+  const int tid = threadIdx.x;
+  const int p = P.p, K = P.K;
+  for (int idx = tid; idx < K * K; idx += kThreads) jP[idx] = __ldcg(P.ctrl + 8 + idx);
+  __syncthreads();
+  const double denom = sqrt((double)P.p * (double)P.K);
   for (int rb = blockIdx.x; rb < P.nrb; rb += gridDim.x) {
     const int i = rb * kRowBlock + tid;
     double nv[4] = {0.0, 0.0, 0.0, 0.0};
@@ -357,7 +479,7 @@ __device__ __forceinline__ int phase3(const Params& P, double* red, double* jA, 
       for (int k = 0; k < KP; ++k) {
         phi[k] = 0.0; tt[k] = 0.0;
         if (k < K) {
-          phi[k] = P.Phi[(size_t)k * p + i];
+          phi[k] = __ldcg(P.Phi + (size_t)k * p + i);
           tt[k] = __dadd_rn(phi[k], __ddiv_rn(P.L2[(size_t)k * p + i], P.rho));
         }
       }
@@ -397,66 +519,93 @@ __device__ __forceinline__ int phase3(const Params& P, double* red, double* jA, 
           }
           P.C[off] = cn;
           P.L2[off] = l2n;
-          P.X[off] = xn;
+          __stcg(P.X + off, xn);
         }
       }
     }
     block_reduce_store<4>(nv, red, P.npart + (size_t)rb * 4);
+    // ticket: the CTA that delivers the last norm partial publishes the stopping decision
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int old = atomicAdd(P.counters + 1, 1);
+      sh_i[0] = (old == P.nrb - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh_i[0]) {
+      __threadfence();
+      if (tid < 128) {                            // 4 norms x 32 lanes, fixed tree over row blocks
+        const int v = tid >> 5, j = tid & 31;
+        double t = 0.0;
+        for (int b = j; b < P.nrb; b += 32) t += __ldcg(P.npart + (size_t)b * 4 + v);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (j == 0) sh_d[v] = sqrt(t) / denom;    // norm(., "fro") / sqrt(p K)  (:175-176, :261-264)
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __stcg(P.ctrl + 0, fmax(fmax(sh_d[0], sh_d[1]), fmax(sh_d[2], sh_d[3])));
+        P.counters[1] = 0;
+      }
+      __syncthreads();
+    }
   }
-  return bad;
 }
 
 template <int KP>
 __global__ void __launch_bounds__(kThreads, (KP <= 8) ? 2 : 1)
 admm_persistent_kernel(Params P) {
-  using C = Cfg<KP>;
   extern __shared__ __align__(16) double dyn[];
-  double* xs = dyn;                       // phase 1 window
-  double* red = dyn;                      // phases 2/3 reduction scratch (aliases xs)
+  double* xs = dyn;                       // stream window
+  double* red = dyn + P.xcap * Cfg<KP>::KX;   // reduction scratch (8 KG + 32 doubles)
   __shared__ double jA[KP * KP], jV[KP * KP], jP[KP * KP];
-  __shared__ double sh_err[4];
-  __shared__ int sh_flag[2];
+  __shared__ double sh_d[4];
+  __shared__ int sh_i[2];
+  TileInfo* tiles = reinterpret_cast<TileInfo*>(dyn + P.xcap * Cfg<KP>::KX + 8 * Cfg<KP>::KG + 32);
 
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const size_t pk = (size_t)P.p * P.K;
 
-  // phase 0
+  // set-up: tile table, tickets, X from the incoming state
+  build_tile_table(P, tiles);
+  if (blockIdx.x == 0) {
+    for (int i = tid; i < P.nrt + 2; i += kThreads) P.counters[i] = 0;
+    if (tid == 0) { __stcg(P.ctrl + 0, 0.0); __stcg(P.ctrl + 1, 0.0); __stcg(P.ctrl + 2, 0.0); }
+  }
   for (size_t idx = (size_t)blockIdx.x * kThreads + tid; idx < pk; idx += (size_t)gridDim.x * kThreads) {
     const double r = (P.mode == 3) ? P.R[idx] : 0.0;
     const double l1 = (P.mode == 3) ? P.L1[idx] : 0.0;
-    P.X[idx] = make_x(P.mode, P.rho, r, P.C[idx], l1, P.L2[idx]);
+    __stcg(P.X + idx, make_x(P.mode, P.rho, r, P.C[idx], l1, P.L2[idx]));
   }
+  __threadfence();
   grid.sync();
 
-  const double denom = sqrt((double)P.p * (double)P.K);
-  int iters = 0, status = 0, sweeps = 0;
-  double errmax = 0.0;
+  int iters = 0, status = 0;
+  double errmax = 0.0, sweeps = 0.0;
   for (int it = 0; it < P.maxit; ++it) {
     iters = it + 1;
-    phase1<KP>(P, xs);
+    SPB_STAMP(0);
+    stream_phase<KP>(P, xs, red, tiles, jA, jV, jP, sh_i, (it & 1) != 0);
+    SPB_STAMP(1);
+    __threadfence();
     grid.sync();
-    phase2<KP>(P, red);
+    SPB_STAMP(2);
+    status = (int)__ldcg(P.ctrl + 1);
+    sweeps = __ldcg(P.ctrl + 2);
+    update_phase<KP>(P, red, jP, sh_d, sh_i);
+    SPB_STAMP(3);
+    __threadfence();
     grid.sync();
-    status = phase3<KP>(P, red, jA, jV, jP, sh_flag);
-    sweeps = sh_flag[1];
-    grid.sync();
-    // stopping rule (:175-179, :260-266): fixed-order sum of the per-row-block partials
-    if (tid < 4) {
-      double t = 0.0;
-      for (int rb = 0; rb < P.nrb; ++rb) t += __ldcg(P.npart + (size_t)rb * 4 + tid);
-      sh_err[tid] = sqrt(t) / denom;
-    }
-    __syncthreads();
-    errmax = fmax(fmax(sh_err[0], sh_err[1]), fmax(sh_err[2], sh_err[3]));
-    __syncthreads();
+    SPB_STAMP(4);
+    errmax = __ldcg(P.ctrl + 0);
     if (status != 0) break;
-    if (errmax <= P.tol) break;
+    if (errmax <= P.tol) break;              // stopping rule (:178, :266)
   }
   if (blockIdx.x == 0 && tid == 0) {
     P.stat[0] = iters;
     P.stat[1] = status;
-    P.stat[2] = sweeps;
+    P.stat[2] = (int)sweeps;
     P.err[0] = errmax;
   }
 }
@@ -465,7 +614,7 @@ struct Geom {
   int KP, RPT, TR, KX, KG;
   int nrt, S, nrb, xcap;
   long long U;
-  size_t part_doubles, gpart_doubles, npart_doubles, x_doubles;
+  size_t part_doubles, gpart_doubles, npart_doubles, x_doubles, ctrl_doubles, counter_ints;
   size_t smem_bytes;
 };
 
@@ -491,16 +640,20 @@ Geom make_geom(int p, int K) {
   g.S = (int)s;
   g.nrb = ceil_div(p, kRowBlock);
   int maxcols = (int)((g.U + g.S - 1) / g.S) + 1;
-  int cap = kXsBytes / (g.KX * (int)sizeof(double));
+  // leave room in the 56 KB window budget for the reduction scratch and the tile table
+  int budget = kXsBytes - (int)((8 * (size_t)g.KG + 32) * sizeof(double)) - g.nrt * 12;
+  if (budget < 4096) budget = 4096;
+  int cap = budget / (g.KX * (int)sizeof(double));
   g.xcap = maxcols < cap ? maxcols : cap;
   if (g.xcap < 1) g.xcap = 1;
   g.part_doubles = (size_t)2 * g.S * g.TR * g.KP;
-  g.gpart_doubles = (size_t)g.nrb * g.KG;
+  g.gpart_doubles = (size_t)g.nrt * g.KG;
   g.npart_doubles = (size_t)g.nrb * 4;
   g.x_doubles = (size_t)p * K;
-  size_t xs_bytes = (size_t)g.xcap * g.KX * sizeof(double);
-  size_t red_bytes = (size_t)(kThreads / 32) * (g.KG > 4 ? g.KG : 4) * sizeof(double);
-  g.smem_bytes = xs_bytes > red_bytes ? xs_bytes : red_bytes;
+  g.ctrl_doubles = 8 + (size_t)SPB_MAX_K * SPB_MAX_K;
+  g.counter_ints = (size_t)g.nrt + 2;
+  // dynamic shared memory: [stream window | reduction scratch (8 KG + 32) | tile table]
+  g.smem_bytes = ((size_t)g.xcap * g.KX + 8 * (size_t)g.KG + 32) * sizeof(double) + (size_t)g.nrt * 3 * sizeof(int);
   return g;
 }
 
@@ -542,7 +695,8 @@ void launch_instance(const Params& P, const Geom& g, cudaStream_t s) {
 
 size_t admm_workspace_bytes(int p, int K) {
   Geom g = make_geom(p, K);
-  return (g.x_doubles + g.part_doubles + g.gpart_doubles + g.npart_doubles) * sizeof(double);
+  return (g.x_doubles + g.part_doubles + g.gpart_doubles + g.npart_doubles + g.ctrl_doubles) * sizeof(double) +
+         g.counter_ints * sizeof(int) + 64;
 }
 
 int admm_num_segments(int p, int K) { return make_geom(p, K).S; }
@@ -560,8 +714,12 @@ void launch_admm(const AdmmCall& c, void* ws, cudaStream_t s) {
   P.X = w; w += g.x_doubles;
   P.part = w; w += g.part_doubles;
   P.gpart = w; w += g.gpart_doubles;
-  P.npart = w;
+  P.npart = w; w += g.npart_doubles;
+  P.ctrl = w; w += g.ctrl_doubles;
+  P.counters = reinterpret_cast<int*>(w);
+  SPB_REQUIRE(g.nrt <= 4096, "p is too large for the ADMM kernel's tile table");
   P.stat = c.stat_slot; P.err = c.err_slot;
+  P.dbg = c.dbg;
   P.nrt = g.nrt; P.S = g.S; P.nrb = g.nrb; P.xcap = g.xcap; P.U = g.U;
   switch (g.KP) {
     case 1: launch_instance<1>(P, g, s); break;

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -473,6 +474,9 @@ int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_pe
     SPB_CUDA(cudaEventCreate(&e0));
     SPB_CUDA(cudaEventCreate(&e1));
     double best = 1e300;
+    const bool dbg_on = std::getenv("SPB_ADMM_DBG") != nullptr;
+    DevBuf<unsigned long long> dbg(16 * 8);
+    SPB_CUDA(cudaMemsetAsync(dbg.get(), 0, sizeof(unsigned long long) * 128, s));
     for (int r = 0; r < repeats + 1; ++r) {
       launch_set_identity(st.C.get(), p, K, p, s);
       launch_set_identity(st.R.get(), p, K, p, s);
@@ -483,6 +487,7 @@ int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_pe
       c.maxit = iters; c.tol = -1.0;          // never satisfied: every call runs `iters` iterations
       c.Phi = st.Phi.get(); c.R = st.R.get(); c.C = st.C.get(); c.L1 = st.L1.get(); c.L2 = st.L2.get();
       c.stat_slot = stat.get(); c.err_slot = err.get();
+      c.dbg = dbg_on ? dbg.get() : nullptr;
       SPB_CUDA(cudaEventRecord(e0, s));
       launch_admm(c, ws.get(), s);
       SPB_CUDA(cudaEventRecord(e1, s));
@@ -496,6 +501,18 @@ int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_pe
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (dbg_on) {
+      unsigned long long h[128];
+      SPB_CUDA(cudaMemcpy(h, dbg.get(), sizeof(h), cudaMemcpyDeviceToHost));
+      const char* names[8] = {"stream+reduce", "barrier1", "update", "barrier2", "(loop)", "-", "-", "-"};
+      for (int it = 2; it < std::min(iters, 6); ++it) {
+        fprintf(stderr, "[admm dbg] p=%d K=%d it=%d:", p, K, it);
+        for (int q = 0; q < 4; ++q) fprintf(stderr, " %s=%.1fus", names[q], (double)(h[it * 8 + q + 1] - h[it * 8 + q]) * 1e-3);
+        fprintf(stderr, " total=%.1fus\n", (double)(h[(it + 1) * 8] - h[it * 8]) * 1e-3);
+      }
+      fprintf(stderr, "[admm dbg] last iteration: gram-reduce=%.1fus jacobi=%.1fus (%llu sweeps) tile0-reduce=%.1fus\n",
+              (double)(h[121] - h[120]) * 1e-3, (double)(h[122] - h[121]) * 1e-3, h[125], (double)(h[124] - h[123]) * 1e-3);
+    }
     *ms_per_iter = best;
   });
 }

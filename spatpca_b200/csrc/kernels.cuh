@@ -54,6 +54,7 @@ struct AdmmCall {
   double *Phi, *R, *C, *L1, *L2;   // p x K, ld = p.  R/L1 unused in mode 2
   int* stat_slot;       // device: {iterations, status, sweeps}
   double* err_slot;     // device: last max error
+  unsigned long long* dbg = nullptr;   // optional phase time stamps (performance debugging)
 };
 
 size_t admm_workspace_bytes(int p, int K);

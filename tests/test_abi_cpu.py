@@ -1,0 +1,86 @@
+"""CPU-only checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/spatpca_b200.h declares, the ctypes table mirrors the header, and compute entry points fail
+loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "spatpca_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"SPB_API\s+[\w\s\*]+?\b(spb_\w+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = declared_symbols()
+    for must in ("spb_tps_matrix", "spb_cv", "spb_eigen_function", "spb_spatial_prediction", "spb_last_error",
+                 "spb_engine_create", "spb_engine_stage1_fold", "spb_select_index"):
+        assert must in syms
+    assert len(syms) >= 30
+
+
+def test_library_exports_every_declared_symbol():
+    from spatpca_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+
+
+def test_ctypes_table_mirrors_header():
+    from spatpca_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    lib = _lib.load()
+    assert lib.spb_abi_version() == 1
+
+
+def test_header_cites_reference_interfaces():
+    src = open(HEADER).read()
+    for cite in ("src/RcppSpatPCA.cpp:58-76", "src/RcppSpatPCA.cpp:94-147", "src/RcppSpatPCA.cpp:543-701",
+                 "src/RcppSpatPCA.cpp:715-770", "R/RcppExports.R"):
+        assert cite in src
+
+
+def test_select_index_matches_armadillo_order():
+    """Host-only helper: index_min(sum(cv, 0)) with two interleaved accumulators, first minimum wins."""
+    from spatpca_b200 import select_index
+    from oracle.spatpca_ref import arma_colsum
+    rng = np.random.default_rng(0)
+    cv = rng.uniform(1, 2, size=(5, 11))
+    cv[:, 7] = cv[:, 3]                       # exact tie: the first one must win
+    cv[:, 3] -= 1.0
+    cv[:, 7] -= 1.0
+    idx, score = select_index(cv)
+    sums = arma_colsum(cv)
+    assert idx == int(np.argmin(sums)) == 3
+    np.testing.assert_array_equal(score, sums / 5)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point must fail with SPB_ERR_NO_DEVICE."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import spatpca_b200 as sp
+    with pytest.raises(sp.SpatpcaError) as ei:
+        sp.thinPlateSplineMatrix(np.random.default_rng(0).uniform(size=(6, 2)))
+    assert ei.value.code == -2
+    with pytest.raises(sp.SpatpcaError):
+        sp.spatpcaCV(np.zeros((6, 1)), np.zeros((8, 6)), 2, 1, [0, 1.0], [0.0], [0.0], np.resize([1, 2], 8), 5, 1e-4,
+                     [1.0])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "spatpca_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f

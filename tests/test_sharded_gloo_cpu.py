@@ -1,0 +1,113 @@
+"""world_size = 2 `gloo` test of the fold-sharded runner (spatpca_b200/distributed.py) on CPU.
+
+The runner's host logic -- fold placement, the per-stage all-gather of score rows, the
+reference-order argmin, the hand-over of (index1, index2) to the next stage, the broadcast of the
+full-data fit -- is exercised with a stand-in engine that serves per-fold rows computed by the CPU
+oracle (the GPU engine cannot run here).  Every rank must end with exactly the single-process
+oracle result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleBackedEngine:
+    """Implements the engine interface used by `run_sharded`; records which folds it was asked for."""
+
+    def __init__(self, case, want):
+        self.case, self.want = case, want
+        self.p, self.K = case["x"].shape[0], case["K"]
+        self.asked = []
+
+    def stage1_fold(self, k):
+        self.asked.append(("s1", k))
+        return self.want["aux"]["cv1"][k].copy()
+
+    def stage1_full(self, index1):
+        self.asked.append(("f1", index1))
+
+    def stage2_fold(self, k, index1):
+        self.asked.append(("s2", k, index1))
+        return self.want["aux"]["cv2"][k].copy()
+
+    def stage2_full(self, index1, index2):
+        self.asked.append(("f2", index1, index2))
+
+    def stage3_fold(self, k, index1, index2):
+        self.asked.append(("s3", k, index1, index2))
+        return self.want["aux"]["cv3"][k].copy()
+
+    def get_eigenfn(self):
+        return self.want["estimated_eigenfn"]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from oracle import spatpca_ref as ref
+    from oracle.spatpca_ref import arma_colsum
+    from spatpca_b200 import distributed as D
+    from spatpca_b200.synth import make_case
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = make_case("grid3d_small")
+    want = ref.spatpca_cv(case["x"], case["Y"], case["M"], case["K"], case["tau1"], case["tau2"], case["gamma"],
+                          case["nk"], 100, 1e-4, case["l2"])
+
+    def select_index(cv):                  # host-only twin of spb_select_index (no GPU library needed)
+        sums = arma_colsum(np.asarray(cv))
+        return int(np.argmin(sums)), sums / cv.shape[0]
+
+    eng = OracleBackedEngine(case, want)
+    coll = D.TorchCollective()
+    got = D.run_sharded(eng, select_index, coll, case["M"], len(case["tau1"]), len(case["tau2"]),
+                        len(case["gamma"]), case["tau1"], case["tau2"], case["gamma"])
+    ok = True
+    for key in ("selected_tau1", "selected_tau2", "selected_gamma"):
+        ok &= got[key] == want[key]
+    for key in ("cv_score_tau1", "cv_score_tau2", "cv_score_gamma"):
+        ok &= bool(np.array_equal(got[key], want[key]))
+    ok &= bool(np.array_equal(got["estimated_eigenfn"], want["estimated_eigenfn"]))
+    # each rank ran only its own folds, and exactly one rank ran the full-data fit
+    my_folds = sorted({a[1] for a in eng.asked if a[0] == "s1"})
+    ok &= my_folds == [k for k in range(case["M"]) if D.fold_owner(k, world) == rank]
+    did_full = any(a[0] == "f1" for a in eng.asked)
+    ok &= did_full == (rank == D.full_fit_owner(case["M"], world))
+    with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+        f.write("ok" if ok else "FAIL %r" % (got,))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_run_sharded_world2_gloo(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"rank{r}.txt").read() == "ok"
+
+
+def test_fold_placement():
+    from spatpca_b200 import distributed as D
+    for world in (1, 2, 4, 8):
+        owners = [D.fold_owner(k, world) for k in range(5)]
+        assert sorted(set(owners)) == list(range(min(world, 5)))
+        fr = D.full_fit_owner(5, world)
+        loads = [owners.count(r) for r in range(world)]
+        assert loads[fr] == min(loads)
+    assert D.full_fit_owner(5, 8) == 7 and D.full_fit_owner(5, 2) == 1 and D.full_fit_owner(5, 1) == 0
