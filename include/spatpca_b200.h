@@ -174,6 +174,16 @@ SPB_API int spb_engine_stage2_full(spb_engine* e, int index1, int index2);
 /* stage 3 (:682-692, worker :459-525).  cv_row receives n_gamma values.    */
 SPB_API int spb_engine_stage3_fold(spb_engine* e, int k, int index1, int index2, double* cv_row);
 
+/* The same stages for a LIST of folds at once: the folds run concurrently on independent streams
+ * ("lanes"), which is how one GPU replaces the reference's fold worker pool.  cv_rows is
+ * nfolds x n_grid, row-major (row f = scores of folds[f]).  The *_full calls only enqueue the
+ * full-data fit on its own lane; it overlaps with the next stage and is waited for by
+ * spb_engine_get_eigenfn / spb_engine_get_stats.                                              */
+SPB_API int spb_engine_stage1_folds(spb_engine* e, const int* folds, int nfolds, double* cv_rows);
+SPB_API int spb_engine_stage2_folds(spb_engine* e, const int* folds, int nfolds, int index1, double* cv_rows);
+SPB_API int spb_engine_stage3_folds(spb_engine* e, const int* folds, int nfolds, int index1, int index2,
+                                    double* cv_rows);
+
 /* estimated_eigenfn (p x K) of the full-data fit, device -> host */
 SPB_API int spb_engine_get_eigenfn(spb_engine* e, double* eigenfn_out);
 SPB_API int spb_engine_get_stats(spb_engine* e, spb_cv_stats* stats);

@@ -73,6 +73,9 @@ SIGNATURES = {
     "spb_engine_stage2_fold": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
     "spb_engine_stage2_full": (C.c_int, [_vp, C.c_int, C.c_int]),
     "spb_engine_stage3_fold": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp]),
+    "spb_engine_stage1_folds": (C.c_int, [_vp, _ip, C.c_int, _dp]),
+    "spb_engine_stage2_folds": (C.c_int, [_vp, _ip, C.c_int, C.c_int, _dp]),
+    "spb_engine_stage3_folds": (C.c_int, [_vp, _ip, C.c_int, C.c_int, C.c_int, _dp]),
     "spb_engine_get_eigenfn": (C.c_int, [_vp, _dp]),
     "spb_engine_get_stats": (C.c_int, [_vp, C.POINTER(CvStats)]),
     "spb_engine_call_log": (C.c_int, [_vp, _ip, C.c_int]),

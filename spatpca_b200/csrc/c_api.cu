@@ -272,6 +272,15 @@ int spb_engine_stage2_full(spb_engine* e, int index1, int index2) {
 int spb_engine_stage3_fold(spb_engine* e, int k, int index1, int index2, double* cv_row) {
   SPB_ENGINE_CALL(e->impl->stage3_fold(k, index1, index2, cv_row));
 }
+int spb_engine_stage1_folds(spb_engine* e, const int* folds, int nfolds, double* cv_rows) {
+  SPB_ENGINE_CALL(e->impl->stage1_folds(folds, nfolds, cv_rows));
+}
+int spb_engine_stage2_folds(spb_engine* e, const int* folds, int nfolds, int index1, double* cv_rows) {
+  SPB_ENGINE_CALL(e->impl->stage2_folds(folds, nfolds, index1, cv_rows));
+}
+int spb_engine_stage3_folds(spb_engine* e, const int* folds, int nfolds, int index1, int index2, double* cv_rows) {
+  SPB_ENGINE_CALL(e->impl->stage3_folds(folds, nfolds, index1, index2, cv_rows));
+}
 int spb_engine_get_eigenfn(spb_engine* e, double* out) { SPB_ENGINE_CALL(e->impl->get_eigenfn(out)); }
 int spb_engine_get_stats(spb_engine* e, spb_cv_stats* st) { SPB_ENGINE_CALL(e->impl->get_stats(st)); }
 int spb_engine_release_fold(spb_engine* e, int k) { SPB_ENGINE_CALL(e->impl->release_fold(k)); }
@@ -296,44 +305,47 @@ int spb_cv(const double* sxy, int p, int d, const double* Y, int n, int M, int K
     Engine eng(p, d, n, M, K, tau1, n_tau1, tau2, n_tau2, gamma, n_gamma, maxit, tol, l2, n_l2);
     eng.upload(sxy, Y, nk);
     eng.prepare();
-    // stage 1 (:592-650)
+    // stage 1 (:592-650): all folds run concurrently on their lanes
     int index1 = 0, index2 = 0, index3 = 0;
-    std::vector<double> cv1((size_t)M * n_tau1, 0.0);
+    std::vector<int> all(M);
+    for (int k = 0; k < M; ++k) all[k] = k;
+    auto to_colmajor = [&](const std::vector<double>& rows, int width) {   // rows: M x width row-major
+      std::vector<double> cv((size_t)M * width);
+      for (int k = 0; k < M; ++k)
+        for (int i = 0; i < width; ++i) cv[(size_t)i * M + k] = rows[(size_t)k * width + i];
+      return cv;
+    };
     {
-      std::vector<double> row(n_tau1);
-      for (int k = 0; k < M; ++k) {
-        eng.stage1_fold(k, row.data());
-        if (n_tau1 > 1)
-          for (int i = 0; i < n_tau1; ++i) cv1[(size_t)i * M + k] = row[i];
+      std::vector<double> rows((size_t)M * n_tau1, 0.0);
+      eng.stage1_folds(all.data(), M, rows.data());
+      if (n_tau1 > 1) {
+        std::vector<double> cv1 = to_colmajor(rows, n_tau1);
+        index1 = select_index_impl(cv1.data(), M, n_tau1, cv_score_tau1);
+      } else {
+        cv_score_tau1[0] = 0.0;                                             // :649
       }
     }
-    if (n_tau1 > 1) index1 = select_index_impl(cv1.data(), M, n_tau1, cv_score_tau1);
-    else cv_score_tau1[0] = 0.0;                                              // :649
-    eng.stage1_full(index1);
+    eng.stage1_full(index1);                 // full-data fit: overlaps with the folds' stage 2
     selected[0] = eng.selected_tau1(index1);
     // stage 2 (:652-680)
     if (n_tau2 > 1) {
-      std::vector<double> cv2((size_t)M * n_tau2, 0.0), row(n_tau2);
-      for (int k = 0; k < M; ++k) {
-        eng.stage2_fold(k, index1, row.data());
-        for (int i = 0; i < n_tau2; ++i) cv2[(size_t)i * M + k] = row[i];
-      }
+      std::vector<double> rows((size_t)M * n_tau2, 0.0);
+      eng.stage2_folds(all.data(), M, index1, rows.data());
+      std::vector<double> cv2 = to_colmajor(rows, n_tau2);
       index2 = select_index_impl(cv2.data(), M, n_tau2, cv_score_tau2);
       selected[1] = tau2[index2];
     } else {
-      cv_score_tau2[0] = 0.0;                                                 // :679
-      selected[1] = tau2[0];                                                  // :671
+      cv_score_tau2[0] = 0.0;                                               // :679
+      selected[1] = tau2[0];                                                // :671
     }
-    eng.stage2_full(index1, index2);
+    eng.stage2_full(index1, index2);         // overlaps with the folds' stage 3
     // stage 3 (:682-692)
     {
-      std::vector<double> cv3((size_t)M * n_gamma, 0.0), row(n_gamma);
-      for (int k = 0; k < M; ++k) {
-        eng.stage3_fold(k, index1, index2, row.data());
-        for (int i = 0; i < n_gamma; ++i) cv3[(size_t)i * M + k] = row[i];
-      }
+      std::vector<double> rows((size_t)M * n_gamma, 0.0);
+      eng.stage3_folds(all.data(), M, index1, index2, rows.data());
+      std::vector<double> cv3 = to_colmajor(rows, n_gamma);
       index3 = select_index_impl(cv3.data(), M, n_gamma, cv_score_gamma);
-      selected[2] = (n_gamma > 1) ? gamma[index3] : gamma[0];                 // :684-691
+      selected[2] = (n_gamma > 1) ? gamma[index3] : gamma[0];               // :684-691
     }
     eng.get_eigenfn(estimated_eigenfn);
     eng.get_stats(stats);
@@ -353,7 +365,7 @@ int spb_inv_sympd(const double* omega, const double* G, int p, double tau1, doub
     upload_square(omega, p, om.get(), ld, ctx.stream);
     upload_square(G, p, g.get(), ld, ctx.stream);
     launch_symmatu_inplace(om.get(), p, ld, 0.0, ctx.stream);
-    Engine::spd_inverse(ctx, om.get(), ld, g.get(), ld, p, tau1, rho, scale, w.get(), ld);
+    Engine::spd_inverse(ctx.exec(), om.get(), ld, g.get(), ld, p, tau1, rho, scale, w.get(), ld);
     download_square(out, p, w.get(), ld, ctx.stream);
     ctx.sync_and_check();
   });
@@ -425,7 +437,7 @@ int spb_cv_loss(const double* Yva, int n_va, int p, const double* Phi, int K, do
         scr(yphi_scratch_doubles(n_va, p, K) + 16), out(1);
     SPB_CUDA(cudaMemcpyAsync(dY.get(), Yva, sizeof(double) * (size_t)n_va * p, cudaMemcpyHostToDevice, s));
     SPB_CUDA(cudaMemcpyAsync(dP.get(), Phi, sizeof(double) * (size_t)p * K, cudaMemcpyHostToDevice, s));
-    Engine::cv_loss(ctx, dY.get(), n_va, p, dP.get(), K, W.get(), scr.get(), out.get());
+    Engine::cv_loss(s, dY.get(), n_va, p, dP.get(), K, W.get(), scr.get(), out.get());
     SPB_CUDA(cudaMemcpyAsync(loss, out.get(), sizeof(double), cudaMemcpyDeviceToHost, s));
     ctx.sync_and_check();
   });
@@ -447,7 +459,7 @@ int spb_gamma_loss(const double* Phi, int p, int K, const double* Ytr, int n_tr,
     SPB_CUDA(cudaMemcpyAsync(&ssq, ss.get(), sizeof(double), cudaMemcpyDeviceToHost, s));
     ctx.sync_and_check();
     std::vector<double> g(gamma, gamma + n_gamma);
-    Engine::gamma_losses(ctx, dP.get(), p, K, dtr.get(), n_tr, ssq / (double)n_tr, dva.get(), n_va, g, out);
+    Engine::gamma_losses(ctx, s, dP.get(), p, K, dtr.get(), n_tr, ssq / (double)n_tr, dva.get(), n_va, g, out);
   });
 }
 
@@ -563,7 +575,7 @@ int spb_bench_inverse(int p, int repeats, double* ms_out) {
     double best = 1e300;
     for (int r = 0; r < repeats + 1; ++r) {
       SPB_CUDA(cudaEventRecord(e0, s));
-      Engine::spd_inverse(ctx, om.get(), ld, g.get(), ld, p, 0.5, 10.0, 2.0, w.get(), ld);
+      Engine::spd_inverse(ctx.exec(), om.get(), ld, g.get(), ld, p, 0.5, 10.0, 2.0, w.get(), ld);
       SPB_CUDA(cudaEventRecord(e1, s));
       ctx.sync_and_check();
       float ms = 0.f;

@@ -130,7 +130,25 @@ DeviceCtx& DeviceCtx::get() {
   return ref;
 }
 
+LaneRes::~LaneRes() {
+  if (blas) cublasDestroy(blas);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+LaneRes& DeviceCtx::lane_res(int i) {
+  while ((int)lane_pool.size() <= i) {
+    std::unique_ptr<LaneRes> r(new LaneRes());
+    SPB_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    SPB_CUBLAS(cublasCreate(&r->blas));
+    SPB_CUBLAS(cublasSetStream(r->blas, r->stream));
+    SPB_CUBLAS(cublasSetPointerMode(r->blas, CUBLAS_POINTER_MODE_HOST));
+    lane_pool.push_back(std::move(r));
+  }
+  return *lane_pool[i];
+}
+
 DeviceCtx::~DeviceCtx() {
+  lane_pool.clear();
   if (solver) cusolverDnDestroy(solver);
   if (blas) cublasDestroy(blas);
   if (stream) cudaStreamDestroy(stream);
@@ -315,12 +333,11 @@ void Engine::build_omega_raw(DeviceCtx& ctx, const double* x_dev, int p, int d, 
   ctx.sync_and_check();     // temporaries are freed on return
 }
 
-void Engine::spd_inverse(DeviceCtx& ctx, const double* omega_u, size_t ldo, const double* G, size_t ldg,
+void Engine::spd_inverse(const Exec& ex, const double* omega_u, size_t ldo, const double* G, size_t ldg,
                          int p, double tau1, double rho, double scale, double* out, size_t ldout) {
-  // inv_sympd(symmatu(scale*(tau1*Omega - G) + rho*I)) (:164-165, :397): upper-triangle assembly,
-  // Cholesky factor + inverse from the factor (dpotrf/dpotri class), then mirror to full storage
-  // for the matrix-stream kernel.
-  cudaStream_t s = ctx.stream;
+  // inv_sympd(symmatu(scale*(tau1*Omega - G) + rho*I)) (:164-165, :397): upper-triangle assembly, then
+  // the inverse in full storage for the matrix-stream kernel.
+  cudaStream_t s = ex.stream;
   launch_assemble_upper(omega_u, ldo, G, ldg, p, tau1, scale, rho, out, ldout, s);
   static const bool use_cusolver = [] {
     const char* e = std::getenv("SPB_INVERSE");
@@ -328,26 +345,30 @@ void Engine::spd_inverse(DeviceCtx& ctx, const double* omega_u, size_t ldo, cons
   }();
   if (!use_cusolver) {
     // GEMM-rate recursive Schur-complement inverse (spd_inverse.cu); result is in full storage
-    ctx.inv_work.ensure(spd_inverse_workspace_doubles(p));
-    spd_inverse_recursive(ctx, out, p, ldout, ctx.inv_work.get());
+    ex.inv_work->ensure(spd_inverse_workspace_doubles(p));
+    spd_inverse_recursive(ex, out, p, ldout, ex.inv_work->get());
     return;
   }
-  // cross-check path: the reference's own algorithm class, dpotrf + dpotri, then mirror
+  // cross-check path (SPB_INVERSE=cusolver): the reference's own algorithm class, dpotrf + dpotri.
+  // cuSOLVER is bound to the main stream, so this path serialises the lanes.
+  DeviceCtx& ctx = DeviceCtx::get();
+  SPB_CUDA(cudaStreamSynchronize(s));
   int lw1 = 0, lw2 = 0;
   SPB_CUSOLVER(cusolverDnDpotrf_bufferSize(ctx.solver, CUBLAS_FILL_MODE_UPPER, p, out, (int)ldout, &lw1));
   SPB_CUSOLVER(cusolverDnDpotri_bufferSize(ctx.solver, CUBLAS_FILL_MODE_UPPER, p, out, (int)ldout, &lw2));
   int lw = std::max(lw1, lw2);
   double* work = ctx.work((size_t)lw);
   SPB_CUSOLVER(cusolverDnDpotrf(ctx.solver, CUBLAS_FILL_MODE_UPPER, p, out, (int)ldout, work, lw, ctx.info.get()));
-  launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_NOT_POSDEF, s);
+  launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_NOT_POSDEF, ctx.stream);
   SPB_CUSOLVER(cusolverDnDpotri(ctx.solver, CUBLAS_FILL_MODE_UPPER, p, out, (int)ldout, work, lw, ctx.info.get()));
-  launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_NOT_POSDEF, s);
-  launch_symmatu_inplace(out, p, ldout, 0.0, s);
+  launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_NOT_POSDEF, ctx.stream);
+  launch_symmatu_inplace(out, p, ldout, 0.0, ctx.stream);
+  SPB_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 
-void Engine::gram_upper(DeviceCtx& ctx, const double* Ymat, int m, int p, double* G, size_t ldg) {
+void Engine::gram_upper(const Exec& ex, const double* Ymat, int m, int p, double* G, size_t ldg) {
   const double one = 1.0, zero = 0.0;
-  SPB_CUBLAS(cublasDsyrk(ctx.blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, p, m, &one, Ymat, m, &zero, G, (int)ldg));
+  SPB_CUBLAS(cublasDsyrk(ex.blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, p, m, &one, Ymat, m, &zero, G, (int)ldg));
 }
 
 void Engine::svd_right(DeviceCtx& ctx, const double* Ymat, int m, int p, int K, std::vector<double>& sv,
@@ -416,24 +437,24 @@ void Engine::svd_right(DeviceCtx& ctx, const double* Ymat, int m, int p, int K, 
   cusolverDnDestroyGesvdjInfo(gi);
 }
 
-void Engine::cv_loss(DeviceCtx& ctx, const double* Yva, int m, int p, const double* Phi, int K, double* W,
+void Engine::cv_loss(cudaStream_t s, const double* Yva, int m, int p, const double* Phi, int K, double* W,
                      double* scratch, double* out_dev) {
-  launch_yphi(Yva, m, p, Phi, K, W, scratch, ctx.stream);
-  launch_residual_sumsq(Yva, m, p, Phi, K, W, scratch, out_dev, ctx.stream);
+  launch_yphi(Yva, m, p, Phi, K, W, scratch, s);
+  launch_residual_sumsq(Yva, m, p, Phi, K, W, scratch, out_dev, s);
 }
 
-void Engine::gamma_losses(DeviceCtx& ctx, const double* Phi, int p, int K, const double* Ytr, int n_tr,
-                          double tv, const double* Yva, int n_va, const std::vector<double>& gamma,
+void Engine::gamma_losses(DeviceCtx& ctx, cudaStream_t s, const double* Phi, int p, int K, const double* Ytr,
+                          int n_tr, double tv, const double* Yva, int n_va, const std::vector<double>& gamma,
                           double* out_host) {
   // stage-3 body for one fold (:489-523).  K x K eigen step and water-filling run on the host
-  // (O(K^3)); everything that touches p runs on the device.
-  cudaStream_t s = ctx.stream;
+  // (O(K^3)); everything that touches p runs on the device, on stream `s`.
   const int ng = (int)gamma.size();
   DevBuf<double> W((size_t)n_tr * K), scr(yphi_scratch_doubles(n_tr, p, K)), H((size_t)K * K);
   launch_yphi(Ytr, n_tr, p, Phi, K, W.get(), scr.get(), s);
   launch_small_gram(W.get(), n_tr, K, 1.0 / (double)n_tr, H.get(), s);
   std::vector<double> Hh((size_t)K * K);
   SPB_CUDA(cudaMemcpyAsync(Hh.data(), H.get(), sizeof(double) * K * K, cudaMemcpyDeviceToHost, s));
+  SPB_CUDA(cudaStreamSynchronize(s));
   ctx.sync_and_check();
   std::vector<double> evals, evecs;
   host_jacobi_eigh(K, Hh, evals, evecs);                 // ascending, like eig_sym (:492)
@@ -460,6 +481,7 @@ void Engine::gamma_losses(DeviceCtx& ctx, const double* Phi, int p, int K, const
                       gscr.get(), out_dev.get() + g0, s);
   }
   SPB_CUDA(cudaMemcpyAsync(out_host, out_dev.get(), sizeof(double) * ng, cudaMemcpyDeviceToHost, s));
+  SPB_CUDA(cudaStreamSynchronize(s));
   ctx.sync_and_check();
 }
 
@@ -487,33 +509,56 @@ Engine::Engine(int p, int d, int n, int M, int K, const double* tau1, int n1, co
   folds_.resize(M);
   const size_t pk = (size_t)p * K;
   full_.alloc(pk);
-  chain_.alloc(pk);
-  admm_ws_.alloc(admm_workspace_bytes(p, K));
-  int max_m = n;
-  lossW_.alloc((size_t)max_m * K);
-  loss_scratch_.alloc(yphi_scratch_doubles(max_m, p, K) + 512);
-  int max_grid = std::max({n1, n2, n3, 1});
-  loss_out_.alloc((size_t)max_grid + 1);
+  max_grid_ = std::max({n1, n2, n3, 1});
+  loss_out_.alloc((size_t)(M + 1) * max_grid_);
+  prep_scratch_.alloc(512);
   slot_cap_ = (n1 + 2 * n2 + nl2 + 8) * (M + 2);
-  stat_slots_.alloc((size_t)slot_cap_ * 4);
-  err_slots_.alloc((size_t)slot_cap_);
+
+  // lanes: one per fold if memory allows (each needs ~2.5 p x p matrices), plus the full-data lane
+  const double per_lane = 2.5 * (double)ld_ * p * sizeof(double) + 64e6;
+  size_t free_b = 0, total_b = 0;
+  SPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const double fixed = (double)(M + 2) * ld_ * p * sizeof(double);      // Omega + per-fold tempinv + slack
+  int nl = (int)std::floor(((double)free_b * 0.8 - fixed) / per_lane) - 1;
+  if (const char* e = std::getenv("SPB_LANES")) nl = std::atoi(e);
+  n_fold_lanes_ = std::max(1, std::min(M, nl));
+  for (int i = 0; i <= n_fold_lanes_; ++i) {
+    std::unique_ptr<Lane> L(new Lane());
+    L->res = &ctx_.lane_res(i);
+    L->chain.alloc(pk);
+    L->admm_ws.alloc(admm_workspace_bytes(p, K));
+    L->lossW.alloc((size_t)n * K);
+    L->loss_scratch.alloc(yphi_scratch_doubles(n, p, K) + 512);
+    L->stat_slots.alloc((size_t)slot_cap_ * 4);
+    L->err_slots.alloc((size_t)slot_cap_);
+    lanes_.push_back(std::move(L));
+  }
   std::memset(&stats_, 0, sizeof(stats_));
   launches_at_start_ = g_launch_count;
   t_created = std::chrono::steady_clock::now();
 }
 
-Engine::~Engine() {}
+Engine::~Engine() {
+  // lanes may still have work in flight if a call failed half-way: drain before buffers are recycled
+  for (auto& L : lanes_) cudaStreamSynchronize(L->res->stream);
+  cudaStreamSynchronize(ctx_.stream);
+}
+
+Lane& Engine::lane_of(int fold) {
+  if (fold < 0) return *lanes_[n_fold_lanes_];
+  return *lanes_[fold % n_fold_lanes_];
+}
 
 double Engine::selected_tau1(int index1) const {
   if (tau1_.size() > 1) return tau1_[index1];
   return *std::max_element(tau1_.begin(), tau1_.end());
 }
 
-void Engine::copy_pk(double* dst, const double* src) {
-  SPB_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)p_ * K_, cudaMemcpyDeviceToDevice, ctx_.stream));
+void Engine::copy_pk(cudaStream_t s, double* dst, const double* src) {
+  SPB_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)p_ * K_, cudaMemcpyDeviceToDevice, s));
 }
-void Engine::zero_pk(double* dst) {
-  SPB_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)p_ * K_, ctx_.stream));
+void Engine::zero_pk(cudaStream_t s, double* dst) {
+  SPB_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)p_ * K_, s));
 }
 
 void Engine::upload(const double* sxy, const double* Y, const double* nk) {
@@ -540,7 +585,7 @@ void Engine::upload(const double* sxy, const double* Y, const double* nk) {
   stats_.ms_h2d += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   omega_ready_ = omega_injected_;
   full_ready_ = false;
-  gram_owner_ = -2;
+  for (auto& L : lanes_) L->gram_owner = -2;
 }
 
 void Engine::set_omega(const double* omega_host) {
@@ -558,7 +603,7 @@ void Engine::set_omega(const double* omega_host) {
   omega_injected_ = true;
 }
 
-void Engine::init_lambda(const double* Phi, const std::vector<double>& sv, double rho, double* L2) {
+void Engine::init_lambda(cudaStream_t s, const double* Phi, const std::vector<double>& sv, double rho, double* L2) {
   // Phi * diagmat(rho - 1 / (rho - 2 * pow(sv, 2)))  (:326, :567, :617, :642)
   double coef[SPB_MAX_K];
   for (int k = 0; k < K_; ++k) {
@@ -567,7 +612,7 @@ void Engine::init_lambda(const double* Phi, const std::vector<double>& sv, doubl
     volatile double inv = 1.0 / den;
     coef[k] = rho - inv;
   }
-  launch_lambda_init_host(Phi, p_, K_, coef, L2, ctx_.stream);
+  launch_lambda_init_host(Phi, p_, K_, coef, L2, s);
 }
 
 void Engine::prepare() {
@@ -578,8 +623,8 @@ void Engine::prepare() {
     Scoped sc(clock_, PH_PROLOGUE, s);
     svd_right(ctx_, dY_.get(), n_, p_, K_, sv_full_, full_.Phi.get());       // :563
     rho_full_ = 10.0 * (sv_full_[0] * sv_full_[0]);                           // :564
-    copy_pk(full_.C.get(), full_.Phi.get());                                  // :566
-    init_lambda(full_.Phi.get(), sv_full_, rho_full_, full_.L2.get());        // :567
+    copy_pk(s, full_.C.get(), full_.Phi.get());                               // :566
+    init_lambda(s, full_.Phi.get(), sv_full_, rho_full_, full_.L2.get());     // :567
     full_ready_ = true;
   }
   const bool need_omega = any_tau_ || tau1_.size() > 1 || tau2_.size() > 1;
@@ -599,8 +644,7 @@ void Engine::prepare() {
     }
     omega_ready_ = true;
   }
-  work_.ensure(ld_ * (size_t)p_);
-  gram_.ensure(ld_ * (size_t)p_);
+  ctx_.sync_and_check();            // the lanes read Omega and the full-data start from other streams
   trace(ctx_, "prepare: done");
 }
 
@@ -635,190 +679,232 @@ void Engine::fold_prepare(int k) {
   svd_right(ctx_, f.Ytr.get(), f.n_tr, p_, K_, f.sv, f.Phi0.get());           // :321
   f.rho = 10.0 * (f.sv[0] * f.sv[0]);                                         // :322
   // trace(Ytr'Ytr) / n_tr (:489, :491)
-  launch_sumsq(f.Ytr.get(), (size_t)f.n_tr * p_, loss_scratch_.get(), loss_out_.get(), s);
+  double* out = loss_out_.get() + (size_t)M_ * max_grid_;
+  launch_sumsq(f.Ytr.get(), (size_t)f.n_tr * p_, prep_scratch_.get(), out, s);
   double ss = 0.0;
-  SPB_CUDA(cudaMemcpyAsync(&ss, loss_out_.get(), sizeof(double), cudaMemcpyDeviceToHost, s));
+  SPB_CUDA(cudaMemcpyAsync(&ss, out, sizeof(double), cudaMemcpyDeviceToHost, s));
   SPB_CUDA(cudaStreamSynchronize(s));
   f.tv = ss / (double)f.n_tr;
   f.prepared = true;
   trace(ctx_, "fold_prepare: done");
 }
 
-void Engine::ensure_gram(int k) {
-  if (gram_owner_ == k) return;
-  Scoped sc(clock_, PH_PROLOGUE, ctx_.stream);
-  gram_.ensure(ld_ * (size_t)p_);
-  if (k < 0) gram_upper(ctx_, dY_.get(), n_, p_, gram_.get(), ld_);           // :561
-  else gram_upper(ctx_, folds_[k].Ytr.get(), folds_[k].n_tr, p_, gram_.get(), ld_);   // :328
-  gram_owner_ = k;
+void Engine::ensure_gram(Lane& L, int k) {
+  if (L.gram_owner == k) return;
+  Scoped sc(L.clock, PH_PROLOGUE, L.res->stream);
+  L.gram.ensure(ld_ * (size_t)p_);
+  Exec ex = L.exec(ctx_.flag.get());
+  if (k < 0) gram_upper(ex, dY_.get(), n_, p_, L.gram.get(), ld_);            // :561
+  else gram_upper(ex, folds_[k].Ytr.get(), folds_[k].n_tr, p_, L.gram.get(), ld_);   // :328
+  L.gram_owner = k;
 }
 
-void Engine::run_core2(int kind, int fold, int idx, double tau1, double rho, ChainState& st) {
+void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double rho, ChainState& st) {
   // spatpcaCore2 / spatpcaCore2p (:150-222): the inverse is rebuilt on every call (:165)
-  ensure_gram(fold);
+  cudaStream_t s = L.res->stream;
+  ensure_gram(L, fold);
   {
-    Scoped sc(clock_, PH_INVERSE, ctx_.stream);
-    work_.ensure(ld_ * (size_t)p_);
-    spd_inverse(ctx_, omega_u_.get(), ld_, gram_.get(), ld_, p_, tau1, rho, 2.0, work_.get(), ld_);
+    Scoped sc(L.clock, PH_INVERSE, s);
+    L.work.ensure(ld_ * (size_t)p_);
+    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, tau1, rho, 2.0, L.work.get(), ld_);
     stats_.n_inverses++;
   }
-  if (next_slot_ >= slot_cap_) flush();
+  if (L.next_slot >= slot_cap_) flush_lane(L);
   AdmmCall c;
-  c.Ainv = work_.get(); c.ld = ld_; c.p = p_; c.K = K_; c.mode = 2; c.rho = rho; c.tau2 = 0.0;
+  c.Ainv = L.work.get(); c.ld = ld_; c.p = p_; c.K = K_; c.mode = 2; c.rho = rho; c.tau2 = 0.0;
   c.maxit = maxit_; c.tol = tol_;
   c.Phi = st.Phi.get(); c.R = nullptr; c.C = st.C.get(); c.L1 = nullptr; c.L2 = st.L2.get();
-  c.stat_slot = stat_slots_.get() + (size_t)next_slot_ * 4;
-  c.err_slot = err_slots_.get() + next_slot_;
+  c.stat_slot = L.stat_slots.get() + (size_t)L.next_slot * 4;
+  c.err_slot = L.err_slots.get() + L.next_slot;
   {
-    Scoped sc(clock_, PH_ADMM, ctx_.stream);
-    SPB_CUDA(cudaMemsetAsync(c.stat_slot, 0, 4 * sizeof(int), ctx_.stream));
-    if (maxit_ > 0) launch_admm(c, admm_ws_.get(), ctx_.stream);
+    Scoped sc(L.clock, PH_ADMM, s);
+    SPB_CUDA(cudaMemsetAsync(c.stat_slot, 0, 4 * sizeof(int), s));
+    if (maxit_ > 0) launch_admm(c, L.admm_ws.get(), s);
   }
-  pending_.push_back({kind, fold, idx, next_slot_});
-  next_slot_++;
+  L.pending.push_back({kind, fold, idx, L.next_slot});
+  L.next_slot++;
+  L.dirty = true;
 }
 
-void Engine::run_core3(int kind, int fold, int idx, const double* tinv, double tau2, double rho,
+void Engine::run_core3(Lane& L, int kind, int fold, int idx, const double* tinv, double tau2, double rho,
                        ChainState& st) {
-  if (next_slot_ >= slot_cap_) flush();
+  cudaStream_t s = L.res->stream;
+  if (L.next_slot >= slot_cap_) flush_lane(L);
   AdmmCall c;
   c.Ainv = tinv; c.ld = ld_; c.p = p_; c.K = K_; c.mode = 3; c.rho = rho; c.tau2 = tau2;
   c.maxit = maxit_; c.tol = tol_;
   c.Phi = st.Phi.get(); c.R = st.R.get(); c.C = st.C.get(); c.L1 = st.L1.get(); c.L2 = st.L2.get();
-  c.stat_slot = stat_slots_.get() + (size_t)next_slot_ * 4;
-  c.err_slot = err_slots_.get() + next_slot_;
+  c.stat_slot = L.stat_slots.get() + (size_t)L.next_slot * 4;
+  c.err_slot = L.err_slots.get() + L.next_slot;
   {
-    Scoped sc(clock_, PH_ADMM, ctx_.stream);
-    SPB_CUDA(cudaMemsetAsync(c.stat_slot, 0, 4 * sizeof(int), ctx_.stream));
-    if (maxit_ > 0) launch_admm(c, admm_ws_.get(), ctx_.stream);
+    Scoped sc(L.clock, PH_ADMM, s);
+    SPB_CUDA(cudaMemsetAsync(c.stat_slot, 0, 4 * sizeof(int), s));
+    if (maxit_ > 0) launch_admm(c, L.admm_ws.get(), s);
   }
-  pending_.push_back({kind, fold, idx, next_slot_});
-  next_slot_++;
+  L.pending.push_back({kind, fold, idx, L.next_slot});
+  L.next_slot++;
+  L.dirty = true;
 }
 
-void Engine::launch_loss(const FoldData& f, const double* Phi, double* out_dev) {
-  Scoped sc(clock_, PH_CVLOSS, ctx_.stream);
+void Engine::launch_loss(Lane& L, const FoldData& f, const double* Phi, double* out_dev) {
+  cudaStream_t s = L.res->stream;
+  Scoped sc(L.clock, PH_CVLOSS, s);
   if (f.n_va == 0) {
-    SPB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), ctx_.stream));
+    SPB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), s));
     return;
   }
-  cv_loss(ctx_, f.Yva.get(), f.n_va, p_, Phi, K_, lossW_.get(), loss_scratch_.get(), out_dev);
+  cv_loss(s, f.Yva.get(), f.n_va, p_, Phi, K_, L.lossW.get(), L.loss_scratch.get(), out_dev);
+  L.dirty = true;
 }
 
-void Engine::flush() {
-  ctx_.sync_and_check();
-  if (next_slot_ > 0) {
-    std::vector<int> st((size_t)next_slot_ * 4);
-    SPB_CUDA(cudaMemcpy(st.data(), stat_slots_.get(), sizeof(int) * st.size(), cudaMemcpyDeviceToHost));
+void Engine::flush_lane(Lane& L) {
+  SPB_CUDA(cudaStreamSynchronize(L.res->stream));
+  L.dirty = false;
+  if (L.next_slot > 0) {
+    std::vector<int> st((size_t)L.next_slot * 4);
+    SPB_CUDA(cudaMemcpy(st.data(), L.stat_slots.get(), sizeof(int) * st.size(), cudaMemcpyDeviceToHost));
     bool polar_failed = false;
-    for (auto& r : pending_) {
+    for (auto& r : L.pending) {
       int iters = st[(size_t)r.slot * 4 + 0];
       if (st[(size_t)r.slot * 4 + 1] != 0) polar_failed = true;
       log_.push_back(r.kind); log_.push_back(r.fold); log_.push_back(r.idx); log_.push_back(iters);
     }
-    pending_.clear();
-    next_slot_ = 0;
+    L.pending.clear();
+    L.next_slot = 0;
     if (polar_failed)
       throw Error(SPB_ERR_POLAR, "svd_econ(): the p x K iterate is rank deficient, Stiefel projection undefined");
   }
 }
 
+void Engine::flush() {
+  for (auto& L : lanes_) flush_lane(*L);
+  ctx_.sync_and_check();
+}
+
 // ---- stage 1 (:592-650) -----------------------------------------------------------------
-void Engine::stage1_fold(int k, double* cv_row) {
-  SPB_REQUIRE(k >= 0 && k < M_, "fold index out of range");
-  SPB_REQUIRE(full_ready_, "prepare() must be called first");
-  fold_prepare(k);
+void Engine::enqueue_stage1(int k) {
   FoldData& f = folds_[k];
+  Lane& L = lane_of(k);
+  cudaStream_t s = L.res->stream;
+  ChainState& ch = L.chain;
   const int n1 = (int)tau1_.size();
   const double max_tau2 = *std::max_element(tau2_.begin(), tau2_.end());
+  double* scores = fold_scores(k);
   if (n1 > 1) {                                                               // worker :312-334
-    init_lambda(f.Phi0.get(), f.sv, f.rho, f.L20.get());
-    copy_pk(chain_.Phi.get(), f.Phi0.get());
-    copy_pk(chain_.C.get(), f.Phi0.get());
-    copy_pk(chain_.L2.get(), f.L20.get());
-    launch_loss(f, f.Phi0.get(), loss_out_.get() + 0);                        // :327 (tau1[0] scored as PCA)
+    init_lambda(s, f.Phi0.get(), f.sv, f.rho, f.L20.get());
+    copy_pk(s, ch.Phi.get(), f.Phi0.get());
+    copy_pk(s, ch.C.get(), f.Phi0.get());
+    copy_pk(s, ch.L2.get(), f.L20.get());
+    launch_loss(L, f, f.Phi0.get(), scores + 0);                              // :327 (tau1[0] scored as PCA)
     for (int i = 1; i < n1; ++i) {                                            // warm-started path :329-332
-      run_core2(2, k, i, tau1_[i], f.rho, chain_);
-      launch_loss(f, chain_.Phi.get(), loss_out_.get() + i);
+      run_core2(L, 2, k, i, tau1_[i], f.rho, ch);
+      launch_loss(L, f, ch.Phi.get(), scores + i);
     }
-    flush();
-    SPB_REQUIRE(cv_row != nullptr, "cv_row is NULL");
-    SPB_CUDA(cudaMemcpy(cv_row, loss_out_.get(), sizeof(double) * n1, cudaMemcpyDeviceToHost));
-    stats_.bytes_d2h += (long long)sizeof(double) * n1;
     return;
   }
   const double sel = tau1_[0];
   if (sel != 0.0 && max_tau2 == 0.0) {                                        // :604-623
-    init_lambda(f.Phi0.get(), f.sv, f.rho, f.L20.get());
-    copy_pk(chain_.Phi.get(), f.Phi0.get());
-    copy_pk(chain_.C.get(), f.Phi0.get());
-    copy_pk(chain_.L2.get(), f.L20.get());
-    run_core2(2, k, 0, sel, f.rho, chain_);
-    copy_pk(f.Phi0.get(), chain_.Phi.get());                                  // Phi_cv.slice(k) (:619)
-    copy_pk(f.L20.get(), chain_.L2.get());                                    // Lambd2_cv.slice(k) (:620)
+    init_lambda(s, f.Phi0.get(), f.sv, f.rho, f.L20.get());
+    copy_pk(s, ch.Phi.get(), f.Phi0.get());
+    copy_pk(s, ch.C.get(), f.Phi0.get());
+    copy_pk(s, ch.L2.get(), f.L20.get());
+    run_core2(L, 2, k, 0, sel, f.rho, ch);
+    copy_pk(s, f.Phi0.get(), ch.Phi.get());                                   // Phi_cv.slice(k) (:619)
+    copy_pk(s, f.L20.get(), ch.L2.get());                                     // Lambd2_cv.slice(k) (:620)
     // (:621 also forms tempinv_cv here; nothing reads it unless stage 2 runs, which recomputes it)
   } else if (sel == 0.0 && max_tau2 == 0.0) {                                 // :624-629, :576-590
     // Phi_cv.slice(k) = fold PCA start (already in Phi0); Lambd2_cv is never read on this path.
-    SPB_CUDA(cudaMemsetAsync(f.L20.get(), 0, sizeof(double) * (size_t)p_ * K_, ctx_.stream));
+    SPB_CUDA(cudaMemsetAsync(f.L20.get(), 0, sizeof(double) * (size_t)p_ * K_, s));
   } else {                                                                    // :630-648
-    init_lambda(f.Phi0.get(), sv_full_, f.rho, f.L20.get());                  // quirk :642: FULL-data singular values
+    init_lambda(s, f.Phi0.get(), sv_full_, f.rho, f.L20.get());               // quirk :642: FULL-data singular values
     if (sel != 0.0) {
-      copy_pk(chain_.Phi.get(), f.Phi0.get());
-      copy_pk(chain_.C.get(), f.Phi0.get());
-      copy_pk(chain_.L2.get(), f.L20.get());
-      run_core2(2, k, 0, sel, f.rho, chain_);
-      copy_pk(f.Phi0.get(), chain_.Phi.get());
-      copy_pk(f.L20.get(), chain_.L2.get());
+      copy_pk(s, ch.Phi.get(), f.Phi0.get());
+      copy_pk(s, ch.C.get(), f.Phi0.get());
+      copy_pk(s, ch.L2.get(), f.L20.get());
+      run_core2(L, 2, k, 0, sel, f.rho, ch);
+      copy_pk(s, f.Phi0.get(), ch.Phi.get());
+      copy_pk(s, f.L20.get(), ch.L2.get());
     }
   }
+  L.dirty = true;
+}
+
+void Engine::stage1_folds(const int* folds, int nfolds, double* rows) {
+  SPB_REQUIRE(full_ready_, "prepare() must be called first");
+  SPB_REQUIRE(folds != nullptr && nfolds >= 0, "invalid fold list");
+  for (int f = 0; f < nfolds; ++f) SPB_REQUIRE(folds[f] >= 0 && folds[f] < M_, "fold index out of range");
+  const int n1 = (int)tau1_.size();
+  for (int f = 0; f < nfolds; ++f) fold_prepare(folds[f]);                    // SVD starts (host-synchronous)
+  for (int f = 0; f < nfolds; ++f) enqueue_stage1(folds[f]);                  // tau1 paths, concurrent lanes
   flush();
+  if (n1 > 1) {
+    SPB_REQUIRE(rows != nullptr, "cv rows pointer is NULL");
+    for (int f = 0; f < nfolds; ++f)
+      SPB_CUDA(cudaMemcpy(rows + (size_t)f * n1, fold_scores(folds[f]), sizeof(double) * n1, cudaMemcpyDeviceToHost));
+    stats_.bytes_d2h += (long long)sizeof(double) * n1 * nfolds;
+  }
 }
 
 void Engine::stage1_full(int index1) {
   SPB_REQUIRE(full_ready_, "prepare() must be called first");
   const int n1 = (int)tau1_.size();
   const double max_tau2 = *std::max_element(tau2_.begin(), tau2_.end());
+  Lane& L = lane_of(-1);
+  // enqueued on the full-data lane and NOT waited for: it overlaps with the folds' next stage
   if (n1 > 1) {
     SPB_REQUIRE(index1 >= 0 && index1 < n1, "index1 out of range");
-    if (index1 > 0) run_core2(20, -1, index1, tau1_[index1], rho_full_, full_);    // :598-599
+    if (index1 > 0) run_core2(L, 20, -1, index1, tau1_[index1], rho_full_, full_);    // :598-599
   } else {
     const double sel = tau1_[0];
-    if (sel != 0.0 && max_tau2 == 0.0) run_core2(20, -1, 0, sel, rho_full_, full_); // :605
+    if (sel != 0.0 && max_tau2 == 0.0) run_core2(L, 20, -1, 0, sel, rho_full_, full_); // :605
   }
-  flush();
 }
 
 // ---- stage 2 (:652-680) -----------------------------------------------------------------
-void Engine::stage2_fold(int k, int index1, double* cv_row) {
-  SPB_REQUIRE(k >= 0 && k < M_, "fold index out of range");
-  const int n2 = (int)tau2_.size();
-  if (n2 <= 1) return;
+void Engine::enqueue_stage2(int k, int index1) {
   FoldData& f = folds_[k];
-  SPB_REQUIRE(f.prepared, "stage1_fold(k) must run before stage2_fold(k)");
+  Lane& L = lane_of(k);
+  cudaStream_t s = L.res->stream;
+  ChainState& ch = L.chain;
+  const int n2 = (int)tau2_.size();
   const double sel1 = selected_tau1(index1);
-  copy_pk(chain_.Phi.get(), f.Phi0.get());                                    // :389
-  copy_pk(chain_.C.get(), f.Phi0.get());
-  zero_pk(chain_.L1.get());                                                   // :390
-  copy_pk(chain_.L2.get(), f.L20.get());                                      // :391
-  if (sel1 != 0.0) run_core2(2, k, 0, sel1, f.rho, chain_);                   // :392-393
-  copy_pk(chain_.R.get(), chain_.Phi.get());                                  // :394
-  copy_pk(f.Phi0.get(), chain_.Phi.get());                                    // :395
-  copy_pk(f.L20.get(), chain_.L2.get());                                      // :396
-  ensure_gram(k);
+  double* scores = fold_scores(k);
+  copy_pk(s, ch.Phi.get(), f.Phi0.get());                                     // :389
+  copy_pk(s, ch.C.get(), f.Phi0.get());
+  zero_pk(s, ch.L1.get());                                                    // :390
+  copy_pk(s, ch.L2.get(), f.L20.get());                                       // :391
+  if (sel1 != 0.0) run_core2(L, 2, k, 0, sel1, f.rho, ch);                    // :392-393
+  copy_pk(s, ch.R.get(), ch.Phi.get());                                       // :394
+  copy_pk(s, f.Phi0.get(), ch.Phi.get());                                     // :395
+  copy_pk(s, f.L20.get(), ch.L2.get());                                       // :396
+  ensure_gram(L, k);
   {
-    Scoped sc(clock_, PH_INVERSE, ctx_.stream);
+    Scoped sc(L.clock, PH_INVERSE, s);
     f.tinv.ensure(ld_ * (size_t)p_);
-    spd_inverse(ctx_, omega_u_.get(), ld_, gram_.get(), ld_, p_, sel1, f.rho, 1.0, f.tinv.get(), ld_);   // :397
+    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, f.rho, 1.0, f.tinv.get(),
+                ld_);                                                         // :397
     stats_.n_inverses++;
   }
   for (int i = 0; i < n2; ++i) {                                              // :398-401
-    run_core3(3, k, i, f.tinv.get(), tau2_[i], f.rho, chain_);
-    launch_loss(f, chain_.Phi.get(), loss_out_.get() + i);
+    run_core3(L, 3, k, i, f.tinv.get(), tau2_[i], f.rho, ch);
+    launch_loss(L, f, ch.Phi.get(), scores + i);
   }
+}
+
+void Engine::stage2_folds(const int* folds, int nfolds, int index1, double* rows) {
+  const int n2 = (int)tau2_.size();
+  if (n2 <= 1) return;
+  SPB_REQUIRE(folds != nullptr && nfolds >= 0, "invalid fold list");
+  for (int f = 0; f < nfolds; ++f) {
+    SPB_REQUIRE(folds[f] >= 0 && folds[f] < M_, "fold index out of range");
+    SPB_REQUIRE(folds_[folds[f]].prepared, "stage 1 must run before stage 2 for every fold");
+  }
+  for (int f = 0; f < nfolds; ++f) enqueue_stage2(folds[f], index1);
   flush();
-  SPB_REQUIRE(cv_row != nullptr, "cv_row is NULL");
-  SPB_CUDA(cudaMemcpy(cv_row, loss_out_.get(), sizeof(double) * n2, cudaMemcpyDeviceToHost));
-  stats_.bytes_d2h += (long long)sizeof(double) * n2;
+  SPB_REQUIRE(rows != nullptr, "cv rows pointer is NULL");
+  for (int f = 0; f < nfolds; ++f)
+    SPB_CUDA(cudaMemcpy(rows + (size_t)f * n2, fold_scores(folds[f]), sizeof(double) * n2, cudaMemcpyDeviceToHost));
+  stats_.bytes_d2h += (long long)sizeof(double) * n2 * nfolds;
 }
 
 void Engine::stage2_full(int index1, int index2) {
@@ -833,48 +919,70 @@ void Engine::stage2_full(int index1, int index2) {
     path = &l2_; upto = (int)l2_.size();                                      // :672-678
   }
   if (!path) return;
-  ensure_gram(-1);
+  Lane& L = lane_of(-1);
+  cudaStream_t s = L.res->stream;
+  ensure_gram(L, -1);
   {
-    Scoped sc(clock_, PH_INVERSE, ctx_.stream);
-    work_.ensure(ld_ * (size_t)p_);
-    spd_inverse(ctx_, omega_u_.get(), ld_, gram_.get(), ld_, p_, sel1, rho_full_, 1.0, work_.get(), ld_);  // :661, :673
+    Scoped sc(L.clock, PH_INVERSE, s);
+    L.work.ensure(ld_ * (size_t)p_);
+    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, rho_full_, 1.0,
+                L.work.get(), ld_);                                           // :661, :673
     stats_.n_inverses++;
   }
-  copy_pk(full_.R.get(), full_.Phi.get());                                    // :662
-  zero_pk(full_.L1.get());                                                    // :663
-  for (int i = 0; i < upto; ++i) run_core3(3, -1, i, work_.get(), (*path)[i], rho_full_, full_);
-  flush();
+  copy_pk(s, full_.R.get(), full_.Phi.get());                                 // :662
+  zero_pk(s, full_.L1.get());                                                 // :663
+  for (int i = 0; i < upto; ++i) run_core3(L, 3, -1, i, L.work.get(), (*path)[i], rho_full_, full_);
 }
 
 // ---- stage 3 (:682-692, worker :459-525) ---------------------------------------------------
-void Engine::stage3_fold(int k, int index1, int index2, double* cv_row) {
-  SPB_REQUIRE(k >= 0 && k < M_, "fold index out of range");
-  SPB_REQUIRE(cv_row != nullptr, "cv_row is NULL");
+void Engine::enqueue_stage3_refit(int k, int index1, int index2) {
   FoldData& f = folds_[k];
-  SPB_REQUIRE(f.prepared, "stage1_fold(k) must run before stage3_fold(k)");
+  Lane& L = lane_of(k);
+  cudaStream_t s = L.res->stream;
+  ChainState& ch = L.chain;
   const int n2 = (int)tau2_.size();
   const double sel1 = selected_tau1(index1);
   const double max_tau2 = *std::max_element(tau2_.begin(), tau2_.end());
-  copy_pk(chain_.Phi.get(), f.Phi0.get());                                    // :469
-  copy_pk(chain_.C.get(), f.Phi0.get());
-  copy_pk(chain_.L2.get(), f.L20.get());                                      // :471
+  copy_pk(s, ch.Phi.get(), f.Phi0.get());                                     // :469
+  copy_pk(s, ch.C.get(), f.Phi0.get());
+  copy_pk(s, ch.L2.get(), f.L20.get());                                       // :471
   if (max_tau2 != 0.0 || sel1 != 0.0) {                                       // :473
     if (n2 == 1) {
-      run_core2(2, k, 0, sel1, f.rho, chain_);                                // :475
+      run_core2(L, 2, k, 0, sel1, f.rho, ch);                                 // :475
     } else {
-      SPB_REQUIRE(f.tinv.get() != nullptr, "stage2_fold(k) must run before stage3_fold(k)");
-      copy_pk(chain_.R.get(), chain_.Phi.get());                              // :478
-      zero_pk(chain_.L1.get());                                               // :479
+      SPB_REQUIRE(f.tinv.get() != nullptr, "stage 2 must run before stage 3 for every fold");
+      copy_pk(s, ch.R.get(), ch.Phi.get());                                   // :478
+      zero_pk(s, ch.L1.get());                                                // :479
       for (int i = 0; i <= index2; ++i)                                       // :480-482
-        run_core3(3, k, i, f.tinv.get(), tau2_[i], f.rho, chain_);
+        run_core3(L, 3, k, i, f.tinv.get(), tau2_[i], f.rho, ch);
     }
   }
-  flush();
-  {
-    Scoped sc(clock_, PH_GAMMA, ctx_.stream);
-    gamma_losses(ctx_, chain_.Phi.get(), p_, K_, f.Ytr.get(), f.n_tr, f.tv, f.Yva.get(), f.n_va, gamma_, cv_row);
+  L.dirty = true;
+}
+
+void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, double* rows) {
+  SPB_REQUIRE(folds != nullptr && nfolds >= 0 && rows != nullptr, "invalid fold list");
+  for (int f = 0; f < nfolds; ++f) {
+    SPB_REQUIRE(folds[f] >= 0 && folds[f] < M_, "fold index out of range");
+    SPB_REQUIRE(folds_[folds[f]].prepared, "stage 1 must run before stage 3 for every fold");
   }
-  stats_.bytes_d2h += (long long)sizeof(double) * gamma_.size();
+  const int ng = (int)gamma_.size();
+  // folds sharing a lane share its chain buffers: refit + loss one lane-round at a time
+  for (int f0 = 0; f0 < nfolds; f0 += n_fold_lanes_) {
+    const int f1 = std::min(nfolds, f0 + n_fold_lanes_);
+    for (int f = f0; f < f1; ++f) enqueue_stage3_refit(folds[f], index1, index2);
+    for (int f = f0; f < f1; ++f) {
+      const int k = folds[f];
+      Lane& L = lane_of(k);
+      flush_lane(L);
+      FoldData& fd = folds_[k];
+      Scoped sc(L.clock, PH_GAMMA, L.res->stream);
+      gamma_losses(ctx_, L.res->stream, L.chain.Phi.get(), p_, K_, fd.Ytr.get(), fd.n_tr, fd.tv, fd.Yva.get(),
+                   fd.n_va, gamma_, rows + (size_t)f * ng);
+    }
+  }
+  ctx_.sync_and_check();
+  stats_.bytes_d2h += (long long)sizeof(double) * ng * nfolds;
 }
 
 void Engine::get_eigenfn(double* out) {
@@ -888,14 +996,20 @@ void Engine::get_eigenfn(double* out) {
 
 void Engine::get_stats(spb_cv_stats* st) {
   flush();
-  double ms[PH_COUNT];
+  double ms[PH_COUNT], sum[PH_COUNT] = {0, 0, 0, 0, 0, 0};
   clock_.collect(ms);
-  stats_.ms_omega = ms[PH_OMEGA];
-  stats_.ms_prologue = ms[PH_PROLOGUE];
-  stats_.ms_inverse = ms[PH_INVERSE];
-  stats_.ms_admm = ms[PH_ADMM];
-  stats_.ms_cv_loss = ms[PH_CVLOSS];
-  stats_.ms_gamma = ms[PH_GAMMA];
+  for (int i = 0; i < PH_COUNT; ++i) sum[i] = ms[i];
+  for (auto& L : lanes_) {
+    L->clock.collect(ms);
+    for (int i = 0; i < PH_COUNT; ++i) sum[i] += ms[i];
+  }
+  // per-phase STREAM time summed over lanes: with concurrent lanes the sum exceeds the wall time
+  stats_.ms_omega = sum[PH_OMEGA];
+  stats_.ms_prologue = sum[PH_PROLOGUE];
+  stats_.ms_inverse = sum[PH_INVERSE];
+  stats_.ms_admm = sum[PH_ADMM];
+  stats_.ms_cv_loss = sum[PH_CVLOSS];
+  stats_.ms_gamma = sum[PH_GAMMA];
   stats_.n_admm_calls = (int)(log_.size() / 4);
   long long it = 0;
   for (size_t i = 0; i < log_.size(); i += 4) it += log_[i + 3];
@@ -917,7 +1031,7 @@ int Engine::call_log(int* log4, int cap) {
 
 void Engine::release_fold(int k) {
   SPB_REQUIRE(k >= 0 && k < M_, "fold index out of range");
-  SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
+  flush();
   folds_[k].tinv.release();
 }
 

@@ -12,6 +12,22 @@ namespace spb {
 
 enum Phase { PH_OMEGA = 0, PH_PROLOGUE, PH_INVERSE, PH_ADMM, PH_CVLOSS, PH_GAMMA, PH_COUNT };
 
+// Where work is enqueued: a stream with its own cuBLAS handle and inverse workspace.
+struct Exec {
+  cudaStream_t stream;
+  cublasHandle_t blas;
+  int* flag;                       // sticky device-side error flag (shared by every lane of the device)
+  DevBuf<double>* inv_work;        // workspace of the recursive SPD inverse
+};
+
+// Pooled per device: creating streams / cuBLAS handles costs milliseconds, engines come and go.
+struct LaneRes {
+  cudaStream_t stream = nullptr;
+  cublasHandle_t blas = nullptr;
+  DevBuf<double> inv_work;
+  ~LaneRes();
+};
+
 // Per-thread, per-device CUDA context (stream + library handles + solver workspaces).
 struct DeviceCtx {
   int device = -1;
@@ -23,6 +39,10 @@ struct DeviceCtx {
   DevBuf<int> flag;               // sticky error flag
   DevBuf<int> ipiv;
   DevBuf<double> inv_work;        // workspace of the recursive SPD inverse
+
+  std::vector<std::unique_ptr<LaneRes>> lane_pool;
+  LaneRes& lane_res(int i);       // i-th pooled lane of this device (created on first use)
+  Exec exec() { return Exec{stream, blas, flag.get(), &inv_work}; }
 
   static DeviceCtx& get();        // context of the calling thread's current device
   void sync_and_check();          // stream sync + translate the sticky flag into an Error
@@ -67,6 +87,26 @@ struct FoldData {
 
 struct CallRec { int kind, fold, idx, slot; };
 
+// One independent chain of work (a fold's tau path, or the full-data fit): its own stream, cuBLAS
+// handle and working set, so that the latency-bound parts of one chain (leaf inverses, small
+// GEMMs, the ADMM serial tail) overlap with the GEMM-bound parts of the others.  This is what
+// replaces the reference's (already removed) RcppParallel fold pool (src/RcppSpatPCA.cpp:312, 384, 459).
+struct Lane {
+  LaneRes* res = nullptr;
+  DevBuf<double> work, gram;       // assembled system -> inverse; Gram matrix of `gram_owner`
+  int gram_owner = -2;
+  ChainState chain;
+  DevBuf<char> admm_ws;
+  DevBuf<double> lossW, loss_scratch;
+  DevBuf<int> stat_slots;
+  DevBuf<double> err_slots;
+  int next_slot = 0;
+  std::vector<CallRec> pending;
+  PhaseClock clock;
+  bool dirty = false;              // work enqueued since the last flush
+  Exec exec(int* flag) { return Exec{res->stream, res->blas, flag, &res->inv_work}; }
+};
+
 class Engine {
  public:
   Engine(int p, int d, int n, int M, int K, const double* tau1, int n1, const double* tau2, int n2,
@@ -78,11 +118,16 @@ class Engine {
   void prepare();
   void get_omega(double* out);
 
-  void stage1_fold(int k, double* cv_row);
+  // per-stage work of a set of folds; the folds run concurrently on their lanes.
+  // rows: nfolds x n_grid, row-major (row f = scores of folds[f])
+  void stage1_folds(const int* folds, int nfolds, double* rows);
   void stage1_full(int index1);
-  void stage2_fold(int k, int index1, double* cv_row);
+  void stage2_folds(const int* folds, int nfolds, int index1, double* rows);
   void stage2_full(int index1, int index2);
-  void stage3_fold(int k, int index1, int index2, double* cv_row);
+  void stage3_folds(const int* folds, int nfolds, int index1, int index2, double* rows);
+  void stage1_fold(int k, double* cv_row) { stage1_folds(&k, 1, cv_row); }
+  void stage2_fold(int k, int index1, double* cv_row) { stage2_folds(&k, 1, index1, cv_row); }
+  void stage3_fold(int k, int index1, int index2, double* cv_row) { stage3_folds(&k, 1, index1, index2, cv_row); }
   void get_eigenfn(double* out);
   void get_stats(spb_cv_stats* st);
   int call_log(int* log4, int cap);
@@ -103,36 +148,43 @@ class Engine {
   // building blocks shared with the kernel-level C entry points
   static void build_omega_raw(DeviceCtx& ctx, const double* x_dev, int p, int d, double* omega_dev,
                               size_t ld);
-  static void spd_inverse(DeviceCtx& ctx, const double* omega_u, size_t ldo, const double* G,
+  static void spd_inverse(const Exec& ex, const double* omega_u, size_t ldo, const double* G,
                           size_t ldg, int p, double tau1, double rho, double scale, double* out,
                           size_t ldout);
-  static void gram_upper(DeviceCtx& ctx, const double* Ymat, int m, int p, double* G, size_t ldg);
+  static void gram_upper(const Exec& ex, const double* Ymat, int m, int p, double* G, size_t ldg);
   // SVD-right start: singular values (host) and the first K right singular vectors (device)
   static void svd_right(DeviceCtx& ctx, const double* Ymat, int m, int p, int K,
                         std::vector<double>& sv, double* Phi_dev);
-  static void cv_loss(DeviceCtx& ctx, const double* Yva, int m, int p, const double* Phi, int K,
+  static void cv_loss(cudaStream_t s, const double* Yva, int m, int p, const double* Phi, int K,
                       double* W, double* scratch, double* out_dev);
   // all-gamma covariance losses of one fold; `out_host` receives n_gamma values
-  static void gamma_losses(DeviceCtx& ctx, const double* Phi, int p, int K, const double* Ytr, int n_tr,
-                           double tv, const double* Yva, int n_va, const std::vector<double>& gamma,
+  static void gamma_losses(DeviceCtx& ctx, cudaStream_t s, const double* Phi, int p, int K, const double* Ytr,
+                           int n_tr, double tv, const double* Yva, int n_va, const std::vector<double>& gamma,
                            double* out_host);
 
  private:
   void fold_prepare(int k);
-  void ensure_gram(int k);                      // k = -1: full data
-  void init_lambda(const double* Phi, const std::vector<double>& sv, double rho, double* L2);
-  void run_core2(int kind, int fold, int idx, double tau1, double rho, ChainState& st);
-  void run_core3(int kind, int fold, int idx, const double* tinv, double tau2, double rho, ChainState& st);
-  void launch_loss(const FoldData& f, const double* Phi, double* out_dev);
-  void flush();                                  // sync, check, move call stats to the host log
-  void copy_pk(double* dst, const double* src);
-  void zero_pk(double* dst);
+  Lane& lane_of(int fold);                       // fold < 0: the full-data lane
+  void ensure_gram(Lane& L, int k);              // k = -1: full data
+  void init_lambda(cudaStream_t s, const double* Phi, const std::vector<double>& sv, double rho, double* L2);
+  void run_core2(Lane& L, int kind, int fold, int idx, double tau1, double rho, ChainState& st);
+  void run_core3(Lane& L, int kind, int fold, int idx, const double* tinv, double tau2, double rho, ChainState& st);
+  void launch_loss(Lane& L, const FoldData& f, const double* Phi, double* out_dev);
+  void enqueue_stage1(int k);
+  void enqueue_stage2(int k, int index1);
+  void enqueue_stage3_refit(int k, int index1, int index2);
+  void flush_lane(Lane& L);                      // sync the lane, move its call stats to the host log
+  void flush();                                  // every lane + the sticky error flag
+  void copy_pk(cudaStream_t s, double* dst, const double* src);
+  void zero_pk(cudaStream_t s, double* dst);
+  double* fold_scores(int k) { return loss_out_.get() + (size_t)k * max_grid_; }
 
   int p_, d_, n_, M_, K_, maxit_;
   double tol_;
   std::vector<double> tau1_, tau2_, gamma_, l2_;
   bool any_tau_ = false;
   size_t ld_ = 0;                                // leading dimension of every p x p matrix
+  int max_grid_ = 1;
   DeviceCtx& ctx_;
 
   DevBuf<double> dY_, dX_;
@@ -140,22 +192,18 @@ class Engine {
   DevBuf<double> omega_u_;                       // symmatu(Omega) + 1e-8 I
   DevBuf<double> omega_diag_raw_;                // diagonal before the ridge (for get_omega)
   bool omega_ready_ = false, omega_injected_ = false;
-  DevBuf<double> gram_;                          // upper triangle of Ytr'Ytr of `gram_owner_`
-  int gram_owner_ = -2;
-  DevBuf<double> work_;                          // assembled matrix -> inverse
   std::vector<FoldData> folds_;
   // full-data fit (:563-567)
   std::vector<double> sv_full_;
   double rho_full_ = 0.0;
-  ChainState full_, chain_;
+  ChainState full_;
   bool full_ready_ = false;
 
-  DevBuf<char> admm_ws_;
-  DevBuf<double> lossW_, loss_scratch_, loss_out_;
-  DevBuf<int> stat_slots_;
-  DevBuf<double> err_slots_;
-  int next_slot_ = 0, slot_cap_ = 0;
-  std::vector<CallRec> pending_;
+  std::vector<std::unique_ptr<Lane>> lanes_;     // n_fold_lanes_ fold lanes + 1 full-data lane
+  int n_fold_lanes_ = 1;
+  int slot_cap_ = 0;
+  DevBuf<double> loss_out_;                      // M x max_grid scores, (M+1)-th row = scratch
+  DevBuf<double> prep_scratch_;
   std::vector<int> log_;                         // 4 ints per call
 
   PhaseClock clock_;
@@ -165,7 +213,7 @@ class Engine {
 
 // recursive GEMM-rate SPD inverse (spd_inverse.cu): A (upper valid) -> A^-1 (full storage)
 size_t spd_inverse_workspace_doubles(int n);
-void spd_inverse_recursive(DeviceCtx& ctx, double* A, int n, size_t ld, double* workspace);
+void spd_inverse_recursive(const Exec& ex, double* A, int n, size_t ld, double* workspace);
 
 // small host helpers (host_math.cpp-like, defined in engine.cu)
 void host_jacobi_eigh(int K, std::vector<double>& A /*K x K col-major, destroyed*/,

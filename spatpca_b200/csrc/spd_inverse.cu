@@ -226,8 +226,8 @@ void invert(const Ctx& c, double* A, int n, size_t ld, double* W) {
 
 size_t spd_inverse_workspace_doubles(int n) { return (size_t)n * n / 2 + 1024; }
 
-void spd_inverse_recursive(DeviceCtx& ctx, double* A, int n, size_t ld, double* workspace) {
-  Ctx c{ctx.blas, ctx.stream, ctx.flag.get()};
+void spd_inverse_recursive(const Exec& ex, double* A, int n, size_t ld, double* workspace) {
+  Ctx c{ex.blas, ex.stream, ex.flag};
   invert(c, A, n, ld, workspace);
   SPB_CUDA(cudaGetLastError());
 }

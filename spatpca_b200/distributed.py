@@ -82,6 +82,17 @@ def _gather_stage(coll: Collective, local: dict, M: int, width: int) -> np.ndarr
     return cv
 
 
+def _run_folds(engine, stage: str, folds, *idx) -> dict:
+    """This rank's folds of one stage: concurrently (`stageN_folds`) when the engine offers it."""
+    if not folds:
+        return {}
+    many = getattr(engine, stage + "_folds", None)
+    if many is not None:
+        return many(folds, *idx)
+    one = getattr(engine, stage + "_fold")
+    return {k: one(k, *idx) for k in folds}
+
+
 def run_sharded(engine, select_index, coll: Collective, M: int, n_tau1: int, n_tau2: int, n_gamma: int,
                 tau1, tau2, gamma):
     """The stage sequence of spatpcaCV (:592-692) over a fold-sharded set of engines.
@@ -94,7 +105,7 @@ def run_sharded(engine, select_index, coll: Collective, M: int, n_tau1: int, n_t
     full_rank = full_fit_owner(M, world)
 
     # ---- stage 1 ----
-    rows = {k: engine.stage1_fold(k) for k in mine}
+    rows = _run_folds(engine, "stage1", mine)
     index1 = 0
     if n_tau1 > 1:
         cv1 = _gather_stage(coll, rows, M, n_tau1)
@@ -109,7 +120,7 @@ def run_sharded(engine, select_index, coll: Collective, M: int, n_tau1: int, n_t
     # ---- stage 2 ----
     index2 = 0
     if n_tau2 > 1:
-        rows = {k: engine.stage2_fold(k, index1) for k in mine}
+        rows = _run_folds(engine, "stage2", mine, index1)
         cv2 = _gather_stage(coll, rows, M, n_tau2)
         index2, score2 = select_index(cv2)
         sel_tau2 = float(tau2[index2])
@@ -120,7 +131,7 @@ def run_sharded(engine, select_index, coll: Collective, M: int, n_tau1: int, n_t
         engine.stage2_full(index1, index2)
 
     # ---- stage 3 ----
-    rows = {k: engine.stage3_fold(k, index1, index2) for k in mine}
+    rows = _run_folds(engine, "stage3", mine, index1, index2)
     cv3 = _gather_stage(coll, rows, M, n_gamma)
     index3, score3 = select_index(cv3)
     sel_gamma = float(gamma[index3]) if n_gamma > 1 else float(np.max(gamma))

@@ -167,6 +167,30 @@ class Engine:
         check(self._lib.spb_engine_stage3_fold(self._h, int(k), int(index1), int(index2), ptr(row)))
         return row
 
+    # ---- the same stages for a list of folds (run concurrently on the GPU's lanes) ----
+    def _folds(self, folds):
+        return np.ascontiguousarray(np.asarray(list(folds), dtype=np.int32))
+
+    def stage1_folds(self, folds):
+        f = self._folds(folds)
+        rows = np.zeros((len(f), max(len(self.tau1), 1)))
+        check(self._lib.spb_engine_stage1_folds(self._h, f.ctypes.data_as(C.POINTER(C.c_int)), len(f), ptr(rows)))
+        return {int(k): rows[i] for i, k in enumerate(f)}
+
+    def stage2_folds(self, folds, index1):
+        f = self._folds(folds)
+        rows = np.zeros((len(f), max(len(self.tau2), 1)))
+        check(self._lib.spb_engine_stage2_folds(self._h, f.ctypes.data_as(C.POINTER(C.c_int)), len(f), int(index1),
+                                                ptr(rows)))
+        return {int(k): rows[i] for i, k in enumerate(f)}
+
+    def stage3_folds(self, folds, index1, index2):
+        f = self._folds(folds)
+        rows = np.zeros((len(f), len(self.gamma)))
+        check(self._lib.spb_engine_stage3_folds(self._h, f.ctypes.data_as(C.POINTER(C.c_int)), len(f), int(index1),
+                                                int(index2), ptr(rows)))
+        return {int(k): rows[i] for i, k in enumerate(f)}
+
     def get_eigenfn(self):
         out = np.empty((self.p, self.K), order="F")
         check(self._lib.spb_engine_get_eigenfn(self._h, ptr(out)))
