@@ -156,12 +156,15 @@ __device__ int jacobi_inv_sqrt_warp(double* Am, double* Vm, double* Pm, int K, i
         const double aqq = Am[qq * K + qq];
         if (apq == 0.0 || apq * apq <= 1e-32 * fabs(app * aqq)) continue;
         rotated = true;
-        const double theta = (aqq - app) / (2.0 * apq);
-        double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+        // rotation angle from short reciprocal / rsqrt chains (any accurate-to-ulps angle does;
+        // c^2 + s^2 = 1 holds to ~2 ulp because s = t c and c = rsqrt(t^2 + 1))
+        const double theta = (aqq - app) * fast_rcp(2.0 * apq);
+        const double th2 = fma(theta, theta, 1.0);
+        double t = fast_rcp(fabs(theta) + th2 * fast_rsqrt(th2));
         if (theta < 0.0) t = -t;
-        const double c = 1.0 / sqrt(t * t + 1.0);
+        const double c = fast_rsqrt(fma(t, t, 1.0));
         const double sn = t * c;
-        const double tau = sn / (1.0 + c);
+        const double tau = sn * fast_rcp(1.0 + c);
         double aip = 0.0, aiq = 0.0, vip = 0.0, viq = 0.0;
         if (lane < K) {
           aip = Am[lane * K + pp];
@@ -201,7 +204,7 @@ __device__ int jacobi_inv_sqrt_warp(double* Am, double* Vm, double* Pm, int K, i
   const int mybad = (lane < K) && (!(lam > 1e-28 * lmax) || !isfinite(lam));
   const int bad = __any_sync(0xffffffffu, mybad) ? 1 : 0;
   __syncwarp();
-  if (lane < K) Am[lane] = 1.0 / sqrt(lam);       // row 0 of Am reused as scratch
+  if (lane < K) Am[lane] = fast_rsqrt(lam);       // row 0 of Am reused as scratch
   __syncwarp();
   for (int idx = lane; idx < K * K; idx += 32) {
     const int a = idx / K, b = idx - a * K;

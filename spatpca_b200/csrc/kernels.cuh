@@ -5,6 +5,31 @@
 
 namespace spb {
 
+#ifdef __CUDACC__
+// Reciprocal / reciprocal square root for LATENCY-bound scalar chains (leaf pivots, Jacobi
+// rotations).  IEEE division and sqrt are ~50-instruction dependent sequences; one warp working
+// alone pays their full latency (ncu: a 128 x 128 leaf spent 340 k cycles, >90 % of them in the
+// per-pivot divisions).  Hardware approximation (>= 20 bits) + two Newton steps: error ~1 ulp.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double h = 0.5 * x;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+}
+#endif
+
 // ---- thin-plate-spline / matrix assembly (tps_kernels.cu) -------------------
 // Bordered TPS system [[E + ridge I, T], [T', ridge I]], T = [1 X], q = p + d + 1
 // (reference: struct thinPlateSpline, src/RcppSpatPCA.cpp:12-45 + symmatu :67 + ridge :69).

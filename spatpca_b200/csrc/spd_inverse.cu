@@ -84,14 +84,15 @@ leaf_inverse_kernel(double* __restrict__ A, int n, size_t ld, int* __restrict__ 
         __syncwarp();
         const double d = Dm[t][t];
         if (tx == 0 && !(d > 0.0)) bad = 1;
-        const double ct = Dm[t][c] / d;            // a_tc / d
+        const double rinv = fast_rcp(d);           // one short reciprocal chain per pivot
+        const double ct = Dm[t][c] * rinv;         // a_tc / d
         const double rt0 = Dm[r0][t], rt1 = Dm[r1][t];
         double n0 = fma(-rt0, ct, e0), n1 = fma(-rt1, ct, e1);
-        if (c == t) { n0 = rt0 / d; n1 = rt1 / d; }
+        if (c == t) { n0 = rt0 * rinv; n1 = rt1 * rinv; }
         if (r0 == t) n0 = ct;
         if (r1 == t) n1 = ct;
-        if (c == t && r0 == t) n0 = -1.0 / d;
-        if (c == t && r1 == t) n1 = -1.0 / d;
+        if (c == t && r0 == t) n0 = -rinv;
+        if (c == t && r1 == t) n1 = -rinv;
         e0 = n0; e1 = n1;
       }
       __syncwarp();
