@@ -26,6 +26,7 @@
 // floating-point atomics.
 #include <cooperative_groups.h>
 
+#include <cmath>
 #include <map>
 #include <mutex>
 
@@ -55,7 +56,8 @@ struct Params {
   const double* A;
   size_t ld;
   int p, K, mode, maxit;
-  double rho, thr, tol, scale;
+  double rdenom;                              // 1 / sqrt(p K)
+  double rho, rinv_rho, thr, tol, scale;     // rinv_rho = RN(1 / rho), computed on the host
   double *Phi, *R, *C, *L1, *L2;
   double *X, *part, *gpart, *npart;
   double* ctrl;        // [0] = max error, [1] = status, [2] = sweeps, [8 ..] = P (K x K)
@@ -118,6 +120,16 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* red,
   __syncthreads();
 }
 
+// a / rho, correctly rounded, in three dependent FP64 operations instead of the ~40 of an IEEE division
+// (Markstein: with y = RN(1/rho), q = RN(a y), r = a - rho q exactly by FMA, RN(q + r y) is the
+// correctly rounded quotient).  A dependent FP64 operation costs ~55 cycles on this part, and these
+// divisions sit on the serial tail of every iteration.
+__device__ __forceinline__ double div_rho(double a, double rho, double rinv) {
+  const double q = __dmul_rn(a, rinv);
+  const double r = fma(-q, rho, a);
+  return fma(r, rinv, q);
+}
+
 // ---- phase 0: X from the incoming state -----------------------------------------
 __device__ __forceinline__ double make_x(int mode, double rho, double r, double c, double l1, double l2) {
   // mode 2: rho*C - Lambda2 (:168);  mode 3: rho*(R+C) - (Lambda1+Lambda2) (:247)
@@ -142,10 +154,12 @@ __device__ __forceinline__ void build_tile_table(const Params& P, TileInfo* tile
 // Am (K x K symmetric, ld K) is destroyed; Pm <- Am^{-1/2}.  Returns 0, or 1 if Am is not
 // numerically positive definite (rank-deficient T).  All lanes execute the same scalar
 // control flow; lanes 0..K-1 apply the rotations.
-__device__ int jacobi_inv_sqrt_warp(double* Am, double* Vm, double* Pm, int K, int* sweeps_out) {
+__device__ int jacobi_inv_sqrt_warp(double* Am, double* Vm, double* Pm, int K, int* sweeps_out,
+                                    unsigned long long* dbg) {
   const int lane = threadIdx.x & 31;
   for (int idx = lane; idx < K * K; idx += 32) Vm[idx] = ((idx / K) == (idx % K)) ? 1.0 : 0.0;
   __syncwarp();
+  if (dbg != nullptr && lane == 0) dbg[126] = gtimer();
   int sweeps = 0;
   for (; sweeps < 64; ++sweeps) {
     bool rotated = false;
@@ -195,22 +209,28 @@ __device__ int jacobi_inv_sqrt_warp(double* Am, double* Vm, double* Pm, int K, i
     if (!rotated) break;
   }
   *sweeps_out = sweeps;
+  if (dbg != nullptr && lane == 0) dbg[127] = gtimer();
   // eigenvalues -> lam^-1/2 (one lane each), positivity check, P = V diag(lam^-1/2) V'
   double lam = 1.0;
   if (lane < K) lam = Am[lane * K + lane];
   double lmax = lam;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-  const int mybad = (lane < K) && (!(lam > 1e-28 * lmax) || !isfinite(lam));
+  const bool mybad = (lane < K) && !(lam > 1e-28 * lmax && lam < 1e300);   // also false for NaN
   const int bad = __any_sync(0xffffffffu, mybad) ? 1 : 0;
   __syncwarp();
   if (lane < K) Am[lane] = fast_rsqrt(lam);       // row 0 of Am reused as scratch
   __syncwarp();
-  for (int idx = lane; idx < K * K; idx += 32) {
-    const int a = idx / K, b = idx - a * K;
-    double acc = 0.0;
-    for (int k = 0; k < K; ++k) acc = fma(Vm[a * K + k] * Am[k], Vm[b * K + k], acc);
-    Pm[idx] = acc;
+  {
+    int a = 0, b = lane;                           // lane -> (a, b) without an integer division
+    while (b >= K) { b -= K; ++a; }
+    for (int idx = lane; idx < K * K; idx += 32) {
+      double acc = 0.0;
+      for (int k = 0; k < K; ++k) acc = fma(Vm[a * K + k] * Am[k], Vm[b * K + k], acc);
+      Pm[idx] = acc;
+      b += 32;
+      while (b >= K) { b -= K; ++a; }
+    }
   }
   __syncwarp();
   return bad;
@@ -281,7 +301,7 @@ __device__ __forceinline__ void reduce_tile(const Params& P, int t, const TileIn
         if (k < K) {
           const double ph = __dmul_rn(P.scale, phi[r][k]);       // 0.5 * (...) in Core3 (:247)
           P.Phi[(size_t)k * p + i] = ph;
-          tt[k] = __dadd_rn(ph, __ddiv_rn(__ldcg(P.L2 + (size_t)k * p + i), P.rho));   // :169, :251
+          tt[k] = __dadd_rn(ph, div_rho(__ldcg(P.L2 + (size_t)k * p + i), P.rho, P.rinv_rho));   // :169, :251
         }
       }
       int q = 0;
@@ -322,7 +342,7 @@ __device__ __forceinline__ void finish_polar(const Params& P, double* jA, double
   if (P.dbg != nullptr && tid == 0) P.dbg[121] = gtimer();
   if (tid < 32) {
     int sweeps = 0;
-    const int bad = jacobi_inv_sqrt_warp(jA, jV, jP, K, &sweeps);
+    const int bad = jacobi_inv_sqrt_warp(jA, jV, jP, K, &sweeps, P.dbg);
     if (P.dbg != nullptr && tid == 0) { P.dbg[122] = gtimer(); P.dbg[125] = (unsigned long long)sweeps; }
     for (int idx = tid; idx < K * K; idx += 32) __stcg(P.ctrl + 8 + idx, jP[idx]);
     if (tid == 0) { __stcg(P.ctrl + 1, (double)bad); __stcg(P.ctrl + 2, (double)sweeps); }
@@ -333,7 +353,7 @@ __device__ __forceinline__ void finish_polar(const Params& P, double* jA, double
 // ---- stream: matrix-stream partials, then ticketed tile / polar reduction ---------------------
 template <int KP>
 __device__ __forceinline__ void stream_phase(const Params& P, double* xs, double* red, const TileInfo* tiles,
-                                             double* jA, double* jV, double* jP, int* sh_i, bool rev) {
+                                             double* jA, double* jV, double* jP, int* sh_i, bool rev, int dbg_it) {
   using C = Cfg<KP>;
   constexpr int RPT = C::RPT, TR = C::TR, KX = C::KX;
   const int tid = threadIdx.x;
@@ -434,35 +454,41 @@ __device__ __forceinline__ void stream_phase(const Params& P, double* xs, double
           }
         }
       }
-      // ticket: the CTA that delivers the last piece of tile t reduces the tile
+      if (P.dbg != nullptr && tid == 0 && dbg_it == 5) { P.dbg[256 + blockIdx.x] = gtimer(); P.dbg[256 + 512 + blockIdx.x] = P.dbg[5 * 8]; }
+      // ticket: the CTA that delivers the last piece of tile t will reduce the tile -- but only after
+      // it has streamed all of its own pieces, so that its reduce never delays another tile's last piece
       __threadfence();
       __syncthreads();
       if (tid == 0) {
         const int npieces = tiles[t].s_hi - tiles[t].s_lo + 1;
         const int old = atomicAdd(P.counters + 2 + t, 1);
-        sh_i[0] = (old == npieces - 1) ? 1 : 0;
-      }
-      __syncthreads();
-      if (sh_i[0]) {
-        __threadfence();
-        if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[123] = gtimer();
-        reduce_tile<KP>(P, t, tiles[t], red);
-        if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[124] = gtimer();
-        if (tid == 0) {
-          P.counters[2 + t] = 0;                       // re-arm for the next iteration
-          __threadfence();
-          const int old = atomicAdd(P.counters + 0, 1);
-          sh_i[1] = (old == P.nrt - 1) ? 1 : 0;
-        }
-        __syncthreads();
-        if (sh_i[1]) {
-          __threadfence();
-          if (tid == 0) P.counters[0] = 0;
-          finish_polar<KP>(P, jA, jV, jP);
-        }
+        if (old == npieces - 1 && sh_i[2] < 8) { sh_i[3 + sh_i[2]] = t; sh_i[2] = sh_i[2] + 1; }
       }
     }
   }
+  __syncthreads();
+  const int nred = sh_i[2];
+  for (int r = 0; r < nred; ++r) {
+    const int t = sh_i[3 + r];
+    __threadfence();
+    if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[123] = gtimer();
+    reduce_tile<KP>(P, t, tiles[t], red);
+    if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[124] = gtimer();
+    if (tid == 0) {
+      P.counters[2 + t] = 0;                       // re-arm for the next iteration
+      __threadfence();
+      const int old = atomicAdd(P.counters + 0, 1);
+      sh_i[1] = (old == P.nrt - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh_i[1]) {
+      __threadfence();
+      if (tid == 0) P.counters[0] = 0;
+      finish_polar<KP>(P, jA, jV, jP);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) sh_i[2] = 0;
 }
 
 // ---- update: polar factor applied, soft threshold, dual updates, norms, next X ------------------
@@ -472,7 +498,7 @@ __device__ __forceinline__ void update_phase(const Params& P, double* red, doubl
   const int p = P.p, K = P.K;
   for (int idx = tid; idx < K * K; idx += kThreads) jP[idx] = __ldcg(P.ctrl + 8 + idx);
   __syncthreads();
-  const double denom = sqrt((double)P.p * (double)P.K);
+  const double rdenom = P.rdenom;
   for (int rb = blockIdx.x; rb < P.nrb; rb += gridDim.x) {
     const int i = rb * kRowBlock + tid;
     double nv[4] = {0.0, 0.0, 0.0, 0.0};
@@ -483,7 +509,7 @@ __device__ __forceinline__ void update_phase(const Params& P, double* red, doubl
         phi[k] = 0.0; tt[k] = 0.0;
         if (k < K) {
           phi[k] = __ldcg(P.Phi + (size_t)k * p + i);
-          tt[k] = __dadd_rn(phi[k], __ddiv_rn(P.L2[(size_t)k * p + i], P.rho));
+          tt[k] = __dadd_rn(phi[k], div_rho(P.L2[(size_t)k * p + i], P.rho, P.rinv_rho));
         }
       }
 #pragma unroll
@@ -505,7 +531,7 @@ __device__ __forceinline__ void update_phase(const Params& P, double* red, doubl
           if (P.mode == 3) {
             const double rold = P.R[off];
             const double l1old = P.L1[off];
-            const double a1 = __dadd_rn(__ddiv_rn(l1old, P.rho), phi[k]);   // :248
+            const double a1 = __dadd_rn(div_rho(l1old, P.rho, P.rinv_rho), phi[k]);   // :248
             const double mag = fmax(0.0, __dsub_rn(fabs(a1), P.thr));
             const double sg = (a1 > 0.0) ? 1.0 : ((a1 < 0.0) ? -1.0 : 0.0);
             const double rn = sg * mag;
@@ -543,7 +569,8 @@ __device__ __forceinline__ void update_phase(const Params& P, double* red, doubl
         for (int b = j; b < P.nrb; b += 32) t += __ldcg(P.npart + (size_t)b * 4 + v);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (j == 0) sh_d[v] = sqrt(t) / denom;    // norm(., "fro") / sqrt(p K)  (:175-176, :261-264)
+        // norm(., "fro") / sqrt(p K)  (:175-176, :261-264); sqrt(t) = t * rsqrt(t) to ~1 ulp
+        if (j == 0) sh_d[v] = (t > 0.0) ? (t * fast_rsqrt(t)) * rdenom : 0.0;
       }
       __syncthreads();
       if (tid == 0) {
@@ -563,7 +590,7 @@ admm_persistent_kernel(Params P) {
   double* red = dyn + P.xcap * Cfg<KP>::KX;   // reduction scratch (8 KG + 32 doubles)
   __shared__ double jA[KP * KP], jV[KP * KP], jP[KP * KP];
   __shared__ double sh_d[4];
-  __shared__ int sh_i[2];
+  __shared__ int sh_i[12];   // [0],[1]: ticket results; [2]: number of tiles to reduce; [3..10]: their ids
   TileInfo* tiles = reinterpret_cast<TileInfo*>(dyn + P.xcap * Cfg<KP>::KX + 8 * Cfg<KP>::KG + 32);
 
   cg::grid_group grid = cg::this_grid();
@@ -572,6 +599,7 @@ admm_persistent_kernel(Params P) {
 
   // set-up: tile table, tickets, X from the incoming state
   build_tile_table(P, tiles);
+  if (threadIdx.x == 0) sh_i[2] = 0;
   if (blockIdx.x == 0) {
     for (int i = tid; i < P.nrt + 2; i += kThreads) P.counters[i] = 0;
     if (tid == 0) { __stcg(P.ctrl + 0, 0.0); __stcg(P.ctrl + 1, 0.0); __stcg(P.ctrl + 2, 0.0); }
@@ -589,7 +617,7 @@ admm_persistent_kernel(Params P) {
   for (int it = 0; it < P.maxit; ++it) {
     iters = it + 1;
     SPB_STAMP(0);
-    stream_phase<KP>(P, xs, red, tiles, jA, jV, jP, sh_i, (it & 1) != 0);
+    stream_phase<KP>(P, xs, red, tiles, jA, jV, jP, sh_i, (it & 1) != 0, it);
     SPB_STAMP(1);
     __threadfence();
     grid.sync();
@@ -710,7 +738,8 @@ void launch_admm(const AdmmCall& c, void* ws, cudaStream_t s) {
   Geom g = make_geom(c.p, c.K);
   Params P;
   P.A = c.Ainv; P.ld = c.ld; P.p = c.p; P.K = c.K; P.mode = c.mode; P.maxit = c.maxit;
-  P.rho = c.rho; P.thr = c.tau2 / c.rho; P.tol = c.tol;
+  P.rdenom = 1.0 / std::sqrt((double)c.p * (double)c.K);
+  P.rho = c.rho; P.rinv_rho = 1.0 / c.rho; P.thr = c.tau2 / c.rho; P.tol = c.tol;
   P.scale = (c.mode == 3) ? 0.5 : 1.0;
   P.Phi = c.Phi; P.R = c.R; P.C = c.C; P.L1 = c.L1; P.L2 = c.L2;
   double* w = reinterpret_cast<double*>(ws);

@@ -487,8 +487,8 @@ int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_pe
     SPB_CUDA(cudaEventCreate(&e1));
     double best = 1e300;
     const bool dbg_on = std::getenv("SPB_ADMM_DBG") != nullptr;
-    DevBuf<unsigned long long> dbg(16 * 8);
-    SPB_CUDA(cudaMemsetAsync(dbg.get(), 0, sizeof(unsigned long long) * 128, s));
+    DevBuf<unsigned long long> dbg(2048);
+    SPB_CUDA(cudaMemsetAsync(dbg.get(), 0, sizeof(unsigned long long) * 2048, s));
     for (int r = 0; r < repeats + 1; ++r) {
       launch_set_identity(st.C.get(), p, K, p, s);
       launch_set_identity(st.R.get(), p, K, p, s);
@@ -514,16 +514,22 @@ int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_pe
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (dbg_on) {
-      unsigned long long h[128];
+      unsigned long long h[2048];
       SPB_CUDA(cudaMemcpy(h, dbg.get(), sizeof(h), cudaMemcpyDeviceToHost));
+      if (std::getenv("SPB_ADMM_DBG_CTAS")) {
+        fprintf(stderr, "[admm dbg] per-CTA stream end (us after CTA0's iteration-5 start):");
+        for (int b = 0; b < 296; ++b) fprintf(stderr, " %.0f", ((double)h[256 + b] - (double)h[5 * 8]) * 1e-3);
+        fprintf(stderr, "\n");
+      }
       const char* names[8] = {"stream+reduce", "barrier1", "update", "barrier2", "(loop)", "-", "-", "-"};
       for (int it = 2; it < std::min(iters, 6); ++it) {
         fprintf(stderr, "[admm dbg] p=%d K=%d it=%d:", p, K, it);
         for (int q = 0; q < 4; ++q) fprintf(stderr, " %s=%.1fus", names[q], (double)(h[it * 8 + q + 1] - h[it * 8 + q]) * 1e-3);
         fprintf(stderr, " total=%.1fus\n", (double)(h[(it + 1) * 8] - h[it * 8]) * 1e-3);
       }
-      fprintf(stderr, "[admm dbg] last iteration: gram-reduce=%.1fus jacobi=%.1fus (%llu sweeps) tile0-reduce=%.1fus\n",
-              (double)(h[121] - h[120]) * 1e-3, (double)(h[122] - h[121]) * 1e-3, h[125], (double)(h[124] - h[123]) * 1e-3);
+      fprintf(stderr, "[admm dbg] last iteration: gram-reduce=%.1fus jacobi=%.1fus (%llu sweeps; init %.1f, sweeps %.1f, epilogue %.1f) tile0-reduce=%.1fus\n",
+              (double)(h[121] - h[120]) * 1e-3, (double)(h[122] - h[121]) * 1e-3, h[125], (double)(h[126] - h[121]) * 1e-3,
+              (double)(h[127] - h[126]) * 1e-3, (double)(h[122] - h[127]) * 1e-3, (double)(h[124] - h[123]) * 1e-3);
     }
     *ms_per_iter = best;
   });

@@ -522,6 +522,14 @@ Engine::Engine(int p, int d, int n, int M, int K, const double* tau1, int n1, co
   int nl = (int)std::floor(((double)free_b * 0.8 - fixed) / per_lane) - 1;
   if (const char* e = std::getenv("SPB_LANES")) nl = std::atoi(e);
   n_fold_lanes_ = std::max(1, std::min(M, nl));
+  // The stage-1 inverse at the selected tau1 is needed again by stage 2 (:393) and, when |tau2| = 1,
+  // by stage 3 (:475): keep the (fold, tau1) inverses when they fit comfortably.
+  {
+    const double cache_bytes = (double)(n1 > 1 ? n1 - 1 : 0) * M * ld_ * p * sizeof(double);
+    const double left = (double)free_b * 0.8 - fixed - (n_fold_lanes_ + 1) * per_lane;
+    cache_inverses_ = n1 > 1 && cache_bytes <= 0.7 * left;
+    if (const char* e = std::getenv("SPB_CACHE_INVERSES")) cache_inverses_ = (std::atoi(e) != 0) && n1 > 1;
+  }
   for (int i = 0; i <= n_fold_lanes_; ++i) {
     std::unique_ptr<Lane> L(new Lane());
     L->res = &ctx_.lane_res(i);
@@ -699,19 +707,25 @@ void Engine::ensure_gram(Lane& L, int k) {
   L.gram_owner = k;
 }
 
-void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double rho, ChainState& st) {
-  // spatpcaCore2 / spatpcaCore2p (:150-222): the inverse is rebuilt on every call (:165)
+void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double rho, ChainState& st,
+                       double* buf, bool have) {
+  // spatpcaCore2 / spatpcaCore2p (:150-222).  The reference rebuilds the inverse on every call (:165);
+  // here a call may reuse the identical matrix built earlier for the same (fold, tau1).
   cudaStream_t s = L.res->stream;
-  ensure_gram(L, fold);
-  {
-    Scoped sc(L.clock, PH_INVERSE, s);
+  if (buf == nullptr) {
     L.work.ensure(ld_ * (size_t)p_);
-    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, tau1, rho, 2.0, L.work.get(), ld_);
+    buf = L.work.get();
+    have = false;
+  }
+  if (!have) {
+    ensure_gram(L, fold);
+    Scoped sc(L.clock, PH_INVERSE, s);
+    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, tau1, rho, 2.0, buf, ld_);
     stats_.n_inverses++;
   }
   if (L.next_slot >= slot_cap_) flush_lane(L);
   AdmmCall c;
-  c.Ainv = L.work.get(); c.ld = ld_; c.p = p_; c.K = K_; c.mode = 2; c.rho = rho; c.tau2 = 0.0;
+  c.Ainv = buf; c.ld = ld_; c.p = p_; c.K = K_; c.mode = 2; c.rho = rho; c.tau2 = 0.0;
   c.maxit = maxit_; c.tol = tol_;
   c.Phi = st.Phi.get(); c.R = nullptr; c.C = st.C.get(); c.L1 = nullptr; c.L2 = st.L2.get();
   c.stat_slot = L.stat_slots.get() + (size_t)L.next_slot * 4;
@@ -724,6 +738,16 @@ void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double
   L.pending.push_back({kind, fold, idx, L.next_slot});
   L.next_slot++;
   L.dirty = true;
+}
+
+double* Engine::cached_inverse(FoldData& f, int index1) {
+  if (!cache_inverses_ || index1 < 1 || index1 >= (int)f.inv_cache.size()) return nullptr;
+  return f.inv_cache[index1].get();
+}
+
+void Engine::drop_cached_inverses(FoldData& f, int keep) {
+  for (int i = 0; i < (int)f.inv_cache.size(); ++i)
+    if (i != keep) f.inv_cache[i].release();
 }
 
 void Engine::run_core3(Lane& L, int kind, int fold, int idx, const double* tinv, double tau2, double rho,
@@ -796,8 +820,14 @@ void Engine::enqueue_stage1(int k) {
     copy_pk(s, ch.C.get(), f.Phi0.get());
     copy_pk(s, ch.L2.get(), f.L20.get());
     launch_loss(L, f, f.Phi0.get(), scores + 0);                              // :327 (tau1[0] scored as PCA)
+    if (cache_inverses_) f.inv_cache.resize(n1);
     for (int i = 1; i < n1; ++i) {                                            // warm-started path :329-332
-      run_core2(L, 2, k, i, tau1_[i], f.rho, ch);
+      double* buf = nullptr;
+      if (cache_inverses_) {
+        f.inv_cache[i].ensure(ld_ * (size_t)p_);
+        buf = f.inv_cache[i].get();
+      }
+      run_core2(L, 2, k, i, tau1_[i], f.rho, ch, buf, false);
       launch_loss(L, f, ch.Phi.get(), scores + i);
     }
     return;
@@ -873,7 +903,12 @@ void Engine::enqueue_stage2(int k, int index1) {
   copy_pk(s, ch.C.get(), f.Phi0.get());
   zero_pk(s, ch.L1.get());                                                    // :390
   copy_pk(s, ch.L2.get(), f.L20.get());                                       // :391
-  if (sel1 != 0.0) run_core2(L, 2, k, 0, sel1, f.rho, ch);                    // :392-393
+  drop_cached_inverses(f, index1);
+  if (sel1 != 0.0) {                                                          // :392-393
+    double* inv = cached_inverse(f, index1);
+    run_core2(L, 2, k, 0, sel1, f.rho, ch, inv, inv != nullptr);
+  }
+  // (the kept inverse is in use on this lane's stream: it is released after stage 3's flush)
   copy_pk(s, ch.R.get(), ch.Phi.get());                                       // :394
   copy_pk(s, f.Phi0.get(), ch.Phi.get());                                     // :395
   copy_pk(s, f.L20.get(), ch.L2.get());                                       // :396
@@ -948,7 +983,9 @@ void Engine::enqueue_stage3_refit(int k, int index1, int index2) {
   copy_pk(s, ch.L2.get(), f.L20.get());                                       // :471
   if (max_tau2 != 0.0 || sel1 != 0.0) {                                       // :473
     if (n2 == 1) {
-      run_core2(L, 2, k, 0, sel1, f.rho, ch);                                 // :475
+      drop_cached_inverses(f, index1);
+      double* inv = cached_inverse(f, index1);
+      run_core2(L, 2, k, 0, sel1, f.rho, ch, inv, inv != nullptr);            // :475
     } else {
       SPB_REQUIRE(f.tinv.get() != nullptr, "stage 2 must run before stage 3 for every fold");
       copy_pk(s, ch.R.get(), ch.Phi.get());                                   // :478
@@ -976,6 +1013,7 @@ void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, 
       Lane& L = lane_of(k);
       flush_lane(L);
       FoldData& fd = folds_[k];
+      drop_cached_inverses(fd, -1);
       Scoped sc(L.clock, PH_GAMMA, L.res->stream);
       gamma_losses(ctx_, L.res->stream, L.chain.Phi.get(), p_, K_, fd.Ytr.get(), fd.n_tr, fd.tv, fd.Yva.get(),
                    fd.n_va, gamma_, rows + (size_t)f * ng);

@@ -80,6 +80,7 @@ struct FoldData {
   DevBuf<double> Ytr, Yva;        // n_tr x p, n_va x p
   DevBuf<double> Phi0, L20;       // Phi_cv / Lambd2_cv slices of the reference (:569)
   DevBuf<double> tinv;            // tempinv_cv slice (p x p), allocated in stage 2
+  std::vector<DevBuf<double>> inv_cache;   // stage-1 inverses by tau1 index (kept when memory allows)
   std::vector<double> sv;         // singular values of Ytr
   double rho = 0.0;
   double tv = 0.0;                // trace(Ytr'Ytr) / n_tr
@@ -167,7 +168,12 @@ class Engine {
   Lane& lane_of(int fold);                       // fold < 0: the full-data lane
   void ensure_gram(Lane& L, int k);              // k = -1: full data
   void init_lambda(cudaStream_t s, const double* Phi, const std::vector<double>& sv, double rho, double* L2);
-  void run_core2(Lane& L, int kind, int fold, int idx, double tau1, double rho, ChainState& st);
+  // buf: matrix buffer to build the inverse in (nullptr: the lane's work buffer);
+  // have: buf already holds inv_sympd(2(tau1 Omega - G) + rho I) for this (fold, tau1)
+  void run_core2(Lane& L, int kind, int fold, int idx, double tau1, double rho, ChainState& st,
+                 double* buf = nullptr, bool have = false);
+  double* cached_inverse(FoldData& f, int index1);   // stage-1 inverse of the selected tau1, or nullptr
+  void drop_cached_inverses(FoldData& f, int keep);
   void run_core3(Lane& L, int kind, int fold, int idx, const double* tinv, double tau2, double rho, ChainState& st);
   void launch_loss(Lane& L, const FoldData& f, const double* Phi, double* out_dev);
   void enqueue_stage1(int k);
@@ -201,6 +207,7 @@ class Engine {
 
   std::vector<std::unique_ptr<Lane>> lanes_;     // n_fold_lanes_ fold lanes + 1 full-data lane
   int n_fold_lanes_ = 1;
+  bool cache_inverses_ = false;                  // keep the (fold, tau1) inverses of stage 1 for stages 2/3
   int slot_cap_ = 0;
   DevBuf<double> loss_out_;                      // M x max_grid scores, (M+1)-th row = scratch
   DevBuf<double> prep_scratch_;
