@@ -365,3 +365,124 @@ def test_error_paths(sp):
         assert not np.all(np.isfinite(om))
     except SpatpcaError:
         pass
+
+
+# ---------------------------------------------------------------------------------------------
+# determinism, sharding, larger sizes
+# ---------------------------------------------------------------------------------------------
+def _run_cv(sp, case, **kw):
+    return sp.spatpcaCV(case["x"], case["Y"], case["M"], case["K"], case["tau1"], case["tau2"], case["gamma"],
+                        case["nk"], kw.get("maxit", 100), kw.get("tol", 1e-4), case["l2"], return_stats=True)
+
+
+def _same_bits(a, b):
+    for key in ("cv_score_tau1", "cv_score_tau2", "cv_score_gamma", "estimated_eigenfn"):
+        assert np.array_equal(a[key], b[key]), key
+    for key in ("selected_tau1", "selected_tau2", "selected_gamma"):
+        assert a[key] == b[key]
+
+
+def test_bitwise_reproducible_across_lanes_and_cache(sp, monkeypatch):
+    """Results must not depend on how many folds run concurrently, on whether stage-1 inverses are
+    reused, or on the run: every reduction has a fixed shape (no floating-point atomics)."""
+    case = make_case("irregular2d_small")
+    base = _run_cv(sp, case)
+    again = _run_cv(sp, case)
+    _same_bits(base, again)
+    monkeypatch.setenv("SPB_LANES", "1")
+    one_lane = _run_cv(sp, case)
+    _same_bits(base, one_lane)
+    monkeypatch.setenv("SPB_LANES", "2")
+    monkeypatch.setenv("SPB_CACHE_INVERSES", "0")
+    no_cache = _run_cv(sp, case)
+    _same_bits(base, no_cache)
+    assert no_cache["stats"]["n_inverses"] > base["stats"]["n_inverses"]
+
+
+def test_inverse_matches_cusolver_path(sp, monkeypatch):
+    """The recursive GEMM-rate inverse against cuSOLVER potrf + potri (the reference's algorithm class)
+    on the same device: same matrix to ~cond * eps."""
+    import subprocess, sys, os, json
+    code = (
+        "import sys, json, numpy as np; sys.path.insert(0, '.'); sys.path.insert(0, 'tests');"
+        "from synth import make_case; import spatpca_b200 as sp;"
+        "c = make_case('grid2d_small');"
+        "r = sp.spatpcaCV(c['x'], c['Y'], c['M'], c['K'], c['tau1'], c['tau2'], c['gamma'], c['nk'], 100, 1e-4, c['l2']);"
+        "print(json.dumps({'s1': list(r['cv_score_tau1']), 's2': list(r['cv_score_tau2']), 's3': list(r['cv_score_gamma']),"
+        "'sel': [r['selected_tau1'], r['selected_tau2'], r['selected_gamma']], 'phi': r['estimated_eigenfn'].ravel().tolist()}))")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ("recursive", "cusolver"):
+        env = dict(os.environ, SPB_INVERSE=mode)
+        res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, check=True)
+        outs.append(json.loads(res.stdout.strip().splitlines()[-1]))
+    a, b = outs
+    assert a["sel"] == b["sel"]
+    for k in ("s1", "s2", "s3"):
+        np.testing.assert_allclose(a[k], b[k], rtol=1e-11)
+    pa, pb = np.array(a["phi"]), np.array(b["phi"])
+    assert np.max(np.abs(pa - pb)) / np.max(np.abs(pb)) <= 1e-10
+
+
+def test_sharded_two_engines_match_single(sp):
+    """Fold sharding as bench.py does under torchrun, emulated with two engines in one process: the
+    per-fold rows, the selections and the final fit must equal the single-engine run bit for bit."""
+    from spatpca_b200 import distributed as D
+    case = make_case("grid3d_small")
+    single = _run_cv(sp, case)
+    M, world = case["M"], 2
+    engines = []
+    for r in range(world):
+        e = sp.Engine(case["x"].shape[0], case["x"].shape[1], case["Y"].shape[0], M, case["K"], case["tau1"],
+                      case["tau2"], case["gamma"], 100, 1e-4, case["l2"])
+        e.upload(case["x"], case["Y"], case["nk"])
+        e.prepare()
+        engines.append(e)
+    mine = [[k for k in range(M) if D.fold_owner(k, world) == r] for r in range(world)]
+    full = D.full_fit_owner(M, world)
+
+    def gather(per_rank_rows, width):
+        cv = np.zeros((M, width))
+        for rows in per_rank_rows:
+            for k, row in rows.items():
+                cv[k] = row
+        return cv
+
+    cv1 = gather([engines[r].stage1_folds(mine[r]) for r in range(world)], len(case["tau1"]))
+    i1, s1 = sp.select_index(cv1)
+    engines[full].stage1_full(i1)
+    cv2 = gather([engines[r].stage2_folds(mine[r], i1) for r in range(world)], len(case["tau2"]))
+    i2, s2 = sp.select_index(cv2)
+    engines[full].stage2_full(i1, i2)
+    cv3 = gather([engines[r].stage3_folds(mine[r], i1, i2) for r in range(world)], len(case["gamma"]))
+    i3, s3 = sp.select_index(cv3)
+    phi = engines[full].get_eigenfn()
+    assert np.array_equal(s1, single["cv_score_tau1"])
+    assert np.array_equal(s2, single["cv_score_tau2"])
+    assert np.array_equal(s3, single["cv_score_gamma"])
+    assert np.array_equal(phi, single["estimated_eigenfn"])
+    assert case["tau1"][i1] == single["selected_tau1"] and case["gamma"][i3] == single["selected_gamma"]
+    for e in engines:
+        e.close()
+
+
+def test_cv_forced_iterations(sp):
+    """thr = 0: every ADMM call runs exactly maxit iterations (the deterministic-denominator mode of
+    SURVEY.md section 8d); iterates still match the oracle."""
+    case = make_case("grid3d_small")
+    args = (case["x"], case["Y"], case["M"], case["K"], case["tau1"], case["tau2"], case["gamma"], case["nk"], 7, 0.0,
+            case["l2"])
+    got = sp.spatpcaCV(*args, return_stats=True)
+    tr = ref.Trace()
+    want = ref.spatpca_cv(*args, trace=tr)
+    assert got["stats"]["admm_iters"] == 7 * got["stats"]["n_admm_calls"] == tr.admm_iters
+    assert_cv_parity(got, want)
+
+
+def test_cv_irregular_1500(sp):
+    """Mid-size irregular 2-D case (p = 1500, n = 200, K = 5, 10 x 10 x 11 grids): the largest size the
+    oracle finishes in well under a minute."""
+    case = make_case("irregular2d_1500")
+    got, want, tr = run_both(sp, case)
+    assert_cv_parity(got, want)
+    assert got["stats"]["admm_iters"] == tr.admm_iters
