@@ -136,6 +136,23 @@ SPB_API int spb_cv(const double* sxy, int p, int d,
            double* cv_score_tau1, double* cv_score_tau2, double* cv_score_gamma,
            double* estimated_eigenfn, double* selected, spb_cv_stats* stats);
 
+/* spb_cv with a one-entry session: identical arguments and results, but the engine of the previous
+ * call on this thread is kept, and when the next call brings the same data, folds and grids (content
+ * hash) only K may differ -- Omega, the fold SVD starts and every p x p inverse are K-independent and
+ * are reused.  This is what the K-selection loop needs (R/SpatPCA.R:23-48 calls spatpcaCV for
+ * K = 1, 2, ... on the same inputs).  The kept engine holds device memory until the next different
+ * call, spb_session_clear() or spb_trim_memory().                                              */
+SPB_API int spb_cv_session(const double* sxy, int p, int d,
+           const double* Y, int n, int M, int K,
+           const double* tau1, int n_tau1,
+           const double* tau2, int n_tau2,
+           const double* gamma, int n_gamma,
+           const double* nk, int maxit, double tol,
+           const double* l2, int n_l2,
+           double* cv_score_tau1, double* cv_score_tau2, double* cv_score_gamma,
+           double* estimated_eigenfn, double* selected, spb_cv_stats* stats);
+SPB_API int spb_session_clear(void);
+
 /* ------------------------------------------------------------------------ */
 /* Engine handle: the same computation as spb_cv, cut at the reference's     */
 /* natural seams (per fold inside each stage, src/RcppSpatPCA.cpp:315, 385,  */
@@ -184,6 +201,8 @@ SPB_API int spb_engine_stage2_folds(spb_engine* e, const int* folds, int nfolds,
 SPB_API int spb_engine_stage3_folds(spb_engine* e, const int* folds, int nfolds, int index1, int index2,
                                     double* cv_rows);
 
+/* Re-arm the engine for another K on the same data and grids (then prepare + the stages again).   */
+SPB_API int spb_engine_reset_k(spb_engine* e, int K);
 /* estimated_eigenfn (p x K) of the full-data fit, device -> host */
 SPB_API int spb_engine_get_eigenfn(spb_engine* e, double* eigenfn_out);
 SPB_API int spb_engine_get_stats(spb_engine* e, spb_cv_stats* stats);

@@ -61,6 +61,10 @@ SIGNATURES = {
     "spb_cv": (C.c_int, [_dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int,
                          _dp, C.c_int, _dp, C.c_int, C.c_double, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp,
                          C.POINTER(CvStats)]),
+    "spb_cv_session": (C.c_int, [_dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int,
+                                 _dp, C.c_int, _dp, C.c_int, C.c_double, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp,
+                                 C.POINTER(CvStats)]),
+    "spb_session_clear": (C.c_int, []),
     "spb_engine_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int,
                                     _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_double, _dp, C.c_int]),
     "spb_engine_destroy": (C.c_int, [_vp]),
@@ -76,6 +80,7 @@ SIGNATURES = {
     "spb_engine_stage1_folds": (C.c_int, [_vp, _ip, C.c_int, _dp]),
     "spb_engine_stage2_folds": (C.c_int, [_vp, _ip, C.c_int, C.c_int, _dp]),
     "spb_engine_stage3_folds": (C.c_int, [_vp, _ip, C.c_int, C.c_int, C.c_int, _dp]),
+    "spb_engine_reset_k": (C.c_int, [_vp, C.c_int]),
     "spb_engine_get_eigenfn": (C.c_int, [_vp, _dp]),
     "spb_engine_get_stats": (C.c_int, [_vp, C.POINTER(CvStats)]),
     "spb_engine_call_log": (C.c_int, [_vp, _ip, C.c_int]),

@@ -163,16 +163,21 @@ class SpatpcaObject(dict):
 def spatpcaCVWithSelectedK(x, Y, M, tau1, tau2, gamma, shuffle_split, maxit, thr, l2):
     """R/SpatPCA.R:23-48: raise K until the selected gamma stops decreasing."""
     upper_bound = fetchUpperBoundNumberEigenfunctions(Y, M)
-    prev_cv_selection = spatpcaCV(x, Y, M, 1, tau1, tau2, gamma, shuffle_split, maxit, thr, l2)
-    cv_selection = prev_cv_selection
-    ks = list(range(2, upper_bound + 1)) if upper_bound >= 2 else list(range(2, upper_bound - 1, -1))
-    k = 2
-    for k in ks:                      # `for (k in 2:upper_bound)`; 2:1 counts down in R
-        cv_selection = spatpcaCV(x, Y, M, k, tau1, tau2, gamma, shuffle_split, maxit, thr, l2)
-        difference = prev_cv_selection["selected_gamma"] - cv_selection["selected_gamma"]
-        prev_cv_selection = cv_selection
-        if difference <= 0 or abs(difference) <= 1e-8:
-            break
+    # every call of the loop sees the same data, folds and grids: the session entry point keeps
+    # Omega, the fold SVD starts and the K-independent p x p inverses between the calls
+    try:
+        prev_cv_selection = spatpcaCV(x, Y, M, 1, tau1, tau2, gamma, shuffle_split, maxit, thr, l2, session=True)
+        cv_selection = prev_cv_selection
+        ks = list(range(2, upper_bound + 1)) if upper_bound >= 2 else list(range(2, upper_bound - 1, -1))
+        k = 2
+        for k in ks:                      # `for (k in 2:upper_bound)`; 2:1 counts down in R
+            cv_selection = spatpcaCV(x, Y, M, k, tau1, tau2, gamma, shuffle_split, maxit, thr, l2, session=True)
+            difference = prev_cv_selection["selected_gamma"] - cv_selection["selected_gamma"]
+            prev_cv_selection = cv_selection
+            if difference <= 0 or abs(difference) <= 1e-8:
+                break
+    finally:
+        _eng.session_clear()
     return {"cv_result": cv_selection, "selected_K": k - 1}
 
 

@@ -677,10 +677,11 @@ Geom make_geom(int p, int K) {
   int cap = budget / (g.KX * (int)sizeof(double));
   g.xcap = maxcols < cap ? maxcols : cap;
   if (g.xcap < 1) g.xcap = 1;
-  g.part_doubles = (size_t)2 * g.S * g.TR * g.KP;
-  g.gpart_doubles = (size_t)g.nrt * g.KG;
-  g.npart_doubles = (size_t)g.nrb * 4;
-  g.x_doubles = (size_t)p * K;
+  // every sub-buffer starts 128-byte aligned (the partial slots are read / written with 16-byte accesses)
+  g.part_doubles = round_up((size_t)2 * g.S * g.TR * g.KP, 16);
+  g.gpart_doubles = round_up((size_t)g.nrt * g.KG, 16);
+  g.npart_doubles = round_up((size_t)g.nrb * 4, 16);
+  g.x_doubles = round_up((size_t)p * K, 16);
   g.ctrl_doubles = 8 + (size_t)SPB_MAX_K * SPB_MAX_K;
   g.counter_ints = (size_t)g.nrt + 2;
   // dynamic shared memory: [stream window | reduction scratch (8 KG + 32) | tile table]

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "engine.cuh"
@@ -97,6 +98,7 @@ int spb_set_device(int ordinal) {
 
 int spb_trim_memory(void) {
   return guarded([&] {
+    spb_session_clear();
     cudaDeviceSynchronize();
     cached_trim();
   });
@@ -281,6 +283,7 @@ int spb_engine_stage2_folds(spb_engine* e, const int* folds, int nfolds, int ind
 int spb_engine_stage3_folds(spb_engine* e, const int* folds, int nfolds, int index1, int index2, double* cv_rows) {
   SPB_ENGINE_CALL(e->impl->stage3_folds(folds, nfolds, index1, index2, cv_rows));
 }
+int spb_engine_reset_k(spb_engine* e, int K) { SPB_ENGINE_CALL(e->impl->reset_k(K)); }
 int spb_engine_get_eigenfn(spb_engine* e, double* out) { SPB_ENGINE_CALL(e->impl->get_eigenfn(out)); }
 int spb_engine_get_stats(spb_engine* e, spb_cv_stats* st) { SPB_ENGINE_CALL(e->impl->get_stats(st)); }
 int spb_engine_release_fold(spb_engine* e, int k) { SPB_ENGINE_CALL(e->impl->release_fold(k)); }
@@ -295,6 +298,78 @@ int spb_engine_call_log(spb_engine* e, int* log4, int cap) {
 }
 
 // ---------------------------------------------------------------------------------------------
+namespace {
+
+// stages of spatpcaCV on a prepared engine (:592-692); fills the caller's outputs
+void run_cv_stages(Engine& eng, int M, const double* tau2, int n_tau1, int n_tau2, const double* gamma, int n_gamma,
+                   double* cv_score_tau1, double* cv_score_tau2, double* cv_score_gamma, double* estimated_eigenfn,
+                   double* selected, spb_cv_stats* stats) {
+  // stage 1 (:592-650): all folds run concurrently on their lanes
+  int index1 = 0, index2 = 0, index3 = 0;
+  std::vector<int> all(M);
+  for (int k = 0; k < M; ++k) all[k] = k;
+  auto to_colmajor = [&](const std::vector<double>& rows, int width) {   // rows: M x width row-major
+    std::vector<double> cv((size_t)M * width);
+    for (int k = 0; k < M; ++k)
+      for (int i = 0; i < width; ++i) cv[(size_t)i * M + k] = rows[(size_t)k * width + i];
+    return cv;
+  };
+  {
+    std::vector<double> rows((size_t)M * n_tau1, 0.0);
+    eng.stage1_folds(all.data(), M, rows.data());
+    if (n_tau1 > 1) {
+      std::vector<double> cv1 = to_colmajor(rows, n_tau1);
+      index1 = select_index_impl(cv1.data(), M, n_tau1, cv_score_tau1);
+    } else {
+      cv_score_tau1[0] = 0.0;                                             // :649
+    }
+  }
+  eng.stage1_full(index1);                 // full-data fit: overlaps with the folds' stage 2
+  selected[0] = eng.selected_tau1(index1);
+  // stage 2 (:652-680)
+  if (n_tau2 > 1) {
+    std::vector<double> rows((size_t)M * n_tau2, 0.0);
+    eng.stage2_folds(all.data(), M, index1, rows.data());
+    std::vector<double> cv2 = to_colmajor(rows, n_tau2);
+    index2 = select_index_impl(cv2.data(), M, n_tau2, cv_score_tau2);
+    selected[1] = tau2[index2];
+  } else {
+    cv_score_tau2[0] = 0.0;                                               // :679
+    selected[1] = tau2[0];                                                // :671
+  }
+  eng.stage2_full(index1, index2);         // overlaps with the folds' stage 3
+  // stage 3 (:682-692)
+  {
+    std::vector<double> rows((size_t)M * n_gamma, 0.0);
+    eng.stage3_folds(all.data(), M, index1, index2, rows.data());
+    std::vector<double> cv3 = to_colmajor(rows, n_gamma);
+    index3 = select_index_impl(cv3.data(), M, n_gamma, cv_score_gamma);
+    selected[2] = (n_gamma > 1) ? gamma[index3] : gamma[0];               // :684-691
+  }
+  eng.get_eigenfn(estimated_eigenfn);
+  eng.get_stats(stats);
+}
+
+// 64-bit content hash (word-wise multiply-xorshift); only used to recognise "same inputs as the last call"
+uint64_t hash_doubles(const double* x, size_t n, uint64_t h) {
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(x);
+  for (size_t i = 0; i < n; ++i) {
+    h ^= w[i] + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 32;
+  }
+  return h;
+}
+
+struct Session {
+  std::unique_ptr<Engine> eng;
+  uint64_t key = 0;
+  int device = -1;
+};
+thread_local Session g_session;
+
+}  // namespace
+
 int spb_cv(const double* sxy, int p, int d, const double* Y, int n, int M, int K, const double* tau1,
            int n_tau1, const double* tau2, int n_tau2, const double* gamma, int n_gamma, const double* nk,
            int maxit, double tol, const double* l2, int n_l2, double* cv_score_tau1, double* cv_score_tau2,
@@ -305,50 +380,59 @@ int spb_cv(const double* sxy, int p, int d, const double* Y, int n, int M, int K
     Engine eng(p, d, n, M, K, tau1, n_tau1, tau2, n_tau2, gamma, n_gamma, maxit, tol, l2, n_l2);
     eng.upload(sxy, Y, nk);
     eng.prepare();
-    // stage 1 (:592-650): all folds run concurrently on their lanes
-    int index1 = 0, index2 = 0, index3 = 0;
-    std::vector<int> all(M);
-    for (int k = 0; k < M; ++k) all[k] = k;
-    auto to_colmajor = [&](const std::vector<double>& rows, int width) {   // rows: M x width row-major
-      std::vector<double> cv((size_t)M * width);
-      for (int k = 0; k < M; ++k)
-        for (int i = 0; i < width; ++i) cv[(size_t)i * M + k] = rows[(size_t)k * width + i];
-      return cv;
-    };
-    {
-      std::vector<double> rows((size_t)M * n_tau1, 0.0);
-      eng.stage1_folds(all.data(), M, rows.data());
-      if (n_tau1 > 1) {
-        std::vector<double> cv1 = to_colmajor(rows, n_tau1);
-        index1 = select_index_impl(cv1.data(), M, n_tau1, cv_score_tau1);
-      } else {
-        cv_score_tau1[0] = 0.0;                                             // :649
-      }
-    }
-    eng.stage1_full(index1);                 // full-data fit: overlaps with the folds' stage 2
-    selected[0] = eng.selected_tau1(index1);
-    // stage 2 (:652-680)
-    if (n_tau2 > 1) {
-      std::vector<double> rows((size_t)M * n_tau2, 0.0);
-      eng.stage2_folds(all.data(), M, index1, rows.data());
-      std::vector<double> cv2 = to_colmajor(rows, n_tau2);
-      index2 = select_index_impl(cv2.data(), M, n_tau2, cv_score_tau2);
-      selected[1] = tau2[index2];
+    run_cv_stages(eng, M, tau2, n_tau1, n_tau2, gamma, n_gamma, cv_score_tau1, cv_score_tau2, cv_score_gamma,
+                  estimated_eigenfn, selected, stats);
+  });
+}
+
+int spb_cv_session(const double* sxy, int p, int d, const double* Y, int n, int M, int K, const double* tau1,
+                   int n_tau1, const double* tau2, int n_tau2, const double* gamma, int n_gamma, const double* nk,
+                   int maxit, double tol, const double* l2, int n_l2, double* cv_score_tau1,
+                   double* cv_score_tau2, double* cv_score_gamma, double* estimated_eigenfn, double* selected,
+                   spb_cv_stats* stats) {
+  return guarded([&] {
+    SPB_REQUIRE(cv_score_tau1 && cv_score_tau2 && cv_score_gamma && estimated_eigenfn && selected,
+                "NULL output");
+    SPB_REQUIRE(sxy && Y && nk && tau1 && tau2 && gamma, "NULL input");
+    SPB_REQUIRE(p >= 1 && n >= 1 && d >= 1 && n_tau1 >= 1 && n_tau2 >= 1 && n_gamma >= 1, "invalid size");
+    int dev = 0;
+    SPB_CUDA(cudaGetDevice(&dev));
+    uint64_t key = 0x243f6a8885a308d3ULL;
+    const double hdr[8] = {(double)p, (double)d, (double)n, (double)M, (double)maxit, tol, (double)n_l2, 0.0};
+    key = hash_doubles(hdr, 8, key);
+    key = hash_doubles(sxy, (size_t)p * d, key);
+    key = hash_doubles(Y, (size_t)n * p, key);
+    key = hash_doubles(nk, (size_t)n, key);
+    key = hash_doubles(tau1, n_tau1, key);
+    key = hash_doubles(tau2, n_tau2, key);
+    key = hash_doubles(gamma, n_gamma, key);
+    if (l2 && n_l2 > 0) key = hash_doubles(l2, n_l2, key);
+    Session& ss = g_session;
+    if (ss.eng && ss.key == key && ss.device == dev) {
+      ss.eng->reset_k(K);                      // same data and grids: Omega, SVD starts, inverses are reused
     } else {
-      cv_score_tau2[0] = 0.0;                                               // :679
-      selected[1] = tau2[0];                                                // :671
+      ss.eng.reset();
+      ss.eng.reset(new Engine(p, d, n, M, K, tau1, n_tau1, tau2, n_tau2, gamma, n_gamma, maxit, tol, l2, n_l2));
+      ss.key = key;
+      ss.device = dev;
+      ss.eng->upload(sxy, Y, nk);
     }
-    eng.stage2_full(index1, index2);         // overlaps with the folds' stage 3
-    // stage 3 (:682-692)
-    {
-      std::vector<double> rows((size_t)M * n_gamma, 0.0);
-      eng.stage3_folds(all.data(), M, index1, index2, rows.data());
-      std::vector<double> cv3 = to_colmajor(rows, n_gamma);
-      index3 = select_index_impl(cv3.data(), M, n_gamma, cv_score_gamma);
-      selected[2] = (n_gamma > 1) ? gamma[index3] : gamma[0];               // :684-691
+    try {
+      ss.eng->prepare();
+      run_cv_stages(*ss.eng, M, tau2, n_tau1, n_tau2, gamma, n_gamma, cv_score_tau1, cv_score_tau2, cv_score_gamma,
+                    estimated_eigenfn, selected, stats);
+    } catch (...) {
+      ss.eng.reset();                          // never keep a half-run engine
+      ss.key = 0;
+      throw;
     }
-    eng.get_eigenfn(estimated_eigenfn);
-    eng.get_stats(stats);
+  });
+}
+
+int spb_session_clear(void) {
+  return guarded([&] {
+    g_session.eng.reset();
+    g_session.key = 0;
   });
 }
 

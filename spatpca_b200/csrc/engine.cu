@@ -507,8 +507,6 @@ Engine::Engine(int p, int d, int n, int M, int K, const double* tau1, int n1, co
              (*std::max_element(tau2_.begin(), tau2_.end()) != 0.0);
   ld_ = padded_ld((size_t)p);
   folds_.resize(M);
-  const size_t pk = (size_t)p * K;
-  full_.alloc(pk);
   max_grid_ = std::max({n1, n2, n3, 1});
   loss_out_.alloc((size_t)(M + 1) * max_grid_);
   prep_scratch_.alloc(512);
@@ -533,15 +531,44 @@ Engine::Engine(int p, int d, int n, int M, int K, const double* tau1, int n1, co
   for (int i = 0; i <= n_fold_lanes_; ++i) {
     std::unique_ptr<Lane> L(new Lane());
     L->res = &ctx_.lane_res(i);
-    L->chain.alloc(pk);
-    L->admm_ws.alloc(admm_workspace_bytes(p, K));
-    L->lossW.alloc((size_t)n * K);
-    L->loss_scratch.alloc(yphi_scratch_doubles(n, p, K) + 512);
     L->stat_slots.alloc((size_t)slot_cap_ * 4);
     L->err_slots.alloc((size_t)slot_cap_);
     lanes_.push_back(std::move(L));
   }
+  alloc_k_state();
   std::memset(&stats_, 0, sizeof(stats_));
+  launches_at_start_ = g_launch_count;
+  t_created = std::chrono::steady_clock::now();
+}
+
+void Engine::alloc_k_state() {
+  const size_t pk = (size_t)p_ * K_;
+  full_.alloc(pk);
+  for (auto& L : lanes_) {
+    L->chain.alloc(pk);
+    L->admm_ws.alloc(admm_workspace_bytes(p_, K_));
+    L->lossW.alloc((size_t)n_ * K_);
+    L->loss_scratch.alloc(yphi_scratch_doubles(n_, p_, K_) + 512);
+  }
+  for (auto& f : folds_) {
+    if (f.prepared) { f.Phi0.alloc(pk); f.L20.alloc(pk); }
+  }
+}
+
+void Engine::reset_k(int K) {
+  SPB_REQUIRE(K >= 1 && K <= SPB_MAX_K, "K must be in 1..SPB_MAX_K");
+  SPB_REQUIRE(K <= p_ && K <= n_, "K must not exceed min(n, p)");
+  for (auto& f : folds_) SPB_REQUIRE(K <= std::min(f.n_tr, p_), "K must not exceed min(training rows, p)");
+  flush();
+  K_ = K;
+  alloc_k_state();
+  full_ready_ = false;                          // prepare() re-derives the full-data start for the new K
+  log_.clear();
+  const long long h2d = stats_.bytes_h2d;
+  std::memset(&stats_, 0, sizeof(stats_));
+  stats_.bytes_h2d = h2d;
+  clock_.reset();
+  for (auto& L : lanes_) L->clock.reset();
   launches_at_start_ = g_launch_count;
   t_created = std::chrono::steady_clock::now();
 }
@@ -593,6 +620,8 @@ void Engine::upload(const double* sxy, const double* Y, const double* nk) {
   stats_.ms_h2d += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   omega_ready_ = omega_injected_;
   full_ready_ = false;
+  full_svd_done_ = false;
+  full_inv2_index_ = full_tinv_index_ = -1;
   for (auto& L : lanes_) L->gram_owner = -2;
 }
 
@@ -627,10 +656,16 @@ void Engine::prepare() {
   SPB_REQUIRE(dY_.get() != nullptr, "upload() must be called before prepare()");
   trace(ctx_, "prepare: enter");
   cudaStream_t s = ctx_.stream;
-  if (!full_ready_) {
+  if (!full_svd_done_) {
     Scoped sc(clock_, PH_PROLOGUE, s);
-    svd_right(ctx_, dY_.get(), n_, p_, K_, sv_full_, full_.Phi.get());       // :563
+    kcap_full_ = std::min(std::min(n_, p_), SPB_MAX_K);
+    Vfull_.alloc((size_t)p_ * kcap_full_);
+    svd_right(ctx_, dY_.get(), n_, p_, kcap_full_, sv_full_, Vfull_.get());   // :563
     rho_full_ = 10.0 * (sv_full_[0] * sv_full_[0]);                           // :564
+    full_svd_done_ = true;
+  }
+  if (!full_ready_) {
+    copy_pk(s, full_.Phi.get(), Vfull_.get());                                // :565 (first K columns)
     copy_pk(s, full_.C.get(), full_.Phi.get());                               // :566
     init_lambda(s, full_.Phi.get(), sv_full_, rho_full_, full_.L2.get());     // :567
     full_ready_ = true;
@@ -684,7 +719,9 @@ void Engine::fold_prepare(int k) {
   }
   f.Phi0.alloc((size_t)p_ * K_);
   f.L20.alloc((size_t)p_ * K_);
-  svd_right(ctx_, f.Ytr.get(), f.n_tr, p_, K_, f.sv, f.Phi0.get());           // :321
+  f.kcap = std::min(std::min(f.n_tr, p_), SPB_MAX_K);
+  f.V.alloc((size_t)p_ * f.kcap);
+  svd_right(ctx_, f.Ytr.get(), f.n_tr, p_, f.kcap, f.sv, f.V.get());          // :321
   f.rho = 10.0 * (f.sv[0] * f.sv[0]);                                         // :322
   // trace(Ytr'Ytr) / n_tr (:489, :491)
   double* out = loss_out_.get() + (size_t)M_ * max_grid_;
@@ -742,12 +779,14 @@ void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double
 
 double* Engine::cached_inverse(FoldData& f, int index1) {
   if (!cache_inverses_ || index1 < 1 || index1 >= (int)f.inv_cache.size()) return nullptr;
+  if (index1 >= (int)f.inv_valid.size() || !f.inv_valid[index1]) return nullptr;
   return f.inv_cache[index1].get();
 }
 
 void Engine::drop_cached_inverses(FoldData& f, int keep) {
-  for (int i = 0; i < (int)f.inv_cache.size(); ++i)
-    if (i != keep) f.inv_cache[i].release();
+  // Kept for the lifetime of the engine: the memory was budgeted at construction, and the K-selection
+  // loop (reset_k) reuses every one of them.
+  (void)f; (void)keep;
 }
 
 void Engine::run_core3(Lane& L, int kind, int fold, int idx, const double* tinv, double tau2, double rho,
@@ -814,20 +853,27 @@ void Engine::enqueue_stage1(int k) {
   const int n1 = (int)tau1_.size();
   const double max_tau2 = *std::max_element(tau2_.begin(), tau2_.end());
   double* scores = fold_scores(k);
+  copy_pk(s, f.Phi0.get(), f.V.get());                                        // Phi_old.cols(0, K-1) (:324)
   if (n1 > 1) {                                                               // worker :312-334
     init_lambda(s, f.Phi0.get(), f.sv, f.rho, f.L20.get());
     copy_pk(s, ch.Phi.get(), f.Phi0.get());
     copy_pk(s, ch.C.get(), f.Phi0.get());
     copy_pk(s, ch.L2.get(), f.L20.get());
     launch_loss(L, f, f.Phi0.get(), scores + 0);                              // :327 (tau1[0] scored as PCA)
-    if (cache_inverses_) f.inv_cache.resize(n1);
+    if (cache_inverses_ && (int)f.inv_cache.size() != n1) {
+      f.inv_cache.resize(n1);
+      f.inv_valid.assign(n1, 0);
+    }
     for (int i = 1; i < n1; ++i) {                                            // warm-started path :329-332
       double* buf = nullptr;
+      bool have = false;
       if (cache_inverses_) {
         f.inv_cache[i].ensure(ld_ * (size_t)p_);
         buf = f.inv_cache[i].get();
+        have = f.inv_valid[i] != 0;            // built by an earlier run on this engine (other K)
+        f.inv_valid[i] = 1;
       }
-      run_core2(L, 2, k, i, tau1_[i], f.rho, ch, buf, false);
+      run_core2(L, 2, k, i, tau1_[i], f.rho, ch, buf, have);
       launch_loss(L, f, ch.Phi.get(), scores + i);
     }
     return;
@@ -883,7 +929,17 @@ void Engine::stage1_full(int index1) {
   // enqueued on the full-data lane and NOT waited for: it overlaps with the folds' next stage
   if (n1 > 1) {
     SPB_REQUIRE(index1 >= 0 && index1 < n1, "index1 out of range");
-    if (index1 > 0) run_core2(L, 20, -1, index1, tau1_[index1], rho_full_, full_);    // :598-599
+    if (index1 > 0) {                                                         // :598-599
+      double* buf = nullptr;
+      bool have = false;
+      if (cache_inverses_) {
+        full_inv2_.ensure(ld_ * (size_t)p_);
+        buf = full_inv2_.get();
+        have = (full_inv2_index_ == index1);
+        full_inv2_index_ = index1;
+      }
+      run_core2(L, 20, -1, index1, tau1_[index1], rho_full_, full_, buf, have);
+    }
   } else {
     const double sel = tau1_[0];
     if (sel != 0.0 && max_tau2 == 0.0) run_core2(L, 20, -1, 0, sel, rho_full_, full_); // :605
@@ -912,13 +968,15 @@ void Engine::enqueue_stage2(int k, int index1) {
   copy_pk(s, ch.R.get(), ch.Phi.get());                                       // :394
   copy_pk(s, f.Phi0.get(), ch.Phi.get());                                     // :395
   copy_pk(s, f.L20.get(), ch.L2.get());                                       // :396
-  ensure_gram(L, k);
-  {
+  const int tag1 = ((int)tau1_.size() > 1) ? index1 : 0;
+  if (!(cache_inverses_ && f.tinv.get() != nullptr && f.tinv_index == tag1)) {
+    ensure_gram(L, k);
     Scoped sc(L.clock, PH_INVERSE, s);
     f.tinv.ensure(ld_ * (size_t)p_);
     spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, f.rho, 1.0, f.tinv.get(),
                 ld_);                                                         // :397
     stats_.n_inverses++;
+    f.tinv_index = tag1;
   }
   for (int i = 0; i < n2; ++i) {                                              // :398-401
     run_core3(L, 3, k, i, f.tinv.get(), tau2_[i], f.rho, ch);
@@ -956,17 +1014,28 @@ void Engine::stage2_full(int index1, int index2) {
   if (!path) return;
   Lane& L = lane_of(-1);
   cudaStream_t s = L.res->stream;
-  ensure_gram(L, -1);
-  {
-    Scoped sc(L.clock, PH_INVERSE, s);
+  const int tag1 = ((int)tau1_.size() > 1) ? index1 : 0;
+  double* tbuf = nullptr;
+  bool have = false;
+  if (cache_inverses_) {
+    full_tinv_.ensure(ld_ * (size_t)p_);
+    tbuf = full_tinv_.get();
+    have = (full_tinv_index_ == tag1);
+    full_tinv_index_ = tag1;
+  } else {
     L.work.ensure(ld_ * (size_t)p_);
-    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, rho_full_, 1.0,
-                L.work.get(), ld_);                                           // :661, :673
+    tbuf = L.work.get();
+  }
+  if (!have) {
+    ensure_gram(L, -1);
+    Scoped sc(L.clock, PH_INVERSE, s);
+    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, rho_full_, 1.0, tbuf,
+                ld_);                                                         // :661, :673
     stats_.n_inverses++;
   }
   copy_pk(s, full_.R.get(), full_.Phi.get());                                 // :662
   zero_pk(s, full_.L1.get());                                                 // :663
-  for (int i = 0; i < upto; ++i) run_core3(L, 3, -1, i, L.work.get(), (*path)[i], rho_full_, full_);
+  for (int i = 0; i < upto; ++i) run_core3(L, 3, -1, i, tbuf, (*path)[i], rho_full_, full_);
 }
 
 // ---- stage 3 (:682-692, worker :459-525) ---------------------------------------------------

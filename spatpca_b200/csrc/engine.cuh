@@ -78,9 +78,13 @@ struct FoldData {
   int n_tr = 0, n_va = 0;
   std::vector<int> rows_tr, rows_va;
   DevBuf<double> Ytr, Yva;        // n_tr x p, n_va x p
+  DevBuf<double> V;               // leading right singular vectors of Ytr (p x kcap), the PCA start for any K
+  int kcap = 0;
   DevBuf<double> Phi0, L20;       // Phi_cv / Lambd2_cv slices of the reference (:569)
   DevBuf<double> tinv;            // tempinv_cv slice (p x p), allocated in stage 2
+  int tinv_index = -1;            // tau1 index `tinv` was built for (reused across K)
   std::vector<DevBuf<double>> inv_cache;   // stage-1 inverses by tau1 index (kept when memory allows)
+  std::vector<char> inv_valid;
   std::vector<double> sv;         // singular values of Ytr
   double rho = 0.0;
   double tv = 0.0;                // trace(Ytr'Ytr) / n_tr
@@ -129,6 +133,10 @@ class Engine {
   void stage1_fold(int k, double* cv_row) { stage1_folds(&k, 1, cv_row); }
   void stage2_fold(int k, int index1, double* cv_row) { stage2_folds(&k, 1, index1, cv_row); }
   void stage3_fold(int k, int index1, int index2, double* cv_row) { stage3_folds(&k, 1, index1, index2, cv_row); }
+  // Re-run with another number of eigenfunctions on the same data and grids (the K-selection loop of
+  // R/SpatPCA.R:23-48).  Omega, the fold gathers, the SVD starts and every cached inverse are
+  // K-independent and are kept.
+  void reset_k(int K);
   void get_eigenfn(double* out);
   void get_stats(spb_cv_stats* st);
   int call_log(int* log4, int cap);
@@ -203,7 +211,13 @@ class Engine {
   std::vector<double> sv_full_;
   double rho_full_ = 0.0;
   ChainState full_;
-  bool full_ready_ = false;
+  bool full_ready_ = false;                      // full_ holds the PCA start for the current K
+  bool full_svd_done_ = false;
+  DevBuf<double> Vfull_;                         // leading right singular vectors of Y (p x kcap_full_)
+  int kcap_full_ = 0;
+  DevBuf<double> full_inv2_, full_tinv_;         // full-data inverses kept across K (when cache_inverses_)
+  int full_inv2_index_ = -1, full_tinv_index_ = -1;
+  void alloc_k_state();                          // everything whose size depends on K
 
   std::vector<std::unique_ptr<Lane>> lanes_;     // n_fold_lanes_ fold lanes + 1 full-data lane
   int n_fold_lanes_ = 1;

@@ -59,8 +59,11 @@ def spatialPrediction(phir, Yr, gamma, predicted_eignefunction) -> dict:
     return {"prediction": pred, "estimated_covariance": cov, "eigenvalue": ev, "error": float(err[0])}
 
 
-def spatpcaCV(sxyr, Yr, M, K, tau1r, tau2r, gammar, nkr, maxit, tol, l2r, return_stats=False) -> dict:
-    """`spatpcaCV(...)` -- src/RcppSpatPCA.cpp:543-701; returns the reference's 7-entry list."""
+def spatpcaCV(sxyr, Yr, M, K, tau1r, tau2r, gammar, nkr, maxit, tol, l2r, return_stats=False,
+              session=False) -> dict:
+    """`spatpcaCV(...)` -- src/RcppSpatPCA.cpp:543-701; returns the reference's 7-entry list.
+    `session=True` goes through `spb_cv_session`: consecutive calls on the same data and grids
+    (the K-selection loop) reuse Omega, the SVD starts and the K-independent inverses."""
     lib = _lib.load()
     Y = fmat(Yr)
     n, p = Y.shape
@@ -76,9 +79,10 @@ def spatpcaCV(sxyr, Yr, M, K, tau1r, tau2r, gammar, nkr, maxit, tol, l2r, return
     eig = np.empty((p, int(K)), order="F")
     sel = np.zeros(3)
     stats = CvStats()
-    check(lib.spb_cv(ptr(x), p, x.shape[1], ptr(Y), n, int(M), int(K), ptr(t1), len(t1), ptr(t2), len(t2),
-                     ptr(g), len(g), ptr(nk), int(maxit), float(tol), ptr(l2), len(l2),
-                     ptr(s1), ptr(s2), ptr(s3), ptr(eig), ptr(sel), C.byref(stats)))
+    entry = lib.spb_cv_session if session else lib.spb_cv
+    check(entry(ptr(x), p, x.shape[1], ptr(Y), n, int(M), int(K), ptr(t1), len(t1), ptr(t2), len(t2),
+                ptr(g), len(g), ptr(nk), int(maxit), float(tol), ptr(l2), len(l2),
+                ptr(s1), ptr(s2), ptr(s3), ptr(eig), ptr(sel), C.byref(stats)))
     out = {
         "cv_score_tau1": s1 if len(t1) > 1 else np.zeros(1),
         "cv_score_tau2": s2 if len(t2) > 1 else np.zeros(1),
@@ -91,6 +95,10 @@ def spatpcaCV(sxyr, Yr, M, K, tau1r, tau2r, gammar, nkr, maxit, tol, l2r, return
     if return_stats:
         out["stats"] = stats.as_dict()
     return out
+
+
+def session_clear():
+    check(_lib.load().spb_session_clear())
 
 
 def select_index(cv: np.ndarray):
@@ -190,6 +198,10 @@ class Engine:
         check(self._lib.spb_engine_stage3_folds(self._h, f.ctypes.data_as(C.POINTER(C.c_int)), len(f), int(index1),
                                                 int(index2), ptr(rows)))
         return {int(k): rows[i] for i, k in enumerate(f)}
+
+    def reset_k(self, K):
+        check(self._lib.spb_engine_reset_k(self._h, int(K)))
+        self.K = int(K)
 
     def get_eigenfn(self):
         out = np.empty((self.p, self.K), order="F")

@@ -486,3 +486,69 @@ def test_cv_irregular_1500(sp):
     got, want, tr = run_both(sp, case)
     assert_cv_parity(got, want)
     assert got["stats"]["admm_iters"] == tr.admm_iters
+
+
+def test_session_reuse_is_bitwise_identical(sp):
+    """spb_cv_session keeps Omega, SVD starts and inverses between calls that differ only in K; every
+    result must equal the stateless spb_cv bit for bit, in any order of K, and fewer inverses are built."""
+    from spatpca_b200 import engine as eng
+    case = make_case("irregular2d_small")
+    args = lambda K: (case["x"], case["Y"], case["M"], K, case["tau1"], case["tau2"], case["gamma"], case["nk"],
+                      100, 1e-4, case["l2"])
+    fresh = {K: sp.spatpcaCV(*args(K), return_stats=True) for K in (1, 2, 4)}
+    eng.session_clear()
+    built = []
+    for K in (1, 4, 2, 4):
+        r = sp.spatpcaCV(*args(K), return_stats=True, session=True)
+        _same_bits(fresh[K], r)
+        built.append(r["stats"]["n_inverses"])
+    assert built[0] == fresh[1]["stats"]["n_inverses"]
+    assert built[1] < built[0] and built[3] <= built[1]
+    # a different data set must not hit the session
+    other = make_case("grid2d_small")
+    r = sp.spatpcaCV(other["x"], other["Y"], other["M"], other["K"], other["tau1"], other["tau2"], other["gamma"],
+                     other["nk"], 100, 1e-4, other["l2"], return_stats=True, session=True)
+    want = sp.spatpcaCV(other["x"], other["Y"], other["M"], other["K"], other["tau1"], other["tau2"], other["gamma"],
+                        other["nk"], 100, 1e-4, other["l2"], return_stats=True)
+    _same_bits(want, r)
+    eng.session_clear()
+
+
+def test_engine_reset_k(sp):
+    case = make_case("grid3d_small")
+    e = sp.Engine(case["x"].shape[0], case["x"].shape[1], case["Y"].shape[0], case["M"], 1, case["tau1"],
+                  case["tau2"], case["gamma"], 100, 1e-4, case["l2"])
+    e.upload(case["x"], case["Y"], case["nk"])
+    folds = list(range(case["M"]))
+    for K in (1, 3, 2):
+        e.reset_k(K)
+        e.prepare()
+        r1 = e.stage1_folds(folds)
+        i1, s1 = sp.select_index(np.array([r1[k] for k in folds]))
+        e.stage1_full(i1)
+        r2 = e.stage2_folds(folds, i1)
+        i2, s2 = sp.select_index(np.array([r2[k] for k in folds]))
+        e.stage2_full(i1, i2)
+        r3 = e.stage3_folds(folds, i1, i2)
+        i3, s3 = sp.select_index(np.array([r3[k] for k in folds]))
+        phi = e.get_eigenfn()
+        want = sp.spatpcaCV(case["x"], case["Y"], case["M"], K, case["tau1"], case["tau2"], case["gamma"], case["nk"],
+                            100, 1e-4, case["l2"])
+        assert phi.shape == (case["x"].shape[0], K)
+        assert np.array_equal(phi, want["estimated_eigenfn"])
+        assert np.array_equal(s1, want["cv_score_tau1"]) and np.array_equal(s3, want["cv_score_gamma"])
+    e.close()
+
+
+@pytest.mark.parametrize("p,K", [(125, 1), (77, 3), (129, 5), (255, 7)])
+def test_core3_odd_sizes(sp, p, K):
+    """Odd p with odd p*K: every workspace sub-buffer must stay 16-byte aligned."""
+    from spatpca_b200 import engine as eng
+    Yt, G, Om, rho, Phi0, L20 = _spd_problem(p, K, 11 * p + K, n=max(40, K + 5))
+    tinv = ref.core3_tempinv(Om, G, 0.05, rho)
+    tr = ref.Trace()
+    want = ref.core3(tinv, Phi0, Phi0.copy(), Phi0, np.zeros_like(Phi0), L20, 1.0, rho, 100, 1e-4, tr)
+    got = eng.admm_core3(tinv, Phi0.copy(), Phi0, np.zeros_like(Phi0), L20, 1.0, rho, 100, 1e-4)
+    assert got[5] == tr.calls[0][3]
+    for g, w in zip(got[:5], want):
+        assert np.max(np.abs(g - w)) / max(np.max(np.abs(w)), 1e-300) <= 1e-10
