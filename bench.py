@@ -127,7 +127,8 @@ def run_job_resident(sp, case, coll=None):
     if coll is None:
         coll = D.Collective()
     res = D.run_sharded(eng, sp.select_index, coll, M, len(case["tau1"]), len(case["tau2"]), len(case["gamma"]),
-                        case["tau1"], case["tau2"], case["gamma"])
+                        case["tau1"], case["tau2"], case["gamma"],
+                        share_inverses=os.environ.get("SPB_SHARE_INVERSES", "1") != "0")
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     return dt, res
@@ -265,7 +266,9 @@ def main():
         coll = D.TorchCollective(torch.device("cuda", local_rank))
 
     case, cfg = make_workload(args.config)
-    cfg["parallelism"] = f"folds sharded over {world} rank(s); full-data fit on rank {D.full_fit_owner(case['M'], world)}"
+    cfg["parallelism"] = (f"folds sharded over {world} rank(s), full-data fit on rank {D.full_fit_owner(case['M'], world)}; "
+                          "stage-1 (fold, tau1) inverses spread over all ranks and shipped to the fold's rank by NCCL "
+                          "send/recv" if world > 1 else "one GPU: folds run concurrently on per-fold streams")
     p, K = cfg["p"], cfg["K"]
     hbm_peak, peak_src = load_peaks()
 

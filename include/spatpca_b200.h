@@ -201,6 +201,18 @@ SPB_API int spb_engine_stage2_folds(spb_engine* e, const int* folds, int nfolds,
 SPB_API int spb_engine_stage3_folds(spb_engine* e, const int* folds, int nfolds, int index1, int index2,
                                     double* cv_rows);
 
+/* (fold k, tau1 index i) inverses as separately schedulable jobs (i in 1..n_tau1-1).  The matrix
+ * inv_sympd(2 (tau1[i] Omega - G_k) + rho_k I) (src/RcppSpatPCA.cpp:165) does not depend on the ADMM
+ * iterates, so with more GPUs than folds any GPU can build it and copy it to the fold's home GPU over
+ * NVLink (the returned pointer is a DEVICE pointer to ld x p doubles, ld = roundup(p, 16)); the home
+ * engine then marks it present and stage 1 only runs the ADMM chain.  Needs the stage-1 inverse cache
+ * (spb_engine_can_share_inverses() == 1, i.e. enough device memory).                               */
+SPB_API int spb_engine_can_share_inverses(spb_engine* e);
+SPB_API int spb_engine_prepare_fold(spb_engine* e, int k);
+SPB_API int spb_engine_inverse_buffer(spb_engine* e, int k, int i, void** dev_ptr, long long* bytes);
+SPB_API int spb_engine_build_inverse(spb_engine* e, int k, int i);
+SPB_API int spb_engine_mark_inverse(spb_engine* e, int k, int i);
+SPB_API int spb_engine_sync(spb_engine* e);
 /* Re-arm the engine for another K on the same data and grids (then prepare + the stages again).   */
 SPB_API int spb_engine_reset_k(spb_engine* e, int K);
 /* estimated_eigenfn (p x K) of the full-data fit, device -> host */

@@ -80,6 +80,12 @@ SIGNATURES = {
     "spb_engine_stage1_folds": (C.c_int, [_vp, _ip, C.c_int, _dp]),
     "spb_engine_stage2_folds": (C.c_int, [_vp, _ip, C.c_int, C.c_int, _dp]),
     "spb_engine_stage3_folds": (C.c_int, [_vp, _ip, C.c_int, C.c_int, C.c_int, _dp]),
+    "spb_engine_can_share_inverses": (C.c_int, [_vp]),
+    "spb_engine_prepare_fold": (C.c_int, [_vp, C.c_int]),
+    "spb_engine_inverse_buffer": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]),
+    "spb_engine_build_inverse": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "spb_engine_mark_inverse": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "spb_engine_sync": (C.c_int, [_vp]),
     "spb_engine_reset_k": (C.c_int, [_vp, C.c_int]),
     "spb_engine_get_eigenfn": (C.c_int, [_vp, _dp]),
     "spb_engine_get_stats": (C.c_int, [_vp, C.POINTER(CvStats)]),

@@ -283,6 +283,21 @@ int spb_engine_stage2_folds(spb_engine* e, const int* folds, int nfolds, int ind
 int spb_engine_stage3_folds(spb_engine* e, const int* folds, int nfolds, int index1, int index2, double* cv_rows) {
   SPB_ENGINE_CALL(e->impl->stage3_folds(folds, nfolds, index1, index2, cv_rows));
 }
+int spb_engine_can_share_inverses(spb_engine* e) {
+  int v = 0;
+  int rc = guarded([&] {
+    SPB_REQUIRE(e != nullptr && e->impl != nullptr, "NULL engine");
+    v = e->impl->can_share_inverses() ? 1 : 0;
+  });
+  return rc == SPB_OK ? v : rc;
+}
+int spb_engine_prepare_fold(spb_engine* e, int k) { SPB_ENGINE_CALL(e->impl->prepare_fold(k)); }
+int spb_engine_inverse_buffer(spb_engine* e, int k, int i, void** dev_ptr, long long* bytes) {
+  SPB_ENGINE_CALL(SPB_REQUIRE(dev_ptr != nullptr, "NULL output"); *dev_ptr = e->impl->inverse_buffer(k, i, bytes));
+}
+int spb_engine_build_inverse(spb_engine* e, int k, int i) { SPB_ENGINE_CALL(e->impl->build_inverse(k, i)); }
+int spb_engine_mark_inverse(spb_engine* e, int k, int i) { SPB_ENGINE_CALL(e->impl->mark_inverse(k, i)); }
+int spb_engine_sync(spb_engine* e) { SPB_ENGINE_CALL(e->impl->sync()); }
 int spb_engine_reset_k(spb_engine* e, int K) { SPB_ENGINE_CALL(e->impl->reset_k(K)); }
 int spb_engine_get_eigenfn(spb_engine* e, double* out) { SPB_ENGINE_CALL(e->impl->get_eigenfn(out)); }
 int spb_engine_get_stats(spb_engine* e, spb_cv_stats* st) { SPB_ENGINE_CALL(e->impl->get_stats(st)); }

@@ -789,6 +789,42 @@ void Engine::drop_cached_inverses(FoldData& f, int keep) {
   (void)f; (void)keep;
 }
 
+void* Engine::inverse_buffer(int k, int i, long long* bytes) {
+  SPB_REQUIRE(cache_inverses_, "the stage-1 inverse cache is disabled (not enough device memory)");
+  SPB_REQUIRE(k >= 0 && k < M_, "fold index out of range");
+  const int n1 = (int)tau1_.size();
+  SPB_REQUIRE(i >= 1 && i < n1, "tau1 index out of range");
+  FoldData& f = folds_[k];
+  if ((int)f.inv_cache.size() != n1) {
+    f.inv_cache.resize(n1);
+    f.inv_valid.assign(n1, 0);
+  }
+  f.inv_cache[i].ensure(ld_ * (size_t)p_);
+  if (bytes) *bytes = (long long)(ld_ * (size_t)p_ * sizeof(double));
+  return f.inv_cache[i].get();
+}
+
+void Engine::build_inverse(int k, int i) {
+  double* buf = static_cast<double*>(inverse_buffer(k, i, nullptr));
+  FoldData& f = folds_[k];
+  SPB_REQUIRE(f.prepared, "prepare_fold(k) must run before build_inverse(k, i)");
+  if (f.inv_valid[i]) return;
+  Lane& L = lane_of(k);
+  ensure_gram(L, k);
+  {
+    Scoped sc(L.clock, PH_INVERSE, L.res->stream);
+    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, tau1_[i], f.rho, 2.0, buf, ld_);
+    stats_.n_inverses++;
+  }
+  f.inv_valid[i] = 1;
+  L.dirty = true;
+}
+
+void Engine::mark_inverse(int k, int i) {
+  inverse_buffer(k, i, nullptr);
+  folds_[k].inv_valid[i] = 1;
+}
+
 void Engine::run_core3(Lane& L, int kind, int fold, int idx, const double* tinv, double tau2, double rho,
                        ChainState& st) {
   cudaStream_t s = L.res->stream;

@@ -133,6 +133,15 @@ class Engine {
   void stage1_fold(int k, double* cv_row) { stage1_folds(&k, 1, cv_row); }
   void stage2_fold(int k, int index1, double* cv_row) { stage2_folds(&k, 1, index1, cv_row); }
   void stage3_fold(int k, int index1, int index2, double* cv_row) { stage3_folds(&k, 1, index1, index2, cv_row); }
+  // (fold, tau1 index) inverses as separately schedulable jobs: they depend on Omega, G_k, rho_k and
+  // tau1[i] only -- not on the ADMM iterates -- so any GPU can build them and ship them to the fold's
+  // home GPU.  Require the stage-1 inverse cache (memory permitting).
+  bool can_share_inverses() const { return cache_inverses_; }
+  void prepare_fold(int k) { fold_prepare(k); }
+  void* inverse_buffer(int k, int i, long long* bytes);   // device buffer of inverse (k, tau1[i]), allocated on demand
+  void build_inverse(int k, int i);                        // enqueue on fold k's lane
+  void mark_inverse(int k, int i);                         // the buffer was filled from outside (peer copy)
+  void sync() { flush(); }
   // Re-run with another number of eigenfunctions on the same data and grids (the K-selection loop of
   // R/SpatPCA.R:23-48).  Omega, the fold gathers, the SVD starts and every cached inverse are
   // K-independent and are kept.

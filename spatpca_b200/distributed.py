@@ -27,11 +27,39 @@ def full_fit_owner(M: int, world: int) -> int:
     return max(r for r in range(world) if loads[r] == best)
 
 
+def plan_inverse_jobs(M: int, n_tau1: int, world: int):
+    """Owner rank of every stage-1 inverse job (fold k, tau1 index i), i = 1..n_tau1-1.
+
+    The job list is ordered by (i, k).  Every home rank first keeps up to ceil(total / world) jobs of
+    its own folds (no transfer needed), the remaining jobs go greedily to the least-loaded rank.
+    Deterministic: every rank computes the same plan."""
+    jobs = [(k, i) for i in range(1, n_tau1) for k in range(M)]
+    total = len(jobs)
+    quota = -(-total // world) if world > 0 else total
+    loads = [0] * world
+    owner = {}
+    for (k, i) in jobs:
+        h = fold_owner(k, world)
+        if loads[h] < quota:
+            owner[(k, i)] = h
+            loads[h] += 1
+    for job in jobs:
+        if job not in owner:
+            r = min(range(world), key=lambda q: (loads[q], q))
+            owner[job] = r
+            loads[r] += 1
+    return jobs, owner
+
+
 class Collective:
     """Minimal collective interface; `TorchCollective` wraps torch.distributed (nccl or gloo)."""
 
     rank = 0
     world = 1
+
+    def exchange(self, sends, recvs):
+        """sends: [(dst_rank, buffer)], recvs: [(src_rank, buffer)] in one global order."""
+        assert not sends and not recvs
 
     def all_gather_rows(self, rows: np.ndarray) -> np.ndarray:      # (n_local, width) -> (world, n_max, width)
         return rows[None]
@@ -65,6 +93,35 @@ class TorchCollective(Collective):
     def barrier(self):
         self.dist.barrier()
 
+    def _tensor(self, buf):
+        """A torch view of an engine buffer: either already a tensor, or (device pointer, bytes)."""
+        if isinstance(buf, self.torch.Tensor):
+            return buf
+        ptr, nbytes = buf
+
+        class _DevArray:                      # zero-copy: the NCCL transfer reads / writes the engine's buffer
+            __cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (ptr, False),
+                                        "version": 2}
+        return self.torch.as_tensor(_DevArray(), device=self.device)
+
+    def exchange(self, sends, recvs):
+        """Point-to-point copies of whole p x p inverses between GPUs (NCCL send/recv over NVLink)."""
+        ops = []
+        keep = []
+        for dst, buf in sends:
+            t = self._tensor(buf)
+            keep.append(t)
+            ops.append(self.dist.P2POp(self.dist.isend, t, dst))
+        for src, buf in recvs:
+            t = self._tensor(buf)
+            keep.append(t)
+            ops.append(self.dist.P2POp(self.dist.irecv, t, src))
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+            if self.device.type == "cuda":
+                self.torch.cuda.synchronize(self.device)
+
 
 def _gather_stage(coll: Collective, local: dict, M: int, width: int) -> np.ndarray:
     """All-gather the per-fold score rows; returns the M x width matrix in fold order."""
@@ -94,7 +151,7 @@ def _run_folds(engine, stage: str, folds, *idx) -> dict:
 
 
 def run_sharded(engine, select_index, coll: Collective, M: int, n_tau1: int, n_tau2: int, n_gamma: int,
-                tau1, tau2, gamma):
+                tau1, tau2, gamma, share_inverses: bool = True):
     """The stage sequence of spatpcaCV (:592-692) over a fold-sharded set of engines.
 
     `engine` is this rank's engine (already uploaded and prepared); `select_index(cv)` returns
@@ -105,6 +162,29 @@ def run_sharded(engine, select_index, coll: Collective, M: int, n_tau1: int, n_t
     full_rank = full_fit_owner(M, world)
 
     # ---- stage 1 ----
+    if share_inverses and world > 1 and n_tau1 > 1 and getattr(engine, "can_share_inverses", lambda: False)():
+        # the (fold, tau1) inverses do not depend on the iterates: spread them over ALL ranks (also the
+        # ones without a fold) and ship each to the fold's home rank; the chains then only iterate
+        jobs, owner = plan_inverse_jobs(M, n_tau1, world)
+        my_jobs = [j for j in jobs if owner[j] == rank]
+        for k in sorted({k for (k, _) in my_jobs} | set(mine)):
+            engine.prepare_fold(k)
+        for (k, i) in my_jobs:
+            engine.build_inverse(k, i)
+        engine.sync()
+        sends, recvs, arrived = [], [], []
+        for (k, i) in jobs:
+            src, dst = owner[(k, i)], fold_owner(k, world)
+            if src == dst:
+                continue
+            if rank == src:
+                sends.append((dst, engine.inverse_buffer(k, i)))
+            if rank == dst:
+                recvs.append((src, engine.inverse_buffer(k, i)))
+                arrived.append((k, i))
+        coll.exchange(sends, recvs)
+        for (k, i) in arrived:
+            engine.mark_inverse(k, i)
     rows = _run_folds(engine, "stage1", mine)
     index1 = 0
     if n_tau1 > 1:

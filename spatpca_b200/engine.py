@@ -199,6 +199,29 @@ class Engine:
                                                 int(index2), ptr(rows)))
         return {int(k): rows[i] for i, k in enumerate(f)}
 
+    # ---- (fold, tau1 index) inverses as jobs that any GPU can build (include/spatpca_b200.h) ----
+    def can_share_inverses(self) -> bool:
+        return check(self._lib.spb_engine_can_share_inverses(self._h)) == 1
+
+    def prepare_fold(self, k):
+        check(self._lib.spb_engine_prepare_fold(self._h, int(k)))
+
+    def inverse_buffer(self, k, i):
+        """(device pointer, bytes) of the buffer that holds / will hold inverse (fold k, tau1[i])."""
+        p = C.c_void_p()
+        nb = C.c_longlong()
+        check(self._lib.spb_engine_inverse_buffer(self._h, int(k), int(i), C.byref(p), C.byref(nb)))
+        return int(p.value), int(nb.value)
+
+    def build_inverse(self, k, i):
+        check(self._lib.spb_engine_build_inverse(self._h, int(k), int(i)))
+
+    def mark_inverse(self, k, i):
+        check(self._lib.spb_engine_mark_inverse(self._h, int(k), int(i)))
+
+    def sync(self):
+        check(self._lib.spb_engine_sync(self._h))
+
     def reset_k(self, K):
         check(self._lib.spb_engine_reset_k(self._h, int(K)))
         self.K = int(K)

@@ -19,12 +19,43 @@ class OracleBackedEngine:
     """Implements the engine interface used by `run_sharded`; records which folds it was asked for."""
 
     def __init__(self, case, want):
+        import torch
+        self.torch = torch
         self.case, self.want = case, want
         self.p, self.K = case["x"].shape[0], case["K"]
         self.asked = []
+        self.bufs, self.present, self.prepared = {}, set(), set()
+
+    # ---- stage-1 inverses as jobs (stand-ins: 8 doubles tagged with the job id) ----
+    def can_share_inverses(self):
+        return True
+
+    def prepare_fold(self, k):
+        self.prepared.add(k)
+
+    def inverse_buffer(self, k, i):
+        if (k, i) not in self.bufs:
+            self.bufs[(k, i)] = self.torch.zeros(8, dtype=self.torch.float64)
+        return self.bufs[(k, i)]
+
+    def build_inverse(self, k, i):
+        assert k in self.prepared
+        self.inverse_buffer(k, i).fill_(1000.0 * k + i)
+        self.present.add((k, i))
+        self.asked.append(("inv", k, i))
+
+    def mark_inverse(self, k, i):
+        self.present.add((k, i))
+
+    def sync(self):
+        pass
 
     def stage1_fold(self, k):
         self.asked.append(("s1", k))
+        n1 = len(self.case["tau1"])
+        for i in range(1, n1):        # every inverse of this fold must be here, with the right contents
+            assert (k, i) in self.present, (k, i)
+            assert float(self.bufs[(k, i)][3]) == 1000.0 * k + i
         return self.want["aux"]["cv1"][k].copy()
 
     def stage1_full(self, index1):
@@ -88,6 +119,10 @@ def _worker(rank, world, port, out_dir):
     ok &= my_folds == [k for k in range(case["M"]) if D.fold_owner(k, world) == rank]
     did_full = any(a[0] == "f1" for a in eng.asked)
     ok &= did_full == (rank == D.full_fit_owner(case["M"], world))
+    # the inverse jobs were spread as planned, and each rank built exactly its share
+    jobs, owner = D.plan_inverse_jobs(case["M"], len(case["tau1"]), world)
+    built = sorted((a[1], a[2]) for a in eng.asked if a[0] == "inv")
+    ok &= built == sorted(j for j in jobs if owner[j] == rank)
     with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
         f.write("ok" if ok else "FAIL %r" % (got,))
     dist.barrier()
@@ -100,6 +135,18 @@ def test_run_sharded_world2_gloo(tmp_path):
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / f"rank{r}.txt").read() == "ok"
+
+
+def test_inverse_job_plan():
+    from spatpca_b200 import distributed as D
+    for world in (1, 2, 3, 4, 8):
+        jobs, owner = D.plan_inverse_jobs(5, 11, world)
+        assert len(jobs) == 50 and set(owner) == set(jobs)
+        loads = [sum(1 for j in jobs if owner[j] == r) for r in range(world)]
+        assert max(loads) == -(-50 // world)                       # no rank above ceil(total / world)
+        kept = sum(1 for (k, i) in jobs if owner[(k, i)] == D.fold_owner(k, world))
+        assert kept >= min(50, sum(min(-(-50 // world), 10 * sum(1 for k in range(5) if D.fold_owner(k, world) == r))
+                                   for r in range(world)))
 
 
 def test_fold_placement():
