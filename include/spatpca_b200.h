@@ -244,6 +244,20 @@ SPB_API int spb_admm_core3(const double* tempinv, int p, int K, double tau2, dou
                    int maxit, double tol,
                    double* Phi, double* R, double* C, double* Lambda1, double* Lambda2,
                    int* iters);
+/* spatpcaCore2 / spatpcaCore3 as the reference calls them: the system
+ * scale * (tau1 * Omega - G) + rho * I is assembled and inverted on the device
+ * (:164-165, :397) and the ADMM loop runs on the result.  `blocks` selects how
+ * the inverse is held: 1 = explicit inverse, m > 1 = block U'DU factor over m
+ * row blocks applied as 2m - 1 matrix-stream phases (csrc/spd_inverse.cu,
+ * csrc/admm_kernels.cu), 0 = the library's default for this p.
+ * mode 2: R / Lambda1 are ignored (may be NULL); Phi is output only.         */
+SPB_API int spb_admm_system(const double* omega, const double* G, int p,
+                    double tau1, double rho, double scale, int blocks,
+                    int mode, int K, double tau2, int maxit, double tol,
+                    double* Phi, double* R, double* C, double* Lambda1, double* Lambda2,
+                    int* iters);
+/* block count the library uses for systems of order p (1 = explicit inverse) */
+SPB_API int spb_default_blocks(int p);
 /* pow(norm(Yva * (I - Phi Phi'), "fro"), 2)   (:327, :331, :400)            */
 SPB_API int spb_cv_loss(const double* Yva, int n_va, int p, const double* Phi, int K, double* loss);
 /* stage-3 losses of one fold for all gammas (:489-523)                      */
@@ -259,10 +273,16 @@ SPB_API int spb_gamma_loss(const double* Phi, int p, int K,
  * (CUDA events on the launching stream) -- the roofline probe of the
  * persistent ADMM kernel.  mode: 2 = Core2 update, 3 = Core3 update.        */
 SPB_API int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_per_iter);
+/* the same with the matrix treated as a block factor of `blocks` blocks
+ * (0 = the library's default for p, 1 = explicit inverse = spb_bench_admm)  */
+SPB_API int spb_bench_admm_blocks(int p, int K, int mode, int iters, int repeats, int blocks,
+                          double* ms_per_iter);
 /* FP64 GEMM peak of this device measured with cuBLAS DGEMM m^3 (TFLOP/s)    */
 SPB_API int spb_bench_dgemm(int m, int repeats, double* tflops);
 /* average device time of one inv_sympd at size p (assembly + potrf + potri + mirror) */
 SPB_API int spb_bench_inverse(int p, int repeats, double* ms);
+/* the same for the block factor (0 = default for p, 1 = explicit inverse)   */
+SPB_API int spb_bench_factor(int p, int repeats, int blocks, double* ms);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,17 @@
 //   barrier
 // Every reduction has a fixed shape that depends only on (p, K), never on the grid size or on
 // floating-point atomics.
+//
+// Factored systems.  Most systems of a spatpcaCV job are used for one to five iterations, so the
+// p^3 explicit inverse is the job's cost, not the stream.  With a Blocking of m > 1 blocks the
+// matrix holds the block factor F of spd_inverse.cu (A = U'DU: D_j^-1 on the diagonal blocks,
+// -U_jk above, mirrored below) and `stream` becomes 2m - 1 dependent phases over disjoint
+// rectangles of F -- together still exactly p^2 entries, 8 p^2 bytes:
+//   FWD(j), j = 0..m-1:   rows [o_j, p) x cols block j  times  z[block j]
+//                         -> w[block j] = D_j^-1 z_j,   z[rows below] += -U_j.' z_j
+//   BWD(k), k = m-1..1:   rows [0, o_k) x cols block k  times  w[block k]  -> w[rows above] += -U_.k w_k
+// (z starts as X, w ends as A^-1 X), each followed by a grid barrier, then one tile pass forms
+// Phi, T and the Gram partials.  m = 1 is the single fused phase described above.
 #include <cooperative_groups.h>
 
 #include <cmath>
@@ -52,6 +63,19 @@ struct Cfg {
   static constexpr int KG = KP * (KP + 1) / 2;         // packed Gram entries
 };
 
+// One matrix-stream phase: the rectangle rows [row0, row0 + nrows) x cols [col0, col0 + ncols) of the
+// matrix times the rows [col0, col0 + ncols) of the input vector.
+enum PhaseKind { PH_FINAL = 0, PH_FWD = 1, PH_BWD = 2 };
+struct PhaseDesc {
+  int row0, nrows, col0, ncols;
+  int kind;
+  int nrt;            // row tiles of this phase (row0 is a multiple of the tile height)
+  int S;              // segments
+  int tile0;          // first entry of this phase in the tile table / ticket counters
+  long long U;        // nrt * ncols units
+};
+constexpr int kMaxPhases = 2 * kMaxBlocks - 1;
+
 struct Params {
   const double* A;
   size_t ld;
@@ -64,8 +88,9 @@ struct Params {
   int* counters;       // [0] = tiles done, [1] = row blocks done, [2 ..] = per-tile piece tickets
   int* stat;
   double* err;
-  int nrt, S, nrb, xcap;
-  long long U;
+  int nrt, nrb, xcap;  // nrt: row tiles of the whole p rows
+  int nphases, ntiles; // ntiles: tile-table entries over all phases
+  PhaseDesc ph[kMaxPhases];
   unsigned long long* dbg;   // optional: globaltimer stamps of CTA 0 (8 per iteration), or nullptr
 };
 
@@ -141,12 +166,15 @@ __device__ __forceinline__ double make_x(int mode, double rho, double r, double 
 struct TileInfo { int s_lo, s_hi, first_w; };
 
 __device__ __forceinline__ void build_tile_table(const Params& P, TileInfo* tiles) {
-  for (int t = threadIdx.x; t < P.nrt; t += kThreads) {
-    TileInfo ti;
-    ti.s_lo = seg_of((long long)t * P.p, P.U, P.S);
-    ti.s_hi = seg_of((long long)(t + 1) * P.p - 1, P.U, P.S);
-    ti.first_w = (seg_begin(ti.s_lo, P.U, P.S) < (long long)t * P.p) ? 1 : 0;   // first piece started in tile t-1
-    tiles[t] = ti;
+  for (int f = 0; f < P.nphases; ++f) {
+    const PhaseDesc& ph = P.ph[f];
+    for (int t = threadIdx.x; t < ph.nrt; t += kThreads) {
+      TileInfo ti;
+      ti.s_lo = seg_of((long long)t * ph.ncols, ph.U, ph.S);
+      ti.s_hi = seg_of((long long)(t + 1) * ph.ncols - 1, ph.U, ph.S);
+      ti.first_w = (seg_begin(ti.s_lo, ph.U, ph.S) < (long long)t * ph.ncols) ? 1 : 0;   // first piece started in tile t-1
+      tiles[ph.tile0 + t] = ti;
+    }
   }
 }
 
@@ -237,25 +265,63 @@ __device__ int jacobi_inv_sqrt_warp(double* Am, double* Vm, double* Pm, int K, i
 }
 
 
-// ---- reduce of one row tile: partials -> Phi, T, Gram partial ------------------------------
+// ---- epilogue of one row tile: Phi, T = Phi + Lambda2 / rho, the tile's Gram partial -----------
+// phi[r][k]: unscaled rows i0 .. i0 + RPT - 1 of A^-1 X held by this thread; tg: global tile index.
+template <int KP>
+__device__ __forceinline__ void tile_epilogue(const Params& P, int tg, int i0,
+                                              const double (&phi)[Cfg<KP>::RPT][KP], double* red) {
+  using C = Cfg<KP>;
+  constexpr int RPT = C::RPT, KG = C::KG;
+  const int p = P.p, K = P.K;
+  double g[KG];
+#pragma unroll
+  for (int q = 0; q < KG; ++q) g[q] = 0.0;
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int i = i0 + r;
+    if (i < p) {
+      double tt[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        tt[k] = 0.0;
+        if (k < K) {
+          const double ph = __dmul_rn(P.scale, phi[r][k]);       // 0.5 * (...) in Core3 (:247)
+          P.Phi[(size_t)k * p + i] = ph;
+          tt[k] = __dadd_rn(ph, div_rho(__ldcg(P.L2 + (size_t)k * p + i), P.rho, P.rinv_rho));   // :169, :251
+        }
+      }
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < KP; ++a)
+#pragma unroll
+        for (int b = a; b < KP; ++b) { g[q] = fma(tt[a], tt[b], g[q]); ++q; }
+    }
+  }
+  block_reduce_store<KG>(g, red, P.gpart + (size_t)tg * KG);
+}
+
+// ---- reduce of one row tile of a phase: partials -> (FINAL) Phi, T, Gram partial; (FWD / BWD) the
+// running vectors of the factored solve -------------------------------------------------------
 // Thread tid owns rows RPT*tid .. RPT*tid+RPT-1 of the tile (the stream's ownership), so one
 // 16-byte load fetches both rows of a slot column; loads of kBatch slots are in flight together
 // and the additions run in slot order.
 template <int KP>
-__device__ __forceinline__ void reduce_tile(const Params& P, int t, const TileInfo& ti, double* red) {
+__device__ __forceinline__ void reduce_tile(const Params& P, const PhaseDesc& ph, int t, const TileInfo& ti,
+                                            double* red) {
   using C = Cfg<KP>;
-  constexpr int RPT = C::RPT, TR = C::TR, KG = C::KG;
+  constexpr int RPT = C::RPT, TR = C::TR;
   constexpr int kBatch = (KP <= 4) ? 8 : ((KP <= 8) ? 4 : 2);
   const int tid = threadIdx.x;
   const int p = P.p, K = P.K;
   const int li = RPT * tid;
-  const int i0 = t * TR + li;
+  const int i0 = ph.row0 + t * TR + li;
+  const int row_end = ph.row0 + ph.nrows;
   double phi[RPT][KP];
 #pragma unroll
   for (int r = 0; r < RPT; ++r)
 #pragma unroll
     for (int k = 0; k < KP; ++k) phi[r][k] = 0.0;
-  if (i0 < p) {
+  if (i0 < row_end) {
     for (int s = ti.s_lo; s <= ti.s_hi; s += kBatch) {
       double v[kBatch][KP][RPT];
 #pragma unroll
@@ -287,31 +353,29 @@ __device__ __forceinline__ void reduce_tile(const Params& P, int t, const TileIn
           for (int r = 0; r < RPT; ++r) phi[r][k] += v[u][k][r];     // adding +0.0 for dead slots is exact
     }
   }
-  double g[KG];
-#pragma unroll
-  for (int q = 0; q < KG; ++q) g[q] = 0.0;
+  if (ph.kind == PH_FINAL) {
+    tile_epilogue<KP>(P, t, i0, phi, red);
+    return;
+  }
+  const int diag_end = ph.col0 + ph.ncols;       // FWD: rows of the diagonal block D_j^-1
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     const int i = i0 + r;
-    if (i < p) {
-      double tt[KP];
+    if (i < row_end) {
 #pragma unroll
       for (int k = 0; k < KP; ++k) {
-        tt[k] = 0.0;
         if (k < K) {
-          const double ph = __dmul_rn(P.scale, phi[r][k]);       // 0.5 * (...) in Core3 (:247)
-          P.Phi[(size_t)k * p + i] = ph;
-          tt[k] = __dadd_rn(ph, div_rho(__ldcg(P.L2 + (size_t)k * p + i), P.rho, P.rinv_rho));   // :169, :251
+          const size_t off = (size_t)k * p + i;
+          if (ph.kind == PH_FWD) {
+            if (i < diag_end) P.Phi[off] = phi[r][k];                       // w_j = D_j^-1 z_j
+            else __stcg(P.X + off, __ldcg(P.X + off) + phi[r][k]);          // z_k -= U_jk' z_j
+          } else {
+            P.Phi[off] = __ldcg(P.Phi + off) + phi[r][k];                   // w_j -= U_jk w_k
+          }
         }
       }
-      int q = 0;
-#pragma unroll
-      for (int a = 0; a < KP; ++a)
-#pragma unroll
-        for (int b = a; b < KP; ++b) { g[q] = fma(tt[a], tt[b], g[q]); ++q; }
     }
   }
-  block_reduce_store<KG>(g, red, P.gpart + (size_t)t * KG);
 }
 
 // ---- Gram reduce + Jacobi by the CTA that finished the last tile ------------------------------
@@ -350,23 +414,28 @@ __device__ __forceinline__ void finish_polar(const Params& P, double* jA, double
   __syncthreads();
 }
 
-// ---- stream: matrix-stream partials, then ticketed tile / polar reduction ---------------------
+// ---- stream: matrix-stream partials of one phase, then ticketed tile (/ polar) reduction ---------
 template <int KP>
-__device__ __forceinline__ void stream_phase(const Params& P, double* xs, double* red, const TileInfo* tiles,
-                                             double* jA, double* jV, double* jP, int* sh_i, bool rev, int dbg_it) {
+__device__ __forceinline__ void stream_phase(const Params& P, const PhaseDesc& ph, double* xs, double* red,
+                                             const TileInfo* tiles_all, double* jA, double* jV, double* jP,
+                                             int* sh_i, bool rev, int dbg_it) {
   using C = Cfg<KP>;
   constexpr int RPT = C::RPT, TR = C::TR, KX = C::KX;
   const int tid = threadIdx.x;
   const int p = P.p, K = P.K;
-  for (int s = blockIdx.x; s < P.S; s += gridDim.x) {
-    const long long u0 = seg_begin(s, P.U, P.S), u1 = seg_begin(s + 1, P.U, P.S);
-    const int t0 = (int)(u0 / p);
+  const int nc = ph.ncols;
+  const TileInfo* tiles = tiles_all + ph.tile0;
+  int* tickets = P.counters + 2 + ph.tile0;
+  const double* vin = (ph.kind == PH_BWD) ? P.Phi : P.X;     // input vector of the phase
+  for (int s = blockIdx.x; s < ph.S; s += gridDim.x) {
+    const long long u0 = seg_begin(s, ph.U, ph.S), u1 = seg_begin(s + 1, ph.U, ph.S);
+    const int t0 = (int)(u0 / nc);
     for (int w = 0; w < 2; ++w) {
       const int t = t0 + w;
-      const long long a = max(u0, (long long)t * p), b = min(u1, (long long)(t + 1) * p);
+      const long long a = max(u0, (long long)t * nc), b = min(u1, (long long)(t + 1) * nc);
       if (a >= b) continue;
-      const int c0 = (int)(a - (long long)t * p), c1 = (int)(b - (long long)t * p);
-      const int r0 = t * TR + RPT * tid;
+      const int c0 = (int)(a - (long long)t * nc), c1 = (int)(b - (long long)t * nc);
+      const int r0 = t * TR + RPT * tid;          // row inside the phase's rectangle
       double acc[RPT][KP];
 #pragma unroll
       for (int r = 0; r < RPT; ++r)
@@ -384,13 +453,13 @@ __device__ __forceinline__ void stream_phase(const Params& P, double* xs, double
         __syncthreads();                       // previous window fully consumed
         for (int idx = tid; idx < ncols * KX; idx += kThreads) {
           const int jj = idx / KX, k = idx - jj * KX;
-          xs[idx] = (k < K) ? __ldcg(P.X + (size_t)k * p + cb + jj) : 0.0;
+          xs[idx] = (k < K) ? __ldcg(vin + (size_t)k * p + ph.col0 + cb + jj) : 0.0;
         }
         __syncthreads();
-        if (r0 < p) {
+        if (r0 < ph.nrows) {
           const long long cs = rev ? -(long long)P.ld : (long long)P.ld;
           const int xstep = rev ? -KX : KX;
-          const double* ap = P.A + (size_t)(rev ? cb + ncols - 1 : cb) * P.ld + r0;
+          const double* ap = P.A + (size_t)(ph.col0 + (rev ? cb + ncols - 1 : cb)) * P.ld + ph.row0 + r0;
           const double* xp = xs + (rev ? (ncols - 1) * KX : 0);
           int jj = 0;
           constexpr int UN = 8;
@@ -441,7 +510,7 @@ __device__ __forceinline__ void stream_phase(const Params& P, double* xs, double
       }
       // partial slot of (segment, piece): [k][row in tile]; thread tid holds rows RPT*tid .. +RPT-1
       double* slot = P.part + ((size_t)(2 * s + w) * KP) * TR;
-      if (r0 < p) {
+      if (r0 < ph.nrows) {
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
           if (k < K) {
@@ -454,14 +523,14 @@ __device__ __forceinline__ void stream_phase(const Params& P, double* xs, double
           }
         }
       }
-      if (P.dbg != nullptr && tid == 0 && dbg_it == 5) { P.dbg[256 + blockIdx.x] = gtimer(); P.dbg[256 + 512 + blockIdx.x] = P.dbg[5 * 8]; }
+      if (P.dbg != nullptr && tid == 0 && dbg_it == 5 && ph.kind == PH_FINAL) { P.dbg[256 + blockIdx.x] = gtimer(); P.dbg[256 + 512 + blockIdx.x] = P.dbg[5 * 8]; }
       // ticket: the CTA that delivers the last piece of tile t will reduce the tile -- but only after
       // it has streamed all of its own pieces, so that its reduce never delays another tile's last piece
       __threadfence();
       __syncthreads();
       if (tid == 0) {
         const int npieces = tiles[t].s_hi - tiles[t].s_lo + 1;
-        const int old = atomicAdd(P.counters + 2 + t, 1);
+        const int old = atomicAdd(tickets + t, 1);
         if (old == npieces - 1 && sh_i[2] < 8) { sh_i[3 + sh_i[2]] = t; sh_i[2] = sh_i[2] + 1; }
       }
     }
@@ -472,10 +541,14 @@ __device__ __forceinline__ void stream_phase(const Params& P, double* xs, double
     const int t = sh_i[3 + r];
     __threadfence();
     if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[123] = gtimer();
-    reduce_tile<KP>(P, t, tiles[t], red);
+    reduce_tile<KP>(P, ph, t, tiles[t], red);
     if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[124] = gtimer();
+    if (ph.kind != PH_FINAL) {
+      if (tid == 0) tickets[t] = 0;                // re-arm for the next iteration
+      continue;
+    }
     if (tid == 0) {
-      P.counters[2 + t] = 0;                       // re-arm for the next iteration
+      tickets[t] = 0;                              // re-arm for the next iteration
       __threadfence();
       const int old = atomicAdd(P.counters + 0, 1);
       sh_i[1] = (old == P.nrt - 1) ? 1 : 0;
@@ -489,6 +562,39 @@ __device__ __forceinline__ void stream_phase(const Params& P, double* xs, double
   }
   __syncthreads();
   if (tid == 0) sh_i[2] = 0;
+}
+
+// ---- factored systems only: after the last BWD phase, Phi / T / Gram partials of every row tile, then
+// the polar factor by the CTA that finishes the last tile ---------------------------------------
+template <int KP>
+__device__ __forceinline__ void epilogue_pass(const Params& P, double* red, double* jA, double* jV, double* jP,
+                                              int* sh_i) {
+  using C = Cfg<KP>;
+  constexpr int RPT = C::RPT, TR = C::TR;
+  const int tid = threadIdx.x;
+  const int p = P.p, K = P.K;
+  for (int t = blockIdx.x; t < P.nrt; t += gridDim.x) {
+    const int i0 = t * TR + RPT * tid;
+    double phi[RPT][KP];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+      for (int k = 0; k < KP; ++k)
+        phi[r][k] = (k < K && i0 + r < p) ? __ldcg(P.Phi + (size_t)k * p + i0 + r) : 0.0;
+    tile_epilogue<KP>(P, t, i0, phi, red);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int old = atomicAdd(P.counters + 0, 1);
+      sh_i[1] = (old == P.nrt - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh_i[1]) {
+      __threadfence();
+      if (tid == 0) P.counters[0] = 0;
+      finish_polar<KP>(P, jA, jV, jP);
+    }
+  }
 }
 
 // ---- update: polar factor applied, soft threshold, dual updates, norms, next X ------------------
@@ -601,7 +707,7 @@ admm_persistent_kernel(Params P) {
   build_tile_table(P, tiles);
   if (threadIdx.x == 0) sh_i[2] = 0;
   if (blockIdx.x == 0) {
-    for (int i = tid; i < P.nrt + 2; i += kThreads) P.counters[i] = 0;
+    for (int i = tid; i < P.ntiles + 2; i += kThreads) P.counters[i] = 0;
     if (tid == 0) { __stcg(P.ctrl + 0, 0.0); __stcg(P.ctrl + 1, 0.0); __stcg(P.ctrl + 2, 0.0); }
   }
   for (size_t idx = (size_t)blockIdx.x * kThreads + tid; idx < pk; idx += (size_t)gridDim.x * kThreads) {
@@ -617,7 +723,15 @@ admm_persistent_kernel(Params P) {
   for (int it = 0; it < P.maxit; ++it) {
     iters = it + 1;
     SPB_STAMP(0);
-    stream_phase<KP>(P, xs, red, tiles, jA, jV, jP, sh_i, (it & 1) != 0, it);
+    for (int f = 0; f < P.nphases; ++f) {
+      if (f > 0) { __threadfence(); grid.sync(); }
+      stream_phase<KP>(P, P.ph[f], xs, red, tiles, jA, jV, jP, sh_i, (it & 1) != 0, it);
+    }
+    if (P.nphases > 1) {
+      __threadfence();
+      grid.sync();
+      epilogue_pass<KP>(P, red, jA, jV, jP, sh_i);
+    }
     SPB_STAMP(1);
     __threadfence();
     grid.sync();
@@ -643,8 +757,9 @@ admm_persistent_kernel(Params P) {
 
 struct Geom {
   int KP, RPT, TR, KX, KG;
-  int nrt, S, nrb, xcap;
-  long long U;
+  int nrt, nrb, xcap;
+  int nphases, ntiles, smax;
+  PhaseDesc ph[kMaxPhases];
   size_t part_doubles, gpart_doubles, npart_doubles, x_doubles, ctrl_doubles, counter_ints;
   size_t smem_bytes;
 };
@@ -655,7 +770,23 @@ int pick_kp(int K) {
   return 32;
 }
 
-Geom make_geom(int p, int K) {
+// One phase over rows [row0, row0 + nrows) x cols [col0, col0 + ncols): stream-K geometry
+void add_phase(Geom& g, int kind, int row0, int nrows, int col0, int ncols) {
+  PhaseDesc& ph = g.ph[g.nphases++];
+  ph.kind = kind; ph.row0 = row0; ph.nrows = nrows; ph.col0 = col0; ph.ncols = ncols;
+  ph.nrt = ceil_div(nrows, g.TR);
+  ph.U = (long long)ph.nrt * ncols;
+  long long s = ph.U / kMinSegCols;
+  if (s > kSegTarget) s = kSegTarget;
+  if (s < ph.nrt) s = ph.nrt;
+  if (s < 1) s = 1;
+  ph.S = (int)s;
+  ph.tile0 = g.ntiles;
+  g.ntiles += ph.nrt;
+  if (ph.S > g.smax) g.smax = ph.S;
+}
+
+Geom make_geom(int p, int K, const Blocking& blk) {
   Geom g;
   g.KP = pick_kp(K);
   g.RPT = (g.KP <= 8) ? 2 : 1;
@@ -663,29 +794,39 @@ Geom make_geom(int p, int K) {
   g.KX = (g.KP + 1) & ~1;
   g.KG = g.KP * (g.KP + 1) / 2;
   g.nrt = ceil_div(p, g.TR);
-  g.U = (long long)g.nrt * p;
-  long long s = g.U / kMinSegCols;
-  if (s > kSegTarget) s = kSegTarget;
-  if (s < g.nrt) s = g.nrt;
-  if (s < 1) s = 1;
-  g.S = (int)s;
+  g.nphases = 0; g.ntiles = 0; g.smax = 1;
+  const int m = blk.m < 1 ? 1 : blk.m;
+  if (m == 1) {
+    add_phase(g, PH_FINAL, 0, p, 0, p);
+  } else {
+    SPB_REQUIRE(m <= kMaxBlocks && blk.off[0] == 0 && blk.off[m] == p, "invalid block partition");
+    for (int j = 0; j < m; ++j) {
+      SPB_REQUIRE(blk.off[j] % g.TR == 0 && blk.off[j + 1] > blk.off[j], "block offsets must be multiples of the row tile");
+      add_phase(g, PH_FWD, blk.off[j], p - blk.off[j], blk.off[j], blk.off[j + 1] - blk.off[j]);
+    }
+    for (int k = m - 1; k >= 1; --k) add_phase(g, PH_BWD, 0, blk.off[k], blk.off[k], blk.off[k + 1] - blk.off[k]);
+  }
   g.nrb = ceil_div(p, kRowBlock);
-  int maxcols = (int)((g.U + g.S - 1) / g.S) + 1;
+  int maxcols = 1;
+  for (int f = 0; f < g.nphases; ++f) {
+    const int mc = (int)((g.ph[f].U + g.ph[f].S - 1) / g.ph[f].S) + 1;
+    if (mc > maxcols) maxcols = mc;
+  }
   // leave room in the 56 KB window budget for the reduction scratch and the tile table
-  int budget = kXsBytes - (int)((8 * (size_t)g.KG + 32) * sizeof(double)) - g.nrt * 12;
+  int budget = kXsBytes - (int)((8 * (size_t)g.KG + 32) * sizeof(double)) - g.ntiles * 12;
   if (budget < 4096) budget = 4096;
   int cap = budget / (g.KX * (int)sizeof(double));
   g.xcap = maxcols < cap ? maxcols : cap;
   if (g.xcap < 1) g.xcap = 1;
   // every sub-buffer starts 128-byte aligned (the partial slots are read / written with 16-byte accesses)
-  g.part_doubles = round_up((size_t)2 * g.S * g.TR * g.KP, 16);
+  g.part_doubles = round_up((size_t)2 * g.smax * g.TR * g.KP, 16);
   g.gpart_doubles = round_up((size_t)g.nrt * g.KG, 16);
   g.npart_doubles = round_up((size_t)g.nrb * 4, 16);
   g.x_doubles = round_up((size_t)p * K, 16);
   g.ctrl_doubles = 8 + (size_t)SPB_MAX_K * SPB_MAX_K;
-  g.counter_ints = (size_t)g.nrt + 2;
+  g.counter_ints = (size_t)g.ntiles + 2;
   // dynamic shared memory: [stream window | reduction scratch (8 KG + 32) | tile table]
-  g.smem_bytes = ((size_t)g.xcap * g.KX + 8 * (size_t)g.KG + 32) * sizeof(double) + (size_t)g.nrt * 3 * sizeof(int);
+  g.smem_bytes = ((size_t)g.xcap * g.KX + 8 * (size_t)g.KG + 32) * sizeof(double) + (size_t)g.ntiles * 3 * sizeof(int);
   return g;
 }
 
@@ -714,7 +855,7 @@ void launch_instance(const Params& P, const Geom& g, cudaStream_t s) {
       max_ctas = it->second;
     }
   }
-  int want = g.S > g.nrb ? g.S : g.nrb;
+  int want = g.smax > g.nrb ? g.smax : g.nrb;
   int grid = want < max_ctas ? want : max_ctas;
   Params Pc = P;
   void* args[] = {&Pc};
@@ -726,17 +867,21 @@ void launch_instance(const Params& P, const Geom& g, cudaStream_t s) {
 }  // namespace
 
 size_t admm_workspace_bytes(int p, int K) {
-  Geom g = make_geom(p, K);
-  return (g.x_doubles + g.part_doubles + g.gpart_doubles + g.npart_doubles + g.ctrl_doubles) * sizeof(double) +
-         g.counter_ints * sizeof(int) + 64;
+  // sized for any Blocking of p: the partial slots are bounded by kSegTarget segments, the ticket
+  // counters by (2 kMaxBlocks - 1) phases of at most nrt tiles
+  Geom g = make_geom(p, K, Blocking());
+  const size_t part = round_up((size_t)2 * kSegTarget * g.TR * g.KP, 16);
+  const size_t counters = (size_t)kMaxPhases * g.nrt + 2;
+  return (g.x_doubles + (part > g.part_doubles ? part : g.part_doubles) + g.gpart_doubles + g.npart_doubles +
+          g.ctrl_doubles) * sizeof(double) + counters * sizeof(int) + 64;
 }
 
-int admm_num_segments(int p, int K) { return make_geom(p, K).S; }
+int admm_num_segments(int p, int K) { return make_geom(p, K, Blocking()).smax; }
 
 void launch_admm(const AdmmCall& c, void* ws, cudaStream_t s) {
   SPB_REQUIRE(c.K >= 1 && c.K <= SPB_MAX_K, "K must be in 1..SPB_MAX_K");
   SPB_REQUIRE(c.mode == 2 || c.mode == 3, "ADMM mode must be 2 or 3");
-  Geom g = make_geom(c.p, c.K);
+  Geom g = make_geom(c.p, c.K, c.blocks);
   Params P;
   P.A = c.Ainv; P.ld = c.ld; P.p = c.p; P.K = c.K; P.mode = c.mode; P.maxit = c.maxit;
   P.rdenom = 1.0 / std::sqrt((double)c.p * (double)c.K);
@@ -750,10 +895,12 @@ void launch_admm(const AdmmCall& c, void* ws, cudaStream_t s) {
   P.npart = w; w += g.npart_doubles;
   P.ctrl = w; w += g.ctrl_doubles;
   P.counters = reinterpret_cast<int*>(w);
-  SPB_REQUIRE(g.nrt <= 4096, "p is too large for the ADMM kernel's tile table");
+  SPB_REQUIRE(g.ntiles <= 4096, "p is too large for the ADMM kernel's tile table");
   P.stat = c.stat_slot; P.err = c.err_slot;
   P.dbg = c.dbg;
-  P.nrt = g.nrt; P.S = g.S; P.nrb = g.nrb; P.xcap = g.xcap; P.U = g.U;
+  P.nrt = g.nrt; P.nrb = g.nrb; P.xcap = g.xcap;
+  P.nphases = g.nphases; P.ntiles = g.ntiles;
+  for (int f = 0; f < kMaxPhases; ++f) P.ph[f] = g.ph[f < g.nphases ? f : 0];
   switch (g.KP) {
     case 1: launch_instance<1>(P, g, s); break;
     case 2: launch_instance<2>(P, g, s); break;

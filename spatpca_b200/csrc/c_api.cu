@@ -319,6 +319,15 @@ namespace {
 void run_cv_stages(Engine& eng, int M, const double* tau2, int n_tau1, int n_tau2, const double* gamma, int n_gamma,
                    double* cv_score_tau1, double* cv_score_tau2, double* cv_score_gamma, double* estimated_eigenfn,
                    double* selected, spb_cv_stats* stats) {
+  // SPB_TRACE=1: host wall clock at every stage boundary (the *_full calls only enqueue)
+  static const bool tr_on = [] { const char* e = std::getenv("SPB_TRACE"); return e && e[0] == '1'; }();
+  auto tr_last = std::chrono::steady_clock::now();
+  auto tr = [&](const char* label) {
+    if (!tr_on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[spb stage] %-14s +%8.3f ms\n", label, std::chrono::duration<double, std::milli>(now - tr_last).count());
+    tr_last = now;
+  };
   // stage 1 (:592-650): all folds run concurrently on their lanes
   int index1 = 0, index2 = 0, index3 = 0;
   std::vector<int> all(M);
@@ -339,7 +348,9 @@ void run_cv_stages(Engine& eng, int M, const double* tau2, int n_tau1, int n_tau
       cv_score_tau1[0] = 0.0;                                             // :649
     }
   }
+  tr("stage1_folds");
   eng.stage1_full(index1);                 // full-data fit: overlaps with the folds' stage 2
+  tr("stage1_full");
   selected[0] = eng.selected_tau1(index1);
   // stage 2 (:652-680)
   if (n_tau2 > 1) {
@@ -352,7 +363,9 @@ void run_cv_stages(Engine& eng, int M, const double* tau2, int n_tau1, int n_tau
     cv_score_tau2[0] = 0.0;                                               // :679
     selected[1] = tau2[0];                                                // :671
   }
+  tr("stage2_folds");
   eng.stage2_full(index1, index2);         // overlaps with the folds' stage 3
+  tr("stage2_full");
   // stage 3 (:682-692)
   {
     std::vector<double> rows((size_t)M * n_gamma, 0.0);
@@ -361,8 +374,10 @@ void run_cv_stages(Engine& eng, int M, const double* tau2, int n_tau1, int n_tau
     index3 = select_index_impl(cv3.data(), M, n_gamma, cv_score_gamma);
     selected[2] = (n_gamma > 1) ? gamma[index3] : gamma[0];               // :684-691
   }
+  tr("stage3_folds");
   eng.get_eigenfn(estimated_eigenfn);
   eng.get_stats(stats);
+  tr("results");
 }
 
 // 64-bit content hash (word-wise multiply-xorshift); only used to recognise "same inputs as the last call"
@@ -470,9 +485,21 @@ int spb_inv_sympd(const double* omega, const double* G, int p, double tau1, doub
   });
 }
 
+struct SystemSpec {            // build the system on the device instead of uploading an inverse
+  const double* omega;
+  const double* G;
+  double tau1, scale;
+  int blocks;
+};
+
+static Blocking blocking_for(int p, int blocks) {
+  return blocks <= 0 ? spd_blocking(p) : spd_blocking_m(p, blocks);
+}
+
 static void run_admm_host(int mode, const double* tempinv, int p, int K, double tau2, double rho, int maxit,
-                          double tol, double* Phi, double* R, double* C, double* L1, double* L2, int* iters) {
-  SPB_REQUIRE(tempinv && Phi && C && L2 && p >= 1, "invalid argument");
+                          double tol, double* Phi, double* R, double* C, double* L1, double* L2, int* iters,
+                          const SystemSpec* sys = nullptr) {
+  SPB_REQUIRE((tempinv || sys) && Phi && C && L2 && p >= 1, "invalid argument");
   SPB_REQUIRE(K >= 1 && K <= SPB_MAX_K && K <= p, "K must be in 1..min(SPB_MAX_K, p)");
   if (mode == 3) SPB_REQUIRE(R && L1, "invalid argument");
   DeviceCtx& ctx = DeviceCtx::get();
@@ -483,7 +510,19 @@ static void run_admm_host(int mode, const double* tempinv, int p, int K, double 
   DevBuf<char> ws(admm_workspace_bytes(p, K));
   ChainState st;
   st.alloc(pk);
-  upload_square(tempinv, p, A.get(), ld, s);
+  Blocking blk;
+  if (sys != nullptr) {
+    SPB_REQUIRE(sys->omega && sys->G, "invalid argument");
+    blk = blocking_for(p, sys->blocks);
+    DevBuf<double> om(ld * (size_t)p), g(ld * (size_t)p);
+    upload_square(sys->omega, p, om.get(), ld, s);
+    upload_square(sys->G, p, g.get(), ld, s);
+    launch_symmatu_inplace(om.get(), p, ld, 0.0, s);
+    Engine::spd_inverse(ctx.exec(), om.get(), ld, g.get(), ld, p, sys->tau1, rho, sys->scale, A.get(), ld, blk);
+    SPB_CUDA(cudaStreamSynchronize(s));          // om / g are released on scope exit
+  } else {
+    upload_square(tempinv, p, A.get(), ld, s);
+  }
   SPB_CUDA(cudaMemsetAsync(st.Phi.get(), 0, sizeof(double) * pk, s));
   SPB_CUDA(cudaMemcpyAsync(st.C.get(), C, sizeof(double) * pk, cudaMemcpyHostToDevice, s));
   SPB_CUDA(cudaMemcpyAsync(st.L2.get(), L2, sizeof(double) * pk, cudaMemcpyHostToDevice, s));
@@ -493,7 +532,7 @@ static void run_admm_host(int mode, const double* tempinv, int p, int K, double 
   }
   SPB_CUDA(cudaMemsetAsync(stat.get(), 0, 4 * sizeof(int), s));
   AdmmCall c;
-  c.Ainv = A.get(); c.ld = ld; c.p = p; c.K = K; c.mode = mode; c.rho = rho; c.tau2 = tau2;
+  c.Ainv = A.get(); c.blocks = blk; c.ld = ld; c.p = p; c.K = K; c.mode = mode; c.rho = rho; c.tau2 = tau2;
   c.maxit = maxit; c.tol = tol;
   c.Phi = st.Phi.get(); c.R = st.R.get(); c.C = st.C.get(); c.L1 = st.L1.get(); c.L2 = st.L2.get();
   c.stat_slot = stat.get(); c.err_slot = err.get();
@@ -525,6 +564,26 @@ int spb_admm_core3(const double* tempinv, int p, int K, double tau2, double rho,
   return guarded([&] {
     run_admm_host(3, tempinv, p, K, tau2, rho, maxit, tol, Phi, R, C, Lambda1, Lambda2, iters);
   });
+}
+
+int spb_admm_system(const double* omega, const double* G, int p, double tau1, double rho, double scale, int blocks,
+                    int mode, int K, double tau2, int maxit, double tol, double* Phi, double* R, double* C,
+                    double* Lambda1, double* Lambda2, int* iters) {
+  return guarded([&] {
+    SPB_REQUIRE(mode == 2 || mode == 3, "mode must be 2 or 3");
+    SPB_REQUIRE(blocks >= 0 && blocks <= kMaxBlocks, "blocks must be in 0..8");
+    SystemSpec sys{omega, G, tau1, scale, blocks};
+    run_admm_host(mode, nullptr, p, K, tau2, rho, maxit, tol, Phi, R, C, Lambda1, Lambda2, iters, &sys);
+  });
+}
+
+int spb_default_blocks(int p) {
+  int m = -1;
+  int rc = guarded([&] {
+    SPB_REQUIRE(p >= 1, "invalid argument");
+    m = spd_blocking(p).m;
+  });
+  return rc < 0 ? rc : m;
 }
 
 int spb_cv_loss(const double* Yva, int n_va, int p, const double* Phi, int K, double* loss) {
@@ -566,7 +625,13 @@ int spb_gamma_loss(const double* Phi, int p, int K, const double* Ytr, int n_tr,
 // device-resident benchmark hooks
 // ---------------------------------------------------------------------------------------------
 int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_per_iter) {
+  return spb_bench_admm_blocks(p, K, mode, iters, repeats, 1, ms_per_iter);
+}
+
+int spb_bench_admm_blocks(int p, int K, int mode, int iters, int repeats, int blocks, double* ms_per_iter) {
   return guarded([&] {
+    SPB_REQUIRE(blocks >= 0 && blocks <= kMaxBlocks, "blocks must be in 0..8");
+    const Blocking blk = blocking_for(p, blocks);
     SPB_REQUIRE(p >= 1 && K >= 1 && K <= SPB_MAX_K && K <= p && iters >= 1 && repeats >= 1 && ms_per_iter,
                 "invalid argument");
     SPB_REQUIRE(mode == 2 || mode == 3, "mode must be 2 or 3");
@@ -578,13 +643,14 @@ int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_pe
     DevBuf<char> ws(admm_workspace_bytes(p, K));
     ChainState st;
     st.alloc(pk);
-    // a well-posed synthetic chain: Ainv = I, C = R = first K unit vectors, duals = 0, rho = 1
+    // a well-posed synthetic chain: Ainv = I (also a valid block factor: D_j^-1 = I, U = 0),
+    // C = R = first K unit vectors, duals = 0, rho = 1
     SPB_CUDA(cudaMemsetAsync(A.get(), 0, sizeof(double) * ld * p, s));
     launch_set_identity(A.get(), p, p, ld, s);
     cudaEvent_t e0, e1;
     SPB_CUDA(cudaEventCreate(&e0));
     SPB_CUDA(cudaEventCreate(&e1));
-    double best = 1e300;
+    double sum_ms = 0.0;
     const bool dbg_on = std::getenv("SPB_ADMM_DBG") != nullptr;
     DevBuf<unsigned long long> dbg(2048);
     SPB_CUDA(cudaMemsetAsync(dbg.get(), 0, sizeof(unsigned long long) * 2048, s));
@@ -594,7 +660,7 @@ int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_pe
       SPB_CUDA(cudaMemsetAsync(st.L1.get(), 0, sizeof(double) * pk, s));
       SPB_CUDA(cudaMemsetAsync(st.L2.get(), 0, sizeof(double) * pk, s));
       AdmmCall c;
-      c.Ainv = A.get(); c.ld = ld; c.p = p; c.K = K; c.mode = mode; c.rho = 1.0; c.tau2 = 1e-3;
+      c.Ainv = A.get(); c.blocks = blk; c.ld = ld; c.p = p; c.K = K; c.mode = mode; c.rho = 1.0; c.tau2 = 1e-3;
       c.maxit = iters; c.tol = -1.0;          // never satisfied: every call runs `iters` iterations
       c.Phi = st.Phi.get(); c.R = st.R.get(); c.C = st.C.get(); c.L1 = st.L1.get(); c.L2 = st.L2.get();
       c.stat_slot = stat.get(); c.err_slot = err.get();
@@ -608,7 +674,7 @@ int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_pe
       if (sth[0] != iters || sth[1] != 0) throw Error(SPB_ERR_INTERNAL, "bench chain did not run all iterations");
       float ms = 0.f;
       SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-      if (r > 0) best = std::min(best, (double)ms / iters);   // r == 0 is the warm-up
+      if (r > 0) sum_ms += (double)ms / iters;   // r == 0 is the warm-up; the rest are averaged
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
@@ -630,7 +696,7 @@ int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_pe
               (double)(h[121] - h[120]) * 1e-3, (double)(h[122] - h[121]) * 1e-3, h[125], (double)(h[126] - h[121]) * 1e-3,
               (double)(h[127] - h[126]) * 1e-3, (double)(h[122] - h[127]) * 1e-3, (double)(h[124] - h[123]) * 1e-3);
     }
-    *ms_per_iter = best;
+    *ms_per_iter = sum_ms / repeats;
   });
 }
 
@@ -664,9 +730,13 @@ int spb_bench_dgemm(int m, int repeats, double* tflops) {
   });
 }
 
-int spb_bench_inverse(int p, int repeats, double* ms_out) {
+int spb_bench_inverse(int p, int repeats, double* ms_out) { return spb_bench_factor(p, repeats, 1, ms_out); }
+
+int spb_bench_factor(int p, int repeats, int blocks, double* ms_out) {
   return guarded([&] {
     SPB_REQUIRE(p >= 1 && repeats >= 1 && ms_out, "invalid argument");
+    SPB_REQUIRE(blocks >= 0 && blocks <= kMaxBlocks, "blocks must be in 0..8");
+    const Blocking blk = blocking_for(p, blocks);
     DeviceCtx& ctx = DeviceCtx::get();
     cudaStream_t s = ctx.stream;
     const size_t ld = padded_ld(p);
@@ -677,19 +747,19 @@ int spb_bench_inverse(int p, int repeats, double* ms_out) {
     cudaEvent_t e0, e1;
     SPB_CUDA(cudaEventCreate(&e0));
     SPB_CUDA(cudaEventCreate(&e1));
-    double best = 1e300;
+    double sum = 0.0;
     for (int r = 0; r < repeats + 1; ++r) {
       SPB_CUDA(cudaEventRecord(e0, s));
-      Engine::spd_inverse(ctx.exec(), om.get(), ld, g.get(), ld, p, 0.5, 10.0, 2.0, w.get(), ld);
+      Engine::spd_inverse(ctx.exec(), om.get(), ld, g.get(), ld, p, 0.5, 10.0, 2.0, w.get(), ld, blk);
       SPB_CUDA(cudaEventRecord(e1, s));
       ctx.sync_and_check();
       float ms = 0.f;
       SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-      if (r > 0) best = std::min(best, (double)ms);
+      if (r > 0) sum += (double)ms;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    *ms_out = best;
+    *ms_out = sum / repeats;
   });
 }
 

@@ -138,6 +138,7 @@ LaneRes::~LaneRes() {
 LaneRes& DeviceCtx::lane_res(int i) {
   while ((int)lane_pool.size() <= i) {
     std::unique_ptr<LaneRes> r(new LaneRes());
+    // (distinct stream priorities per lane were tried and change nothing: profiles/r01_notes.md section 6)
     SPB_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     SPB_CUBLAS(cublasCreate(&r->blas));
     SPB_CUBLAS(cublasSetStream(r->blas, r->stream));
@@ -334,9 +335,10 @@ void Engine::build_omega_raw(DeviceCtx& ctx, const double* x_dev, int p, int d, 
 }
 
 void Engine::spd_inverse(const Exec& ex, const double* omega_u, size_t ldo, const double* G, size_t ldg,
-                         int p, double tau1, double rho, double scale, double* out, size_t ldout) {
+                         int p, double tau1, double rho, double scale, double* out, size_t ldout,
+                         const Blocking& blk) {
   // inv_sympd(symmatu(scale*(tau1*Omega - G) + rho*I)) (:164-165, :397): upper-triangle assembly, then
-  // the inverse in full storage for the matrix-stream kernel.
+  // the inverse -- or its block factor -- in full storage for the matrix-stream kernel.
   cudaStream_t s = ex.stream;
   launch_assemble_upper(omega_u, ldo, G, ldg, p, tau1, scale, rho, out, ldout, s);
   static const bool use_cusolver = [] {
@@ -346,7 +348,8 @@ void Engine::spd_inverse(const Exec& ex, const double* omega_u, size_t ldo, cons
   if (!use_cusolver) {
     // GEMM-rate recursive Schur-complement inverse (spd_inverse.cu); result is in full storage
     ex.inv_work->ensure(spd_inverse_workspace_doubles(p));
-    spd_inverse_recursive(ex, out, p, ldout, ex.inv_work->get());
+    if (blk.m > 1) spd_factor_blocked(ex, out, p, ldout, ex.inv_work->get(), blk);
+    else spd_inverse_recursive(ex, out, p, ldout, ex.inv_work->get());
     return;
   }
   // cross-check path (SPB_INVERSE=cusolver): the reference's own algorithm class, dpotrf + dpotri.
@@ -506,6 +509,7 @@ Engine::Engine(int p, int d, int n, int M, int K, const double* tau1, int n1, co
   any_tau_ = (*std::max_element(tau1_.begin(), tau1_.end()) != 0.0) ||
              (*std::max_element(tau2_.begin(), tau2_.end()) != 0.0);
   ld_ = padded_ld((size_t)p);
+  blocks_ = spd_blocking(p);
   folds_.resize(M);
   max_grid_ = std::max({n1, n2, n3, 1});
   loss_out_.alloc((size_t)(M + 1) * max_grid_);
@@ -757,12 +761,12 @@ void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double
   if (!have) {
     ensure_gram(L, fold);
     Scoped sc(L.clock, PH_INVERSE, s);
-    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, tau1, rho, 2.0, buf, ld_);
+    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, tau1, rho, 2.0, buf, ld_, blocks_);
     stats_.n_inverses++;
   }
   if (L.next_slot >= slot_cap_) flush_lane(L);
   AdmmCall c;
-  c.Ainv = buf; c.ld = ld_; c.p = p_; c.K = K_; c.mode = 2; c.rho = rho; c.tau2 = 0.0;
+  c.Ainv = buf; c.blocks = blocks_; c.ld = ld_; c.p = p_; c.K = K_; c.mode = 2; c.rho = rho; c.tau2 = 0.0;
   c.maxit = maxit_; c.tol = tol_;
   c.Phi = st.Phi.get(); c.R = nullptr; c.C = st.C.get(); c.L1 = nullptr; c.L2 = st.L2.get();
   c.stat_slot = L.stat_slots.get() + (size_t)L.next_slot * 4;
@@ -813,7 +817,7 @@ void Engine::build_inverse(int k, int i) {
   ensure_gram(L, k);
   {
     Scoped sc(L.clock, PH_INVERSE, L.res->stream);
-    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, tau1_[i], f.rho, 2.0, buf, ld_);
+    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, tau1_[i], f.rho, 2.0, buf, ld_, blocks_);
     stats_.n_inverses++;
   }
   f.inv_valid[i] = 1;
@@ -830,7 +834,7 @@ void Engine::run_core3(Lane& L, int kind, int fold, int idx, const double* tinv,
   cudaStream_t s = L.res->stream;
   if (L.next_slot >= slot_cap_) flush_lane(L);
   AdmmCall c;
-  c.Ainv = tinv; c.ld = ld_; c.p = p_; c.K = K_; c.mode = 3; c.rho = rho; c.tau2 = tau2;
+  c.Ainv = tinv; c.blocks = blocks_; c.ld = ld_; c.p = p_; c.K = K_; c.mode = 3; c.rho = rho; c.tau2 = tau2;
   c.maxit = maxit_; c.tol = tol_;
   c.Phi = st.Phi.get(); c.R = st.R.get(); c.C = st.C.get(); c.L1 = st.L1.get(); c.L2 = st.L2.get();
   c.stat_slot = L.stat_slots.get() + (size_t)L.next_slot * 4;
@@ -881,7 +885,27 @@ void Engine::flush() {
 }
 
 // ---- stage 1 (:592-650) -----------------------------------------------------------------
-void Engine::enqueue_stage1(int k) {
+// Folds of a stage grouped into rounds of folds that live on DISTINCT lanes (folds that share a lane share
+// its chain buffers and run one after the other).  Within a round the host feeds the lanes round-robin, one
+// (fold, grid point) unit at a time: a unit is ~10^3 launches at p = 10 000, more than a stream's launch
+// queue holds, so enqueueing a whole tau path of one fold before the next would block the host on the
+// first lane and serialise the lanes (measured: 5 lanes = 1 lane at p = 10 000, profiles/r01_notes.md).
+std::vector<std::vector<int>> Engine::lane_rounds(const int* folds, int nfolds) const {
+  std::vector<std::vector<int>> per_lane(n_fold_lanes_);
+  for (int f = 0; f < nfolds; ++f) per_lane[folds[f] % n_fold_lanes_].push_back(folds[f]);
+  std::vector<std::vector<int>> rounds;
+  for (size_t r = 0;; ++r) {
+    std::vector<int> cur;
+    for (auto& q : per_lane)
+      if (r < q.size()) cur.push_back(q[r]);
+    if (cur.empty()) break;
+    rounds.push_back(cur);
+  }
+  return rounds;
+}
+
+// step 0: the fold's start (and the whole single-tau1 branch); step i >= 1: the i-th unit of the tau1 path
+void Engine::enqueue_stage1(int k, int step) {
   FoldData& f = folds_[k];
   Lane& L = lane_of(k);
   cudaStream_t s = L.res->stream;
@@ -889,6 +913,20 @@ void Engine::enqueue_stage1(int k) {
   const int n1 = (int)tau1_.size();
   const double max_tau2 = *std::max_element(tau2_.begin(), tau2_.end());
   double* scores = fold_scores(k);
+  if (step > 0) {                                                             // warm-started path :329-332
+    const int i = step;
+    double* buf = nullptr;
+    bool have = false;
+    if (cache_inverses_) {
+      f.inv_cache[i].ensure(ld_ * (size_t)p_);
+      buf = f.inv_cache[i].get();
+      have = f.inv_valid[i] != 0;              // built by an earlier run on this engine (other K)
+      f.inv_valid[i] = 1;
+    }
+    run_core2(L, 2, k, i, tau1_[i], f.rho, ch, buf, have);
+    launch_loss(L, f, ch.Phi.get(), scores + i);
+    return;
+  }
   copy_pk(s, f.Phi0.get(), f.V.get());                                        // Phi_old.cols(0, K-1) (:324)
   if (n1 > 1) {                                                               // worker :312-334
     init_lambda(s, f.Phi0.get(), f.sv, f.rho, f.L20.get());
@@ -900,18 +938,7 @@ void Engine::enqueue_stage1(int k) {
       f.inv_cache.resize(n1);
       f.inv_valid.assign(n1, 0);
     }
-    for (int i = 1; i < n1; ++i) {                                            // warm-started path :329-332
-      double* buf = nullptr;
-      bool have = false;
-      if (cache_inverses_) {
-        f.inv_cache[i].ensure(ld_ * (size_t)p_);
-        buf = f.inv_cache[i].get();
-        have = f.inv_valid[i] != 0;            // built by an earlier run on this engine (other K)
-        f.inv_valid[i] = 1;
-      }
-      run_core2(L, 2, k, i, tau1_[i], f.rho, ch, buf, have);
-      launch_loss(L, f, ch.Phi.get(), scores + i);
-    }
+    L.dirty = true;
     return;
   }
   const double sel = tau1_[0];
@@ -947,7 +974,11 @@ void Engine::stage1_folds(const int* folds, int nfolds, double* rows) {
   for (int f = 0; f < nfolds; ++f) SPB_REQUIRE(folds[f] >= 0 && folds[f] < M_, "fold index out of range");
   const int n1 = (int)tau1_.size();
   for (int f = 0; f < nfolds; ++f) fold_prepare(folds[f]);                    // SVD starts (host-synchronous)
-  for (int f = 0; f < nfolds; ++f) enqueue_stage1(folds[f]);                  // tau1 paths, concurrent lanes
+  for (const auto& round : lane_rounds(folds, nfolds)) {                      // tau1 paths, concurrent lanes
+    for (int k : round) enqueue_stage1(k, 0);
+    for (int i = 1; i < n1; ++i)
+      for (int k : round) enqueue_stage1(k, i);
+  }
   flush();
   if (n1 > 1) {
     SPB_REQUIRE(rows != nullptr, "cv rows pointer is NULL");
@@ -983,7 +1014,8 @@ void Engine::stage1_full(int index1) {
 }
 
 // ---- stage 2 (:652-680) -----------------------------------------------------------------
-void Engine::enqueue_stage2(int k, int index1) {
+// step 0: Core2 at the selected tau1 and the fold's tempinv; step 1: the tau2 path
+void Engine::enqueue_stage2(int k, int index1, int step) {
   FoldData& f = folds_[k];
   Lane& L = lane_of(k);
   cudaStream_t s = L.res->stream;
@@ -991,6 +1023,13 @@ void Engine::enqueue_stage2(int k, int index1) {
   const int n2 = (int)tau2_.size();
   const double sel1 = selected_tau1(index1);
   double* scores = fold_scores(k);
+  if (step == 1) {
+    for (int i = 0; i < n2; ++i) {                                            // :398-401
+      run_core3(L, 3, k, i, f.tinv.get(), tau2_[i], f.rho, ch);
+      launch_loss(L, f, ch.Phi.get(), scores + i);
+    }
+    return;
+  }
   copy_pk(s, ch.Phi.get(), f.Phi0.get());                                     // :389
   copy_pk(s, ch.C.get(), f.Phi0.get());
   zero_pk(s, ch.L1.get());                                                    // :390
@@ -1010,13 +1049,9 @@ void Engine::enqueue_stage2(int k, int index1) {
     Scoped sc(L.clock, PH_INVERSE, s);
     f.tinv.ensure(ld_ * (size_t)p_);
     spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, f.rho, 1.0, f.tinv.get(),
-                ld_);                                                         // :397
+                ld_, blocks_);                                                // :397
     stats_.n_inverses++;
     f.tinv_index = tag1;
-  }
-  for (int i = 0; i < n2; ++i) {                                              // :398-401
-    run_core3(L, 3, k, i, f.tinv.get(), tau2_[i], f.rho, ch);
-    launch_loss(L, f, ch.Phi.get(), scores + i);
   }
 }
 
@@ -1028,7 +1063,9 @@ void Engine::stage2_folds(const int* folds, int nfolds, int index1, double* rows
     SPB_REQUIRE(folds[f] >= 0 && folds[f] < M_, "fold index out of range");
     SPB_REQUIRE(folds_[folds[f]].prepared, "stage 1 must run before stage 2 for every fold");
   }
-  for (int f = 0; f < nfolds; ++f) enqueue_stage2(folds[f], index1);
+  for (const auto& round : lane_rounds(folds, nfolds))
+    for (int step = 0; step < 2; ++step)
+      for (int k : round) enqueue_stage2(k, index1, step);
   flush();
   SPB_REQUIRE(rows != nullptr, "cv rows pointer is NULL");
   for (int f = 0; f < nfolds; ++f)
@@ -1066,7 +1103,7 @@ void Engine::stage2_full(int index1, int index2) {
     ensure_gram(L, -1);
     Scoped sc(L.clock, PH_INVERSE, s);
     spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, rho_full_, 1.0, tbuf,
-                ld_);                                                         // :661, :673
+                ld_, blocks_);                                                // :661, :673
     stats_.n_inverses++;
   }
   copy_pk(s, full_.R.get(), full_.Phi.get());                                 // :662

@@ -166,9 +166,10 @@ class Engine {
   // building blocks shared with the kernel-level C entry points
   static void build_omega_raw(DeviceCtx& ctx, const double* x_dev, int p, int d, double* omega_dev,
                               size_t ld);
+  // blk.m == 1: explicit inverse; blk.m > 1: block U'DU factor for the multi-phase ADMM stream
   static void spd_inverse(const Exec& ex, const double* omega_u, size_t ldo, const double* G,
                           size_t ldg, int p, double tau1, double rho, double scale, double* out,
-                          size_t ldout);
+                          size_t ldout, const Blocking& blk = Blocking());
   static void gram_upper(const Exec& ex, const double* Ymat, int m, int p, double* G, size_t ldg);
   // SVD-right start: singular values (host) and the first K right singular vectors (device)
   static void svd_right(DeviceCtx& ctx, const double* Ymat, int m, int p, int K,
@@ -193,8 +194,9 @@ class Engine {
   void drop_cached_inverses(FoldData& f, int keep);
   void run_core3(Lane& L, int kind, int fold, int idx, const double* tinv, double tau2, double rho, ChainState& st);
   void launch_loss(Lane& L, const FoldData& f, const double* Phi, double* out_dev);
-  void enqueue_stage1(int k);
-  void enqueue_stage2(int k, int index1);
+  std::vector<std::vector<int>> lane_rounds(const int* folds, int nfolds) const;
+  void enqueue_stage1(int k, int step);
+  void enqueue_stage2(int k, int index1, int step);
   void enqueue_stage3_refit(int k, int index1, int index2);
   void flush_lane(Lane& L);                      // sync the lane, move its call stats to the host log
   void flush();                                  // every lane + the sticky error flag
@@ -207,6 +209,7 @@ class Engine {
   std::vector<double> tau1_, tau2_, gamma_, l2_;
   bool any_tau_ = false;
   size_t ld_ = 0;                                // leading dimension of every p x p matrix
+  Blocking blocks_;                              // partition of every system of this engine (spd_blocking(p))
   int max_grid_ = 1;
   DeviceCtx& ctx_;
 
@@ -244,6 +247,8 @@ class Engine {
 // recursive GEMM-rate SPD inverse (spd_inverse.cu): A (upper valid) -> A^-1 (full storage)
 size_t spd_inverse_workspace_doubles(int n);
 void spd_inverse_recursive(const Exec& ex, double* A, int n, size_t ld, double* workspace);
+// block U'DU factor for the multi-phase ADMM stream (blk.m == 1: the explicit inverse)
+void spd_factor_blocked(const Exec& ex, double* A, int n, size_t ld, double* workspace, const Blocking& blk);
 
 // small host helpers (host_math.cpp-like, defined in engine.cu)
 void host_jacobi_eigh(int K, std::vector<double>& A /*K x K col-major, destroyed*/,

@@ -68,8 +68,23 @@ void launch_small_rmul(const double* Phi, int p, int K, const double* Q_dev, dou
 // ---- persistent ADMM kernel (admm_kernels.cu) --------------------------------
 struct AdmmWorkspace;   // partial-sum buffers, sized by (p, K)
 
+// Row / column partition of a p x p system into m diagonal blocks (offsets are multiples of 512 = the
+// ADMM kernel's row tile, off[m] = p).  m = 1 means "explicit inverse".  m > 1 selects the block
+// U'DU factor of spd_inverse.cu, which costs ~p^3/3 + p^3/m flop instead of p^3 and is applied by the
+// ADMM kernel as 2m - 1 dependent matrix-stream phases over the same 8 p^2 bytes.
+constexpr int kMaxBlocks = 8;
+struct Blocking {
+  int m = 1;
+  int off[kMaxBlocks + 1] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+};
+// Default partition for a system of order p (SPB_FACTOR_BLOCKS overrides the block count; 1 = explicit
+// inverse everywhere).  Deterministic in p, so every rank of a multi-GPU job agrees on it.
+Blocking spd_blocking(int p);
+Blocking spd_blocking_m(int p, int m_request);
+
 struct AdmmCall {
-  const double* Ainv;   // p x p symmetric inverse, full storage
+  const double* Ainv;   // p x p symmetric, full storage: the inverse, or (blocks.m > 1) its block factor F
+  Blocking blocks;      // partition F was built with (default: m = 1, explicit inverse)
   size_t ld;
   int p, K;
   int mode;             // 2 = spatpcaCore2 / 2p update, 3 = spatpcaCore3 update

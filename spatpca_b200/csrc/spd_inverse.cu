@@ -14,6 +14,9 @@
 // exactly the "not positive definite" condition of a Cholesky factorisation and raises the same
 // status.  For the matrices of this path (rho = 10 sigma_1^2 dominates, cond ~ 1..1e3) the
 // forward error is ~cond * eps, the same class as potrf/potri.
+#include <cstdlib>
+#include <string>
+
 #include "kernels.cuh"
 #include "engine.cuh"
 
@@ -223,9 +226,77 @@ void invert(const Ctx& c, double* A, int n, size_t ld, double* W) {
   launch_symmatu_inplace(A, n, ld, 0.0, c.s);                            // full storage for the parent
 }
 
+// dst (rows x cols, ldd) <- src (rows x cols, lds)
+__global__ void copy_block_kernel(const double* __restrict__ src, size_t lds, double* __restrict__ dst, size_t ldd,
+                                  int rows, int cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  for (int j = blockIdx.y; j < cols; j += gridDim.y) dst[(size_t)j * ldd + i] = src[(size_t)j * lds + i];
+}
+
 }  // namespace
 
 size_t spd_inverse_workspace_doubles(int n) { return (size_t)n * n / 2 + 1024; }
+
+Blocking spd_blocking_m(int p, int m_request) {
+  Blocking b;
+  constexpr int kAlign = 512;                      // the ADMM kernel's largest row tile
+  int m = m_request < 1 ? 1 : (m_request > kMaxBlocks ? kMaxBlocks : m_request);
+  int bs = (int)round_up((size_t)ceil_div(p, m), kAlign);
+  m = ceil_div(p, bs);
+  b.m = m;
+  for (int j = 0; j < m; ++j) b.off[j] = j * bs;
+  b.off[m] = p;
+  return b;
+}
+
+Blocking spd_blocking(int p) {
+  // SPB_FACTOR_BLOCKS = 1 forces explicit inverses.  Default: factor whenever the p^3 work dominates;
+  // below ~3000 the job is latency-bound and the single-phase stream of an explicit inverse is cheaper.
+  static const int env_m = [] {
+    const char* e = std::getenv("SPB_FACTOR_BLOCKS");
+    return e != nullptr ? std::atoi(e) : 0;
+  }();
+  static const bool cusolver = [] {
+    const char* e = std::getenv("SPB_INVERSE");
+    return e != nullptr && std::string(e) == "cusolver";
+  }();
+  if (cusolver) return spd_blocking_m(p, 1);
+  if (env_m > 0) return spd_blocking_m(p, env_m);
+  return spd_blocking_m(p, p >= 6144 ? 4 : (p >= 3072 ? 2 : 1));
+}
+
+// A (n x n, upper triangle valid) -> block factor F of A = U'DU over the partition `blk` (full storage):
+// diagonal blocks D_j^-1 (D_j = the j-th Schur complement), blocks above the diagonal -U_jk =
+// -D_j^-1 A_jk^(j), mirrored below.  Right-looking, every flop a cuBLAS GEMM or the leaf kernel:
+// per block row  invert(D_j), Wm = -D_j^-1 R_j, trailing upper += R_j' Wm, R_j <- Wm.
+void spd_factor_blocked(const Exec& ex, double* A, int n, size_t ld, double* workspace, const Blocking& blk) {
+  Ctx c{ex.blas, ex.stream, ex.flag};
+  if (blk.m <= 1) {
+    invert(c, A, n, ld, workspace);
+    SPB_CUDA(cudaGetLastError());
+    return;
+  }
+  SPB_REQUIRE(blk.off[0] == 0 && blk.off[blk.m] == n, "invalid block partition");
+  const double zero = 0.0, mone = -1.0;
+  for (int j = 0; j < blk.m; ++j) {
+    const int o = blk.off[j], bj = blk.off[j + 1] - o, rest = n - blk.off[j + 1];
+    double* Ajj = A + (size_t)o * ld + o;
+    invert(c, Ajj, bj, ld, workspace);                                   // D_j^-1 (full)
+    if (rest <= 0) break;
+    double* Rj = Ajj + (size_t)bj * ld;                                  // bj x rest
+    double* A22 = Rj + bj;
+    double* Wm = workspace;                                              // bj x rest, ld = bj
+    SPB_CUBLAS(cublasDgemm(c.blas, CUBLAS_OP_N, CUBLAS_OP_N, bj, rest, bj, &mone, Ajj, (int)ld, Rj, (int)ld, &zero,
+                           Wm, bj));                                     // Wm = -D_j^-1 R_j
+    gemm_upper_TN(c, rest, bj, 1.0, Rj, ld, Wm, (size_t)bj, A22, ld);    // S = A22 - R_j' D_j^-1 R_j (upper)
+    copy_block_kernel<<<dim3(ceil_div(bj, 256), rest < 1024 ? rest : 1024), 256, 0, c.s>>>(Wm, (size_t)bj, Rj, ld, bj,
+                                                                                         rest);
+    count_launch();
+  }
+  launch_symmatu_inplace(A, n, ld, 0.0, c.s);                            // full storage for the stream
+  SPB_CUDA(cudaGetLastError());
+}
 
 void spd_inverse_recursive(const Exec& ex, double* A, int n, size_t ld, double* workspace) {
   Ctx c{ex.blas, ex.stream, ex.flag};

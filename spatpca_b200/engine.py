@@ -281,6 +281,27 @@ def admm_core3(tempinv, R, C_, Lambda1, Lambda2, tau2, rho, maxit, tol):
     return Phi, Rm, Cm, L1, L2, it.value
 
 
+def admm_system(omega, G, tau1, rho, scale, blocks, mode, C_, Lambda2, maxit, tol, R=None, Lambda1=None, tau2=0.0):
+    """spatpcaCore2 (mode 2) / spatpcaCore3 (mode 3) with the system built and inverted -- or block-factored
+    (`blocks` > 1; 0 = the library's default for p) -- on the device (spb_admm_system)."""
+    lib = _lib.load()
+    om, g = fmat(omega), fmat(G)
+    Cm, L2 = fmat(C_).copy(order="F"), fmat(Lambda2).copy(order="F")
+    p, K = Cm.shape
+    Rm = fmat(R).copy(order="F") if R is not None else np.zeros((p, K), order="F")
+    L1 = fmat(Lambda1).copy(order="F") if Lambda1 is not None else np.zeros((p, K), order="F")
+    Phi = np.zeros((p, K), order="F")
+    it = C.c_int(0)
+    check(lib.spb_admm_system(ptr(om), ptr(g), p, float(tau1), float(rho), float(scale), int(blocks), int(mode), K,
+                              float(tau2), int(maxit), float(tol), ptr(Phi), ptr(Rm), ptr(Cm), ptr(L1), ptr(L2),
+                              C.byref(it)))
+    return Phi, Rm, Cm, L1, L2, it.value
+
+
+def default_blocks(p):
+    return check(_lib.load().spb_default_blocks(int(p)))
+
+
 def cv_loss(Yva, Phi):
     lib = _lib.load()
     Y, P = fmat(Yva), fmat(Phi)
@@ -302,6 +323,20 @@ def bench_admm(p, K, mode, iters, repeats=3):
     lib = _lib.load()
     out = np.zeros(1)
     check(lib.spb_bench_admm(int(p), int(K), int(mode), int(iters), int(repeats), ptr(out)))
+    return float(out[0])
+
+
+def bench_admm_blocks(p, K, mode, iters, repeats=3, blocks=0):
+    lib = _lib.load()
+    out = np.zeros(1)
+    check(lib.spb_bench_admm_blocks(int(p), int(K), int(mode), int(iters), int(repeats), int(blocks), ptr(out)))
+    return float(out[0])
+
+
+def bench_factor(p, repeats=2, blocks=0):
+    lib = _lib.load()
+    out = np.zeros(1)
+    check(lib.spb_bench_factor(int(p), int(repeats), int(blocks), ptr(out)))
     return float(out[0])
 
 

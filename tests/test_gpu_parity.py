@@ -212,6 +212,51 @@ def test_core3_forced_iterations(sp):
     assert np.max(np.abs(got[0] - want[0])) / np.max(np.abs(want[0])) <= 1e-10
 
 
+# block U'DU factor + multi-phase stream (csrc/spd_inverse.cu, csrc/admm_kernels.cu) against the oracle's
+# explicit inv_sympd: same iterates to 1e-10, same iteration counts, for every block count incl. ragged
+# last blocks (p not a multiple of 512), K > 8 (256-row tiles) and blocks = 1 (explicit inverse).
+@pytest.mark.parametrize("p,K,blocks", [(1000, 5, 2), (1300, 3, 3), (1537, 5, 4), (2048, 2, 4), (1100, 12, 3),
+                                        (4100, 5, 8), (700, 4, 1)])
+def test_factored_core2_vs_oracle(sp, p, K, blocks):
+    from spatpca_b200 import engine as eng
+    Yt, G, Om, rho, Phi0, L20 = _spd_problem(p, K, 11 * p + K)
+    tau1 = 0.01
+    tr = ref.Trace()
+    wPhi, wC, wL2 = ref.core2(G, None, Phi0, L20, Om, tau1, rho, 100, 1e-4, tr)
+    gPhi, _, gC, _, gL2, it = eng.admm_system(Om, G, tau1, rho, 2.0, blocks, 2, Phi0, L20, 100, 1e-4)
+    assert it == tr.calls[0][3]
+    for g, w in ((gPhi, wPhi), (gC, wC), (gL2, wL2)):
+        assert np.max(np.abs(g - w)) / np.max(np.abs(w)) <= 1e-10
+
+
+@pytest.mark.parametrize("p,K,blocks,tau2,maxit,tol", [(1300, 3, 3, 5.0, 100, 1e-4), (1537, 5, 4, 50.0, 100, 1e-4),
+                                                       (2000, 4, 2, 2.0, 25, 0.0), (1100, 9, 3, 1.0, 100, 1e-4)])
+def test_factored_core3_vs_oracle(sp, p, K, blocks, tau2, maxit, tol):
+    from spatpca_b200 import engine as eng
+    Yt, G, Om, rho, Phi0, L20 = _spd_problem(p, K, 13 * p + K)
+    tinv = ref.core3_tempinv(Om, G, 0.01, rho)
+    R0, L10 = Phi0.copy(), np.zeros_like(Phi0)
+    tr = ref.Trace()
+    want = ref.core3(tinv, Phi0, R0, Phi0, L10, L20, tau2, rho, maxit, tol, tr)
+    got = eng.admm_system(Om, G, 0.01, rho, 1.0, blocks, 3, Phi0, L20, maxit, tol, R=R0, Lambda1=L10, tau2=tau2)
+    assert got[5] == tr.calls[0][3]
+    for g, w in zip(got[:5], want):
+        scale = max(np.max(np.abs(w)), 1e-300)
+        assert np.max(np.abs(g - w)) / scale <= 1e-10
+
+
+def test_factored_matches_explicit_and_is_reproducible(sp):
+    """blocks = 4 vs the explicit inverse on the same system; two runs of the factored path are bitwise equal."""
+    from spatpca_b200 import engine as eng
+    Yt, G, Om, rho, Phi0, L20 = _spd_problem(2100, 5, 4242)
+    a = eng.admm_system(Om, G, 0.1, rho, 2.0, 4, 2, Phi0, L20, 30, 0.0)
+    b = eng.admm_system(Om, G, 0.1, rho, 2.0, 4, 2, Phi0, L20, 30, 0.0)
+    e = eng.admm_system(Om, G, 0.1, rho, 2.0, 1, 2, Phi0, L20, 30, 0.0)
+    assert a[5] == b[5] == e[5] == 30
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and np.array_equal(a[4], b[4])
+    assert np.max(np.abs(a[0] - e[0])) / np.max(np.abs(e[0])) <= 1e-11
+
+
 @pytest.mark.parametrize("m,p,K", [(1, 10, 1), (20, 50, 2), (40, 1000, 5), (100, 333, 8), (7, 4097, 3)])
 def test_cv_loss_vs_oracle(sp, m, p, K):
     from spatpca_b200 import engine as eng
