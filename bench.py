@@ -228,12 +228,30 @@ def reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
 # ------------------------------------------------------------------------------------------------
+def protect_stdout():
+    """Rank 0 must print ONE JSON line: libraries (NCCL prints its version banner to stdout) get stderr."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -350,26 +368,42 @@ def main():
         return 0
 
     # ---- roofline of the dominant own kernel: the persistent ADMM kernel (HBM-bound) ----
+    # Timed alone with CUDA events on the library's stream, 10 forced Core3 iterations per launch, averaged
+    # over 3 launches after a warm-up launch.  The kernel applies a system either as an explicit inverse
+    # (one matrix-stream phase) or as a block U'DU factor (2m - 1 phases over the same 8 p^2 bytes); the
+    # headline figure is the mode the job uses for the tau2-path systems (stages 2-3, where ~70 % of the
+    # job's ADMM iterations run), the other modes are listed beside it.
     roof_iters = 10
-    ms_iter = eng_mod.bench_admm(p, K, 3, roof_iters, 3)
     alg_bytes_iter = 8.0 * p * p + 72.0 * p * K                     # SURVEY.md section 8d, U-iter (Core3)
+    m_path, m_stage1 = eng_mod.default_path_blocks(p), eng_mod.default_blocks(p)
+    modes = {}
+    for label, m in (("path_systems", m_path), ("stage1_systems", m_stage1), ("explicit_inverse", 1)):
+        ms = eng_mod.bench_admm_blocks(p, K, 3, roof_iters, 3, m)
+        modes[label] = {"blocks": m, "phases": 2 * m - 1, "us_per_iteration": ms * 1e3,
+                        "achieved_gbs": alg_bytes_iter / (ms * 1e-3) / 1e9,
+                        "frac": alg_bytes_iter / (ms * 1e-3) / 1e9 / hbm_peak}
+    ms_iter = modes["path_systems"]["us_per_iteration"] * 1e-3
     achieved = alg_bytes_iter / (ms_iter * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_admm_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        if tj.get("p") == p and tj.get("K") == K:
-            traffic = tj["dram_bytes_per_iteration"] * roof_iters
+        by_blocks = tj.get("dram_bytes_per_iteration_by_blocks", {})
+        if tj.get("p") == p and tj.get("K") == K and str(m_path) in by_blocks:
+            traffic = by_blocks[str(m_path)] * roof_iters
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "kernel": "admm_persistent_kernel<K> (one launch = %d Core3 iterations)" % roof_iters,
+                "traffic": traffic,
+                "kernel": "admm_persistent_kernel<K>, %d-block factor (one launch = %d Core3 iterations)" % (m_path, roof_iters),
                 "algorithmic_bytes_per_launch": alg_bytes_iter * roof_iters, "ms_per_launch": ms_iter * roof_iters,
-                "peak_source": peak_src}
-    # second bound: the p^3 SPD inverse against the FP64 GEMM rate measured in the same run
+                "peak_source": peak_src, "modes": modes}
+    # second bound: the p^3 work against the FP64 GEMM rate measured in the same run
     dgemm_tf = eng_mod.bench_dgemm(8192, 2)
     inv_ms = eng_mod.bench_inverse(p, 2)
+    fac_ms = eng_mod.bench_factor(p, 2, m_stage1)
     fp64 = {"dgemm_8192_tflops": dgemm_tf, "inverse_ms": inv_ms, "inverse_tflops_p3": (float(p) ** 3) / (inv_ms * 1e-3) / 1e12,
-            "inverse_frac_of_dgemm": (float(p) ** 3) / (inv_ms * 1e-3) / 1e12 / dgemm_tf}
+            "inverse_frac_of_dgemm": (float(p) ** 3) / (inv_ms * 1e-3) / 1e12 / dgemm_tf,
+            "factor_blocks": m_stage1, "factor_ms": fac_ms}
 
     # ---- CPU baseline on a bounded sample (oracle port, host cores) ----
     cpu = None
@@ -396,7 +430,7 @@ def main():
         "roofline": roofline, "fp64": fp64, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_job,
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

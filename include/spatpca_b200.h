@@ -258,6 +258,8 @@ SPB_API int spb_admm_system(const double* omega, const double* G, int p,
                     int* iters);
 /* block count the library uses for systems of order p (1 = explicit inverse) */
 SPB_API int spb_default_blocks(int p);
+/* the same for the systems reused along a whole tau2 path (tempinv, :397)    */
+SPB_API int spb_default_path_blocks(int p);
 /* pow(norm(Yva * (I - Phi Phi'), "fro"), 2)   (:327, :331, :400)            */
 SPB_API int spb_cv_loss(const double* Yva, int n_va, int p, const double* Phi, int K, double* loss);
 /* stage-3 losses of one fold for all gammas (:489-523)                      */

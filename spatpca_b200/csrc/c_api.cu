@@ -122,7 +122,11 @@ int spb_tps_matrix(const double* location, int p, int d, double* omega_out) {
     const size_t ld = padded_ld(p);
     DevBuf<double> x((size_t)p * d), om(ld * (size_t)p);
     SPB_CUDA(cudaMemcpyAsync(x.get(), location, sizeof(double) * p * d, cudaMemcpyHostToDevice, ctx.stream));
-    Engine::build_omega_raw(ctx, x.get(), p, d, om.get(), ld);
+    SPB_CUDA(cudaStreamSynchronize(ctx.stream));
+    OmegaRes& R = ctx.omega();
+    OmegaTemps tmp;
+    Engine::build_omega_raw(R, ctx.flag.get(), x.get(), p, d, om.get(), ld, false, tmp);   // the full raw product (:75)
+    SPB_CUDA(cudaStreamSynchronize(R.stream));
     download_square(omega_out, p, om.get(), ld, ctx.stream);
     ctx.sync_and_check();
   });
@@ -407,11 +411,26 @@ int spb_cv(const double* sxy, int p, int d, const double* Y, int n, int M, int K
   return guarded([&] {
     SPB_REQUIRE(cv_score_tau1 && cv_score_tau2 && cv_score_gamma && estimated_eigenfn && selected,
                 "NULL output");
-    Engine eng(p, d, n, M, K, tau1, n_tau1, tau2, n_tau2, gamma, n_gamma, maxit, tol, l2, n_l2);
-    eng.upload(sxy, Y, nk);
-    eng.prepare();
-    run_cv_stages(eng, M, tau2, n_tau1, n_tau2, gamma, n_gamma, cv_score_tau1, cv_score_tau2, cv_score_gamma,
-                  estimated_eigenfn, selected, stats);
+    static const bool tr_on = [] { const char* e = std::getenv("SPB_TRACE"); return e && e[0] == '1'; }();
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* label) {
+      if (!tr_on) return;
+      auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[spb cv] %-14s +%8.3f ms\n", label, std::chrono::duration<double, std::milli>(now - t0).count());
+      t0 = now;
+    };
+    {
+      Engine eng(p, d, n, M, K, tau1, n_tau1, tau2, n_tau2, gamma, n_gamma, maxit, tol, l2, n_l2);
+      lap("engine ctor");
+      eng.upload(sxy, Y, nk);
+      lap("upload");
+      eng.prepare();
+      lap("prepare");
+      run_cv_stages(eng, M, tau2, n_tau1, n_tau2, gamma, n_gamma, cv_score_tau1, cv_score_tau2, cv_score_gamma,
+                    estimated_eigenfn, selected, stats);
+      lap("stages");
+    }
+    lap("engine dtor");
   });
 }
 
@@ -582,6 +601,15 @@ int spb_default_blocks(int p) {
   int rc = guarded([&] {
     SPB_REQUIRE(p >= 1, "invalid argument");
     m = spd_blocking(p).m;
+  });
+  return rc < 0 ? rc : m;
+}
+
+int spb_default_path_blocks(int p) {
+  int m = -1;
+  int rc = guarded([&] {
+    SPB_REQUIRE(p >= 1, "invalid argument");
+    m = spd_blocking_path(p).m;
   });
   return rc < 0 ? rc : m;
 }

@@ -130,6 +130,27 @@ DeviceCtx& DeviceCtx::get() {
   return ref;
 }
 
+OmegaRes::~OmegaRes() {
+  if (solver) cusolverDnDestroy(solver);
+  if (blas) cublasDestroy(blas);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+OmegaRes& DeviceCtx::omega() {
+  if (!omega_res) {
+    std::unique_ptr<OmegaRes> r(new OmegaRes());
+    SPB_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    SPB_CUBLAS(cublasCreate(&r->blas));
+    SPB_CUBLAS(cublasSetStream(r->blas, r->stream));
+    SPB_CUBLAS(cublasSetPointerMode(r->blas, CUBLAS_POINTER_MODE_HOST));
+    SPB_CUSOLVER(cusolverDnCreate(&r->solver));
+    SPB_CUSOLVER(cusolverDnSetStream(r->solver, r->stream));
+    r->info.alloc(4);
+    omega_res = std::move(r);
+  }
+  return *omega_res;
+}
+
 LaneRes::~LaneRes() {
   if (blas) cublasDestroy(blas);
   if (stream) cudaStreamDestroy(stream);
@@ -150,6 +171,7 @@ LaneRes& DeviceCtx::lane_res(int i) {
 
 DeviceCtx::~DeviceCtx() {
   lane_pool.clear();
+  omega_res.reset();
   if (solver) cusolverDnDestroy(solver);
   if (blas) cublasDestroy(blas);
   if (stream) cudaStreamDestroy(stream);
@@ -306,32 +328,52 @@ double water_filling(const std::vector<double>& d, double total, double tv, doub
 // ---------------------------------------------------------------------------------------
 // static building blocks
 // ---------------------------------------------------------------------------------------
-void Engine::build_omega_raw(DeviceCtx& ctx, const double* x_dev, int p, int d, double* omega_dev,
-                             size_t ld) {
+void Engine::build_omega_raw(OmegaRes& R, int* flag, const double* x_dev, int p, int d, double* omega_dev,
+                             size_t ld, bool upper_only, OmegaTemps& tmp) {
   // thinPlateSplineMatrix (:58-76): Lp = top-left block of inv(L + 1e-8 I) by LU with partial
   // pivoting (the reference's dgetrf/dgetri class; here getrf + getrs on [I_p; 0]); Omega = Lp'(E Lp).
   const int q = p + d + 1;
   const size_t ldq = padded_ld(q);
-  DevBuf<double> L(ldq * (size_t)q), Bm(ldq * (size_t)p), T1(ld * (size_t)p);
-  cudaStream_t s = ctx.stream;
-  launch_tps_fill(x_dev, p, d, L.get(), ldq, 1e-8, true, s);
-  launch_set_identity(Bm.get(), q, p, ldq, s);
+  tmp.L.ensure(ldq * (size_t)q);
+  tmp.Bm.ensure(ldq * (size_t)p);
+  tmp.T1.ensure(ld * (size_t)p);
+  double *L = tmp.L.get(), *Bm = tmp.Bm.get(), *T1 = tmp.T1.get();
+  cudaStream_t s = R.stream;
+  auto lap = [&](const char* label) {               // SPB_TRACE=1: synchronous per-step timing
+    if (!trace_on()) return;
+    static auto last = std::chrono::steady_clock::now();
+    cudaStreamSynchronize(s);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[spb omega] %-12s +%8.3f ms\n", label, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+  };
+  lap("enter");
+  launch_tps_fill(x_dev, p, d, L, ldq, 1e-8, true, s);
+  launch_set_identity(Bm, q, p, ldq, s);
   int lwork = 0;
-  SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(ctx.solver, q, q, L.get(), (int)ldq, &lwork));
-  ctx.ipiv.ensure(q);
-  double* work = ctx.work((size_t)lwork);
-  SPB_CUSOLVER(cusolverDnDgetrf(ctx.solver, q, q, L.get(), (int)ldq, work, ctx.ipiv.get(), ctx.info.get()));
-  launch_check_info(ctx.info.get(), ctx.flag.get(), SPB_ERR_SINGULAR, s);
-  SPB_CUSOLVER(cusolverDnDgetrs(ctx.solver, CUBLAS_OP_N, q, p, L.get(), (int)ldq, ctx.ipiv.get(), Bm.get(),
-                                (int)ldq, ctx.info.get()));
+  SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(R.solver, q, q, L, (int)ldq, &lwork));
+  R.ipiv.ensure(q);
+  R.work.ensure((size_t)lwork);
+  SPB_CUSOLVER(cusolverDnDgetrf(R.solver, q, q, L, (int)ldq, R.work.get(), R.ipiv.get(), R.info.get()));
+  launch_check_info(R.info.get(), flag, SPB_ERR_SINGULAR, s);
+  lap("fill+getrf");
+  SPB_CUSOLVER(cusolverDnDgetrs(R.solver, CUBLAS_OP_N, q, p, L, (int)ldq, R.ipiv.get(), Bm, (int)ldq, R.info.get()));
+  lap("getrs");
   // E (p x p, zero diagonal) regenerated into L's storage
-  launch_tps_fill(x_dev, p, d, L.get(), ldq, 0.0, false, s);
+  launch_tps_fill(x_dev, p, d, L, ldq, 0.0, false, s);
   const double one = 1.0, zero = 0.0;
-  SPB_CUBLAS(cublasDgemm(ctx.blas, CUBLAS_OP_N, CUBLAS_OP_N, p, p, p, &one, L.get(), (int)ldq, Bm.get(),
-                         (int)ldq, &zero, T1.get(), (int)ld));
-  SPB_CUBLAS(cublasDgemm(ctx.blas, CUBLAS_OP_T, CUBLAS_OP_N, p, p, p, &one, Bm.get(), (int)ldq, T1.get(),
-                         (int)ld, &zero, omega_dev, (int)ld));
-  ctx.sync_and_check();     // temporaries are freed on return
+  SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, p, p, p, &one, L, (int)ldq, Bm, (int)ldq, &zero, T1,
+                         (int)ld));
+  lap("E*Lp");
+  if (upper_only) {
+    // every downstream use of Omega is under symmatu (:165, 203, 397, 621, 661, 673)
+    SPB_CUDA(cudaMemsetAsync(omega_dev, 0, sizeof(double) * ld * p, s));
+    gemm_upper_tn(R.blas, p, p, 1.0, Bm, ldq, T1, ld, omega_dev, ld);
+  } else {
+    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_T, CUBLAS_OP_N, p, p, p, &one, Bm, (int)ldq, T1, (int)ld, &zero,
+                           omega_dev, (int)ld));
+  }
+  lap("Lp'*(E*Lp)");
 }
 
 void Engine::spd_inverse(const Exec& ex, const double* omega_u, size_t ldo, const double* G, size_t ldg,
@@ -510,6 +552,7 @@ Engine::Engine(int p, int d, int n, int M, int K, const double* tau1, int n1, co
              (*std::max_element(tau2_.begin(), tau2_.end()) != 0.0);
   ld_ = padded_ld((size_t)p);
   blocks_ = spd_blocking(p);
+  blocks_path_ = spd_blocking_path(p);
   folds_.resize(M);
   max_grid_ = std::max({n1, n2, n3, 1});
   loss_out_.alloc((size_t)(M + 1) * max_grid_);
@@ -579,8 +622,10 @@ void Engine::reset_k(int K) {
 
 Engine::~Engine() {
   // lanes may still have work in flight if a call failed half-way: drain before buffers are recycled
+  if (omega_pending_) cudaStreamSynchronize(ctx_.omega().stream);
   for (auto& L : lanes_) cudaStreamSynchronize(L->res->stream);
   cudaStreamSynchronize(ctx_.stream);
+  if (omega_evt_) cudaEventDestroy(omega_evt_);
 }
 
 Lane& Engine::lane_of(int fold) {
@@ -676,15 +721,31 @@ void Engine::prepare() {
   }
   const bool need_omega = any_tau_ || tau1_.size() > 1 || tau2_.size() > 1;
   if (need_omega && !omega_ready_) {
-    Scoped sc(clock_, PH_OMEGA, s);
     omega_u_.alloc(ld_ * (size_t)p_);
     omega_diag_raw_.alloc(p_);
     if (any_tau_) {
-      SPB_CUDA(cudaMemsetAsync(omega_u_.get(), 0, sizeof(double) * ld_ * p_, s));
-      build_omega_raw(ctx_, dX_.get(), p_, d_, omega_u_.get(), ld_);          // :574
-      SPB_CUDA(cudaMemcpy2DAsync(omega_diag_raw_.get(), sizeof(double), omega_u_.get(),
-                                 (ld_ + 1) * sizeof(double), sizeof(double), p_, cudaMemcpyDeviceToDevice, s));
-      launch_symmatu_inplace(omega_u_.get(), p_, ld_, 1e-8, s);
+      // enqueued on the Omega stream and not waited for here: the fold SVD prologues run meanwhile, every
+      // lane waits for `omega_evt_` before its first use of Omega (wait_omega)
+      OmegaRes& R = ctx_.omega();
+      SPB_CUDA(cudaStreamSynchronize(s));                                     // dX_ was uploaded on the main stream
+      omega_tmp_.reset(new OmegaTemps());
+      {
+        Scoped so(clock_, PH_OMEGA, R.stream);
+        build_omega_raw(R, ctx_.flag.get(), dX_.get(), p_, d_, omega_u_.get(), ld_, true, *omega_tmp_);   // :574
+        SPB_CUDA(cudaMemcpy2DAsync(omega_diag_raw_.get(), sizeof(double), omega_u_.get(),
+                                   (ld_ + 1) * sizeof(double), sizeof(double), p_, cudaMemcpyDeviceToDevice,
+                                   R.stream));
+        launch_symmatu_inplace(omega_u_.get(), p_, ld_, 1e-8, R.stream);
+      }
+      if (!omega_evt_) SPB_CUDA(cudaEventCreateWithFlags(&omega_evt_, cudaEventDisableTiming));
+      SPB_CUDA(cudaEventRecord(omega_evt_, R.stream));
+      omega_pending_ = true;
+      for (auto& L : lanes_) L->omega_synced = false;
+      // the temporaries (3 p x p matrices) stay alive until the first flush; when memory is tight
+      // (C5: 38 GB) finish the build here instead so that the lanes can have it
+      size_t free_b = 0, total_b = 0;
+      SPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      if (3.0 * (double)ld_ * p_ * sizeof(double) > 0.15 * (double)free_b) finish_omega();
     } else {
       // all taus are zero but a grid has several entries: Omega = I (:578); tau * Omega vanishes.
       launch_set_identity(omega_u_.get(), p_, p_, ld_, s);
@@ -695,8 +756,22 @@ void Engine::prepare() {
   trace(ctx_, "prepare: done");
 }
 
+void Engine::wait_omega(Lane& L) {
+  if (!omega_pending_ || L.omega_synced) return;
+  SPB_CUDA(cudaStreamWaitEvent(L.res->stream, omega_evt_, 0));
+  L.omega_synced = true;
+}
+
+void Engine::finish_omega() {
+  if (!omega_pending_) return;
+  SPB_CUDA(cudaStreamSynchronize(ctx_.omega().stream));
+  omega_tmp_.reset();
+  omega_pending_ = false;
+}
+
 void Engine::get_omega(double* out) {
   SPB_REQUIRE(omega_ready_ && any_tau_, "no thin-plate-spline matrix has been built");
+  finish_omega();
   SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
   SPB_CUDA(cudaMemcpy2D(out, (size_t)p_ * sizeof(double), omega_u_.get(), ld_ * sizeof(double),
                         (size_t)p_ * sizeof(double), p_, cudaMemcpyDeviceToHost));
@@ -760,6 +835,7 @@ void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double
   }
   if (!have) {
     ensure_gram(L, fold);
+    wait_omega(L);
     Scoped sc(L.clock, PH_INVERSE, s);
     spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, tau1, rho, 2.0, buf, ld_, blocks_);
     stats_.n_inverses++;
@@ -815,6 +891,7 @@ void Engine::build_inverse(int k, int i) {
   if (f.inv_valid[i]) return;
   Lane& L = lane_of(k);
   ensure_gram(L, k);
+  wait_omega(L);
   {
     Scoped sc(L.clock, PH_INVERSE, L.res->stream);
     spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, tau1_[i], f.rho, 2.0, buf, ld_, blocks_);
@@ -834,7 +911,7 @@ void Engine::run_core3(Lane& L, int kind, int fold, int idx, const double* tinv,
   cudaStream_t s = L.res->stream;
   if (L.next_slot >= slot_cap_) flush_lane(L);
   AdmmCall c;
-  c.Ainv = tinv; c.blocks = blocks_; c.ld = ld_; c.p = p_; c.K = K_; c.mode = 3; c.rho = rho; c.tau2 = tau2;
+  c.Ainv = tinv; c.blocks = blocks_path_; c.ld = ld_; c.p = p_; c.K = K_; c.mode = 3; c.rho = rho; c.tau2 = tau2;
   c.maxit = maxit_; c.tol = tol_;
   c.Phi = st.Phi.get(); c.R = st.R.get(); c.C = st.C.get(); c.L1 = st.L1.get(); c.L2 = st.L2.get();
   c.stat_slot = L.stat_slots.get() + (size_t)L.next_slot * 4;
@@ -880,6 +957,7 @@ void Engine::flush_lane(Lane& L) {
 }
 
 void Engine::flush() {
+  finish_omega();
   for (auto& L : lanes_) flush_lane(*L);
   ctx_.sync_and_check();
 }
@@ -1046,10 +1124,11 @@ void Engine::enqueue_stage2(int k, int index1, int step) {
   const int tag1 = ((int)tau1_.size() > 1) ? index1 : 0;
   if (!(cache_inverses_ && f.tinv.get() != nullptr && f.tinv_index == tag1)) {
     ensure_gram(L, k);
+    wait_omega(L);
     Scoped sc(L.clock, PH_INVERSE, s);
     f.tinv.ensure(ld_ * (size_t)p_);
     spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, f.rho, 1.0, f.tinv.get(),
-                ld_, blocks_);                                                // :397
+                ld_, blocks_path_);                                           // :397
     stats_.n_inverses++;
     f.tinv_index = tag1;
   }
@@ -1101,9 +1180,10 @@ void Engine::stage2_full(int index1, int index2) {
   }
   if (!have) {
     ensure_gram(L, -1);
+    wait_omega(L);
     Scoped sc(L.clock, PH_INVERSE, s);
     spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, rho_full_, 1.0, tbuf,
-                ld_, blocks_);                                                // :661, :673
+                ld_, blocks_path_);                                           // :661, :673
     stats_.n_inverses++;
   }
   copy_pk(s, full_.R.get(), full_.Phi.get());                                 // :662

@@ -28,6 +28,21 @@ struct LaneRes {
   ~LaneRes();
 };
 
+// Stream + library handles + workspaces of the thin-plate-spline build, separate from the main stream so
+// that the Omega build (260 ms at p = 10 000) overlaps with the SVD prologues of the folds.
+struct OmegaRes {
+  cudaStream_t stream = nullptr;
+  cublasHandle_t blas = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+  DevBuf<double> work;
+  DevBuf<int> ipiv, info;
+  ~OmegaRes();
+};
+// temporaries of one build; must outlive the enqueued work
+struct OmegaTemps {
+  DevBuf<double> L, Bm, T1;
+};
+
 // Per-thread, per-device CUDA context (stream + library handles + solver workspaces).
 struct DeviceCtx {
   int device = -1;
@@ -40,6 +55,8 @@ struct DeviceCtx {
   DevBuf<int> ipiv;
   DevBuf<double> inv_work;        // workspace of the recursive SPD inverse
 
+  std::unique_ptr<OmegaRes> omega_res;
+  OmegaRes& omega();              // created on first use
   std::vector<std::unique_ptr<LaneRes>> lane_pool;
   LaneRes& lane_res(int i);       // i-th pooled lane of this device (created on first use)
   Exec exec() { return Exec{stream, blas, flag.get(), &inv_work}; }
@@ -109,6 +126,7 @@ struct Lane {
   std::vector<CallRec> pending;
   PhaseClock clock;
   bool dirty = false;              // work enqueued since the last flush
+  bool omega_synced = false;       // this lane's stream already waits for the Omega build
   Exec exec(int* flag) { return Exec{res->stream, res->blas, flag, &res->inv_work}; }
 };
 
@@ -164,8 +182,10 @@ class Engine {
   std::chrono::steady_clock::time_point t_created;
 
   // building blocks shared with the kernel-level C entry points
-  static void build_omega_raw(DeviceCtx& ctx, const double* x_dev, int p, int d, double* omega_dev,
-                              size_t ld);
+  // Enqueues thinPlateSplineMatrix on R.stream (asynchronous; `tmp` must stay alive until that stream has
+  // drained).  upper_only: only the tiles on / above the diagonal of the final product are formed.
+  static void build_omega_raw(OmegaRes& R, int* flag, const double* x_dev, int p, int d, double* omega_dev,
+                              size_t ld, bool upper_only, OmegaTemps& tmp);
   // blk.m == 1: explicit inverse; blk.m > 1: block U'DU factor for the multi-phase ADMM stream
   static void spd_inverse(const Exec& ex, const double* omega_u, size_t ldo, const double* G,
                           size_t ldg, int p, double tau1, double rho, double scale, double* out,
@@ -209,7 +229,8 @@ class Engine {
   std::vector<double> tau1_, tau2_, gamma_, l2_;
   bool any_tau_ = false;
   size_t ld_ = 0;                                // leading dimension of every p x p matrix
-  Blocking blocks_;                              // partition of every system of this engine (spd_blocking(p))
+  Blocking blocks_;                              // partition of the Core2 systems (each used by ONE ADMM call, 1-5 iterations)
+  Blocking blocks_path_;                         // partition of the tempinv systems (each reused along a whole tau2 path)
   int max_grid_ = 1;
   DeviceCtx& ctx_;
 
@@ -218,6 +239,11 @@ class Engine {
   DevBuf<double> omega_u_;                       // symmatu(Omega) + 1e-8 I
   DevBuf<double> omega_diag_raw_;                // diagonal before the ridge (for get_omega)
   bool omega_ready_ = false, omega_injected_ = false;
+  bool omega_pending_ = false;                   // the build is in flight on the Omega stream
+  cudaEvent_t omega_evt_ = nullptr;
+  std::unique_ptr<OmegaTemps> omega_tmp_;
+  void wait_omega(Lane& L);                      // first use of Omega on a lane: wait for the build
+  void finish_omega();                           // host wait + release of the temporaries
   std::vector<FoldData> folds_;
   // full-data fit (:563-567)
   std::vector<double> sv_full_;
@@ -247,6 +273,9 @@ class Engine {
 // recursive GEMM-rate SPD inverse (spd_inverse.cu): A (upper valid) -> A^-1 (full storage)
 size_t spd_inverse_workspace_doubles(int n);
 void spd_inverse_recursive(const Exec& ex, double* A, int n, size_t ld, double* workspace);
+// upper(C) += alpha * A' * B  (A, B: k x n; C: n x n symmetric result) as a recursion of cuBLAS GEMMs
+void gemm_upper_tn(cublasHandle_t blas, int n, int k, double alpha, const double* A, size_t lda, const double* B,
+                   size_t ldb, double* C, size_t ldc);
 // block U'DU factor for the multi-phase ADMM stream (blk.m == 1: the explicit inverse)
 void spd_factor_blocked(const Exec& ex, double* A, int n, size_t ld, double* workspace, const Blocking& blk);
 

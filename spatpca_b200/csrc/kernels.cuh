@@ -80,6 +80,9 @@ struct Blocking {
 // Default partition for a system of order p (SPB_FACTOR_BLOCKS overrides the block count; 1 = explicit
 // inverse everywhere).  Deterministic in p, so every rank of a multi-GPU job agrees on it.
 Blocking spd_blocking(int p);
+// Partition for systems that are reused by many ADMM calls (the tempinv of a tau2 path): fewer blocks,
+// because there the per-iteration phases cost more than the factorisation saves (SPB_PATH_BLOCKS overrides).
+Blocking spd_blocking_path(int p);
 Blocking spd_blocking_m(int p, int m_request);
 
 struct AdmmCall {

@@ -238,6 +238,12 @@ __global__ void copy_block_kernel(const double* __restrict__ src, size_t lds, do
 
 size_t spd_inverse_workspace_doubles(int n) { return (size_t)n * n / 2 + 1024; }
 
+void gemm_upper_tn(cublasHandle_t blas, int n, int k, double alpha, const double* A, size_t lda, const double* B,
+                   size_t ldb, double* C, size_t ldc) {
+  Ctx c{blas, nullptr, nullptr};
+  gemm_upper_TN(c, n, k, alpha, A, lda, B, ldb, C, ldc);
+}
+
 Blocking spd_blocking_m(int p, int m_request) {
   Blocking b;
   constexpr int kAlign = 512;                      // the ADMM kernel's largest row tile
@@ -251,8 +257,10 @@ Blocking spd_blocking_m(int p, int m_request) {
 }
 
 Blocking spd_blocking(int p) {
-  // SPB_FACTOR_BLOCKS = 1 forces explicit inverses.  Default: factor whenever the p^3 work dominates;
-  // below ~3000 the job is latency-bound and the single-phase stream of an explicit inverse is cheaper.
+  // SPB_FACTOR_BLOCKS = 1 forces explicit inverses.  Default: blocks of ~1024 rows (~1536 from p = 8192 on,
+  // at most kMaxBlocks): measured on the C3 / C4 jobs (profiles/r01_notes.md section 6) -- the factor's flop
+  // count falls as p^3/3 + p^3/m while every block adds two dependent stream phases to an ADMM iteration.
+  // Below p = 2048 everything is latency-bound and the single-phase stream of an explicit inverse wins.
   static const int env_m = [] {
     const char* e = std::getenv("SPB_FACTOR_BLOCKS");
     return e != nullptr ? std::atoi(e) : 0;
@@ -263,7 +271,23 @@ Blocking spd_blocking(int p) {
   }();
   if (cusolver) return spd_blocking_m(p, 1);
   if (env_m > 0) return spd_blocking_m(p, env_m);
-  return spd_blocking_m(p, p >= 6144 ? 4 : (p >= 3072 ? 2 : 1));
+  if (p < 2048) return spd_blocking_m(p, 1);
+  const int bs = p >= 8192 ? 1536 : 1024;
+  return spd_blocking_m(p, ceil_div(p, bs));
+}
+
+Blocking spd_blocking_path(int p) {
+  static const int env_m = [] {
+    const char* e = std::getenv("SPB_PATH_BLOCKS");
+    return e != nullptr ? std::atoi(e) : 0;
+  }();
+  if (env_m > 0) return spd_blocking_m(p, env_m);
+  // Measured at C4 (p = 10 000, ~25 iterations per path system): against spd_blocking(p)'s 7 blocks, 2 blocks
+  // cost +20 ms per job and explicit inverses +80 ms, while an iteration takes 358 us with 7 blocks, 203 us
+  // with 2 and 146 us explicit -- 2 blocks win from ~46 iterations per system on and lose little before
+  // (profiles/r01_notes.md section 6).
+  const Blocking b = spd_blocking(p);
+  return b.m <= 2 ? b : spd_blocking_m(p, 2);
 }
 
 // A (n x n, upper triangle valid) -> block factor F of A = U'DU over the partition `blk` (full storage):

@@ -302,6 +302,10 @@ def default_blocks(p):
     return check(_lib.load().spb_default_blocks(int(p)))
 
 
+def default_path_blocks(p):
+    return check(_lib.load().spb_default_path_blocks(int(p)))
+
+
 def cv_loss(Yva, Phi):
     lib = _lib.load()
     Y, P = fmat(Yva), fmat(Phi)
