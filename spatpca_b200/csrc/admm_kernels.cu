@@ -33,8 +33,10 @@
 //   FWD(j), j = 0..m-1:   rows [o_j, p) x cols block j  times  z[block j]
 //                         -> w[block j] = D_j^-1 z_j,   z[rows below] += -U_j.' z_j
 //   BWD(k), k = m-1..1:   rows [0, o_k) x cols block k  times  w[block k]  -> w[rows above] += -U_.k w_k
-// (z starts as X, w ends as A^-1 X), each followed by a grid barrier, then one tile pass forms
-// Phi, T and the Gram partials.  m = 1 is the single fused phase described above.
+// (z starts as X, w ends as A^-1 X), separated by grid barriers.  Block m-1 of w is final after FWD(m-1),
+// block k-1 after BWD(k): the reducer that finalises a row tile forms its Phi, T and Gram partial on the
+// spot, so the polar step follows the last phase without an extra pass.  m = 1 is the single fused phase
+// described above.
 #include <cooperative_groups.h>
 
 #include <cmath>
@@ -72,6 +74,7 @@ struct PhaseDesc {
   int nrt;            // row tiles of this phase (row0 is a multiple of the tile height)
   int S;              // segments
   int tile0;          // first entry of this phase in the tile table / ticket counters
+  int fin0, fin1;     // rows [fin0, fin1) of A^-1 X become final in this phase: their reducer runs the tile epilogue
   long long U;        // nrt * ncols units
 };
 constexpr int kMaxPhases = 2 * kMaxBlocks - 1;
@@ -82,10 +85,12 @@ struct Params {
   int p, K, mode, maxit;
   double rdenom;                              // 1 / sqrt(p K)
   double rho, rinv_rho, thr, tol, scale;     // rinv_rho = RN(1 / rho), computed on the host
+  double inv_scale;                           // 1 / scale (scale is 1 or 0.5, so this is exact)
   double *Phi, *R, *C, *L1, *L2;
   double *X, *part, *gpart, *npart;
   double* ctrl;        // [0] = max error, [1] = status, [2] = sweeps, [8 ..] = P (K x K)
-  int* counters;       // [0] = tiles done, [1] = row blocks done, [2 ..] = per-tile piece tickets
+  int* counters;       // [0] = tiles done, [1] = row blocks done, [2 .. 2 + ntiles) = per-tile piece tickets,
+                       // [2 + ntiles] = arrival counter of grid_barrier
   int* stat;
   double* err;
   int nrt, nrb, xcap;  // nrt: row tiles of the whole p rows
@@ -115,6 +120,26 @@ __device__ __forceinline__ double ld_stream1(const double* ptr) {
   double v;
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
   return v;
+}
+
+// Grid-wide barrier of the (co-resident) cooperative grid: one arrival counter that only grows -- the
+// barrier of generation g opens when it reaches g * gridDim.x -- so there is nothing to reset and no second
+// flag.  Same guarantees as cooperative_groups' grid.sync() for this use (all global writes before the
+// barrier are visible after it) at roughly half its latency.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++gen;
+    const unsigned int target = gen * gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while ((int)(v - target) < 0);
+    __threadfence();
+  }
+  __syncthreads();
 }
 
 __device__ __forceinline__ long long seg_begin(long long s, long long U, int S) { return s * U / S; }
@@ -310,7 +335,7 @@ __device__ __forceinline__ void reduce_tile(const Params& P, const PhaseDesc& ph
                                             double* red) {
   using C = Cfg<KP>;
   constexpr int RPT = C::RPT, TR = C::TR;
-  constexpr int kBatch = (KP <= 4) ? 8 : ((KP <= 8) ? 4 : 2);
+  constexpr int kBatch = (KP <= 4) ? 8 : ((KP <= 8) ? 4 : 2);      // slots whose loads are in flight together
   const int tid = threadIdx.x;
   const int p = P.p, K = P.K;
   const int li = RPT * tid;
@@ -358,6 +383,8 @@ __device__ __forceinline__ void reduce_tile(const Params& P, const PhaseDesc& ph
     return;
   }
   const int diag_end = ph.col0 + ph.ncols;       // FWD: rows of the diagonal block D_j^-1
+  const int tile_row0 = ph.row0 + t * TR;
+  const bool final_tile = (tile_row0 >= ph.fin0 && tile_row0 < ph.fin1);   // uniform over the CTA
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     const int i = i0 + r;
@@ -367,15 +394,20 @@ __device__ __forceinline__ void reduce_tile(const Params& P, const PhaseDesc& ph
         if (k < K) {
           const size_t off = (size_t)k * p + i;
           if (ph.kind == PH_FWD) {
-            if (i < diag_end) P.Phi[off] = phi[r][k];                       // w_j = D_j^-1 z_j
-            else __stcg(P.X + off, __ldcg(P.X + off) + phi[r][k]);          // z_k -= U_jk' z_j
+            if (i < diag_end) {                                             // w_j = D_j^-1 z_j
+              if (!final_tile) P.Phi[off] = phi[r][k];
+            } else {
+              __stcg(P.X + off, __ldcg(P.X + off) + phi[r][k]);             // z_k -= U_jk' z_j
+            }
           } else {
-            P.Phi[off] = __ldcg(P.Phi + off) + phi[r][k];                   // w_j -= U_jk w_k
+            phi[r][k] = __ldcg(P.Phi + off) + phi[r][k];                    // w_j -= U_jk w_k
+            if (!final_tile) P.Phi[off] = phi[r][k];
           }
         }
       }
     }
   }
+  if (final_tile) tile_epilogue<KP>(P, tile_row0 / TR, i0, phi, red);       // Phi = scale * w, T, Gram partial
 }
 
 // ---- Gram reduce + Jacobi by the CTA that finished the last tile ------------------------------
@@ -427,6 +459,9 @@ __device__ __forceinline__ void stream_phase(const Params& P, const PhaseDesc& p
   const TileInfo* tiles = tiles_all + ph.tile0;
   int* tickets = P.counters + 2 + ph.tile0;
   const double* vin = (ph.kind == PH_BWD) ? P.Phi : P.X;     // input vector of the phase
+  // the input block of a BWD phase was finalised earlier, i.e. it already holds Phi = scale * w with
+  // scale = 1 or 0.5: undo the (exact, power-of-two) scaling on the way into shared memory
+  const double vscale = (ph.kind == PH_BWD) ? P.inv_scale : 1.0;
   for (int s = blockIdx.x; s < ph.S; s += gridDim.x) {
     const long long u0 = seg_begin(s, ph.U, ph.S), u1 = seg_begin(s + 1, ph.U, ph.S);
     const int t0 = (int)(u0 / nc);
@@ -453,7 +488,7 @@ __device__ __forceinline__ void stream_phase(const Params& P, const PhaseDesc& p
         __syncthreads();                       // previous window fully consumed
         for (int idx = tid; idx < ncols * KX; idx += kThreads) {
           const int jj = idx / KX, k = idx - jj * KX;
-          xs[idx] = (k < K) ? __ldcg(vin + (size_t)k * p + ph.col0 + cb + jj) : 0.0;
+          xs[idx] = (k < K) ? vscale * __ldcg(vin + (size_t)k * p + ph.col0 + cb + jj) : 0.0;
         }
         __syncthreads();
         if (r0 < ph.nrows) {
@@ -543,7 +578,8 @@ __device__ __forceinline__ void stream_phase(const Params& P, const PhaseDesc& p
     if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[123] = gtimer();
     reduce_tile<KP>(P, ph, t, tiles[t], red);
     if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[124] = gtimer();
-    if (ph.kind != PH_FINAL) {
+    const int tile_row0 = ph.row0 + t * TR;
+    if (ph.kind != PH_FINAL && !(tile_row0 >= ph.fin0 && tile_row0 < ph.fin1)) {
       if (tid == 0) tickets[t] = 0;                // re-arm for the next iteration
       continue;
     }
@@ -562,39 +598,6 @@ __device__ __forceinline__ void stream_phase(const Params& P, const PhaseDesc& p
   }
   __syncthreads();
   if (tid == 0) sh_i[2] = 0;
-}
-
-// ---- factored systems only: after the last BWD phase, Phi / T / Gram partials of every row tile, then
-// the polar factor by the CTA that finishes the last tile ---------------------------------------
-template <int KP>
-__device__ __forceinline__ void epilogue_pass(const Params& P, double* red, double* jA, double* jV, double* jP,
-                                              int* sh_i) {
-  using C = Cfg<KP>;
-  constexpr int RPT = C::RPT, TR = C::TR;
-  const int tid = threadIdx.x;
-  const int p = P.p, K = P.K;
-  for (int t = blockIdx.x; t < P.nrt; t += gridDim.x) {
-    const int i0 = t * TR + RPT * tid;
-    double phi[RPT][KP];
-#pragma unroll
-    for (int r = 0; r < RPT; ++r)
-#pragma unroll
-      for (int k = 0; k < KP; ++k)
-        phi[r][k] = (k < K && i0 + r < p) ? __ldcg(P.Phi + (size_t)k * p + i0 + r) : 0.0;
-    tile_epilogue<KP>(P, t, i0, phi, red);
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      const int old = atomicAdd(P.counters + 0, 1);
-      sh_i[1] = (old == P.nrt - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (sh_i[1]) {
-      __threadfence();
-      if (tid == 0) P.counters[0] = 0;
-      finish_polar<KP>(P, jA, jV, jP);
-    }
-  }
 }
 
 // ---- update: polar factor applied, soft threshold, dual updates, norms, next X ------------------
@@ -707,7 +710,7 @@ admm_persistent_kernel(Params P) {
   build_tile_table(P, tiles);
   if (threadIdx.x == 0) sh_i[2] = 0;
   if (blockIdx.x == 0) {
-    for (int i = tid; i < P.ntiles + 2; i += kThreads) P.counters[i] = 0;
+    for (int i = tid; i < P.ntiles + 3; i += kThreads) P.counters[i] = 0;
     if (tid == 0) { __stcg(P.ctrl + 0, 0.0); __stcg(P.ctrl + 1, 0.0); __stcg(P.ctrl + 2, 0.0); }
   }
   for (size_t idx = (size_t)blockIdx.x * kThreads + tid; idx < pk; idx += (size_t)gridDim.x * kThreads) {
@@ -715,8 +718,11 @@ admm_persistent_kernel(Params P) {
     const double l1 = (P.mode == 3) ? P.L1[idx] : 0.0;
     __stcg(P.X + idx, make_x(P.mode, P.rho, r, P.C[idx], l1, P.L2[idx]));
   }
+  // the first barrier is cooperative_groups' own: it also orders the counter reset above
   __threadfence();
   grid.sync();
+  unsigned int* bar = reinterpret_cast<unsigned int*>(P.counters + 2 + P.ntiles);
+  unsigned int bar_gen = 0;
 
   int iters = 0, status = 0;
   double errmax = 0.0, sweeps = 0.0;
@@ -724,24 +730,19 @@ admm_persistent_kernel(Params P) {
     iters = it + 1;
     SPB_STAMP(0);
     for (int f = 0; f < P.nphases; ++f) {
-      if (f > 0) { __threadfence(); grid.sync(); }
+      if (f > 0) grid_barrier(bar, bar_gen);
+      if (P.dbg != nullptr && it == 3 && tid == 0 && blockIdx.x < 4) P.dbg[1024 + blockIdx.x * 64 + f * 2] = gtimer();
       stream_phase<KP>(P, P.ph[f], xs, red, tiles, jA, jV, jP, sh_i, (it & 1) != 0, it);
-    }
-    if (P.nphases > 1) {
-      __threadfence();
-      grid.sync();
-      epilogue_pass<KP>(P, red, jA, jV, jP, sh_i);
+      if (P.dbg != nullptr && it == 3 && tid == 0 && blockIdx.x < 4) P.dbg[1024 + blockIdx.x * 64 + f * 2 + 1] = gtimer();
     }
     SPB_STAMP(1);
-    __threadfence();
-    grid.sync();
+    grid_barrier(bar, bar_gen);
     SPB_STAMP(2);
     status = (int)__ldcg(P.ctrl + 1);
     sweeps = __ldcg(P.ctrl + 2);
     update_phase<KP>(P, red, jP, sh_d, sh_i);
     SPB_STAMP(3);
-    __threadfence();
-    grid.sync();
+    grid_barrier(bar, bar_gen);
     SPB_STAMP(4);
     errmax = __ldcg(P.ctrl + 0);
     if (status != 0) break;
@@ -782,6 +783,7 @@ void add_phase(Geom& g, int kind, int row0, int nrows, int col0, int ncols) {
   if (s < 1) s = 1;
   ph.S = (int)s;
   ph.tile0 = g.ntiles;
+  ph.fin0 = ph.fin1 = 0;
   g.ntiles += ph.nrt;
   if (ph.S > g.smax) g.smax = ph.S;
 }
@@ -804,7 +806,11 @@ Geom make_geom(int p, int K, const Blocking& blk) {
       SPB_REQUIRE(blk.off[j] % g.TR == 0 && blk.off[j + 1] > blk.off[j], "block offsets must be multiples of the row tile");
       add_phase(g, PH_FWD, blk.off[j], p - blk.off[j], blk.off[j], blk.off[j + 1] - blk.off[j]);
     }
-    for (int k = m - 1; k >= 1; --k) add_phase(g, PH_BWD, 0, blk.off[k], blk.off[k], blk.off[k + 1] - blk.off[k]);
+    g.ph[m - 1].fin0 = blk.off[m - 1]; g.ph[m - 1].fin1 = p;                // w_{m-1} = D^-1 z is final
+    for (int k = m - 1; k >= 1; --k) {
+      add_phase(g, PH_BWD, 0, blk.off[k], blk.off[k], blk.off[k + 1] - blk.off[k]);
+      g.ph[g.nphases - 1].fin0 = blk.off[k - 1]; g.ph[g.nphases - 1].fin1 = blk.off[k];   // block k-1 is final
+    }
   }
   g.nrb = ceil_div(p, kRowBlock);
   int maxcols = 1;
@@ -824,7 +830,7 @@ Geom make_geom(int p, int K, const Blocking& blk) {
   g.npart_doubles = round_up((size_t)g.nrb * 4, 16);
   g.x_doubles = round_up((size_t)p * K, 16);
   g.ctrl_doubles = 8 + (size_t)SPB_MAX_K * SPB_MAX_K;
-  g.counter_ints = (size_t)g.ntiles + 2;
+  g.counter_ints = (size_t)g.ntiles + 3;
   // dynamic shared memory: [stream window | reduction scratch (8 KG + 32) | tile table]
   g.smem_bytes = ((size_t)g.xcap * g.KX + 8 * (size_t)g.KG + 32) * sizeof(double) + (size_t)g.ntiles * 3 * sizeof(int);
   return g;
@@ -871,7 +877,7 @@ size_t admm_workspace_bytes(int p, int K) {
   // counters by (2 kMaxBlocks - 1) phases of at most nrt tiles
   Geom g = make_geom(p, K, Blocking());
   const size_t part = round_up((size_t)2 * kSegTarget * g.TR * g.KP, 16);
-  const size_t counters = (size_t)kMaxPhases * g.nrt + 2;
+  const size_t counters = (size_t)kMaxPhases * g.nrt + 3;
   return (g.x_doubles + (part > g.part_doubles ? part : g.part_doubles) + g.gpart_doubles + g.npart_doubles +
           g.ctrl_doubles) * sizeof(double) + counters * sizeof(int) + 64;
 }
@@ -887,6 +893,7 @@ void launch_admm(const AdmmCall& c, void* ws, cudaStream_t s) {
   P.rdenom = 1.0 / std::sqrt((double)c.p * (double)c.K);
   P.rho = c.rho; P.rinv_rho = 1.0 / c.rho; P.thr = c.tau2 / c.rho; P.tol = c.tol;
   P.scale = (c.mode == 3) ? 0.5 : 1.0;
+  P.inv_scale = 1.0 / P.scale;
   P.Phi = c.Phi; P.R = c.R; P.C = c.C; P.L1 = c.L1; P.L2 = c.L2;
   double* w = reinterpret_cast<double*>(ws);
   P.X = w; w += g.x_doubles;

@@ -714,6 +714,14 @@ int spb_bench_admm_blocks(int p, int K, int mode, int iters, int repeats, int bl
         for (int b = 0; b < 296; ++b) fprintf(stderr, " %.0f", ((double)h[256 + b] - (double)h[5 * 8]) * 1e-3);
         fprintf(stderr, "\n");
       }
+      for (int b = 0; b < 4 && blk.m > 1; ++b) {
+        fprintf(stderr, "[admm dbg] CTA %d, iteration 3, per phase (us): busy / wait-at-barrier:", b);
+        const unsigned long long* q = h + 1024 + b * 64;
+        for (int f = 0; f < 2 * blk.m - 1; ++f)
+          fprintf(stderr, " %.1f/%.1f", (double)(q[2 * f + 1] - q[2 * f]) * 1e-3,
+                  f + 1 < 2 * blk.m - 1 ? (double)(q[2 * f + 2] - q[2 * f + 1]) * 1e-3 : 0.0);
+        fprintf(stderr, "\n");
+      }
       const char* names[8] = {"stream+reduce", "barrier1", "update", "barrier2", "(loop)", "-", "-", "-"};
       for (int it = 2; it < std::min(iters, 6); ++it) {
         fprintf(stderr, "[admm dbg] p=%d K=%d it=%d:", p, K, it);
