@@ -123,9 +123,9 @@ def run_job_resident(sp, case, coll=None):
     if coll is not None and coll.world > 1:
         coll.barrier()
     t0 = time.perf_counter()
-    eng.prepare()
     if coll is None:
         coll = D.Collective()
+    D.prepare_sharded(eng, coll)           # Omega shared by the ranks (column blocks over NCCL), SVD start
     res = D.run_sharded(eng, sp.select_index, coll, M, len(case["tau1"]), len(case["tau2"]), len(case["gamma"]),
                         case["tau1"], case["tau2"], case["gamma"],
                         share_inverses=os.environ.get("SPB_SHARE_INVERSES", "1") != "0")
@@ -285,8 +285,8 @@ def main():
 
     case, cfg = make_workload(args.config)
     cfg["parallelism"] = (f"folds sharded over {world} rank(s), full-data fit on rank {D.full_fit_owner(case['M'], world)}; "
-                          "stage-1 (fold, tau1) inverses spread over all ranks and shipped to the fold's rank by NCCL "
-                          "send/recv" if world > 1 else "one GPU: folds run concurrently on per-fold streams")
+                          "stage-1 (fold, tau1) systems spread over all ranks and shipped to the fold's rank by NCCL "
+                          "send/recv; Omega built in column blocks (one per rank) exchanged by NCCL broadcast" if world > 1 else "one GPU: folds run concurrently on per-fold streams")
     p, K = cfg["p"], cfg["K"]
     hbm_peak, peak_src = load_peaks()
 

@@ -213,6 +213,19 @@ SPB_API int spb_engine_inverse_buffer(spb_engine* e, int k, int i, void** dev_pt
 SPB_API int spb_engine_build_inverse(spb_engine* e, int k, int i);
 SPB_API int spb_engine_mark_inverse(spb_engine* e, int k, int i);
 SPB_API int spb_engine_sync(spb_engine* e);
+/* thinPlateSplineMatrix (:58-76) built in column blocks so that the GPUs of one job share its p^3 work:
+ * every rank calls omega_begin (LU of the bordered system; *needed = 0 when this job needs no Omega or it
+ * is already there -- then skip the rest), solves its columns [c0, c1) of Lp, receives the other ranks'
+ * column blocks into omega_buffer(which = 0), forms its columns of Omega = Lp'(E Lp), receives the other
+ * ranks' into omega_buffer(which = 1), and calls omega_finish (mirror + the ridge of :574).  The buffers
+ * are device memory; call omega_sync before handing them to a collective.  spb_engine_prepare() afterwards
+ * only adds the full-data SVD start.                                          */
+SPB_API int spb_engine_omega_begin(spb_engine* e, int* needed);
+SPB_API int spb_engine_omega_solve_cols(spb_engine* e, int c0, int c1);
+SPB_API int spb_engine_omega_product_cols(spb_engine* e, int c0, int c1);
+SPB_API int spb_engine_omega_buffer(spb_engine* e, int which, int c0, int c1, void** dev_ptr, long long* bytes);
+SPB_API int spb_engine_omega_sync(spb_engine* e);
+SPB_API int spb_engine_omega_finish(spb_engine* e);
 /* Re-arm the engine for another K on the same data and grids (then prepare + the stages again).   */
 SPB_API int spb_engine_reset_k(spb_engine* e, int K);
 /* estimated_eigenfn (p x K) of the full-data fit, device -> host */

@@ -86,6 +86,12 @@ SIGNATURES = {
     "spb_engine_build_inverse": (C.c_int, [_vp, C.c_int, C.c_int]),
     "spb_engine_mark_inverse": (C.c_int, [_vp, C.c_int, C.c_int]),
     "spb_engine_sync": (C.c_int, [_vp]),
+    "spb_engine_omega_begin": (C.c_int, [_vp, _ip]),
+    "spb_engine_omega_solve_cols": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "spb_engine_omega_product_cols": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "spb_engine_omega_buffer": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]),
+    "spb_engine_omega_sync": (C.c_int, [_vp]),
+    "spb_engine_omega_finish": (C.c_int, [_vp]),
     "spb_engine_reset_k": (C.c_int, [_vp, C.c_int]),
     "spb_engine_get_eigenfn": (C.c_int, [_vp, _dp]),
     "spb_engine_get_stats": (C.c_int, [_vp, C.POINTER(CvStats)]),

@@ -302,6 +302,18 @@ int spb_engine_inverse_buffer(spb_engine* e, int k, int i, void** dev_ptr, long 
 int spb_engine_build_inverse(spb_engine* e, int k, int i) { SPB_ENGINE_CALL(e->impl->build_inverse(k, i)); }
 int spb_engine_mark_inverse(spb_engine* e, int k, int i) { SPB_ENGINE_CALL(e->impl->mark_inverse(k, i)); }
 int spb_engine_sync(spb_engine* e) { SPB_ENGINE_CALL(e->impl->sync()); }
+int spb_engine_omega_begin(spb_engine* e, int* needed) {
+  SPB_ENGINE_CALL(SPB_REQUIRE(needed != nullptr, "NULL output"); *needed = e->impl->omega_begin() ? 1 : 0);
+}
+int spb_engine_omega_solve_cols(spb_engine* e, int c0, int c1) { SPB_ENGINE_CALL(e->impl->omega_solve_cols(c0, c1)); }
+int spb_engine_omega_product_cols(spb_engine* e, int c0, int c1) {
+  SPB_ENGINE_CALL(e->impl->omega_product_cols(c0, c1));
+}
+int spb_engine_omega_buffer(spb_engine* e, int which, int c0, int c1, void** dev_ptr, long long* bytes) {
+  SPB_ENGINE_CALL(SPB_REQUIRE(dev_ptr != nullptr, "NULL output"); *dev_ptr = e->impl->omega_buffer(which, c0, c1, bytes));
+}
+int spb_engine_omega_sync(spb_engine* e) { SPB_ENGINE_CALL(e->impl->omega_stream_sync()); }
+int spb_engine_omega_finish(spb_engine* e) { SPB_ENGINE_CALL(e->impl->omega_finish()); }
 int spb_engine_reset_k(spb_engine* e, int K) { SPB_ENGINE_CALL(e->impl->reset_k(K)); }
 int spb_engine_get_eigenfn(spb_engine* e, double* out) { SPB_ENGINE_CALL(e->impl->get_eigenfn(out)); }
 int spb_engine_get_stats(spb_engine* e, spb_cv_stats* st) { SPB_ENGINE_CALL(e->impl->get_stats(st)); }

@@ -769,6 +769,103 @@ void Engine::finish_omega() {
   omega_pending_ = false;
 }
 
+// ---- column-sharded Omega build (multi-GPU) ---------------------------------------------------
+bool Engine::omega_begin() {
+  SPB_REQUIRE(dX_.get() != nullptr, "upload() must be called before omega_begin()");
+  const bool need_omega = any_tau_ || tau1_.size() > 1 || tau2_.size() > 1;
+  if (!need_omega || !any_tau_ || omega_ready_) return false;
+  OmegaRes& R = ctx_.omega();
+  cudaStream_t s = R.stream;
+  SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
+  const int q = p_ + d_ + 1;
+  const size_t ldq = padded_ld(q);
+  omega_u_.alloc(ld_ * (size_t)p_);
+  omega_diag_raw_.alloc(p_);
+  omega_tmp_.reset(new OmegaTemps());
+  OmegaTemps& T = *omega_tmp_;
+  T.L.ensure(ldq * (size_t)q);
+  T.Bm.ensure(ldq * (size_t)p_);
+  T.T1.ensure(ld_ * (size_t)p_);
+  clock_.begin(PH_OMEGA, s);
+  launch_tps_fill(dX_.get(), p_, d_, T.L.get(), ldq, 1e-8, true, s);
+  launch_set_identity(T.Bm.get(), q, p_, ldq, s);
+  int lwork = 0;
+  SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(R.solver, q, q, T.L.get(), (int)ldq, &lwork));
+  R.ipiv.ensure(q);
+  R.work.ensure((size_t)lwork);
+  SPB_CUSOLVER(cusolverDnDgetrf(R.solver, q, q, T.L.get(), (int)ldq, R.work.get(), R.ipiv.get(), R.info.get()));
+  launch_check_info(R.info.get(), ctx_.flag.get(), SPB_ERR_SINGULAR, s);
+  clock_.end(s);
+  omega_cols_open_ = true;
+  return true;
+}
+
+void Engine::omega_solve_cols(int c0, int c1) {
+  SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
+  SPB_REQUIRE(c0 >= 0 && c0 <= c1 && c1 <= p_, "column range out of bounds");
+  if (c0 == c1) return;
+  OmegaRes& R = ctx_.omega();
+  const int q = p_ + d_ + 1;
+  const size_t ldq = padded_ld(q);
+  clock_.begin(PH_OMEGA, R.stream);
+  SPB_CUSOLVER(cusolverDnDgetrs(R.solver, CUBLAS_OP_N, q, c1 - c0, omega_tmp_->L.get(), (int)ldq, R.ipiv.get(),
+                                omega_tmp_->Bm.get() + (size_t)c0 * ldq, (int)ldq, R.info.get()));
+  clock_.end(R.stream);
+}
+
+void Engine::omega_product_cols(int c0, int c1) {
+  SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
+  SPB_REQUIRE(c0 >= 0 && c0 <= c1 && c1 <= p_, "column range out of bounds");
+  OmegaRes& R = ctx_.omega();
+  cudaStream_t s = R.stream;
+  const int q = p_ + d_ + 1;
+  const size_t ldq = padded_ld(q);
+  OmegaTemps& T = *omega_tmp_;
+  clock_.begin(PH_OMEGA, s);
+  // E (p x p, zero diagonal) regenerated into L's storage: the LU factors are not needed any more
+  launch_tps_fill(dX_.get(), p_, d_, T.L.get(), ldq, 0.0, false, s);
+  if (c1 > c0) {
+    const double one = 1.0, zero = 0.0;
+    const int nc = c1 - c0;
+    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, p_, nc, p_, &one, T.L.get(), (int)ldq,
+                           T.Bm.get() + (size_t)c0 * ldq, (int)ldq, &zero, T.T1.get() + (size_t)c0 * ld_, (int)ld_));
+    // rows 0 .. c1-1 of these columns cover the upper triangle, which is all that is used downstream
+    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_T, CUBLAS_OP_N, c1, nc, p_, &one, T.Bm.get(), (int)ldq,
+                           T.T1.get() + (size_t)c0 * ld_, (int)ld_, &zero, omega_u_.get() + (size_t)c0 * ld_, (int)ld_));
+  }
+  clock_.end(s);
+}
+
+void* Engine::omega_buffer(int which, int c0, int c1, long long* bytes) {
+  SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
+  SPB_REQUIRE(c0 >= 0 && c0 <= c1 && c1 <= p_, "column range out of bounds");
+  SPB_REQUIRE(which == 0 || which == 1, "which must be 0 (Lp) or 1 (Omega)");
+  const size_t ldq = padded_ld(p_ + d_ + 1);
+  if (which == 0) {
+    if (bytes) *bytes = (long long)((size_t)(c1 - c0) * ldq * sizeof(double));
+    return omega_tmp_->Bm.get() + (size_t)c0 * ldq;
+  }
+  if (bytes) *bytes = (long long)((size_t)(c1 - c0) * ld_ * sizeof(double));
+  return omega_u_.get() + (size_t)c0 * ld_;
+}
+
+void Engine::omega_stream_sync() { SPB_CUDA(cudaStreamSynchronize(ctx_.omega().stream)); }
+
+void Engine::omega_finish() {
+  SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
+  OmegaRes& R = ctx_.omega();
+  cudaStream_t s = R.stream;
+  clock_.begin(PH_OMEGA, s);
+  SPB_CUDA(cudaMemcpy2DAsync(omega_diag_raw_.get(), sizeof(double), omega_u_.get(), (ld_ + 1) * sizeof(double),
+                             sizeof(double), p_, cudaMemcpyDeviceToDevice, s));
+  launch_symmatu_inplace(omega_u_.get(), p_, ld_, 1e-8, s);                 // symmatu + the ridge of :574
+  clock_.end(s);
+  SPB_CUDA(cudaStreamSynchronize(s));
+  omega_tmp_.reset();
+  omega_cols_open_ = false;
+  omega_ready_ = true;
+}
+
 void Engine::get_omega(double* out) {
   SPB_REQUIRE(omega_ready_ && any_tau_, "no thin-plate-spline matrix has been built");
   finish_omega();

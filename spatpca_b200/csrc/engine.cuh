@@ -160,6 +160,17 @@ class Engine {
   void build_inverse(int k, int i);                        // enqueue on fold k's lane
   void mark_inverse(int k, int i);                         // the buffer was filled from outside (peer copy)
   void sync() { flush(); }
+  // Omega built in column blocks, so that the ranks of a multi-GPU job share its 6.7 p^3 flop (SURVEY.md
+  // section 8e): every rank factors the bordered system (omega_begin), solves for its own columns of
+  // Lp (omega_solve_cols), receives the others' (omega_buffer(0, ..) is the NCCL target), forms its
+  // columns of Omega = Lp'(E Lp) (omega_product_cols), receives the others' (omega_buffer(1, ..)) and
+  // finishes with the mirror + ridge (omega_finish).  Returns false from omega_begin when no Omega is needed.
+  bool omega_begin();
+  void omega_solve_cols(int c0, int c1);
+  void omega_product_cols(int c0, int c1);
+  void* omega_buffer(int which, int c0, int c1, long long* bytes);   // which: 0 = Lp columns, 1 = Omega columns
+  void omega_stream_sync();
+  void omega_finish();
   // Re-run with another number of eigenfunctions on the same data and grids (the K-selection loop of
   // R/SpatPCA.R:23-48).  Omega, the fold gathers, the SVD starts and every cached inverse are
   // K-independent and are kept.
@@ -242,6 +253,7 @@ class Engine {
   bool omega_pending_ = false;                   // the build is in flight on the Omega stream
   cudaEvent_t omega_evt_ = nullptr;
   std::unique_ptr<OmegaTemps> omega_tmp_;
+  bool omega_cols_open_ = false;                 // between omega_begin() and omega_finish()
   void wait_omega(Lane& L);                      // first use of Omega on a lane: wait for the build
   void finish_omega();                           // host wait + release of the temporaries
   std::vector<FoldData> folds_;

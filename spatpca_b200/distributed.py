@@ -61,6 +61,9 @@ class Collective:
         """sends: [(dst_rank, buffer)], recvs: [(src_rank, buffer)] in one global order."""
         assert not sends and not recvs
 
+    def broadcast_buffers(self, items):
+        """items: [(src_rank, buffer)] in one global order; every rank ends with every buffer filled."""
+
     def all_gather_rows(self, rows: np.ndarray) -> np.ndarray:      # (n_local, width) -> (world, n_max, width)
         return rows[None]
 
@@ -104,6 +107,21 @@ class TorchCollective(Collective):
                                         "version": 2}
         return self.torch.as_tensor(_DevArray(), device=self.device)
 
+    def broadcast_buffers(self, items):
+        """Column blocks of Lp / Omega: one NCCL broadcast per owner, straight from / into the engines' buffers."""
+        keep = []
+        works = []
+        for src, buf in items:
+            t = self._tensor(buf)
+            if t.numel() == 0:
+                continue
+            keep.append(t)
+            works.append(self.dist.broadcast(t, src=src, async_op=True))
+        for w in works:
+            w.wait()
+        if self.device.type == "cuda":
+            self.torch.cuda.synchronize(self.device)
+
     def exchange(self, sends, recvs):
         """Point-to-point copies of whole p x p inverses between GPUs (NCCL send/recv over NVLink)."""
         ops = []
@@ -121,6 +139,32 @@ class TorchCollective(Collective):
                 req.wait()
             if self.device.type == "cuda":
                 self.torch.cuda.synchronize(self.device)
+
+
+def omega_columns(p: int, world: int):
+    """Column range [c0, c1) of Lp / Omega owned by each rank: an even split, boundaries on multiples of 16
+    (128-byte aligned columns blocks for the GEMMs)."""
+    step = -(-p // world)
+    step = -(-step // 16) * 16
+    return [(min(p, r * step), min(p, (r + 1) * step)) for r in range(world)]
+
+
+def prepare_sharded(engine, coll: Collective):
+    """`engine.prepare()` with thinPlateSplineMatrix (:58-76) shared by the ranks: the LU of the bordered
+    system is replicated, the p solves and the two p^3 products are split by columns, and the column
+    blocks travel by NCCL broadcast (2 x 8 p^2 bytes in total).  With one rank, or an engine without the
+    column API, this is `engine.prepare()`."""
+    if coll.world > 1 and hasattr(engine, "omega_begin") and engine.omega_begin():
+        cols = omega_columns(engine.p, coll.world)
+        c0, c1 = cols[coll.rank]
+        engine.omega_solve_cols(c0, c1)
+        engine.omega_sync()
+        coll.broadcast_buffers([(r, engine.omega_buffer(0, a, b)) for r, (a, b) in enumerate(cols)])
+        engine.omega_product_cols(c0, c1)
+        engine.omega_sync()
+        coll.broadcast_buffers([(r, engine.omega_buffer(1, a, b)) for r, (a, b) in enumerate(cols)])
+        engine.omega_finish()
+    engine.prepare()
 
 
 def _gather_stage(coll: Collective, local: dict, M: int, width: int) -> np.ndarray:

@@ -216,6 +216,30 @@ class Engine:
     def build_inverse(self, k, i):
         check(self._lib.spb_engine_build_inverse(self._h, int(k), int(i)))
 
+    # ---- Omega in column blocks (shared between the ranks of a multi-GPU job) ----
+    def omega_begin(self):
+        needed = C.c_int(0)
+        check(self._lib.spb_engine_omega_begin(self._h, C.byref(needed)))
+        return bool(needed.value)
+
+    def omega_solve_cols(self, c0, c1):
+        check(self._lib.spb_engine_omega_solve_cols(self._h, int(c0), int(c1)))
+
+    def omega_product_cols(self, c0, c1):
+        check(self._lib.spb_engine_omega_product_cols(self._h, int(c0), int(c1)))
+
+    def omega_buffer(self, which, c0, c1):
+        p = C.c_void_p()
+        nb = C.c_longlong()
+        check(self._lib.spb_engine_omega_buffer(self._h, int(which), int(c0), int(c1), C.byref(p), C.byref(nb)))
+        return int(p.value), int(nb.value)
+
+    def omega_sync(self):
+        check(self._lib.spb_engine_omega_sync(self._h))
+
+    def omega_finish(self):
+        check(self._lib.spb_engine_omega_finish(self._h))
+
     def mark_inverse(self, k, i):
         check(self._lib.spb_engine_mark_inverse(self._h, int(k), int(i)))
 

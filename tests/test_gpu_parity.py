@@ -415,6 +415,36 @@ def test_error_paths(sp):
 # ---------------------------------------------------------------------------------------------
 # determinism, sharding, larger sizes
 # ---------------------------------------------------------------------------------------------
+def test_omega_column_blocks_match_single_build(sp):
+    """The multi-GPU Omega build (column blocks of Lp and of Lp'(E Lp)) against the one-piece build: the same
+    LU, the same right-hand sides, only the GEMM / solve calls are split by columns."""
+    from spatpca_b200 import distributed as D
+    case = make_case("irregular2d_small")
+    p = case["x"].shape[0]
+    whole = sp.thinPlateSplineMatrix(case["x"])
+    e = sp.Engine(p, case["x"].shape[1], case["Y"].shape[0], case["M"], case["K"], case["tau1"], case["tau2"],
+                  case["gamma"], 100, 1e-4, case["l2"])
+    try:
+        e.upload(case["x"], case["Y"], case["nk"])
+        assert e.omega_begin()
+        cols = D.omega_columns(p, 3)
+        for c0, c1 in cols:
+            e.omega_solve_cols(c0, c1)
+        for c0, c1 in cols:
+            e.omega_product_cols(c0, c1)
+        e.omega_finish()
+        assert not e.omega_begin()                     # already there
+        e.prepare()
+        got = e.get_omega()
+    finally:
+        e.close()
+    iu = np.triu_indices(p)
+    assert np.max(np.abs(got[iu] - whole[iu])) / np.max(np.abs(whole)) <= 1e-11
+    # the engine keeps symmatu(Omega): the lower triangle is the mirror of the upper one
+    il = np.tril_indices(p, -1)
+    assert np.array_equal(got[il], got.T[il])
+
+
 def _run_cv(sp, case, **kw):
     return sp.spatpcaCV(case["x"], case["Y"], case["M"], case["K"], case["tau1"], case["tau2"], case["gamma"],
                         case["nk"], kw.get("maxit", 100), kw.get("tol", 1e-4), case["l2"], return_stats=True)

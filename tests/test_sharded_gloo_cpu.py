@@ -26,6 +26,37 @@ class OracleBackedEngine:
         self.asked = []
         self.bufs, self.present, self.prepared = {}, set(), set()
 
+    # ---- Omega in column blocks (stand-ins: one double per column, tagged by the owner's column index) ----
+    def omega_begin(self):
+        self.lp = self.torch.full((self.p,), -1.0, dtype=self.torch.float64)
+        self.om = self.torch.full((self.p,), -1.0, dtype=self.torch.float64)
+        self.asked.append(("omega_begin",))
+        return True
+
+    def omega_solve_cols(self, c0, c1):
+        self.lp[c0:c1] = self.torch.arange(c0, c1, dtype=self.torch.float64)
+        self.asked.append(("omega_solve", c0, c1))
+
+    def omega_product_cols(self, c0, c1):
+        # the product needs every column of Lp, i.e. the other ranks' blocks must have arrived
+        assert bool((self.lp == self.torch.arange(self.p, dtype=self.torch.float64)).all())
+        self.om[c0:c1] = 2.0 * self.torch.arange(c0, c1, dtype=self.torch.float64)
+        self.asked.append(("omega_product", c0, c1))
+
+    def omega_buffer(self, which, c0, c1):
+        return (self.lp if which == 0 else self.om)[c0:c1]
+
+    def omega_sync(self):
+        pass
+
+    def omega_finish(self):
+        assert bool((self.om == 2.0 * self.torch.arange(self.p, dtype=self.torch.float64)).all())
+        self.asked.append(("omega_finish",))
+
+    def prepare(self):
+        assert ("omega_finish",) in self.asked
+        self.asked.append(("prepare",))
+
     # ---- stage-1 inverses as jobs (stand-ins: 8 doubles tagged with the job id) ----
     def can_share_inverses(self):
         return True
@@ -106,6 +137,7 @@ def _worker(rank, world, port, out_dir):
 
     eng = OracleBackedEngine(case, want)
     coll = D.TorchCollective()
+    D.prepare_sharded(eng, coll)
     got = D.run_sharded(eng, select_index, coll, case["M"], len(case["tau1"]), len(case["tau2"]),
                         len(case["gamma"]), case["tau1"], case["tau2"], case["gamma"])
     ok = True
@@ -119,6 +151,10 @@ def _worker(rank, world, port, out_dir):
     ok &= my_folds == [k for k in range(case["M"]) if D.fold_owner(k, world) == rank]
     did_full = any(a[0] == "f1" for a in eng.asked)
     ok &= did_full == (rank == D.full_fit_owner(case["M"], world))
+    # Omega: this rank solved and multiplied exactly its own column block, then prepare() ran
+    c0, c1 = D.omega_columns(eng.p, world)[rank]
+    ok &= ("omega_solve", c0, c1) in eng.asked and ("omega_product", c0, c1) in eng.asked
+    ok &= sum(1 for a in eng.asked if a[0] == "omega_solve") == 1 and ("prepare",) in eng.asked
     # the inverse jobs were spread as planned, and each rank built exactly its share
     jobs, owner = D.plan_inverse_jobs(case["M"], len(case["tau1"]), world)
     built = sorted((a[1], a[2]) for a in eng.asked if a[0] == "inv")
@@ -147,6 +183,17 @@ def test_inverse_job_plan():
         kept = sum(1 for (k, i) in jobs if owner[(k, i)] == D.fold_owner(k, world))
         assert kept >= min(50, sum(min(-(-50 // world), 10 * sum(1 for k in range(5) if D.fold_owner(k, world) == r))
                                    for r in range(world)))
+
+
+def test_omega_column_split():
+    from spatpca_b200 import distributed as D
+    for p in (1, 15, 50, 900, 4096, 10000, 40000):
+        for world in (1, 2, 3, 4, 8):
+            cols = D.omega_columns(p, world)
+            assert len(cols) == world and cols[0][0] == 0 and cols[-1][1] == p
+            for (a, b), (c, d) in zip(cols, cols[1:]):
+                assert b == c and a <= b and c <= d
+            assert all(a % 16 == 0 for a, _ in cols if a < p)
 
 
 def test_fold_placement():
