@@ -89,12 +89,13 @@ struct Params {
   double *Phi, *R, *C, *L1, *L2;
   double *X, *part, *gpart, *npart;
   double* ctrl;        // [0] = max error, [1] = status, [2] = sweeps, [8 ..] = P (K x K)
-  int* counters;       // [0] = tiles done, [1] = row blocks done, [2 .. 2 + ntiles) = per-tile piece tickets,
+  int* counters;       // [0] = final slices done, [1] = row blocks done, [2 .. 2 + ntiles) = per-tile arrival counters (only grow),
                        // [2 + ntiles] = arrival counter of grid_barrier
   int* stat;
   double* err;
   int nrt, nrb, xcap;  // nrt: row tiles of the whole p rows
   int nphases, ntiles; // ntiles: tile-table entries over all phases
+  int total_slices;    // final row slices per iteration (the last one to finish runs the polar step)
   PhaseDesc ph[kMaxPhases];
   unsigned long long* dbg;   // optional: globaltimer stamps of CTA 0 (8 per iteration), or nullptr
 };
@@ -142,9 +143,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
-__device__ __forceinline__ long long seg_begin(long long s, long long U, int S) { return s * U / S; }
+__host__ __device__ __forceinline__ long long seg_begin(long long s, long long U, int S) { return s * U / S; }
 // index of the segment that contains unit u
-__device__ __forceinline__ int seg_of(long long u, long long U, int S) {
+__host__ __device__ __forceinline__ int seg_of(long long u, long long U, int S) {
   return (int)(((u + 1) * S + U - 1) / U - 1);
 }
 
@@ -290,124 +291,131 @@ __device__ int jacobi_inv_sqrt_warp(double* Am, double* Vm, double* Pm, int K, i
 }
 
 
-// ---- epilogue of one row tile: Phi, T = Phi + Lambda2 / rho, the tile's Gram partial -----------
-// phi[r][k]: unscaled rows i0 .. i0 + RPT - 1 of A^-1 X held by this thread; tg: global tile index.
-template <int KP>
-__device__ __forceinline__ void tile_epilogue(const Params& P, int tg, int i0,
-                                              const double (&phi)[Cfg<KP>::RPT][KP], double* red) {
-  using C = Cfg<KP>;
-  constexpr int RPT = C::RPT, KG = C::KG;
-  const int p = P.p, K = P.K;
-  double g[KG];
-#pragma unroll
-  for (int q = 0; q < KG; ++q) g[q] = 0.0;
-#pragma unroll
-  for (int r = 0; r < RPT; ++r) {
-    const int i = i0 + r;
-    if (i < p) {
-      double tt[KP];
-#pragma unroll
-      for (int k = 0; k < KP; ++k) {
-        tt[k] = 0.0;
-        if (k < K) {
-          const double ph = __dmul_rn(P.scale, phi[r][k]);       // 0.5 * (...) in Core3 (:247)
-          P.Phi[(size_t)k * p + i] = ph;
-          tt[k] = __dadd_rn(ph, div_rho(__ldcg(P.L2 + (size_t)k * p + i), P.rho, P.rinv_rho));   // :169, :251
-        }
-      }
-      int q = 0;
-#pragma unroll
-      for (int a = 0; a < KP; ++a)
-#pragma unroll
-        for (int b = a; b < KP; ++b) { g[q] = fma(tt[a], tt[b], g[q]); ++q; }
-    }
-  }
-  block_reduce_store<KG>(g, red, P.gpart + (size_t)tg * KG);
-}
+// ---- fix-up of one row tile, split over the CTAs that contributed to it ---------------------------
+// The pieces of a row tile (one partial per segment that crosses it, 12-30 of them) used to be summed by
+// the CTA that delivered the last one: ~10 us of dependent L2 round trips on every phase's critical path.
+// Now the tile is cut into ns = min(pieces, kMaxSlices) row slices and the CTA of piece q < ns reduces slice
+// q as soon as the tile's ticket counter shows that all pieces have arrived: every thread has at most a few
+// 16-byte loads, all in flight together.  Thread (pair, group) sums the pieces group, group + G, ... of one
+// row pair in increasing order; the G group sums are combined through shared memory in group order -- the
+// shape depends on (p, K, blocking) only, never on arrival order, so results stay bitwise reproducible.
+// The slice of a tile whose rows become final in this phase also forms Phi = scale * (A^-1 X) and the slice's
+// T'T partial (T = Phi + Lambda2 / rho, :169, :251).  Returns true if the slice was a final one.
+constexpr int kMaxSlices = 8;
 
-// ---- reduce of one row tile of a phase: partials -> (FINAL) Phi, T, Gram partial; (FWD / BWD) the
-// running vectors of the factored solve -------------------------------------------------------
-// Thread tid owns rows RPT*tid .. RPT*tid+RPT-1 of the tile (the stream's ownership), so one
-// 16-byte load fetches both rows of a slot column; loads of kBatch slots are in flight together
-// and the additions run in slot order.
+__host__ __device__ inline int slice_rows(int TR, int ns) { return (((TR + ns - 1) / ns) + 1) & ~1; }
+
 template <int KP>
-__device__ __forceinline__ void reduce_tile(const Params& P, const PhaseDesc& ph, int t, const TileInfo& ti,
-                                            double* red) {
+__device__ __forceinline__ bool reduce_slice(const Params& P, const PhaseDesc& ph, int t, const TileInfo& ti, int q,
+                                             double* scratch, double* red) {
   using C = Cfg<KP>;
-  constexpr int RPT = C::RPT, TR = C::TR;
-  constexpr int kBatch = (KP <= 4) ? 8 : ((KP <= 8) ? 4 : 2);      // slots whose loads are in flight together
+  constexpr int TR = C::TR, KG = C::KG;
+  constexpr int KC = (KP <= 8) ? KP : 8;                 // columns per pass (bounds the shared scratch)
   const int tid = threadIdx.x;
   const int p = P.p, K = P.K;
-  const int li = RPT * tid;
-  const int i0 = ph.row0 + t * TR + li;
-  const int row_end = ph.row0 + ph.nrows;
-  double phi[RPT][KP];
-#pragma unroll
-  for (int r = 0; r < RPT; ++r)
-#pragma unroll
-    for (int k = 0; k < KP; ++k) phi[r][k] = 0.0;
-  if (i0 < row_end) {
-    for (int s = ti.s_lo; s <= ti.s_hi; s += kBatch) {
-      double v[kBatch][KP][RPT];
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const int su = s + u;
-        const bool live = (su <= ti.s_hi);
-        const int w = (su == ti.s_lo) ? ti.first_w : 0;
-        const double* slot = P.part + ((size_t)(2 * (live ? su : ti.s_lo) + w) * KP) * TR + li;
-#pragma unroll
-        for (int k = 0; k < KP; ++k) {
-          if (live && k < K) {
-            if (RPT == 2) {
-              const double2 x = __ldcg(reinterpret_cast<const double2*>(slot + (size_t)k * TR));
-              v[u][k][0] = x.x; v[u][k][RPT - 1] = x.y;
-            } else {
-              v[u][k][0] = __ldcg(slot + (size_t)k * TR);
-            }
-          } else {
-#pragma unroll
-            for (int r = 0; r < RPT; ++r) v[u][k][r] = 0.0;
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u)
-#pragma unroll
-        for (int k = 0; k < KP; ++k)
-#pragma unroll
-          for (int r = 0; r < RPT; ++r) phi[r][k] += v[u][k][r];     // adding +0.0 for dead slots is exact
-    }
-  }
-  if (ph.kind == PH_FINAL) {
-    tile_epilogue<KP>(P, t, i0, phi, red);
-    return;
-  }
-  const int diag_end = ph.col0 + ph.ncols;       // FWD: rows of the diagonal block D_j^-1
+  const int np = ti.s_hi - ti.s_lo + 1;
+  const int ns = np < kMaxSlices ? np : kMaxSlices;
+  const int SR = slice_rows(TR, ns);
+  const int l0 = q * SR;                                 // first row of the slice inside the tile (even)
+  const int nrows = max(0, min(TR, l0 + SR) - l0);       // even: TR and SR are
+  const int npairs = nrows >> 1;
   const int tile_row0 = ph.row0 + t * TR;
-  const bool final_tile = (tile_row0 >= ph.fin0 && tile_row0 < ph.fin1);   // uniform over the CTA
+  const int row_end = ph.row0 + ph.nrows;
+  const bool final_tile = (ph.kind == PH_FINAL) || (tile_row0 >= ph.fin0 && tile_row0 < ph.fin1);
+  const int diag_end = ph.col0 + ph.ncols;               // FWD: rows of the diagonal block D_j^-1
+  int NP2 = 1, sh = 0;
+  while (NP2 < npairs) { NP2 <<= 1; ++sh; }
+  const int G = kThreads >> sh;                          // piece groups
+  const int pi = tid & (NP2 - 1), g = tid >> sh;
+  if (npairs > 0) {
+    for (int kc0 = 0; kc0 < K; kc0 += KC) {
+      double a0[KC], a1[KC];
 #pragma unroll
-  for (int r = 0; r < RPT; ++r) {
-    const int i = i0 + r;
-    if (i < row_end) {
+      for (int k = 0; k < KC; ++k) { a0[k] = 0.0; a1[k] = 0.0; }
+      if (pi < npairs) {
+        constexpr int kB = 4;                            // pieces whose loads are in flight together
+        for (int s0 = g; s0 < np; s0 += kB * G) {
+          double2 v[kB][KC];
 #pragma unroll
-      for (int k = 0; k < KP; ++k) {
-        if (k < K) {
-          const size_t off = (size_t)k * p + i;
-          if (ph.kind == PH_FWD) {
-            if (i < diag_end) {                                             // w_j = D_j^-1 z_j
-              if (!final_tile) P.Phi[off] = phi[r][k];
-            } else {
-              __stcg(P.X + off, __ldcg(P.X + off) + phi[r][k]);             // z_k -= U_jk' z_j
+          for (int u = 0; u < kB; ++u) {
+            const int sp = s0 + u * G;
+            const bool live = sp < np;
+            const int w = (sp == 0) ? ti.first_w : 0;
+            const double* slot = P.part + ((size_t)(2 * (ti.s_lo + (live ? sp : 0)) + w) * KP) * TR + l0 + 2 * pi;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+              if (live && kc0 + k < K) v[u][k] = __ldcg(reinterpret_cast<const double2*>(slot + (size_t)(kc0 + k) * TR));
+              else v[u][k] = make_double2(0.0, 0.0);
             }
-          } else {
-            phi[r][k] = __ldcg(P.Phi + off) + phi[r][k];                    // w_j -= U_jk w_k
-            if (!final_tile) P.Phi[off] = phi[r][k];
           }
+#pragma unroll
+          for (int u = 0; u < kB; ++u)
+#pragma unroll
+            for (int k = 0; k < KC; ++k) { a0[k] += v[u][k].x; a1[k] += v[u][k].y; }   // + 0.0 for dead slots is exact
+        }
+      }
+      __syncthreads();                                   // scratch free (previous pass / the stream window)
+      if (pi < npairs) {
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          double2 o; o.x = a0[k]; o.y = a1[k];
+          reinterpret_cast<double2*>(scratch)[(size_t)(g * NP2 + pi) * KC + k] = o;
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < NP2 * KC; e += kThreads) {
+        const int pj = e & (NP2 - 1), k = e >> sh;
+        const int kk = kc0 + k;
+        if (pj >= npairs || kk >= K) continue;
+        double2 v = reinterpret_cast<const double2*>(scratch)[(size_t)pj * KC + k];
+        for (int gg = 1; gg < G; ++gg) {
+          const double2 x = reinterpret_cast<const double2*>(scratch)[(size_t)(gg * NP2 + pj) * KC + k];
+          v.x += x.x; v.y += x.y;
+        }
+        const int i = tile_row0 + l0 + 2 * pj;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int ir = i + r;
+          if (ir >= row_end) continue;
+          double val = r == 0 ? v.x : v.y;
+          const size_t off = (size_t)kk * p + ir;
+          if (ph.kind == PH_FWD) {
+            if (ir >= diag_end) { __stcg(P.X + off, __ldcg(P.X + off) + val); continue; }   // z_k -= U_jk' z_j
+          } else if (ph.kind == PH_BWD) {
+            val = __ldcg(P.Phi + off) + val;                                               // w_j -= U_jk w_k
+          }
+          // FINAL / FWD diagonal rows / BWD: the running w; a final tile gets Phi = scale * w (0.5 * ... in Core3, :247)
+          __stcg(P.Phi + off, final_tile ? __dmul_rn(P.scale, val) : val);
         }
       }
     }
   }
-  if (final_tile) tile_epilogue<KP>(P, tile_row0 / TR, i0, phi, red);       // Phi = scale * w, T, Gram partial
+  if (!final_tile) return false;
+  // T'T partial of the slice: rows re-read from L2 (this CTA wrote them just above)
+  __syncthreads();
+  double gq[KG];
+#pragma unroll
+  for (int e = 0; e < KG; ++e) gq[e] = 0.0;
+  for (int r = tid; r < nrows; r += kThreads) {
+    const int i = tile_row0 + l0 + r;
+    if (i >= row_end) continue;
+    double tt[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      tt[k] = 0.0;
+      if (k < K) {
+        const size_t off = (size_t)k * p + i;
+        tt[k] = __dadd_rn(__ldcg(P.Phi + off), div_rho(__ldcg(P.L2 + off), P.rho, P.rinv_rho));   // :169, :251
+      }
+    }
+    int e = 0;
+#pragma unroll
+    for (int a = 0; a < KP; ++a)
+#pragma unroll
+      for (int b = a; b < KP; ++b) { gq[e] = fma(tt[a], tt[b], gq[e]); ++e; }
+  }
+  block_reduce_store<KG>(gq, red, P.gpart + ((size_t)(tile_row0 / TR) * kMaxSlices + q) * KG);
+  return true;
 }
 
 // ---- Gram reduce + Jacobi by the CTA that finished the last tile ------------------------------
@@ -423,8 +431,11 @@ __device__ __forceinline__ void finish_polar(const Params& P, double* jA, double
   for (int q0 = 0; q0 < KG; q0 += kThreads / 16) {
     const int q = q0 + (tid >> 4), j = tid & 15;
     double t = 0.0;
-    if (q < KG)
-      for (int tb = j; tb < P.nrt; tb += 16) t += __ldcg(P.gpart + (size_t)tb * KG + q);
+    if (q < KG) {
+      const int nslots = P.nrt * kMaxSlices;           // unused slots hold zeros
+#pragma unroll 8
+      for (int tb = j; tb < nslots; tb += 16) t += __ldcg(P.gpart + (size_t)tb * KG + q);
+    }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     if (q < KG && j == 0) {
@@ -559,35 +570,43 @@ __device__ __forceinline__ void stream_phase(const Params& P, const PhaseDesc& p
         }
       }
       if (P.dbg != nullptr && tid == 0 && dbg_it == 5 && ph.kind == PH_FINAL) { P.dbg[256 + blockIdx.x] = gtimer(); P.dbg[256 + 512 + blockIdx.x] = P.dbg[5 * 8]; }
-      // ticket: the CTA that delivers the last piece of tile t will reduce the tile -- but only after
-      // it has streamed all of its own pieces, so that its reduce never delays another tile's last piece
+      // ticket: announce the piece; if this piece's index is below the tile's slice count this CTA reduces
+      // that slice later -- after it has streamed all of its own pieces, so its fix-up never delays a stream
       __threadfence();
       __syncthreads();
       if (tid == 0) {
+        atomicAdd(tickets + t, 1);
         const int npieces = tiles[t].s_hi - tiles[t].s_lo + 1;
-        const int old = atomicAdd(tickets + t, 1);
-        if (old == npieces - 1 && sh_i[2] < 8) { sh_i[3 + sh_i[2]] = t; sh_i[2] = sh_i[2] + 1; }
+        const int q = s - tiles[t].s_lo;
+        if (q < (npieces < kMaxSlices ? npieces : kMaxSlices) && sh_i[2] < 8) {
+          sh_i[3 + sh_i[2]] = t | (q << 16);
+          sh_i[2] = sh_i[2] + 1;
+        }
       }
     }
   }
   __syncthreads();
   const int nred = sh_i[2];
   for (int r = 0; r < nred; ++r) {
-    const int t = sh_i[3 + r];
-    __threadfence();
-    if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[123] = gtimer();
-    reduce_tile<KP>(P, ph, t, tiles[t], red);
-    if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[124] = gtimer();
-    const int tile_row0 = ph.row0 + t * TR;
-    if (ph.kind != PH_FINAL && !(tile_row0 >= ph.fin0 && tile_row0 < ph.fin1)) {
-      if (tid == 0) tickets[t] = 0;                // re-arm for the next iteration
-      continue;
-    }
+    const int t = sh_i[3 + r] & 0xffff, q = sh_i[3 + r] >> 16;
     if (tid == 0) {
-      tickets[t] = 0;                              // re-arm for the next iteration
-      __threadfence();
+      // the counters only grow: after this phase's pass of iteration `it` tile t has seen (it + 1) * pieces arrivals
+      const unsigned int target = (unsigned int)(tiles[t].s_hi - tiles[t].s_lo + 1) * (unsigned int)(dbg_it + 1);
+      unsigned int v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tickets + t) : "memory");
+      } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+    if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[123] = gtimer();
+    const bool fin = reduce_slice<KP>(P, ph, t, tiles[t], q, xs, red);
+    if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[124] = gtimer();
+    if (!fin) continue;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
       const int old = atomicAdd(P.counters + 0, 1);
-      sh_i[1] = (old == P.nrt - 1) ? 1 : 0;
+      sh_i[1] = (old == P.total_slices - 1) ? 1 : 0;
     }
     __syncthreads();
     if (sh_i[1]) {
@@ -711,6 +730,7 @@ admm_persistent_kernel(Params P) {
   if (threadIdx.x == 0) sh_i[2] = 0;
   if (blockIdx.x == 0) {
     for (int i = tid; i < P.ntiles + 3; i += kThreads) P.counters[i] = 0;
+    for (int i = tid; i < P.nrt * kMaxSlices * Cfg<KP>::KG; i += kThreads) P.gpart[i] = 0.0;   // unused slice slots stay 0
     if (tid == 0) { __stcg(P.ctrl + 0, 0.0); __stcg(P.ctrl + 1, 0.0); __stcg(P.ctrl + 2, 0.0); }
   }
   for (size_t idx = (size_t)blockIdx.x * kThreads + tid; idx < pk; idx += (size_t)gridDim.x * kThreads) {
@@ -759,7 +779,7 @@ admm_persistent_kernel(Params P) {
 struct Geom {
   int KP, RPT, TR, KX, KG;
   int nrt, nrb, xcap;
-  int nphases, ntiles, smax;
+  int nphases, ntiles, smax, total_slices;
   PhaseDesc ph[kMaxPhases];
   size_t part_doubles, gpart_doubles, npart_doubles, x_doubles, ctrl_doubles, counter_ints;
   size_t smem_bytes;
@@ -812,6 +832,17 @@ Geom make_geom(int p, int K, const Blocking& blk) {
       g.ph[g.nphases - 1].fin0 = blk.off[k - 1]; g.ph[g.nphases - 1].fin1 = blk.off[k];   // block k-1 is final
     }
   }
+  // final row slices per iteration: for every tile of the rows a phase finalises, min(pieces, kMaxSlices)
+  g.total_slices = 0;
+  for (int f = 0; f < g.nphases; ++f) {
+    const PhaseDesc& ph = g.ph[f];
+    for (int t = 0; t < ph.nrt; ++t) {
+      const int row0 = ph.row0 + t * g.TR;
+      if (!(ph.kind == PH_FINAL || (row0 >= ph.fin0 && row0 < ph.fin1))) continue;
+      const int np = seg_of((long long)(t + 1) * ph.ncols - 1, ph.U, ph.S) - seg_of((long long)t * ph.ncols, ph.U, ph.S) + 1;
+      g.total_slices += np < kMaxSlices ? np : kMaxSlices;
+    }
+  }
   g.nrb = ceil_div(p, kRowBlock);
   int maxcols = 1;
   for (int f = 0; f < g.nphases; ++f) {
@@ -826,11 +857,14 @@ Geom make_geom(int p, int K, const Blocking& blk) {
   if (g.xcap < 1) g.xcap = 1;
   // every sub-buffer starts 128-byte aligned (the partial slots are read / written with 16-byte accesses)
   g.part_doubles = round_up((size_t)2 * g.smax * g.TR * g.KP, 16);
-  g.gpart_doubles = round_up((size_t)g.nrt * g.KG, 16);
+  g.gpart_doubles = round_up((size_t)g.nrt * kMaxSlices * g.KG, 16);
   g.npart_doubles = round_up((size_t)g.nrb * 4, 16);
   g.x_doubles = round_up((size_t)p * K, 16);
   g.ctrl_doubles = 8 + (size_t)SPB_MAX_K * SPB_MAX_K;
   g.counter_ints = (size_t)g.ntiles + 3;
+  // the stream window doubles as the scratch of the slice fix-up (kThreads x min(KP, 8) double2)
+  const int kc = g.KP <= 8 ? g.KP : 8;
+  while ((size_t)g.xcap * g.KX < (size_t)2 * kThreads * kc) ++g.xcap;
   // dynamic shared memory: [stream window | reduction scratch (8 KG + 32) | tile table]
   g.smem_bytes = ((size_t)g.xcap * g.KX + 8 * (size_t)g.KG + 32) * sizeof(double) + (size_t)g.ntiles * 3 * sizeof(int);
   return g;
@@ -906,7 +940,7 @@ void launch_admm(const AdmmCall& c, void* ws, cudaStream_t s) {
   P.stat = c.stat_slot; P.err = c.err_slot;
   P.dbg = c.dbg;
   P.nrt = g.nrt; P.nrb = g.nrb; P.xcap = g.xcap;
-  P.nphases = g.nphases; P.ntiles = g.ntiles;
+  P.nphases = g.nphases; P.ntiles = g.ntiles; P.total_slices = g.total_slices;
   for (int f = 0; f < kMaxPhases; ++f) P.ph[f] = g.ph[f < g.nphases ? f : 0];
   switch (g.KP) {
     case 1: launch_instance<1>(P, g, s); break;

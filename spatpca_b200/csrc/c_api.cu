@@ -336,7 +336,7 @@ void run_cv_stages(Engine& eng, int M, const double* tau2, int n_tau1, int n_tau
                    double* cv_score_tau1, double* cv_score_tau2, double* cv_score_gamma, double* estimated_eigenfn,
                    double* selected, spb_cv_stats* stats) {
   // SPB_TRACE=1: host wall clock at every stage boundary (the *_full calls only enqueue)
-  static const bool tr_on = [] { const char* e = std::getenv("SPB_TRACE"); return e && e[0] == '1'; }();
+  static const bool tr_on = [] { const char* e = std::getenv("SPB_TRACE"); return e && (e[0] == '1' || e[0] == '2'); }();
   auto tr_last = std::chrono::steady_clock::now();
   auto tr = [&](const char* label) {
     if (!tr_on) return;
@@ -423,7 +423,8 @@ int spb_cv(const double* sxy, int p, int d, const double* Y, int n, int M, int K
   return guarded([&] {
     SPB_REQUIRE(cv_score_tau1 && cv_score_tau2 && cv_score_gamma && estimated_eigenfn && selected,
                 "NULL output");
-    static const bool tr_on = [] { const char* e = std::getenv("SPB_TRACE"); return e && e[0] == '1'; }();
+    // SPB_TRACE=2: host laps only (no extra synchronisation); SPB_TRACE=1 adds the synchronous prologue trace
+    static const bool tr_on = [] { const char* e = std::getenv("SPB_TRACE"); return e && (e[0] == '1' || e[0] == '2'); }();
     auto t0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* label) {
       if (!tr_on) return;
