@@ -695,9 +695,23 @@ int spb_bench_admm_blocks(int p, int K, int mode, int iters, int repeats, int bl
     const bool dbg_on = std::getenv("SPB_ADMM_DBG") != nullptr;
     DevBuf<unsigned long long> dbg(2048);
     SPB_CUDA(cudaMemsetAsync(dbg.get(), 0, sizeof(unsigned long long) * 2048, s));
+    // start: C = R = Q with NON-orthogonal columns (e_k + 0.15 e_{k+1} + 0.1 e_{k+2}), so that T'T is not
+    // diagonal and the Jacobi step of every iteration does real sweeps, as in a job (SPB_BENCH_DIAG=1: Q = E,
+    // the zero-sweep best case)
+    std::vector<double> q0(pk, 0.0);
+    const bool diag_start = std::getenv("SPB_BENCH_DIAG") != nullptr;
+    for (int k = 0; k < K; ++k) {
+      q0[(size_t)k * p + k] = 1.0;
+      if (!diag_start && k + 1 < p) q0[(size_t)k * p + k + 1] = 0.15;
+      if (!diag_start && k + 2 < p) q0[(size_t)k * p + k + 2] = 0.1;
+    }
+    DevBuf<double> Q0(pk);
+    SPB_CUDA(cudaMemcpyAsync(Q0.get(), q0.data(), sizeof(double) * pk, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaStreamSynchronize(s));
+    int last_sweeps = 0;
     for (int r = 0; r < repeats + 1; ++r) {
-      launch_set_identity(st.C.get(), p, K, p, s);
-      launch_set_identity(st.R.get(), p, K, p, s);
+      SPB_CUDA(cudaMemcpyAsync(st.C.get(), Q0.get(), sizeof(double) * pk, cudaMemcpyDeviceToDevice, s));
+      SPB_CUDA(cudaMemcpyAsync(st.R.get(), Q0.get(), sizeof(double) * pk, cudaMemcpyDeviceToDevice, s));
       SPB_CUDA(cudaMemsetAsync(st.L1.get(), 0, sizeof(double) * pk, s));
       SPB_CUDA(cudaMemsetAsync(st.L2.get(), 0, sizeof(double) * pk, s));
       AdmmCall c;
@@ -713,6 +727,7 @@ int spb_bench_admm_blocks(int p, int K, int mode, int iters, int repeats, int bl
       int sth[4];
       SPB_CUDA(cudaMemcpy(sth, stat.get(), sizeof(sth), cudaMemcpyDeviceToHost));
       if (sth[0] != iters || sth[1] != 0) throw Error(SPB_ERR_INTERNAL, "bench chain did not run all iterations");
+      last_sweeps = sth[2];
       float ms = 0.f;
       SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
       if (r > 0) sum_ms += (double)ms / iters;   // r == 0 is the warm-up; the rest are averaged
@@ -745,6 +760,7 @@ int spb_bench_admm_blocks(int p, int K, int mode, int iters, int repeats, int bl
               (double)(h[121] - h[120]) * 1e-3, (double)(h[122] - h[121]) * 1e-3, h[125], (double)(h[126] - h[121]) * 1e-3,
               (double)(h[127] - h[126]) * 1e-3, (double)(h[122] - h[127]) * 1e-3, (double)(h[124] - h[123]) * 1e-3);
     }
+    if (dbg_on) fprintf(stderr, "[admm dbg] Jacobi sweeps in the last iteration: %d\n", last_sweeps);
     *ms_per_iter = sum_ms / repeats;
   });
 }
