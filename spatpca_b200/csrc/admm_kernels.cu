@@ -42,6 +42,8 @@
 #include <cmath>
 #include <map>
 #include <mutex>
+#include <string>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -86,6 +88,7 @@ struct Params {
   double rdenom;                              // 1 / sqrt(p K)
   double rho, rinv_rho, thr, tol, scale;     // rinv_rho = RN(1 / rho), computed on the host
   double inv_scale;                           // 1 / scale (scale is 1 or 0.5, so this is exact)
+  int force_jacobi;                           // SPB_POLAR=jacobi: skip Newton-Schulz (cross-checks)
   double *Phi, *R, *C, *L1, *L2;
   double *X, *part, *gpart, *npart;
   double* ctrl;        // [0] = max error, [1] = status, [2] = sweeps, [8 ..] = P (K x K)
@@ -418,9 +421,70 @@ __device__ __forceinline__ bool reduce_slice(const Params& P, const PhaseDesc& p
   return true;
 }
 
-// ---- Gram reduce + Jacobi by the CTA that finished the last tile ------------------------------
+// ---- K x K inverse square root by the coupled Newton-Schulz iteration, whole CTA (K*K <= kThreads) -------
+//   Y0 = G / s, Z0 = I;   M = 3I - Z Y;   Y <- Y M / 2,   Z <- M Z / 2;   Z -> (G / s)^(-1/2)
+// with s = max row sum >= lambda_max, so the spectrum of Y0 is in (0, 1] and the iteration converges for
+// every SPD G, quadratically once ||I - Z Y|| is small.  On this path G = T'T has cond <= ~1.3:
+// 4-6 iterations of three K x K products, ~2 us, against 5 Jacobi sweeps of 10 dependent rotations each
+// (~45 us at K = 5: every rotation is a chain of ~35 dependent FP64 operations at ~55 cycles).  Thread
+// (a, b) owns one entry; the error is tested BEFORE a step, so the step after ||.|| < 3e-9 leaves ~1e-17.
+// Returns false (G untouched) when it does not converge in 24 steps -- an ill-conditioned, indefinite or
+// non-finite G -- and the caller falls back to the Jacobi eigen-solve, which also classifies the failure.
+__device__ bool ns_inv_sqrt_cta(const double* G, double* Y, double* Z, double* M, double* Pout, int K,
+                                int* iters_out) {
+  __shared__ double rowsum[32];
+  const int tid = threadIdx.x;
+  const int a = tid / K, b = tid - a * K;
+  const bool act = tid < K * K;
+  if (tid < K) {
+    double r = 0.0;
+    for (int j = 0; j < K; ++j) r += fabs(G[tid * K + j]);
+    rowsum[tid] = r;
+  }
+  __syncthreads();
+  double sc = 0.0;
+  for (int i = 0; i < K; ++i) sc = fmax(sc, rowsum[i]);
+  if (!(sc > 0.0) || !(sc < 1e300)) return false;          // uniform: every thread sees the same sc
+  const double sinv = fast_rcp(sc);
+  if (act) { Y[tid] = G[tid] * sinv; Z[tid] = (a == b) ? 1.0 : 0.0; }
+  __syncthreads();
+  bool ok = false;
+  int it = 0;
+  for (; it < 24; ++it) {
+    double e = 0.0;
+    if (act) {
+      double acc = 0.0;
+      for (int k = 0; k < K; ++k) acc = fma(Z[a * K + k], Y[k * K + b], acc);
+      const double m = ((a == b) ? 3.0 : 0.0) - acc;
+      e = fabs(m - ((a == b) ? 2.0 : 0.0));
+      M[tid] = m;
+    }
+    const int big = __syncthreads_or((act && !(e < 3e-9)) ? 1 : 0);     // also publishes M
+    double yn = 0.0, zn = 0.0;
+    if (act) {
+      double ay = 0.0, az = 0.0;
+      for (int k = 0; k < K; ++k) {
+        ay = fma(Y[a * K + k], M[k * K + b], ay);
+        az = fma(M[a * K + k], Z[k * K + b], az);
+      }
+      yn = 0.5 * ay; zn = 0.5 * az;
+    }
+    __syncthreads();
+    if (act) { Y[tid] = yn; Z[tid] = zn; }
+    __syncthreads();
+    if (!big) { ok = true; ++it; break; }
+  }
+  if (!ok) return false;
+  const double rs = fast_rsqrt(sc);
+  if (act) Pout[tid] = (0.5 * (Z[a * K + b] + Z[b * K + a])) * rs;      // exactly symmetric
+  *iters_out = it;
+  __syncthreads();
+  return true;
+}
+
+// ---- Gram reduce + polar factor by the CTA that finished the last slice ------------------------------
 template <int KP>
-__device__ __forceinline__ void finish_polar(const Params& P, double* jA, double* jV, double* jP) {
+__device__ __forceinline__ void finish_polar(const Params& P, double* jA, double* jV, double* jP, double* scratch) {
   using C = Cfg<KP>;
   constexpr int KG = C::KG;
   const int tid = threadIdx.x;
@@ -447,12 +511,22 @@ __device__ __forceinline__ void finish_polar(const Params& P, double* jA, double
   }
   __syncthreads();
   if (P.dbg != nullptr && tid == 0) P.dbg[121] = gtimer();
-  if (tid < 32) {
+  // P = (T'T)^(-1/2): Newton-Schulz on the whole CTA; Jacobi eigen-solve in one warp as the fallback (and for
+  // K > 16, where K*K entries no longer map to one thread each)
+  int steps = 0;
+  bool done = false;
+  if (K * K <= kThreads && !P.force_jacobi)
+    done = ns_inv_sqrt_cta(jA, scratch, scratch + K * K, scratch + 2 * K * K, jP, K, &steps);
+  if (done) {
+    if (P.dbg != nullptr && tid == 0) { P.dbg[122] = gtimer(); P.dbg[125] = (unsigned long long)steps; P.dbg[126] = P.dbg[127] = P.dbg[121]; }
+    for (int idx = tid; idx < K * K; idx += kThreads) __stcg(P.ctrl + 8 + idx, jP[idx]);
+    if (tid == 0) { __stcg(P.ctrl + 1, 0.0); __stcg(P.ctrl + 2, (double)steps); }
+  } else if (tid < 32) {
     int sweeps = 0;
     const int bad = jacobi_inv_sqrt_warp(jA, jV, jP, K, &sweeps, P.dbg);
     if (P.dbg != nullptr && tid == 0) { P.dbg[122] = gtimer(); P.dbg[125] = (unsigned long long)sweeps; }
     for (int idx = tid; idx < K * K; idx += 32) __stcg(P.ctrl + 8 + idx, jP[idx]);
-    if (tid == 0) { __stcg(P.ctrl + 1, (double)bad); __stcg(P.ctrl + 2, (double)sweeps); }
+    if (tid == 0) { __stcg(P.ctrl + 1, (double)bad); __stcg(P.ctrl + 2, (double)(100 + sweeps)); }
   }
   __syncthreads();
 }
@@ -612,7 +686,7 @@ __device__ __forceinline__ void stream_phase(const Params& P, const PhaseDesc& p
     if (sh_i[1]) {
       __threadfence();
       if (tid == 0) P.counters[0] = 0;
-      finish_polar<KP>(P, jA, jV, jP);
+      finish_polar<KP>(P, jA, jV, jP, xs);
     }
   }
   __syncthreads();
@@ -928,6 +1002,11 @@ void launch_admm(const AdmmCall& c, void* ws, cudaStream_t s) {
   P.rho = c.rho; P.rinv_rho = 1.0 / c.rho; P.thr = c.tau2 / c.rho; P.tol = c.tol;
   P.scale = (c.mode == 3) ? 0.5 : 1.0;
   P.inv_scale = 1.0 / P.scale;
+  static const int force_jacobi = [] {
+    const char* e = std::getenv("SPB_POLAR");
+    return (e != nullptr && std::string(e) == "jacobi") ? 1 : 0;
+  }();
+  P.force_jacobi = force_jacobi;
   P.Phi = c.Phi; P.R = c.R; P.C = c.C; P.L1 = c.L1; P.L2 = c.L2;
   double* w = reinterpret_cast<double*>(ws);
   P.X = w; w += g.x_doubles;
