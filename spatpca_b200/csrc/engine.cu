@@ -1186,6 +1186,8 @@ void Engine::stage1_full(int index1) {
     const double sel = tau1_[0];
     if (sel != 0.0 && max_tau2 == 0.0) run_core2(L, 20, -1, 0, sel, rho_full_, full_); // :605
   }
+  const bool stage2_needs_tempinv = tau2_.size() > 1 || tau2_[0] > 0.0;       // the cases in which stage2_full() works
+  if (cache_inverses_ && stage2_needs_tempinv) full_tempinv(index1);
 }
 
 // ---- stage 2 (:652-680) -----------------------------------------------------------------
@@ -1249,20 +1251,12 @@ void Engine::stage2_folds(const int* folds, int nfolds, int index1, double* rows
   stats_.bytes_d2h += (long long)sizeof(double) * n2 * nfolds;
 }
 
-void Engine::stage2_full(int index1, int index2) {
-  const int n2 = (int)tau2_.size();
-  const double sel1 = selected_tau1(index1);
-  const std::vector<double>* path = nullptr;
-  int upto = 0;
-  if (n2 > 1) {
-    SPB_REQUIRE(index2 >= 0 && index2 < n2, "index2 out of range");
-    path = &tau2_; upto = index2 + 1;                                         // :665-666
-  } else if (tau2_[0] > 0.0) {
-    path = &l2_; upto = (int)l2_.size();                                      // :672-678
-  }
-  if (!path) return;
+// tempinv of the full-data fit (:661, :673): depends on the selected tau1 only, so stage1_full() already
+// enqueues it (when it has its own buffer) and it overlaps with the folds' stage 2 instead of trailing the job
+double* Engine::full_tempinv(int index1) {
   Lane& L = lane_of(-1);
   cudaStream_t s = L.res->stream;
+  const double sel1 = selected_tau1(index1);
   const int tag1 = ((int)tau1_.size() > 1) ? index1 : 0;
   double* tbuf = nullptr;
   bool have = false;
@@ -1283,6 +1277,24 @@ void Engine::stage2_full(int index1, int index2) {
                 ld_, blocks_path_);                                           // :661, :673
     stats_.n_inverses++;
   }
+  return tbuf;
+}
+
+void Engine::stage2_full(int index1, int index2) {
+  const int n2 = (int)tau2_.size();
+  const double sel1 = selected_tau1(index1);
+  const std::vector<double>* path = nullptr;
+  int upto = 0;
+  if (n2 > 1) {
+    SPB_REQUIRE(index2 >= 0 && index2 < n2, "index2 out of range");
+    path = &tau2_; upto = index2 + 1;                                         // :665-666
+  } else if (tau2_[0] > 0.0) {
+    path = &l2_; upto = (int)l2_.size();                                      // :672-678
+  }
+  if (!path) return;
+  Lane& L = lane_of(-1);
+  cudaStream_t s = L.res->stream;
+  double* tbuf = full_tempinv(index1);
   copy_pk(s, full_.R.get(), full_.Phi.get());                                 // :662
   zero_pk(s, full_.L1.get());                                                 // :663
   for (int i = 0; i < upto; ++i) run_core3(L, 3, -1, i, tbuf, (*path)[i], rho_full_, full_);

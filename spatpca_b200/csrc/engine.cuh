@@ -229,6 +229,7 @@ class Engine {
   void enqueue_stage1(int k, int step);
   void enqueue_stage2(int k, int index1, int step);
   void enqueue_stage3_refit(int k, int index1, int index2);
+  double* full_tempinv(int index1);              // tempinv of the full-data fit, built on first request
   void flush_lane(Lane& L);                      // sync the lane, move its call stats to the host log
   void flush();                                  // every lane + the sticky error flag
   void copy_pk(cudaStream_t s, double* dst, const double* src);
