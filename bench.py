@@ -5,12 +5,12 @@ p = 10 000, n = 200, K = 5, 1-8 B200 vs host CPU).
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
 
-One "step" is one complete spatpcaCV job (Omega, 62 SPD inverses, every ADMM call, all CV losses,
+One "step" is one complete spatpcaCV job (Omega, the 57 SPD systems, every ADMM call, all CV losses,
 selection of tau1 / tau2 / gamma, final fit) on the synthetic field of SURVEY.md section 8d.
 `value` is ADMM iterations per second of the whole job with the inputs already resident in HBM;
 `e2e` is the same through the reference-facing C-ABI call `spb_cv` with host buffers (H2D and D2H
-copies inside the timed region).  Under torchrun (N > 1) the folds of the same job are sharded over
-the ranks ("strong" scaling) and timing is the max over ranks.
+copies inside the timed region).  Under torchrun (N > 1) the folds, the stage-1 systems and Omega's
+columns of the same job are spread over the ranks ("strong" scaling) and timing is the max over ranks.
 """
 from __future__ import annotations
 

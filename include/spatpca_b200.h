@@ -283,10 +283,13 @@ SPB_API int spb_gamma_loss(const double* Phi, int p, int K,
 /* ------------------------------------------------------------------------ */
 /* Device-resident benchmark hooks (bench.py).                               */
 /* ------------------------------------------------------------------------ */
-/* Runs `iters` forced Core3 iterations on a synthetic SPD p x p matrix that
- * lives in device memory and returns the average device time per iteration
- * (CUDA events on the launching stream) -- the roofline probe of the
- * persistent ADMM kernel.  mode: 2 = Core2 update, 3 = Core3 update.        */
+/* Runs `iters` forced iterations on a synthetic p x p system that lives in
+ * device memory (identity: the bytes streamed are what matters; the iterate
+ * starts from non-orthogonal columns so that every polar step does real
+ * work) and returns the device time per iteration averaged over `repeats`
+ * launches after one warm-up launch (CUDA events on the launching stream) --
+ * the roofline probe of the persistent ADMM kernel.
+ * mode: 2 = Core2 update, 3 = Core3 update.                                  */
 SPB_API int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_per_iter);
 /* the same with the matrix treated as a block factor of `blocks` blocks
  * (0 = the library's default for p, 1 = explicit inverse = spb_bench_admm)  */

@@ -956,8 +956,12 @@ void launch_instance(const Params& P, const Geom& g, cudaStream_t s) {
     auto key = std::make_pair(dev, g.smem_bytes);
     auto it = occ_cache.find(key);
     if (it == occ_cache.end()) {
+      // 2 CTAs per SM for K <= 8 (56 KB each); the padded instances run 1 CTA per SM and their reduction
+      // scratch alone is 34 KB at KP = 32, so they get a larger cap
+      constexpr int kSmemCap = (KP <= 8) ? kXsBytes : 100 * 1024;
+      if (g.smem_bytes > (size_t)kSmemCap) throw Error(SPB_ERR_INTERNAL, "ADMM kernel: shared memory request too large");
       SPB_CUDA(cudaFuncSetAttribute(admm_persistent_kernel<KP>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXsBytes));
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap));
       int per_sm = 0, sms = 0;
       SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, admm_persistent_kernel<KP>,
                                                              kThreads, g.smem_bytes));

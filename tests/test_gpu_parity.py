@@ -166,7 +166,7 @@ def _spd_problem(p, K, seed, n=40):
     return Yt, G, Om, rho, Phi0, L20
 
 
-@pytest.mark.parametrize("p,K", [(50, 1), (300, 3), (1000, 5), (513, 8), (700, 12)])
+@pytest.mark.parametrize("p,K", [(50, 1), (300, 3), (1000, 5), (513, 8), (700, 12), (640, 20)])
 def test_inverse_and_core2_vs_oracle(sp, p, K):
     from spatpca_b200 import engine as eng
     Yt, G, Om, rho, Phi0, L20 = _spd_problem(p, K, 3 * p + K)
@@ -198,6 +198,29 @@ def test_core3_vs_oracle(sp, p, K, tau2):
     for g, w in zip(got[:5], want):
         scale = max(np.max(np.abs(w)), 1e-300)
         assert np.max(np.abs(g - w)) / scale <= 1e-10
+
+
+@pytest.mark.parametrize("scales", [(1.0, 0.2, 0.05), (1.0, 0.03, 0.001)])
+def test_polar_step_on_ill_conditioned_iterate(sp, scales):
+    """The polar step (svd_econ's U V', :169-171) when T'T is far from the identity: with Ainv = I / rho and
+    Lambda2 = 0 the first T equals the start C, whose columns are scaled to cond(T'T) = 400 resp. 1e6.  The
+    Newton-Schulz iteration converges slowly or not at all there and the kernel must fall back to the Jacobi
+    eigen-solve; either way the iterates have to match the oracle's SVD-based ones."""
+    from spatpca_b200 import engine as eng
+    rng = np.random.default_rng(5)
+    p, K, rho = 700, 3, 7.0
+    Q, _ = np.linalg.qr(rng.normal(size=(p, K)))
+    mix = np.array([[1.0, 0.3, 0.1], [0.0, 1.0, 0.4], [0.0, 0.0, 1.0]])
+    C0 = (Q * np.array(scales)) @ mix
+    L20 = np.zeros((p, K))
+    Z = np.zeros((p, p))
+    tr = ref.Trace()
+    wPhi, wC, wL2 = ref.core2(Z, None, C0, L20, Z, 0.0, rho, 3, 0.0, tr)
+    gPhi, gC, gL2, it = eng.admm_core2(np.eye(p) / rho, C0, L20, rho, 3, 0.0)
+    assert it == 3 == tr.calls[0][3]
+    scale = np.max(np.abs(wPhi))            # Lambda2 ends at rounding-noise level: compare on Phi's scale
+    for g, w in ((gPhi, wPhi), (gC, wC), (gL2, wL2)):
+        assert np.max(np.abs(g - w)) / max(np.max(np.abs(w)), scale) <= 1e-8
 
 
 def test_core3_forced_iterations(sp):
