@@ -975,6 +975,10 @@ void launch_instance(const Params& P, const Geom& g, cudaStream_t s) {
   }
   int want = g.smax > g.nrb ? g.smax : g.nrb;
   int grid = want < max_ctas ? want : max_ctas;
+  // a CTA streams ceil(S / grid) segments of up to two pieces each and remembers at most 8 (tile, slice)
+  // fix-ups in shared memory: true on any device with >= 74 co-resident CTAs (B200: 148 or 296)
+  if (2 * ceil_div(g.smax, grid) > 8)
+    throw Error(SPB_ERR_INTERNAL, "ADMM kernel: too few co-resident CTAs on this device for the segment count");
   Params Pc = P;
   void* args[] = {&Pc};
   SPB_CUDA(cudaLaunchCooperativeKernel((void*)admm_persistent_kernel<KP>, dim3(grid), dim3(kThreads),
