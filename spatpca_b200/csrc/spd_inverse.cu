@@ -170,37 +170,84 @@ void leaf(const Ctx& c, double* A, int n, size_t ld) {
   count_launch();
 }
 
+// Symmetric products  upper(C) += alpha * op(A) op(B)  on a UNIFORM grid of hb x hb blocks (hb ~ 528, a
+// multiple of 16; the last block may be ragged): all diagonal blocks in ONE strided-batched GEMM (they are
+// computed as full squares: hb / n of the product is wasted, 6 % at n = 8464), the blocks above the diagonal
+// by bisection over block ranges -- one GEMM per node, square at the top (4232 x 4232 x k runs at the DGEMM
+// rate), single blocks at the bottom.  The former element-wise recursion ended in sixteen separate
+// 530-wide GEMMs of 41 us each at 22 TFLOP/s (profiles/r01_notes.md section 6).
+struct SymGrid {
+  int n, hb, nb, last;      // nb blocks: nb - 1 of hb rows and a last one of `last` rows (1 <= last <= hb)
+  int off(int b) const { return b * hb; }
+  int width(int b0, int b1) const { return (b1 == nb ? n : b1 * hb) - b0 * hb; }
+};
+
+SymGrid sym_grid(int n) {
+  SymGrid g;
+  g.n = n;
+  int nb = (n + 264) / 528;
+  if (nb < 2) nb = 2;
+  g.hb = (int)round_up((size_t)ceil_div(n, nb), 16);
+  g.nb = ceil_div(n, g.hb);
+  g.last = n - (g.nb - 1) * g.hb;
+  return g;
+}
+
+// blocks above the diagonal inside the block range [b0, b1): C[rows b0..bm, cols bm..b1] then both halves
+template <bool TN>
+void sym_offdiag(const Ctx& c, const SymGrid& g, int b0, int b1, int k, double alpha, const double* A, size_t lda,
+                 const double* B, size_t ldb, double* C, size_t ldc) {
+  if (b1 - b0 < 2) return;
+  const int bm = (b0 + b1) / 2;
+  const int r0 = g.off(b0), c0 = g.off(bm);
+  const int m = g.width(b0, bm), w = g.width(bm, b1);
+  const double one = 1.0;
+  if (TN) {   // C[r0.., c0..] += alpha * A[:, r0..]' * B[:, c0..]
+    SPB_CUBLAS(cublasDgemm(c.blas, CUBLAS_OP_T, CUBLAS_OP_N, m, w, k, &alpha, A + (size_t)r0 * lda, (int)lda,
+                           B + (size_t)c0 * ldb, (int)ldb, &one, C + (size_t)c0 * ldc + r0, (int)ldc));
+  } else {    // C[r0.., c0..] += alpha * A[r0.., :] * B[c0.., :]'
+    SPB_CUBLAS(cublasDgemm(c.blas, CUBLAS_OP_N, CUBLAS_OP_T, m, w, k, &alpha, A + r0, (int)lda, B + c0, (int)ldb, &one,
+                           C + (size_t)c0 * ldc + r0, (int)ldc));
+  }
+  sym_offdiag<TN>(c, g, b0, bm, k, alpha, A, lda, B, ldb, C, ldc);
+  sym_offdiag<TN>(c, g, bm, b1, k, alpha, A, lda, B, ldb, C, ldc);
+}
+
+template <bool TN>
+void gemm_upper(const Ctx& c, int n, int k, double alpha, const double* A, size_t lda, const double* B, size_t ldb,
+                double* C, size_t ldc) {
+  const double one = 1.0;
+  const cublasOperation_t ta = TN ? CUBLAS_OP_T : CUBLAS_OP_N, tb = TN ? CUBLAS_OP_N : CUBLAS_OP_T;
+  if (n <= kSymGemmMin) {
+    SPB_CUBLAS(cublasDgemm(c.blas, ta, tb, n, n, k, &alpha, A, (int)lda, B, (int)ldb, &one, C, (int)ldc));
+    return;
+  }
+  const SymGrid g = sym_grid(n);
+  const int nfull = (g.last == g.hb) ? g.nb : g.nb - 1;
+  // operand strides from one diagonal block to the next: TN walks columns of A and B, NT walks rows
+  const long long sa = TN ? (long long)g.hb * (long long)lda : (long long)g.hb;
+  const long long sb = TN ? (long long)g.hb * (long long)ldb : (long long)g.hb;
+  const long long sc = (long long)g.hb * ((long long)ldc + 1);
+  SPB_CUBLAS(cublasDgemmStridedBatched(c.blas, ta, tb, g.hb, g.hb, k, &alpha, A, (int)lda, sa, B, (int)ldb, sb, &one, C,
+                                       (int)ldc, sc, nfull));
+  if (nfull < g.nb) {
+    const size_t o = (size_t)g.off(g.nb - 1);
+    SPB_CUBLAS(cublasDgemm(c.blas, ta, tb, g.last, g.last, k, &alpha, A + (TN ? o * lda : o), (int)lda,
+                           B + (TN ? o * ldb : o), (int)ldb, &one, C + o * ldc + o, (int)ldc));
+  }
+  sym_offdiag<TN>(c, g, 0, g.nb, k, alpha, A, lda, B, ldb, C, ldc);
+}
+
 // upper(C) += alpha * A' * B,   A: k x n, B: k x n, C: n x n symmetric result
 void gemm_upper_TN(const Ctx& c, int n, int k, double alpha, const double* A, size_t lda, const double* B,
                    size_t ldb, double* C, size_t ldc) {
-  const double one = 1.0;
-  if (n <= kSymGemmMin) {
-    SPB_CUBLAS(cublasDgemm(c.blas, CUBLAS_OP_T, CUBLAS_OP_N, n, n, k, &alpha, A, (int)lda, B, (int)ldb, &one, C,
-                           (int)ldc));
-    return;
-  }
-  const int h = (n / 2 + 15) / 16 * 16;
-  gemm_upper_TN(c, h, k, alpha, A, lda, B, ldb, C, ldc);
-  SPB_CUBLAS(cublasDgemm(c.blas, CUBLAS_OP_T, CUBLAS_OP_N, h, n - h, k, &alpha, A, (int)lda, B + (size_t)h * ldb,
-                         (int)ldb, &one, C + (size_t)h * ldc, (int)ldc));
-  gemm_upper_TN(c, n - h, k, alpha, A + (size_t)h * lda, lda, B + (size_t)h * ldb, ldb,
-                C + (size_t)h * ldc + h, ldc);
+  gemm_upper<true>(c, n, k, alpha, A, lda, B, ldb, C, ldc);
 }
 
 // upper(C) += alpha * A * B',   A: n x k, B: n x k
 void gemm_upper_NT(const Ctx& c, int n, int k, double alpha, const double* A, size_t lda, const double* B,
                    size_t ldb, double* C, size_t ldc) {
-  const double one = 1.0;
-  if (n <= kSymGemmMin) {
-    SPB_CUBLAS(cublasDgemm(c.blas, CUBLAS_OP_N, CUBLAS_OP_T, n, n, k, &alpha, A, (int)lda, B, (int)ldb, &one, C,
-                           (int)ldc));
-    return;
-  }
-  const int h = (n / 2 + 15) / 16 * 16;
-  gemm_upper_NT(c, h, k, alpha, A, lda, B, ldb, C, ldc);
-  SPB_CUBLAS(cublasDgemm(c.blas, CUBLAS_OP_N, CUBLAS_OP_T, h, n - h, k, &alpha, A, (int)lda, B + h, (int)ldb, &one,
-                         C + (size_t)h * ldc, (int)ldc));
-  gemm_upper_NT(c, n - h, k, alpha, A + h, lda, B + h, ldb, C + (size_t)h * ldc + h, ldc);
+  gemm_upper<false>(c, n, k, alpha, A, lda, B, ldb, C, ldc);
 }
 
 // A (n x n, upper triangle valid) -> A^-1 in full storage.  W: workspace of >= n*n/2 doubles.
