@@ -206,7 +206,13 @@ def run_sharded(engine, select_index, coll: Collective, M: int, n_tau1: int, n_t
     full_rank = full_fit_owner(M, world)
 
     # ---- stage 1 ----
-    if share_inverses and world > 1 and n_tau1 > 1 and getattr(engine, "can_share_inverses", lambda: False)():
+    # whether the stage-1 systems are shared is decided by free device memory on each rank: every rank must take
+    # the same branch (the exchange below is collective), so the ranks agree on the minimum first
+    can_share = bool(share_inverses and world > 1 and n_tau1 > 1 and
+                     getattr(engine, "can_share_inverses", lambda: False)())
+    if world > 1:
+        can_share = bool(np.min(coll.all_gather_rows(np.array([[1.0 if can_share else 0.0]]))) > 0.5)
+    if can_share:
         # the (fold, tau1) inverses do not depend on the iterates: spread them over ALL ranks (also the
         # ones without a fold) and ship each to the fold's home rank; the chains then only iterate
         jobs, owner = plan_inverse_jobs(M, n_tau1, world)
