@@ -603,7 +603,7 @@ int spb_admm_system(const double* omega, const double* G, int p, double tau1, do
                     double* Lambda1, double* Lambda2, int* iters) {
   return guarded([&] {
     SPB_REQUIRE(mode == 2 || mode == 3, "mode must be 2 or 3");
-    SPB_REQUIRE(blocks >= 0 && blocks <= kMaxBlocks, "blocks must be in 0..8");
+    SPB_REQUIRE(blocks >= 0 && blocks <= kMaxBlocks, "blocks must be in 0..kMaxBlocks");
     SystemSpec sys{omega, G, tau1, scale, blocks};
     run_admm_host(mode, nullptr, p, K, tau2, rho, maxit, tol, Phi, R, C, Lambda1, Lambda2, iters, &sys);
   });
@@ -671,7 +671,7 @@ int spb_bench_admm(int p, int K, int mode, int iters, int repeats, double* ms_pe
 
 int spb_bench_admm_blocks(int p, int K, int mode, int iters, int repeats, int blocks, double* ms_per_iter) {
   return guarded([&] {
-    SPB_REQUIRE(blocks >= 0 && blocks <= kMaxBlocks, "blocks must be in 0..8");
+    SPB_REQUIRE(blocks >= 0 && blocks <= kMaxBlocks, "blocks must be in 0..kMaxBlocks");
     const Blocking blk = blocking_for(p, blocks);
     SPB_REQUIRE(p >= 1 && K >= 1 && K <= SPB_MAX_K && K <= p && iters >= 1 && repeats >= 1 && ms_per_iter,
                 "invalid argument");
@@ -800,7 +800,7 @@ int spb_bench_inverse(int p, int repeats, double* ms_out) { return spb_bench_fac
 int spb_bench_factor(int p, int repeats, int blocks, double* ms_out) {
   return guarded([&] {
     SPB_REQUIRE(p >= 1 && repeats >= 1 && ms_out, "invalid argument");
-    SPB_REQUIRE(blocks >= 0 && blocks <= kMaxBlocks, "blocks must be in 0..8");
+    SPB_REQUIRE(blocks >= 0 && blocks <= kMaxBlocks, "blocks must be in 0..kMaxBlocks");
     const Blocking blk = blocking_for(p, blocks);
     DeviceCtx& ctx = DeviceCtx::get();
     cudaStream_t s = ctx.stream;

@@ -72,10 +72,10 @@ struct AdmmWorkspace;   // partial-sum buffers, sized by (p, K)
 // ADMM kernel's row tile, off[m] = p).  m = 1 means "explicit inverse".  m > 1 selects the block
 // U'DU factor of spd_inverse.cu, which costs ~p^3/3 + p^3/m flop instead of p^3 and is applied by the
 // ADMM kernel as 2m - 1 dependent matrix-stream phases over the same 8 p^2 bytes.
-constexpr int kMaxBlocks = 8;
+constexpr int kMaxBlocks = 12;     // 2 * 12 - 1 = 23 stream phases at most
 struct Blocking {
   int m = 1;
-  int off[kMaxBlocks + 1] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int off[kMaxBlocks + 1] = {};
 };
 // Default partition for a system of order p (SPB_FACTOR_BLOCKS overrides the block count; 1 = explicit
 // inverse everywhere).  Deterministic in p, so every rank of a multi-GPU job agrees on it.

@@ -304,9 +304,11 @@ Blocking spd_blocking_m(int p, int m_request) {
 }
 
 Blocking spd_blocking(int p) {
-  // SPB_FACTOR_BLOCKS = 1 forces explicit inverses.  Default: blocks of ~1024 rows (~1536 from p = 8192 on,
-  // at most kMaxBlocks): measured on the C3 / C4 jobs (profiles/r01_notes.md section 6) -- the factor's flop
-  // count falls as p^3/3 + p^3/m while every block adds two dependent stream phases to an ADMM iteration.
+  // SPB_FACTOR_BLOCKS = 1 forces explicit inverses.  Default: blocks of 1024 rows (larger ones once kMaxBlocks
+  // = 12 would be exceeded, i.e. above p = 12288).  Measured on the C4 job (profiles/r01_notes.md sections 6, 9):
+  // 5 / 7 / 10 / 20 blocks -> 1.43 / 1.22 / 1.17 / 1.16 s per job while an ADMM iteration on such a system takes
+  // 258 / 282 / 344 / 609 us -- the factor's flop count falls as p^3/3 + p^3/m while every block adds two
+  // dependent stream phases; 1024 rows keep the GEMMs deep enough (k = 1024) and the phase count moderate.
   // Below p = 2048 everything is latency-bound and the single-phase stream of an explicit inverse wins.
   static const int env_m = [] {
     const char* e = std::getenv("SPB_FACTOR_BLOCKS");
@@ -319,8 +321,7 @@ Blocking spd_blocking(int p) {
   if (cusolver) return spd_blocking_m(p, 1);
   if (env_m > 0) return spd_blocking_m(p, env_m);
   if (p < 2048) return spd_blocking_m(p, 1);
-  const int bs = p >= 8192 ? 1536 : 1024;
-  return spd_blocking_m(p, ceil_div(p, bs));
+  return spd_blocking_m(p, ceil_div(p, 1024));
 }
 
 Blocking spd_blocking_path(int p) {
@@ -329,10 +330,10 @@ Blocking spd_blocking_path(int p) {
     return e != nullptr ? std::atoi(e) : 0;
   }();
   if (env_m > 0) return spd_blocking_m(p, env_m);
-  // Measured at C4 (p = 10 000, ~25 iterations per path system): against spd_blocking(p)'s 7 blocks, 2 blocks
-  // cost +20 ms per job and explicit inverses +80 ms, while an iteration takes 358 us with 7 blocks, 203 us
-  // with 2 and 146 us explicit -- 2 blocks win from ~46 iterations per system on and lose little before
-  // (profiles/r01_notes.md section 6).
+  // Measured at C4 (p = 10 000, ~25 iterations per path system): against spd_blocking(p)'s many blocks, 2 blocks
+  // cost +20 ms per job and explicit inverses +80 ms, while an iteration takes 344 us with 10 blocks, 170 us
+  // with 2 and 144 us explicit -- 2 blocks win from ~46 iterations per system on and lose little before
+  // (profiles/r01_notes.md sections 6, 8).
   const Blocking b = spd_blocking(p);
   return b.m <= 2 ? b : spd_blocking_m(p, 2);
 }

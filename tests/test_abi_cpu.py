@@ -65,14 +65,14 @@ def test_select_index_matches_armadillo_order():
 
 def test_block_partition_policy():
     """Host-only: how many row blocks the SPD systems of order p get (csrc/spd_inverse.cu).  Explicit inverses
-    below p = 2048, ~1024-row blocks above, ~1536-row blocks from p = 8192, never more than 8; the systems that
-    are reused along a tau2 path get at most 2 blocks."""
+    below p = 2048, 1024-row blocks above, never more than 12 blocks; the systems that are reused along a tau2
+    path get at most 2 blocks."""
     from spatpca_b200 import engine as eng
     if any(os.environ.get(v) for v in ("SPB_FACTOR_BLOCKS", "SPB_PATH_BLOCKS", "SPB_INVERSE")):
         pytest.skip("block policy overridden by the environment")
     assert [eng.default_blocks(p) for p in (1, 50, 900, 2047)] == [1, 1, 1, 1]
     assert eng.default_blocks(2048) == 2 and eng.default_blocks(4096) == 4
-    assert eng.default_blocks(10000) == 7 and eng.default_blocks(40000) == 8
+    assert eng.default_blocks(10000) == 10 and eng.default_blocks(40000) == 12
     for p in (50, 2047, 2048, 4096, 10000, 40000):
         m, mp = eng.default_blocks(p), eng.default_path_blocks(p)
         assert 1 <= mp <= min(m, 2) or (m == 1 and mp == 1)
