@@ -273,6 +273,12 @@ SPB_API int spb_admm_system(const double* omega, const double* G, int p,
 SPB_API int spb_default_blocks(int p);
 /* the same for the systems reused along a whole tau2 path (tempinv, :397)    */
 SPB_API int spb_default_path_blocks(int p);
+/* Host-only introspection of the factored solve (no device needed; used by the CPU tests):
+ * block offsets off[0..m] of the partition (returns m), and the per-iteration stream phases of the ADMM
+ * kernel, 8 ints each {kind (0 single fused phase, 1 forward, 2 backward), row0, nrows, col0, ncols,
+ * first / one-past-last row that becomes final in the phase, segments} (returns the phase count).        */
+SPB_API int spb_block_offsets(int p, int blocks, int* off, int cap);
+SPB_API int spb_admm_phase_plan(int p, int K, int blocks, int* plan8, int cap);
 /* pow(norm(Yva * (I - Phi Phi'), "fro"), 2)   (:327, :331, :400)            */
 SPB_API int spb_cv_loss(const double* Yva, int n_va, int p, const double* Phi, int K, double* loss);
 /* stage-3 losses of one fold for all gammas (:489-523)                      */

@@ -106,6 +106,8 @@ SIGNATURES = {
                                   C.c_double, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp, _ip]),
     "spb_default_blocks": (C.c_int, [C.c_int]),
     "spb_default_path_blocks": (C.c_int, [C.c_int]),
+    "spb_block_offsets": (C.c_int, [C.c_int, C.c_int, _ip, C.c_int]),
+    "spb_admm_phase_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, C.c_int]),
     "spb_cv_loss": (C.c_int, [_dp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
     "spb_gamma_loss": (C.c_int, [_dp, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp]),
     "spb_bench_admm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),

@@ -1000,6 +1000,18 @@ size_t admm_workspace_bytes(int p, int K) {
 
 int admm_num_segments(int p, int K) { return make_geom(p, K, Blocking()).smax; }
 
+int admm_phase_plan(int p, int K, const Blocking& blk, int* out, int cap) {
+  const Geom g = make_geom(p, K, blk);
+  for (int f = 0; f < g.nphases && f < cap; ++f) {
+    const PhaseDesc& ph = g.ph[f];
+    int* o = out + 8 * f;
+    o[0] = ph.kind; o[1] = ph.row0; o[2] = ph.nrows; o[3] = ph.col0; o[4] = ph.ncols;
+    // a single-phase (explicit inverse) stream finalises every row
+    o[5] = ph.kind == PH_FINAL ? 0 : ph.fin0; o[6] = ph.kind == PH_FINAL ? p : ph.fin1; o[7] = ph.S;
+  }
+  return g.nphases;
+}
+
 void launch_admm(const AdmmCall& c, void* ws, cudaStream_t s) {
   SPB_REQUIRE(c.K >= 1 && c.K <= SPB_MAX_K, "K must be in 1..SPB_MAX_K");
   SPB_REQUIRE(c.mode == 2 || c.mode == 3, "ADMM mode must be 2 or 3");

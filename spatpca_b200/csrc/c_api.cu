@@ -618,6 +618,29 @@ int spb_default_blocks(int p) {
   return rc < 0 ? rc : m;
 }
 
+int spb_block_offsets(int p, int blocks, int* off, int cap) {
+  int m = -1;
+  int rc = guarded([&] {
+    SPB_REQUIRE(p >= 1 && off != nullptr && blocks >= 0 && blocks <= kMaxBlocks, "invalid argument");
+    const Blocking b = blocking_for(p, blocks);
+    SPB_REQUIRE(cap >= b.m + 1, "offset buffer too small");
+    for (int j = 0; j <= b.m; ++j) off[j] = j == 0 ? 0 : b.off[j];
+    if (b.m == 1) off[1] = p;
+    m = b.m;
+  });
+  return rc < 0 ? rc : m;
+}
+
+int spb_admm_phase_plan(int p, int K, int blocks, int* plan8, int cap) {
+  int n = -1;
+  int rc = guarded([&] {
+    SPB_REQUIRE(p >= 1 && K >= 1 && K <= SPB_MAX_K && plan8 != nullptr && cap >= 1, "invalid argument");
+    SPB_REQUIRE(blocks >= 0 && blocks <= kMaxBlocks, "blocks must be in 0..kMaxBlocks");
+    n = admm_phase_plan(p, K, blocking_for(p, blocks), plan8, cap);
+  });
+  return rc < 0 ? rc : n;
+}
+
 int spb_default_path_blocks(int p) {
   int m = -1;
   int rc = guarded([&] {

@@ -105,6 +105,10 @@ size_t admm_workspace_bytes(int p, int K);
 void launch_admm(const AdmmCall& c, void* ws, cudaStream_t s);
 // deterministic segment count used by phase 1 (exposed for DESIGN/bench reporting)
 int admm_num_segments(int p, int K);
+// The stream phases the kernel runs per iteration for this (p, K, partition): 8 ints per phase
+// {kind (0 = single fused phase, 1 = FWD, 2 = BWD), row0, nrows, col0, ncols, fin0, fin1, segments}; returns the
+// number of phases.  Host-only (tests check that the rectangles tile the matrix and solve the system).
+int admm_phase_plan(int p, int K, const Blocking& blk, int* out, int cap);
 
 // ---- losses (loss_kernels.cu) --------------------------------------------------
 // W (m x K) <- Ymat (m x p) * Phi (p x K); scratch must hold cvloss_scratch_doubles(m, p, K)

@@ -330,6 +330,21 @@ def default_path_blocks(p):
     return check(_lib.load().spb_default_path_blocks(int(p)))
 
 
+def block_offsets(p, blocks=0):
+    """Row offsets off[0..m] of the block partition the library uses for a system of order p (host-only)."""
+    off = np.zeros(64, dtype=np.int32)
+    m = check(_lib.load().spb_block_offsets(int(p), int(blocks), off.ctypes.data_as(C.POINTER(C.c_int)), 64))
+    return [int(v) for v in off[:m + 1]]
+
+
+def admm_phase_plan(p, K, blocks=0):
+    """The ADMM kernel's stream phases for one iteration: dicts with kind / rows / cols / final rows (host-only)."""
+    buf = np.zeros(8 * 64, dtype=np.int32)
+    n = check(_lib.load().spb_admm_phase_plan(int(p), int(K), int(blocks), buf.ctypes.data_as(C.POINTER(C.c_int)), 64))
+    keys = ("kind", "row0", "nrows", "col0", "ncols", "fin0", "fin1", "segments")
+    return [dict(zip(keys, (int(v) for v in buf[8 * f:8 * f + 8]))) for f in range(n)]
+
+
 def cv_loss(Yva, Phi):
     lib = _lib.load()
     Y, P = fmat(Yva), fmat(Phi)
