@@ -7,28 +7,37 @@ from oracle import r_api
 from oracle import spatpca_ref as ref
 from oracle.r_rng import RRng, r_seq_len
 
+import json
+import os
+
 from ref_cases import case_1d, case_3d, tps_locations
 
-TOL = 1e-6          # the reference's own tolerance (test-SpatPCA.R:3)
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_goldens.json")) as _f:
+    GOLD = json.load(_f)          # the reference's own known-answer values, each with its testthat file:line
+TOL = GOLD["tolerance"]           # the reference's own tolerance (test-SpatPCA.R:3)
+
+
+def gold(name):
+    return GOLD[name]["value"]
 
 
 def test_r_rng_known_values():
     r = RRng(1234)
-    np.testing.assert_allclose(r.rnorm(3), [-1.2070657, 0.2774292, 1.0844412], atol=5e-8)
+    np.testing.assert_allclose(r.rnorm(3), GOLD["r_rng"]["set_seed_1234_rnorm3"], atol=5e-8)
     r = RRng(42)
-    assert list(r.sample(np.arange(1, 11))) == [1, 5, 10, 8, 2, 4, 6, 9, 7, 3]
+    assert list(r.sample(np.arange(1, 11))) == GOLD["r_rng"]["set_seed_42_sample_1_10"]
 
 
 def test_tps_matrix_goldens():                       # test-RcppExports.R:10-15
     l2d, l3d = tps_locations()
-    assert abs(np.linalg.norm(ref.thin_plate_spline_matrix(l2d)) - 0.362588) <= TOL
-    assert abs(np.linalg.norm(ref.thin_plate_spline_matrix(l3d)) - 8.191034) <= TOL
+    assert abs(np.linalg.norm(ref.thin_plate_spline_matrix(l2d)) - gold("tps_matrix_frobenius_norm_2d")) <= TOL
+    assert abs(np.linalg.norm(ref.thin_plate_spline_matrix(l3d)) - gold("tps_matrix_frobenius_norm_3d")) <= TOL
 
 
 def test_eigen_function_golden():                    # test-RcppExports.R:18-23
     l2d, _ = tps_locations()
     v = ref.eigen_function(np.array([[0.1, 0.2]]), l2d, np.array([[1.0], [0], [0], [0]]))
-    assert abs(v[0, 0] - 0.2352884) <= TOL
+    assert abs(v[0, 0] - gold("eigen_function_value")) <= TOL
 
 
 @pytest.fixture(scope="module")
@@ -48,14 +57,14 @@ def seq_1d():
 
 def test_selected_tuning_parameters(seq_1d):         # test-SpatPCA.R:97-122
     s = seq_1d
-    assert abs(s["cv_1D"]["selected_tau1"] - 0.00046416) <= TOL
+    assert abs(s["cv_1D"]["selected_tau1"] - gold("cv_1D_selected_tau1")) <= TOL
     assert abs(s["cv_1D"]["selected_tau2"]) <= TOL
-    assert abs(s["cv_1D"]["selected_gamma"] - 0.44503397) <= 1.0001 * TOL
+    assert abs(s["cv_1D"]["selected_gamma"] - gold("cv_1D_selected_gamma")) <= 1.0001 * TOL
     assert s["cv_1D"]["selected_K"] is None
     assert s["cv_1D"]["eigenfn"].shape == (10, 2)     # quirk: fit for selected_K + 1
     assert s["multi_tau2"]["selected_K"] == 1
-    assert abs(s["multi_tau2"]["selected_tau1"] - 0.002154435) <= TOL
-    assert s["multi_tau2"]["selected_tau2"] == 1
+    assert abs(s["multi_tau2"]["selected_tau1"] - gold("multi_tau2_selected_tau1")) <= TOL
+    assert s["multi_tau2"]["selected_tau2"] == gold("multi_tau2_selected_tau2")
     assert s["multi_gamma"]["selected_gamma"] == 0
     assert s["fixed_both"]["selected_tau1"] == 10
     assert s["fixed_both"]["selected_tau2"] == 100
@@ -71,9 +80,9 @@ def test_spatial_prediction_eigenvalues(seq_1d):     # test-SpatPCA.R:52-88, 123
     assert sp(f["eigenfn"], f["detrended_Y"], 1000, f["eigenfn"])["eigenvalue"].sum() == 0
     assert sp(z["eigenfn"], z["detrended_Y"], 10, z["eigenfn"])["eigenvalue"].sum() == 0
     assert abs(sp(z["eigenfn"], z["detrended_Y"], 0.5, z["eigenfn"])["eigenvalue"].sum()
-               - 9.397599) <= TOL
+               - gold("zero_zero_K5_eigenvalue_sum_gamma_0.5")) <= TOL
     # one-sided in the reference (expect_lte without abs)
-    assert sp(f["eigenfn"], f["detrended_Y"], 5, f["eigenfn"])["eigenvalue"].sum() - 0.1066821 <= TOL
+    assert sp(f["eigenfn"], f["detrended_Y"], 5, f["eigenfn"])["eigenvalue"].sum() - gold("fixed_tau1_eigenvalue_sum_gamma_5_upper") <= TOL
 
 
 def test_predict_shapes(seq_1d):                     # test-SpatPCA.R:138-146
@@ -90,10 +99,11 @@ def test_k_selection_aux():                          # test-SpatPCA.R:150-165
     tau2 = r_api.set_tau2(None, M)
     r = r_api.spatpca_cv_with_selected_k(x, Y, M, r_api.set_tau1(None, M), tau2, [1.0], split,
                                          10, 1e-4, r_api.set_l2(tau2))
-    assert r["selected_K"] == 1
-    assert r["cv_result"]["selected_gamma"] == 1
-    assert r["cv_result"]["selected_tau1"] == 1
-    assert r["cv_result"]["selected_tau2"] == 0
+    k = GOLD["k_selection"]
+    assert r["selected_K"] == k["selected_K"]
+    assert r["cv_result"]["selected_gamma"] == k["selected_gamma"]
+    assert r["cv_result"]["selected_tau1"] == k["selected_tau1"]
+    assert r["cv_result"]["selected_tau2"] == k["selected_tau2"]
 
 
 def test_3d_case():                                  # test-SpatPCA.R:169-187
@@ -101,7 +111,7 @@ def test_3d_case():                                  # test-SpatPCA.R:169-187
     cv = r_api.spatpca(d, Y, rng)
     assert cv["eigenfn"].shape == (64, 2)
     pred = ref.eigen_function(np.zeros((1, 3)), d, cv["eigenfn"])
-    assert np.sum(np.abs(pred[0] - np.array([0.232199, 0.007501031]))) <= TOL
+    assert np.sum(np.abs(pred[0] - np.array(gold("predict_3d_at_origin")))) <= TOL
 
 
 def test_helper_grids():                             # test-helper.R:20-25, 85-120
