@@ -89,3 +89,62 @@ def test_default_partitions_are_consistent():
         sizes = np.diff(off)
         assert sizes.max() - sizes[:-1].min() == 0 or len(sizes) == 1       # uniform except the last block
         assert sizes[-1] <= sizes[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# NumPy model of the polar step's inverse square root (csrc/admm_kernels.cu: ns_inv_sqrt_cta): the same
+# scaling, iteration and stopping rule, to pin the constants (24 steps, test at 3e-9 before a step).
+# ---------------------------------------------------------------------------------------------
+def ns_inv_sqrt_model(G, max_steps=24, tol=3e-9):
+    K = G.shape[0]
+    sc = np.max(np.sum(np.abs(G), axis=1))
+    if not (sc > 0.0) or not np.isfinite(sc):
+        return None, 0
+    Y, Z = G / sc, np.eye(K)
+    for it in range(max_steps):
+        M = 3.0 * np.eye(K) - Z @ Y
+        big = not (np.max(np.abs(M - 2.0 * np.eye(K))) < tol)
+        Y, Z = 0.5 * (Y @ M), 0.5 * (M @ Z)
+        if not big:
+            return 0.5 * (Z + Z.T) / np.sqrt(sc), it + 1
+    return None, max_steps
+
+
+def _gram(K, cond, rng):
+    Q, _ = np.linalg.qr(rng.normal(size=(K, K)))
+    lam = np.geomspace(1.0, 1.0 / cond, K) * rng.uniform(0.5, 50.0)
+    return (Q * lam) @ Q.T
+
+
+@pytest.mark.parametrize("K", [1, 2, 5, 8, 16])
+def test_newton_schulz_model_on_the_paths_gram_matrices(K):
+    """cond(T'T) <= ~1.5 on this path: a handful of steps, eigen-solve accuracy."""
+    rng = np.random.default_rng(K)
+    for cond in (1.0, 1.05, 1.5, 4.0, 30.0):
+        G = _gram(K, cond if K > 1 else 1.0, rng)
+        P, steps = ns_inv_sqrt_model(G)
+        assert P is not None and steps <= (8 if cond <= 1.5 else 16)
+        lam, V = np.linalg.eigh(G)
+        want = (V / np.sqrt(lam)) @ V.T
+        assert np.max(np.abs(P - want)) / np.max(np.abs(want)) <= 1e-13 * max(cond, 1.0)
+        assert np.max(np.abs(P @ G @ P - np.eye(K))) <= 1e-13 * max(cond, 1.0)
+
+
+def test_newton_schulz_model_gives_up_on_bad_gram_matrices():
+    """Ill-conditioned, singular, indefinite or non-finite input must end in 'not converged' (the kernel then
+    runs the Jacobi eigen-solve, which classifies the failure) -- never in a wrong answer."""
+    rng = np.random.default_rng(0)
+    # the smallest eigenvalue of Z Y grows 2.25x per step, so cond = 1e6 still converges (~22 steps, accuracy
+    # ~cond * eps like the eigen-solve); cond = 1e13 does not
+    G6 = _gram(5, 1e6, rng)
+    P6, steps6 = ns_inv_sqrt_model(G6)
+    assert P6 is not None and 16 <= steps6 <= 24
+    assert np.max(np.abs(P6 @ G6 @ P6 - np.eye(5))) <= 1e-8
+    assert ns_inv_sqrt_model(_gram(5, 1e13, rng))[0] is None
+    S = _gram(4, 2.0, rng)
+    S[:, 0] = S[:, 1]; S[0, :] = S[1, :]                      # singular
+    assert ns_inv_sqrt_model(S)[0] is None
+    assert ns_inv_sqrt_model(-_gram(3, 2.0, rng))[0] is None    # negative definite
+    N = _gram(3, 2.0, rng); N[1, 1] = np.nan
+    assert ns_inv_sqrt_model(N)[0] is None
+    assert ns_inv_sqrt_model(np.zeros((3, 3)))[0] is None
