@@ -101,12 +101,13 @@ def ns_inv_sqrt_model(G, max_steps=24, tol=3e-9):
     if not (sc > 0.0) or not np.isfinite(sc):
         return None, 0
     Y, Z = G / sc, np.eye(K)
-    for it in range(max_steps):
-        M = 3.0 * np.eye(K) - Z @ Y
-        big = not (np.max(np.abs(M - 2.0 * np.eye(K))) < tol)
-        Y, Z = 0.5 * (Y @ M), 0.5 * (M @ Z)
-        if not big:
-            return 0.5 * (Z + Z.T) / np.sqrt(sc), it + 1
+    with np.errstate(all="ignore"):            # a diverging iteration overflows; it then simply never converges
+        for it in range(max_steps):
+            M = 3.0 * np.eye(K) - Z @ Y
+            big = not (np.max(np.abs(M - 2.0 * np.eye(K))) < tol)
+            Y, Z = 0.5 * (Y @ M), 0.5 * (M @ Z)
+            if not big:
+                return 0.5 * (Z + Z.T) / np.sqrt(sc), it + 1
     return None, max_steps
 
 
