@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SPB_ABI_VERSION 1
+#define SPB_ABI_VERSION 2
 
 /* status codes */
 #define SPB_OK                 0
@@ -112,6 +112,8 @@ typedef struct spb_cv_stats {
   long long bytes_h2d;
   long long bytes_d2h;
   int       gpu_launches;     /* kernels of this library launched (library calls not counted) */
+  int       n_cg_calls;       /* spatpcaCore2/2p calls solved matrix-free (conjugate gradients, no inv_sympd) */
+  long long cg_passes;        /* p x p matrix passes streamed by those calls                                   */
 } spb_cv_stats;
 
 /*
@@ -269,6 +271,15 @@ SPB_API int spb_admm_system(const double* omega, const double* G, int p,
                     int mode, int K, double tau2, int maxit, double tol,
                     double* Phi, double* R, double* C, double* Lambda1, double* Lambda2,
                     int* iters);
+/* spatpcaCore2 (:150-185) WITHOUT inv_sympd: the Phi-update solves
+ * (2 (tau1 Omega_u - Ytr'Ytr) + rho I) Phi = rho C - Lambda2 by conjugate gradients inside the persistent
+ * kernel (csrc/admm_kernels.cu, cg_core2_kernel); Omega_u = symmatu(omega) is streamed once per CG step, the
+ * Gram matrix is applied through Ytr (n_tr x p).  Phi is the warm start on entry.  cg_tol: relative residual
+ * per column (<= 0: the library default 1e-14).  passes (may be NULL): p x p matrix passes streamed.
+ * K <= 8.                                                                                              */
+SPB_API int spb_core2_matrix_free(const double* omega, const double* Ytr, int n_tr, int p, int K,
+                          double tau1, double rho, int maxit, double tol, double cg_tol,
+                          double* Phi, double* C, double* Lambda2, int* iters, int* passes);
 /* block count the library uses for systems of order p (1 = explicit inverse) */
 SPB_API int spb_default_blocks(int p);
 /* the same for the systems reused along a whole tau2 path (tempinv, :397)    */
@@ -289,6 +300,11 @@ SPB_API int spb_gamma_loss(const double* Phi, int p, int K,
 /* ------------------------------------------------------------------------ */
 /* Device-resident benchmark hooks (bench.py).                               */
 /* ------------------------------------------------------------------------ */
+/* The matrix-free Core2 kernel on a synthetic system in device memory (Omega_u = a banded SPD matrix with
+ * lambda_max ~ rho / 2, Ytr random-sign, n_tr rows): `iters` forced ADMM iterations per launch; returns the
+ * device time per launch (ms, mean of `repeats` after a warm-up) and the p x p matrix passes per launch.      */
+SPB_API int spb_bench_core2_cg(int p, int K, int n_tr, int iters, int repeats, double* ms_per_launch,
+                       int* passes_per_launch);
 /* Runs `iters` forced iterations on a synthetic p x p system that lives in
  * device memory (identity: the bytes streamed are what matters; the iterate
  * starts from non-orthogonal columns so that every polar step does real

@@ -433,6 +433,7 @@ def spatpca_cv(sxy, Y, M, K, tau1, tau2, gamma, nk, maxit, tol, l2, trace=None,
             Omega = thin_plate_spline_matrix(sxy, trace)
         else:
             Omega = _F(omega).copy(order="F")
+        omega_raw_diag = Omega[np.diag_indices(p)].copy()
         Omega[np.diag_indices(p)] += 1e-8
     elif len(gamma) > 1:                                          # :576-590
         Omega = np.eye(p, order="F")
@@ -579,8 +580,18 @@ def spatpca_cv(sxy, Y, M, K, tau1, tau2, gamma, nk, maxit, tol, l2, trace=None,
         "selected_tau1": sel_tau1,
         "selected_tau2": sel_tau2,
         "selected_gamma": sel_gamma,
-        "aux": {"cv1": cv1, "cv2": cv2, "cv3": cv3, "rho_cv": rho_cv, "rho": rho_hat},
+        "aux": {"cv1": cv1, "cv2": cv2, "cv3": cv3, "rho_cv": rho_cv, "rho": rho_hat,
+                "omega": _omega_without_ridge(Omega, omega_raw_diag if any_tau else None)},
     }
+
+
+def _omega_without_ridge(Omega, raw_diag):
+    """thinPlateSplineMatrix(sxy) as this run used it (the +1e-8 I of :574 undone), for injected-Omega parity runs."""
+    if Omega is None or raw_diag is None:
+        return None
+    out = Omega.copy(order="F")
+    out[np.diag_indices(out.shape[0])] = raw_diag
+    return out
 
 
 # --------------------------------------------------------------------------

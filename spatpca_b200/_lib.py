@@ -37,6 +37,7 @@ class CvStats(C.Structure):
         ("ms_omega", C.c_double), ("ms_prologue", C.c_double), ("ms_inverse", C.c_double),
         ("ms_admm", C.c_double), ("ms_cv_loss", C.c_double), ("ms_gamma", C.c_double),
         ("bytes_h2d", C.c_longlong), ("bytes_d2h", C.c_longlong), ("gpu_launches", C.c_int),
+        ("n_cg_calls", C.c_int), ("cg_passes", C.c_longlong),
     ]
 
     def as_dict(self):
@@ -104,6 +105,9 @@ SIGNATURES = {
                                  _dp, _dp, _dp, _dp, _dp, _ip]),
     "spb_admm_system": (C.c_int, [_dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                   C.c_double, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp, _ip]),
+    "spb_core2_matrix_free": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                        C.c_double, C.c_double, _dp, _dp, _dp, _ip, _ip]),
+    "spb_bench_core2_cg": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _ip]),
     "spb_default_blocks": (C.c_int, [C.c_int]),
     "spb_default_path_blocks": (C.c_int, [C.c_int]),
     "spb_block_offsets": (C.c_int, [C.c_int, C.c_int, _ip, C.c_int]),

@@ -103,6 +103,27 @@ struct Params {
   unsigned long long* dbg;   // optional: globaltimer stamps of CTA 0 (8 per iteration), or nullptr
 };
 
+// Extra state of the matrix-free Core2 kernel (conjugate gradients on the ADMM system, see cg_core2_kernel).
+constexpr int kCgStride = SPB_MAX_K;
+enum CgSlot { CG_GAMMA = 0, CG_GAMMA_OLD, CG_ALPHA, CG_ALPHA_OLD, CG_BETA, CG_BN, CG_SS, CG_FROZEN, CG_FRESH, CG_MISC,
+              CG_SLOTS };
+// CG_MISC: [0] done, [1] matrix passes of the whole call, [2] status, [3] iterations of the running solve
+struct CgExtra {
+  const double* Ytr;          // n_tr x p (ld n_tr): training rows of the fold (or all of Y)
+  const double* Yt;           // p x n_tr (ld p): its transpose
+  int n_tr;
+  double c_omega, c_gram;     // operator A = c_omega * Omega_u + rho I - c_gram * Ytr'Ytr
+  double tol2;                // squared relative residual at which a column is frozen
+  int cg_cap;                 // iteration cap of one solve
+  int scap;                   // rows of S staged in shared memory at a time
+  double *Rv, *Pv, *Qv, *Uv;  // p x K work vectors
+  double* Spart;              // nrb x (n_tr x K): row-block partials of Ytr * v
+  double* Sg;                 // n_tr x K: Ytr * (current residual / iterate)
+  double* rupart;             // nrt * kMaxSlices x KP: slice partials of r . (Omega_u r)
+  double* npart2;             // nrb x 2 KP: row-block partials of |r|^2 and |b|^2
+  double* cgc;                // CG_SLOTS x kCgStride scalars
+};
+
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -308,9 +329,9 @@ constexpr int kMaxSlices = 8;
 
 __host__ __device__ inline int slice_rows(int TR, int ns) { return (((TR + ns - 1) / ns) + 1) & ~1; }
 
-template <int KP>
+template <int KP, int EPI>
 __device__ __forceinline__ bool reduce_slice(const Params& P, const PhaseDesc& ph, int t, const TileInfo& ti, int q,
-                                             double* scratch, double* red) {
+                                             double* scratch, double* red, const double* cg_vin, const CgExtra* cx) {
   using C = Cfg<KP>;
   constexpr int TR = C::TR, KG = C::KG;
   constexpr int KC = (KP <= 8) ? KP : 8;                 // columns per pass (bounds the shared scratch)
@@ -382,6 +403,7 @@ __device__ __forceinline__ bool reduce_slice(const Params& P, const PhaseDesc& p
           if (ir >= row_end) continue;
           double val = r == 0 ? v.x : v.y;
           const size_t off = (size_t)kk * p + ir;
+          if (EPI == 1) { __stcg(cx->Uv + off, val); continue; }                               // U = Omega_u v
           if (ph.kind == PH_FWD) {
             if (ir >= diag_end) { __stcg(P.X + off, __ldcg(P.X + off) + val); continue; }   // z_k -= U_jk' z_j
           } else if (ph.kind == PH_BWD) {
@@ -392,6 +414,25 @@ __device__ __forceinline__ bool reduce_slice(const Params& P, const PhaseDesc& p
         }
       }
     }
+  }
+  if (EPI == 1) {
+    // slice partial of v . (Omega_u v) per column (the only inner product of a CG step that needs the stream)
+    __syncthreads();
+    double dq[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) dq[k] = 0.0;
+    for (int r = tid; r < nrows; r += kThreads) {
+      const int i = tile_row0 + l0 + r;
+      if (i >= row_end) continue;
+#pragma unroll
+      for (int k = 0; k < KP; ++k)
+        if (k < K) {
+          const size_t off = (size_t)k * p + i;
+          dq[k] = fma(__ldcg(cg_vin + off), __ldcg(cx->Uv + off), dq[k]);
+        }
+    }
+    block_reduce_store<KP>(dq, red, cx->rupart + ((size_t)(tile_row0 / TR) * kMaxSlices + q) * KP);
+    return true;
   }
   if (!final_tile) return false;
   // T'T partial of the slice: rows re-read from L2 (this CTA wrote them just above)
@@ -533,9 +574,13 @@ __device__ __forceinline__ void finish_polar(const Params& P, double* jA, double
 
 // ---- stream: matrix-stream partials of one phase, then ticketed tile (/ polar) reduction ---------
 template <int KP>
+__device__ void cg_finish_stream(const Params& P, const CgExtra& X, int stage);
+
+template <int KP, int EPI = 0>
 __device__ __forceinline__ void stream_phase(const Params& P, const PhaseDesc& ph, double* xs, double* red,
                                              const TileInfo* tiles_all, double* jA, double* jV, double* jP,
-                                             int* sh_i, bool rev, int dbg_it) {
+                                             int* sh_i, bool rev, int dbg_it, const double* cg_vin = nullptr,
+                                             const CgExtra* cx = nullptr, int cg_stage = 0) {
   using C = Cfg<KP>;
   constexpr int RPT = C::RPT, TR = C::TR, KX = C::KX;
   const int tid = threadIdx.x;
@@ -543,7 +588,7 @@ __device__ __forceinline__ void stream_phase(const Params& P, const PhaseDesc& p
   const int nc = ph.ncols;
   const TileInfo* tiles = tiles_all + ph.tile0;
   int* tickets = P.counters + 2 + ph.tile0;
-  const double* vin = (ph.kind == PH_BWD) ? P.Phi : P.X;     // input vector of the phase
+  const double* vin = (EPI == 1) ? cg_vin : ((ph.kind == PH_BWD) ? P.Phi : P.X);     // input vector of the phase
   // the input block of a BWD phase was finalised earlier, i.e. it already holds Phi = scale * w with
   // scale = 1 or 0.5: undo the (exact, power-of-two) scaling on the way into shared memory
   const double vscale = (ph.kind == PH_BWD) ? P.inv_scale : 1.0;
@@ -673,7 +718,7 @@ __device__ __forceinline__ void stream_phase(const Params& P, const PhaseDesc& p
     }
     __syncthreads();
     if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[123] = gtimer();
-    const bool fin = reduce_slice<KP>(P, ph, t, tiles[t], q, xs, red);
+    const bool fin = reduce_slice<KP, EPI>(P, ph, t, tiles[t], q, xs, red, cg_vin, cx);
     if (P.dbg != nullptr && tid == 0 && t == 0) P.dbg[124] = gtimer();
     if (!fin) continue;
     __threadfence();
@@ -686,7 +731,8 @@ __device__ __forceinline__ void stream_phase(const Params& P, const PhaseDesc& p
     if (sh_i[1]) {
       __threadfence();
       if (tid == 0) P.counters[0] = 0;
-      finish_polar<KP>(P, jA, jV, jP, xs);
+      if (EPI == 1) cg_finish_stream<KP>(P, *cx, cg_stage);
+      else finish_polar<KP>(P, jA, jV, jP, xs);
     }
   }
   __syncthreads();
@@ -850,6 +896,400 @@ admm_persistent_kernel(Params P) {
   }
 }
 
+// =============================================================================================
+// Matrix-free Core2: the ADMM Phi-update  Phi = inv_sympd(2 (tau1 Omega - G) + rho I) (rho C - Lambda2)
+// (reference src/RcppSpatPCA.cpp:164-168) WITHOUT the p^3 inverse.
+//
+// Most systems of a spatpcaCV job serve one warm-started spatpcaCore2 call of 1-5 iterations (:329-332), and
+// the system  A = c Omega_u + rho I - c' Ytr'Ytr  is very well conditioned on this path: rho = 10 sigma_1^2
+// dominates Ytr'Ytr (<= sigma_1^2) and the thin-plate-spline matrix is bounded by its own ridge
+// (lambda_max(Omega) <= 1 / (4e-8)), so cond(A) is 1.25 .. ~10 and conjugate gradients reach 1e-15 in 5-40
+// steps.  A step streams Omega_u once (8 p^2 bytes, the same HBM-bound stream as an ADMM iteration on an explicit
+// inverse) and applies the rank-n_tr part through two skinny products with the L2-resident data block -- the
+// p x n contractions of the north-star -- so a whole Core2 call costs ~10^2 matrix passes instead of a
+// 0.4 p^3 factorisation (~150 passes at p = 10 000) plus its multi-phase applies.
+//
+// Chronopoulos-Gear CG (one global reduction point per step), K independent columns sharing the stream:
+//     w = A r,  gamma = r.r,  delta = r.w = c (r.Omega_u r) + rho gamma - c' |Ytr r|^2
+//     beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old)
+//     p = r + beta p,  q = w + beta q,  x += alpha p,  r -= alpha q
+// so only r.(Omega_u r) needs the stream's output: it is formed per row slice in the fix-up, the CTA finishing
+// the last slice publishes alpha / beta, and w itself is assembled row by row in the update phase.  A column whose
+// relative residual falls below cg_tol is frozen (alpha = beta = 0).  Every reduction has a fixed shape.
+// The host decides per call between this kernel and the factored path from a condition-number bound
+// (Engine::use_cg); the cap on the CG steps is a safety net that raises an error, never a silent fallback.
+// =============================================================================================
+__device__ __forceinline__ double* cg_slot(const CgExtra& X, int slot) { return X.cgc + (size_t)slot * kCgStride; }
+
+template <int KP>
+__device__ void cg_finish_stream(const Params& P, const CgExtra& X, int stage) {
+  if (stage == 0) return;                    // the stream of the initial residual: only U = Omega_u x is needed
+  __shared__ double ru_s[KP];
+  const int tid = threadIdx.x, K = P.K;
+  const int nslots = P.nrt * kMaxSlices;     // unused slots hold zeros
+  for (int q0 = 0; q0 < K; q0 += kThreads / 16) {
+    const int q = q0 + (tid >> 4), j = tid & 15;
+    double t = 0.0;
+    if (q < K) {
+#pragma unroll 8
+      for (int tb = j; tb < nslots; tb += 16) t += __ldcg(X.rupart + (size_t)tb * KP + q);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (q < K && j == 0) ru_s[q] = t;
+  }
+  __syncthreads();
+  if (tid < K) {
+    const int k = tid;
+    const double gam = __ldcg(cg_slot(X, CG_GAMMA) + k);
+    const double ss = __ldcg(cg_slot(X, CG_SS) + k);
+    const bool frozen = __ldcg(cg_slot(X, CG_FROZEN) + k) != 0.0;
+    const bool fresh = __ldcg(cg_slot(X, CG_FRESH) + k) != 0.0;
+    double alpha = 0.0, beta = 0.0;
+    if (!frozen) {
+      const double delta = fma(X.c_omega, ru_s[k], fma(P.rho, gam, -X.c_gram * ss));      // r . A r
+      double den = delta;
+      if (!fresh) {
+        beta = gam * fast_rcp(__ldcg(cg_slot(X, CG_GAMMA_OLD) + k));
+        den = delta - beta * gam * fast_rcp(__ldcg(cg_slot(X, CG_ALPHA_OLD) + k));
+      }
+      if (!(delta > 0.0) || !(den > 0.0) || !(den < 1e300)) {
+        __stcg(cg_slot(X, CG_MISC) + 2, (double)SPB_ERR_NOT_POSDEF);   // r.Ar <= 0: the system is not positive definite
+        den = 1.0;
+      }
+      alpha = gam * fast_rcp(den);
+    }
+    __stcg(cg_slot(X, CG_ALPHA) + k, alpha);
+    __stcg(cg_slot(X, CG_BETA) + k, beta);
+    if (!frozen) __stcg(cg_slot(X, CG_ALPHA_OLD) + k, alpha);
+  }
+  __syncthreads();
+}
+
+// Row-block phases of the CG solve (one row per thread, kRowBlock rows per block, fixed block -> CTA map):
+//   STAGE 0   S = Ytr Phi                      (warm start of the solve)
+//   STAGE 1   r = b - A Phi,  gamma, |b|^2, S = Ytr r
+//   STAGE 2   w = A r;  p, q, Phi, r updates;  gamma, S = Ytr r
+// The block partials of S (n_tr x K) and of the norms are summed in block order by the CTA that delivers the
+// last partial (ticket), which also takes the per-column decisions.
+template <int KP, int STAGE>
+__device__ __forceinline__ void cg_row_phase(const Params& P, const CgExtra& X, double* sm, double* red, int* sh_i) {
+  const int tid = threadIdx.x, p = P.p, K = P.K, n_tr = X.n_tr;
+  const int scap = X.scap;
+  double* s_sm = sm;                          // [scap][KP]     chunk of S
+  double* v_sm = sm + (size_t)scap * KP;      // [kRowBlock][KP] rows of the vector whose S partial is formed
+  const size_t nS = (size_t)n_tr * K;
+  double al[KP], be[KP];
+  bool fr[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) { al[k] = 0.0; be[k] = 0.0; fr[k] = true; }
+  if (STAGE == 2) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+      if (k < K) {
+        al[k] = __ldcg(cg_slot(X, CG_ALPHA) + k);
+        be[k] = __ldcg(cg_slot(X, CG_BETA) + k);
+        fr[k] = __ldcg(cg_slot(X, CG_FRESH) + k) != 0.0 || __ldcg(cg_slot(X, CG_FROZEN) + k) != 0.0;
+      }
+  }
+  for (int rb = blockIdx.x; rb < P.nrb; rb += gridDim.x) {
+    const int i = rb * kRowBlock + tid;
+    const bool live = i < p;
+    double z[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) z[k] = 0.0;
+    if (STAGE != 0) {
+      // z = (Ytr' S)(i, :): the transposed block is read row-contiguously across threads, S from shared memory
+      for (int r0 = 0; r0 < n_tr; r0 += scap) {
+        const int nr = min(scap, n_tr - r0);
+        __syncthreads();
+        for (int idx = tid; idx < nr * KP; idx += kThreads) {
+          const int r = idx / KP, k = idx - r * KP;
+          s_sm[idx] = (k < K) ? __ldcg(X.Sg + (size_t)k * n_tr + r0 + r) : 0.0;
+        }
+        __syncthreads();
+        if (live) {
+          const double* yp = X.Yt + (size_t)r0 * p + i;
+          int r = 0;
+          for (; r + 4 <= nr; r += 4) {
+            double y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) y[u] = __ldcg(yp + (size_t)(r + u) * p);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int k = 0; k < KP; ++k) z[k] = fma(y[u], s_sm[(r + u) * KP + k], z[k]);
+          }
+          for (; r < nr; ++r) {
+            const double y = __ldcg(yp + (size_t)r * p);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) z[k] = fma(y, s_sm[r * KP + k], z[k]);
+          }
+        }
+      }
+    }
+    double vnew[KP], nv[2 * KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) { vnew[k] = 0.0; nv[k] = 0.0; nv[KP + k] = 0.0; }
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        if (k < K) {
+          const size_t off = (size_t)k * p + i;
+          if (STAGE == 0) {
+            vnew[k] = __ldcg(P.Phi + off);
+          } else if (STAGE == 1) {
+            const double x = __ldcg(P.Phi + off);
+            const double w = fma(X.c_omega, __ldcg(X.Uv + off), fma(P.rho, x, -X.c_gram * z[k]));
+            const double b = __ldcg(P.X + off);
+            const double r = b - w;
+            __stcg(X.Rv + off, r);
+            vnew[k] = r;
+            nv[k] = r * r;
+            nv[KP + k] = b * b;
+          } else {
+            const double r = __ldcg(X.Rv + off);
+            const double w = fma(X.c_omega, __ldcg(X.Uv + off), fma(P.rho, r, -X.c_gram * z[k]));
+            double pn = r, qn = w;
+            if (!fr[k]) {
+              pn = fma(be[k], __ldcg(X.Pv + off), r);
+              qn = fma(be[k], __ldcg(X.Qv + off), w);
+            }
+            __stcg(X.Pv + off, pn);
+            __stcg(X.Qv + off, qn);
+            __stcg(P.Phi + off, fma(al[k], pn, __ldcg(P.Phi + off)));
+            const double rn = fma(-al[k], qn, r);
+            __stcg(X.Rv + off, rn);
+            vnew[k] = rn;
+            nv[k] = rn * rn;
+          }
+        }
+      }
+    }
+    // S partial of the block: thread r owns row r of Ytr[:, block] * v[block, :]
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < KP; ++k) v_sm[tid * KP + k] = vnew[k];
+    __syncthreads();
+    {
+      const int rows = min(kRowBlock, p - rb * kRowBlock);
+      for (int r = tid; r < n_tr; r += kThreads) {
+        double acc[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[k] = 0.0;
+        const double* yp = X.Ytr + (size_t)rb * kRowBlock * n_tr + r;
+        int ii = 0;
+        for (; ii + 8 <= rows; ii += 8) {
+          double y[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) y[u] = __ldcg(yp + (size_t)(ii + u) * n_tr);
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int k = 0; k < KP; ++k) acc[k] = fma(y[u], v_sm[(ii + u) * KP + k], acc[k]);
+        }
+        for (; ii < rows; ++ii) {
+          const double y = __ldcg(yp + (size_t)ii * n_tr);
+#pragma unroll
+          for (int k = 0; k < KP; ++k) acc[k] = fma(y, v_sm[ii * KP + k], acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+          if (k < K) __stcg(X.Spart + (size_t)rb * nS + (size_t)k * n_tr + r, acc[k]);
+      }
+    }
+    block_reduce_store<2 * KP>(nv, red, X.npart2 + (size_t)rb * 2 * KP);
+    // ticket: the CTA that delivers the last block sums the partials in block order and decides
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int old = atomicAdd(P.counters + 1, 1);
+      sh_i[0] = (old == P.nrb - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh_i[0]) {
+      __threadfence();
+      for (size_t e = tid; e < nS; e += kThreads) {
+        double t = 0.0;
+#pragma unroll 8
+        for (int b = 0; b < P.nrb; ++b) t += __ldcg(X.Spart + (size_t)b * nS + e);
+        __stcg(X.Sg + e, t);
+      }
+      __syncthreads();
+      // per column: |S_k|^2, gamma_k (and |b_k|^2): one warp per column, lane-strided sums + xor tree
+      const int w = tid >> 5, l = tid & 31;
+      for (int k = w; k < K; k += kThreads / 32) {
+        double ss = 0.0, g = 0.0, bn = 0.0;
+        for (int r = l; r < n_tr; r += 32) { const double v = __ldcg(X.Sg + (size_t)k * n_tr + r); ss = fma(v, v, ss); }
+        for (int b = l; b < P.nrb; b += 32) {
+          g += __ldcg(X.npart2 + (size_t)b * 2 * KP + k);
+          bn += __ldcg(X.npart2 + (size_t)b * 2 * KP + KP + k);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          g += __shfl_xor_sync(0xffffffffu, g, o);
+          bn += __shfl_xor_sync(0xffffffffu, bn, o);
+        }
+        if (l == 0 && STAGE != 0) {
+          __stcg(cg_slot(X, CG_SS) + k, ss);
+          if (STAGE == 1) {
+            __stcg(cg_slot(X, CG_GAMMA) + k, g);
+            __stcg(cg_slot(X, CG_BN) + k, bn);
+            __stcg(cg_slot(X, CG_FRESH) + k, 1.0);
+            __stcg(cg_slot(X, CG_ALPHA_OLD) + k, 1.0);
+            __stcg(cg_slot(X, CG_GAMMA_OLD) + k, 1.0);
+            __stcg(cg_slot(X, CG_FROZEN) + k, (g <= X.tol2 * bn) ? 1.0 : 0.0);
+          } else {
+            const double bnk = __ldcg(cg_slot(X, CG_BN) + k);
+            const bool was = __ldcg(cg_slot(X, CG_FROZEN) + k) != 0.0;
+            if (!was) {
+              __stcg(cg_slot(X, CG_GAMMA_OLD) + k, __ldcg(cg_slot(X, CG_GAMMA) + k));
+              __stcg(cg_slot(X, CG_GAMMA) + k, g);
+              __stcg(cg_slot(X, CG_FRESH) + k, 0.0);
+              if (g <= X.tol2 * bnk || !(g < 1e300)) __stcg(cg_slot(X, CG_FROZEN) + k, 1.0);
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (STAGE != 0 && tid == 0) {
+        int done = 1;
+        for (int k = 0; k < K; ++k) done &= (__ldcg(cg_slot(X, CG_FROZEN) + k) != 0.0) ? 1 : 0;
+        double* misc = cg_slot(X, CG_MISC);
+        if (STAGE == 1) {
+          __stcg(misc + 3, 0.0);
+        } else {
+          const double its = __ldcg(misc + 3) + 1.0;
+          __stcg(misc + 3, its);
+          if (!done && its >= (double)X.cg_cap) { __stcg(misc + 2, (double)SPB_ERR_INTERNAL); done = 1; }
+        }
+        __stcg(misc + 0, (double)done);
+      }
+      if (tid == 0) P.counters[1] = 0;
+      __syncthreads();
+    }
+  }
+}
+
+// Gram partials of T = Phi + Lambda2 / rho per row block; the CTA delivering the last one runs the polar step
+template <int KP>
+__device__ __forceinline__ void cg_gram_phase(const Params& P, double* sm, double* red, double* jA, double* jV,
+                                              double* jP, int* sh_i) {
+  using C = Cfg<KP>;
+  constexpr int KG = C::KG;
+  const int tid = threadIdx.x, p = P.p, K = P.K;
+  for (int rb = blockIdx.x; rb < P.nrb; rb += gridDim.x) {
+    const int i = rb * kRowBlock + tid;
+    double gq[KG];
+#pragma unroll
+    for (int e = 0; e < KG; ++e) gq[e] = 0.0;
+    if (i < p) {
+      double tt[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        tt[k] = 0.0;
+        if (k < K) {
+          const size_t off = (size_t)k * p + i;
+          tt[k] = __dadd_rn(__ldcg(P.Phi + off), div_rho(__ldcg(P.L2 + off), P.rho, P.rinv_rho));   // :169
+        }
+      }
+      int e = 0;
+#pragma unroll
+      for (int a = 0; a < KP; ++a)
+#pragma unroll
+        for (int b = a; b < KP; ++b) { gq[e] = fma(tt[a], tt[b], gq[e]); ++e; }
+    }
+    block_reduce_store<KG>(gq, red, P.gpart + (size_t)rb * KG);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int old = atomicAdd(P.counters + 1, 1);
+      sh_i[0] = (old == P.nrb - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh_i[0]) {
+      __threadfence();
+      if (tid == 0) P.counters[1] = 0;
+      finish_polar<KP>(P, jA, jV, jP, sm);
+    }
+  }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(kThreads, 2)
+cg_core2_kernel(Params P, CgExtra X) {
+  extern __shared__ __align__(16) double dyn[];
+  double* xs = dyn;
+  double* red = dyn + P.xcap * Cfg<KP>::KX;
+  __shared__ double jA[KP * KP], jV[KP * KP], jP[KP * KP];
+  __shared__ double sh_d[4];
+  __shared__ int sh_i[12];
+  TileInfo* tiles = reinterpret_cast<TileInfo*>(dyn + P.xcap * Cfg<KP>::KX + 8 * Cfg<KP>::KG + 32);
+
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x;
+  const size_t pk = (size_t)P.p * P.K;
+
+  build_tile_table(P, tiles);
+  if (threadIdx.x == 0) sh_i[2] = 0;
+  if (blockIdx.x == 0) {
+    for (int i = tid; i < P.ntiles + 3; i += kThreads) P.counters[i] = 0;
+    for (int i = tid; i < P.nrt * kMaxSlices * Cfg<KP>::KG; i += kThreads) P.gpart[i] = 0.0;
+    for (int i = tid; i < P.nrt * kMaxSlices * KP; i += kThreads) X.rupart[i] = 0.0;
+    for (int i = tid; i < CG_SLOTS * kCgStride; i += kThreads) X.cgc[i] = 0.0;
+    if (tid == 0) { __stcg(P.ctrl + 0, 0.0); __stcg(P.ctrl + 1, 0.0); __stcg(P.ctrl + 2, 0.0); }
+  }
+  for (size_t idx = (size_t)blockIdx.x * kThreads + tid; idx < pk; idx += (size_t)gridDim.x * kThreads)
+    __stcg(P.X + idx, make_x(2, P.rho, 0.0, P.C[idx], 0.0, P.L2[idx]));        // b = rho C - Lambda2 (:168)
+  __threadfence();
+  grid.sync();
+  unsigned int* bar = reinterpret_cast<unsigned int*>(P.counters + 2 + P.ntiles);
+  unsigned int bar_gen = 0;
+
+  int iters = 0, status = 0, pass = 0;
+  double errmax = 0.0, sweeps = 0.0;
+  for (int it = 0; it < P.maxit; ++it) {
+    iters = it + 1;
+    // ---- solve A Phi = b by CG, warm-started from the incoming Phi ----
+    cg_row_phase<KP, 0>(P, X, xs, red, sh_i);
+    grid_barrier(bar, bar_gen);
+    stream_phase<KP, 1>(P, P.ph[0], xs, red, tiles, jA, jV, jP, sh_i, (pass & 1) != 0, pass, P.Phi, &X, 0);
+    ++pass;
+    grid_barrier(bar, bar_gen);
+    cg_row_phase<KP, 1>(P, X, xs, red, sh_i);
+    grid_barrier(bar, bar_gen);
+    int done = (int)__ldcg(cg_slot(X, CG_MISC) + 0);
+    while (!done) {
+      stream_phase<KP, 1>(P, P.ph[0], xs, red, tiles, jA, jV, jP, sh_i, (pass & 1) != 0, pass, X.Rv, &X, 1);
+      ++pass;
+      grid_barrier(bar, bar_gen);
+      cg_row_phase<KP, 2>(P, X, xs, red, sh_i);
+      grid_barrier(bar, bar_gen);
+      done = (int)__ldcg(cg_slot(X, CG_MISC) + 0);
+    }
+    status = (int)__ldcg(cg_slot(X, CG_MISC) + 2);
+    if (status != 0) break;
+    // ---- Stiefel projection, dual update, stopping rule (:169-179) ----
+    cg_gram_phase<KP>(P, xs, red, jA, jV, jP, sh_i);
+    grid_barrier(bar, bar_gen);
+    status = (int)__ldcg(P.ctrl + 1);
+    sweeps = __ldcg(P.ctrl + 2);
+    update_phase<KP>(P, red, jP, sh_d, sh_i);
+    grid_barrier(bar, bar_gen);
+    errmax = __ldcg(P.ctrl + 0);
+    if (status != 0) break;
+    if (errmax <= P.tol) break;
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    P.stat[0] = iters;
+    P.stat[1] = status;
+    P.stat[2] = (int)sweeps;
+    P.stat[3] = pass;
+    P.err[0] = errmax;
+  }
+}
+
 struct Geom {
   int KP, RPT, TR, KX, KG;
   int nrt, nrb, xcap;
@@ -986,6 +1426,67 @@ void launch_instance(const Params& P, const Geom& g, cudaStream_t s) {
   count_launch();
 }
 
+// ---- matrix-free Core2: geometry, workspace, launch ---------------------------------------------------
+struct CgGeom {
+  Geom g;
+  int scap;
+  size_t vec_doubles, spart_doubles, sg_doubles, rupart_doubles, npart2_doubles, cgc_doubles;
+};
+
+CgGeom make_cg_geom(int p, int K, int n_tr) {
+  CgGeom c;
+  c.g = make_geom(p, K, Blocking());
+  Geom& g = c.g;
+  c.scap = n_tr < 256 ? n_tr : 256;
+  if (c.scap < 1) c.scap = 1;
+  // the stream window doubles as the scratch of the row phases: [scap][KP] of S + [kRowBlock][KP] of v
+  const size_t need = (size_t)(c.scap + kRowBlock) * g.KP;
+  while ((size_t)g.xcap * g.KX < need) ++g.xcap;
+  g.smem_bytes = ((size_t)g.xcap * g.KX + 8 * (size_t)g.KG + 32) * sizeof(double) + (size_t)g.ntiles * 3 * sizeof(int);
+  c.vec_doubles = round_up((size_t)p * K, 16);
+  c.spart_doubles = round_up((size_t)g.nrb * n_tr * K, 16);
+  c.sg_doubles = round_up((size_t)n_tr * K, 16);
+  c.rupart_doubles = round_up((size_t)g.nrt * kMaxSlices * g.KP, 16);
+  c.npart2_doubles = round_up((size_t)g.nrb * 2 * g.KP, 16);
+  c.cgc_doubles = round_up((size_t)CG_SLOTS * kCgStride, 16);
+  return c;
+}
+
+template <int KP>
+void launch_cg_instance(const Params& P, const CgExtra& X, const Geom& g, cudaStream_t s) {
+  static std::mutex mu;
+  static std::map<std::pair<int, size_t>, int> occ_cache;
+  int dev = 0;
+  SPB_CUDA(cudaGetDevice(&dev));
+  int max_ctas = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(dev, g.smem_bytes);
+    auto it = occ_cache.find(key);
+    if (it == occ_cache.end()) {
+      if (g.smem_bytes > (size_t)kXsBytes) throw Error(SPB_ERR_INTERNAL, "CG kernel: shared memory request too large");
+      SPB_CUDA(cudaFuncSetAttribute(cg_core2_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kXsBytes));
+      int per_sm = 0, sms = 0;
+      SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_core2_kernel<KP>, kThreads, g.smem_bytes));
+      SPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      if (per_sm < 1) throw Error(SPB_ERR_INTERNAL, "CG kernel does not fit on an SM");
+      max_ctas = per_sm * sms;
+      occ_cache[key] = max_ctas;
+    } else {
+      max_ctas = it->second;
+    }
+  }
+  int want = g.smax > g.nrb ? g.smax : g.nrb;
+  int grid = want < max_ctas ? want : max_ctas;
+  if (2 * ceil_div(g.smax, grid) > 8)
+    throw Error(SPB_ERR_INTERNAL, "CG kernel: too few co-resident CTAs on this device for the segment count");
+  Params Pc = P;
+  CgExtra Xc = X;
+  void* args[] = {&Pc, &Xc};
+  SPB_CUDA(cudaLaunchCooperativeKernel((void*)cg_core2_kernel<KP>, dim3(grid), dim3(kThreads), args, g.smem_bytes, s));
+  count_launch();
+}
+
 }  // namespace
 
 size_t admm_workspace_bytes(int p, int K) {
@@ -1053,6 +1554,72 @@ void launch_admm(const AdmmCall& c, void* ws, cudaStream_t s) {
     case 16: launch_instance<16>(P, g, s); break;
     case 32: launch_instance<32>(P, g, s); break;
     default: throw Error(SPB_ERR_INTERNAL, "no ADMM kernel instance for this K");
+  }
+}
+
+size_t cg_workspace_bytes(int p, int K, int n_tr) {
+  if (K > kCgMaxK) return 0;
+  const CgGeom c = make_cg_geom(p, K, n_tr);
+  return admm_workspace_bytes(p, K) +
+         (4 * c.vec_doubles + c.spart_doubles + c.sg_doubles + c.rupart_doubles + c.npart2_doubles + c.cgc_doubles) *
+             sizeof(double) + 256;
+}
+
+void launch_core2_cg(const CgCall& c, void* ws, cudaStream_t s) {
+  SPB_REQUIRE(c.K >= 1 && c.K <= kCgMaxK, "the matrix-free Core2 kernel is built for K <= 8");
+  SPB_REQUIRE(c.n_tr >= 1 && c.Ytr && c.Yt && c.omega_u, "invalid argument");
+  CgGeom cgm = make_cg_geom(c.p, c.K, c.n_tr);
+  const Geom& g = cgm.g;
+  Params P;
+  P.A = c.omega_u; P.ld = c.ld; P.p = c.p; P.K = c.K; P.mode = 2; P.maxit = c.maxit;
+  P.rdenom = 1.0 / std::sqrt((double)c.p * (double)c.K);
+  P.rho = c.rho; P.rinv_rho = 1.0 / c.rho; P.thr = 0.0; P.tol = c.tol;
+  P.scale = 1.0; P.inv_scale = 1.0;
+  static const int force_jacobi = [] {
+    const char* e = std::getenv("SPB_POLAR");
+    return (e != nullptr && std::string(e) == "jacobi") ? 1 : 0;
+  }();
+  P.force_jacobi = force_jacobi;
+  P.Phi = c.Phi; P.R = nullptr; P.C = c.C; P.L1 = nullptr; P.L2 = c.L2;
+  // base workspace exactly as launch_admm lays it out (sized by admm_workspace_bytes), CG extras behind it
+  double* w = reinterpret_cast<double*>(ws);
+  double* const w_end_base = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + admm_workspace_bytes(c.p, c.K));
+  P.X = w; w += g.x_doubles;
+  P.part = w; w += g.part_doubles;
+  P.gpart = w; w += g.gpart_doubles;
+  P.npart = w; w += g.npart_doubles;
+  P.ctrl = w; w += g.ctrl_doubles;
+  P.counters = reinterpret_cast<int*>(w);
+  SPB_REQUIRE(g.ntiles <= 4096, "p is too large for the ADMM kernel's tile table");
+  P.stat = c.stat_slot; P.err = c.err_slot;
+  P.dbg = nullptr;
+  P.nrt = g.nrt; P.nrb = g.nrb; P.xcap = g.xcap;
+  P.nphases = g.nphases; P.ntiles = g.ntiles; P.total_slices = g.total_slices;
+  for (int f = 0; f < kMaxPhases; ++f) P.ph[f] = g.ph[f < g.nphases ? f : 0];
+  CgExtra X;
+  X.Ytr = c.Ytr; X.Yt = c.Yt; X.n_tr = c.n_tr;
+  X.c_omega = c.c_omega; X.c_gram = c.c_gram;
+  X.tol2 = c.cg_tol * c.cg_tol; X.cg_cap = c.cg_cap; X.scap = cgm.scap;
+  double* e = reinterpret_cast<double*>(round_up(reinterpret_cast<size_t>(w_end_base), 128));
+  X.Rv = e; e += cgm.vec_doubles;
+  X.Pv = e; e += cgm.vec_doubles;
+  X.Qv = e; e += cgm.vec_doubles;
+  X.Uv = e; e += cgm.vec_doubles;
+  X.Spart = e; e += cgm.spart_doubles;
+  X.Sg = e; e += cgm.sg_doubles;
+  X.rupart = e; e += cgm.rupart_doubles;
+  X.npart2 = e; e += cgm.npart2_doubles;
+  X.cgc = e; e += cgm.cgc_doubles;
+  switch (g.KP) {
+    case 1: launch_cg_instance<1>(P, X, g, s); break;
+    case 2: launch_cg_instance<2>(P, X, g, s); break;
+    case 3: launch_cg_instance<3>(P, X, g, s); break;
+    case 4: launch_cg_instance<4>(P, X, g, s); break;
+    case 5: launch_cg_instance<5>(P, X, g, s); break;
+    case 6: launch_cg_instance<6>(P, X, g, s); break;
+    case 7: launch_cg_instance<7>(P, X, g, s); break;
+    case 8: launch_cg_instance<8>(P, X, g, s); break;
+    default: throw Error(SPB_ERR_INTERNAL, "no CG kernel instance for this K");
   }
 }
 

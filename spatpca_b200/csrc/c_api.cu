@@ -460,8 +460,10 @@ int spb_cv_session(const double* sxy, int p, int d, const double* Y, int n, int 
     int dev = 0;
     SPB_CUDA(cudaGetDevice(&dev));
     uint64_t key = 0x243f6a8885a308d3ULL;
-    const double hdr[8] = {(double)p, (double)d, (double)n, (double)M, (double)maxit, tol, (double)n_l2, 0.0};
-    key = hash_doubles(hdr, 8, key);
+    // the grid lengths are part of the key: tau1 = [a, b], tau2 = [c] must not collide with tau1 = [a], tau2 = [b, c]
+    const double hdr[10] = {(double)p, (double)d, (double)n, (double)M, (double)maxit, tol, (double)n_l2,
+                            (double)n_tau1, (double)n_tau2, (double)n_gamma};
+    key = hash_doubles(hdr, 10, key);
     key = hash_doubles(sxy, (size_t)p * d, key);
     key = hash_doubles(Y, (size_t)n * p, key);
     key = hash_doubles(nk, (size_t)n, key);
@@ -606,6 +608,50 @@ int spb_admm_system(const double* omega, const double* G, int p, double tau1, do
     SPB_REQUIRE(blocks >= 0 && blocks <= kMaxBlocks, "blocks must be in 0..kMaxBlocks");
     SystemSpec sys{omega, G, tau1, scale, blocks};
     run_admm_host(mode, nullptr, p, K, tau2, rho, maxit, tol, Phi, R, C, Lambda1, Lambda2, iters, &sys);
+  });
+}
+
+int spb_core2_matrix_free(const double* omega, const double* Ytr, int n_tr, int p, int K, double tau1, double rho,
+                          int maxit, double tol, double cg_tol, double* Phi, double* C, double* Lambda2, int* iters,
+                          int* passes) {
+  return guarded([&] {
+    SPB_REQUIRE(omega && Ytr && Phi && C && Lambda2 && p >= 1 && n_tr >= 1, "invalid argument");
+    SPB_REQUIRE(K >= 1 && K <= kCgMaxK && K <= p, "K must be in 1..8");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    const size_t ld = padded_ld(p), pk = (size_t)p * K;
+    DevBuf<double> om(ld * (size_t)p), yt((size_t)n_tr * p), ytt((size_t)n_tr * p), err(1);
+    DevBuf<int> stat(4);
+    DevBuf<char> ws(cg_workspace_bytes(p, K, n_tr));
+    ChainState st;
+    st.alloc(pk);
+    upload_square(omega, p, om.get(), ld, s);
+    launch_symmatu_inplace(om.get(), p, ld, 0.0, s);
+    SPB_CUDA(cudaMemcpyAsync(yt.get(), Ytr, sizeof(double) * (size_t)n_tr * p, cudaMemcpyHostToDevice, s));
+    launch_transpose(yt.get(), n_tr, p, ytt.get(), s);
+    SPB_CUDA(cudaMemcpyAsync(st.Phi.get(), Phi, sizeof(double) * pk, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(st.C.get(), C, sizeof(double) * pk, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(st.L2.get(), Lambda2, sizeof(double) * pk, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemsetAsync(stat.get(), 0, 4 * sizeof(int), s));
+    CgCall c;
+    c.omega_u = om.get(); c.ld = ld; c.p = p; c.K = K; c.Ytr = yt.get(); c.Yt = ytt.get(); c.n_tr = n_tr;
+    c.c_omega = 2.0 * tau1; c.c_gram = 2.0; c.rho = rho; c.maxit = maxit; c.tol = tol;
+    c.cg_tol = cg_tol > 0.0 ? cg_tol : 1e-14; c.cg_cap = 2000;
+    c.Phi = st.Phi.get(); c.C = st.C.get(); c.L2 = st.L2.get();
+    c.stat_slot = stat.get(); c.err_slot = err.get();
+    if (maxit > 0) launch_core2_cg(c, ws.get(), s);
+    int sth[4] = {0, 0, 0, 0};
+    SPB_CUDA(cudaMemcpyAsync(sth, stat.get(), sizeof(sth), cudaMemcpyDeviceToHost, s));
+    SPB_CUDA(cudaMemcpyAsync(Phi, st.Phi.get(), sizeof(double) * pk, cudaMemcpyDeviceToHost, s));
+    SPB_CUDA(cudaMemcpyAsync(C, st.C.get(), sizeof(double) * pk, cudaMemcpyDeviceToHost, s));
+    SPB_CUDA(cudaMemcpyAsync(Lambda2, st.L2.get(), sizeof(double) * pk, cudaMemcpyDeviceToHost, s));
+    ctx.sync_and_check();
+    if (iters) *iters = sth[0];
+    if (passes) *passes = sth[3];
+    if (sth[1] == SPB_ERR_NOT_POSDEF) throw Error(SPB_ERR_NOT_POSDEF, "inv_sympd(): matrix is singular or not positive definite");
+    if (sth[1] == SPB_ERR_INTERNAL) throw Error(SPB_ERR_INTERNAL, "matrix-free Core2: conjugate gradients did not converge");
+    if (sth[1] != 0)
+      throw Error(SPB_ERR_POLAR, "svd_econ(): the p x K iterate is rank deficient, Stiefel projection undefined");
   });
 }
 
@@ -785,6 +831,85 @@ int spb_bench_admm_blocks(int p, int K, int mode, int iters, int repeats, int bl
     }
     if (dbg_on) fprintf(stderr, "[admm dbg] Jacobi sweeps in the last iteration: %d\n", last_sweeps);
     *ms_per_iter = sum_ms / repeats;
+  });
+}
+
+namespace {
+__global__ void bench_fill_kernel(double* A, size_t ld, int p, double diag, double off) {
+  // banded symmetric matrix: diag on the diagonal, off / (1 + |i - j|) within 8 of it -- SPD and non-trivial
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)p * p) return;
+  const int i = (int)(e % p), j = (int)(e / p);
+  const int d = i > j ? i - j : j - i;
+  A[(size_t)j * ld + i] = d == 0 ? diag : (d <= 8 ? off / (1.0 + d) : 0.0);
+}
+__global__ void bench_sign_kernel(double* Y, size_t n, double scale) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  unsigned int h = (unsigned int)e * 2654435761u + 12345u;
+  h ^= h >> 15; h *= 0x85ebca6bu; h ^= h >> 13;
+  Y[e] = (h & 1u) ? scale : -scale;
+}
+}  // namespace
+
+int spb_bench_core2_cg(int p, int K, int n_tr, int iters, int repeats, double* ms_per_launch, int* passes_per_launch) {
+  return guarded([&] {
+    SPB_REQUIRE(p >= 1 && K >= 1 && K <= kCgMaxK && K <= p && n_tr >= 1 && iters >= 1 && repeats >= 1 && ms_per_launch,
+                "invalid argument");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    const size_t ld = padded_ld(p), pk = (size_t)p * K;
+    DevBuf<double> om(ld * (size_t)p), yt((size_t)n_tr * p), ytt((size_t)n_tr * p), err(1), Q0(pk);
+    DevBuf<int> stat(4);
+    DevBuf<char> ws(cg_workspace_bytes(p, K, n_tr));
+    ChainState st;
+    st.alloc(pk);
+    // rho = 1; Omega_u has lambda_max ~ 0.25 / c_omega-scaled, the Gram part ~0.1: cond(A) ~ 1.6, as on the C4 job
+    SPB_CUDA(cudaMemsetAsync(om.get(), 0, sizeof(double) * ld * p, s));
+    bench_fill_kernel<<<ceil_div((long long)p * p, 256), 256, 0, s>>>(om.get(), ld, p, 0.1, 0.03);
+    bench_sign_kernel<<<ceil_div((long long)n_tr * p, 256), 256, 0, s>>>(yt.get(), (size_t)n_tr * p,
+                                                                         std::sqrt(0.05 / ((double)n_tr * p)));
+    count_launch(2);
+    launch_transpose(yt.get(), n_tr, p, ytt.get(), s);
+    std::vector<double> q0(pk, 0.0);
+    for (int k = 0; k < K; ++k) {
+      q0[(size_t)k * p + k] = 1.0;
+      if (k + 1 < p) q0[(size_t)k * p + k + 1] = 0.15;
+      if (k + 2 < p) q0[(size_t)k * p + k + 2] = 0.1;
+    }
+    SPB_CUDA(cudaMemcpyAsync(Q0.get(), q0.data(), sizeof(double) * pk, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaStreamSynchronize(s));
+    cudaEvent_t e0, e1;
+    SPB_CUDA(cudaEventCreate(&e0));
+    SPB_CUDA(cudaEventCreate(&e1));
+    double sum_ms = 0.0;
+    int passes = 0;
+    for (int r = 0; r < repeats + 1; ++r) {
+      SPB_CUDA(cudaMemcpyAsync(st.C.get(), Q0.get(), sizeof(double) * pk, cudaMemcpyDeviceToDevice, s));
+      SPB_CUDA(cudaMemcpyAsync(st.Phi.get(), Q0.get(), sizeof(double) * pk, cudaMemcpyDeviceToDevice, s));
+      SPB_CUDA(cudaMemsetAsync(st.L2.get(), 0, sizeof(double) * pk, s));
+      CgCall c;
+      c.omega_u = om.get(); c.ld = ld; c.p = p; c.K = K; c.Ytr = yt.get(); c.Yt = ytt.get(); c.n_tr = n_tr;
+      c.c_omega = 2.0; c.c_gram = 2.0; c.rho = 1.0; c.maxit = iters; c.tol = -1.0;
+      c.cg_tol = 1e-14; c.cg_cap = 2000;
+      c.Phi = st.Phi.get(); c.C = st.C.get(); c.L2 = st.L2.get();
+      c.stat_slot = stat.get(); c.err_slot = err.get();
+      SPB_CUDA(cudaEventRecord(e0, s));
+      launch_core2_cg(c, ws.get(), s);
+      SPB_CUDA(cudaEventRecord(e1, s));
+      SPB_CUDA(cudaStreamSynchronize(s));
+      int sth[4];
+      SPB_CUDA(cudaMemcpy(sth, stat.get(), sizeof(sth), cudaMemcpyDeviceToHost));
+      if (sth[0] != iters || sth[1] != 0) throw Error(SPB_ERR_INTERNAL, "bench chain did not run all iterations");
+      passes = sth[3];
+      float ms = 0.f;
+      SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (r > 0) sum_ms += (double)ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_launch = sum_ms / repeats;
+    if (passes_per_launch) *passes_per_launch = passes;
   });
 }
 

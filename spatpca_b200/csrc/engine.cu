@@ -582,6 +582,11 @@ Engine::Engine(int p, int d, int n, int M, int K, const double* tau1, int n1, co
     L->err_slots.alloc((size_t)slot_cap_);
     lanes_.push_back(std::move(L));
   }
+  if (const char* e = std::getenv("SPB_CORE2")) {
+    const std::string m(e);
+    cg_mode_ = (m == "cg") ? 1 : ((m == "factor") ? 2 : 0);
+  }
+  if (const char* e = std::getenv("SPB_CG_TOL")) { const double t = std::atof(e); if (t > 0.0 && t < 1e-6) cg_tol_ = t; }
   alloc_k_state();
   std::memset(&stats_, 0, sizeof(stats_));
   launches_at_start_ = g_launch_count;
@@ -593,7 +598,7 @@ void Engine::alloc_k_state() {
   full_.alloc(pk);
   for (auto& L : lanes_) {
     L->chain.alloc(pk);
-    L->admm_ws.alloc(admm_workspace_bytes(p_, K_));
+    L->admm_ws.alloc(std::max(admm_workspace_bytes(p_, K_), cg_workspace_bytes(p_, K_, n_)));
     L->lossW.alloc((size_t)n_ * K_);
     L->loss_scratch.alloc(yphi_scratch_doubles(n_, p_, K_) + 512);
   }
@@ -664,10 +669,13 @@ void Engine::upload(const double* sxy, const double* Y, const double* nk) {
     SPB_REQUIRE(f.n_tr >= 1, "a fold has no training rows");
     SPB_REQUIRE(K_ <= std::min(f.n_tr, p_), "K must not exceed min(training rows, p)");
   }
+  dYt_.alloc((size_t)n_ * p_);
+  launch_transpose(dY_.get(), n_, p_, dYt_.get(), ctx_.stream);             // p x n, for the matrix-free Core2p
   SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
   stats_.bytes_h2d += (long long)sizeof(double) * ((size_t)n_ * p_ + (size_t)p_ * d_ + n_);
   stats_.ms_h2d += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   omega_ready_ = omega_injected_;
+  if (!omega_injected_) { lmax_ = -1.0; lmax_enqueued_ = false; }
   full_ready_ = false;
   full_svd_done_ = false;
   full_inv2_index_ = full_tinv_index_ = -1;
@@ -684,9 +692,73 @@ void Engine::set_omega(const double* omega_host) {
   SPB_CUDA(cudaMemcpy2DAsync(omega_diag_raw_.get(), sizeof(double), omega_u_.get(), (ld_ + 1) * sizeof(double),
                              sizeof(double), p_, cudaMemcpyDeviceToDevice, ctx_.stream));
   launch_symmatu_inplace(omega_u_.get(), p_, ld_, 1e-8, ctx_.stream);     // symmatu + the ridge of :574
+  lmax_ = -1.0;
+  enqueue_lmax(ctx_.stream, ctx_.blas);
   SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
   omega_ready_ = true;
   omega_injected_ = true;
+}
+
+// lambda_max(Omega_u) by 12 steps of power iteration from a fixed start (DGEMV + one-CTA normalisation, ~2 ms at
+// p = 10 000, on the stream that built Omega).  Only the choice between the matrix-free and the factored Core2
+// depends on it (use_cg multiplies the estimate by 1.5), never a result.
+void Engine::enqueue_lmax(cudaStream_t s, cublasHandle_t blas) {
+  constexpr int kSteps = 12;
+  lmax_vec_.ensure(2 * (size_t)p_);
+  lmax_out_.ensure(kSteps);
+  double* x = lmax_vec_.get();
+  double* y = x + p_;
+  launch_power_init(x, p_, s);
+  const double one = 1.0, zero = 0.0;
+  for (int it = 0; it < kSteps; ++it) {
+    SPB_CUBLAS(cublasDgemv(blas, CUBLAS_OP_N, p_, p_, &one, omega_u_.get(), (int)ld_, x, 1, &zero, y, 1));
+    launch_power_normalize(y, p_, x, lmax_out_.get() + it, s);
+  }
+  lmax_enqueued_ = true;
+}
+
+double Engine::omega_lmax() {
+  if (lmax_ >= 0.0) return lmax_;
+  if (!any_tau_) { lmax_ = 1.0; return lmax_; }                    // Omega = I when all taus are 0 (:578)
+  if (!lmax_enqueued_) return 1e300;                                // no estimate: the factored path
+  finish_omega();
+  SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
+  double h[12];
+  SPB_CUDA(cudaMemcpy(h, lmax_out_.get(), sizeof(h), cudaMemcpyDeviceToHost));
+  double m = 0.0;
+  for (int i = 0; i < 12; ++i) if (h[i] == h[i]) m = std::max(m, h[i]);   // |Omega x| with |x| = 1 (the first entry has |x| != 1)
+  lmax_ = std::max(m, h[11]);
+  return lmax_;
+}
+
+bool Engine::use_cg(double c_omega, double rho, double gram_top, int expected_iters) {
+  if (K_ > kCgMaxK || cg_mode_ == 2) return false;
+  if (cg_mode_ == 1) return true;
+  if (p_ < 2048) return false;                   // small systems: latency-bound, the explicit inverse wins
+  const double lo = rho - gram_top;              // lambda_min(A) >= rho - c_gram sigma_1^2 (Omega_u is PSD up to rounding)
+  if (!(lo > 0.0)) return false;
+  const double kappa = (rho + c_omega * 1.5 * omega_lmax()) / lo;
+  if (!(kappa < 1e6)) return false;
+  const double sq = std::sqrt(kappa);
+  const double rate = (sq - 1.0) / (sq + 1.0);
+  const double steps = rate <= 1e-12 ? 1.0 : std::ceil(std::log(5e-16) / std::log(rate));
+  // cost model in units of one p x p matrix pass (measured on B200, profiles/): a block factorisation costs
+  // ~65 + 0.0085 p passes and each ADMM iteration on it ~2.4; a CG solve costs its steps + 3 passes
+  const double factor_cost = 65.0 + 0.0085 * p_ + 2.4 * expected_iters;
+  return expected_iters * (steps + 3.0) < factor_cost;
+}
+
+bool Engine::core2_matrix_free(int fold, double tau1, double rho, int expected_iters) {
+  if (maxit_ <= 0) return false;
+  const double sv1 = fold < 0 ? sv_full_[0] : folds_[fold].sv[0];
+  return use_cg(2.0 * tau1, rho, 2.0 * sv1 * sv1, tol_ > 0.0 ? expected_iters : maxit_);
+}
+
+bool Engine::can_share_inverses() {
+  if (!cache_inverses_) return false;
+  if (!full_svd_done_) return true;
+  const double tmax = *std::max_element(tau1_.begin(), tau1_.end());
+  return !use_cg(2.0 * tmax, rho_full_, 2.0 * sv_full_[0] * sv_full_[0], tol_ > 0.0 ? 3 : maxit_);
 }
 
 void Engine::init_lambda(cudaStream_t s, const double* Phi, const std::vector<double>& sv, double rho, double* L2) {
@@ -736,6 +808,7 @@ void Engine::prepare() {
                                    (ld_ + 1) * sizeof(double), sizeof(double), p_, cudaMemcpyDeviceToDevice,
                                    R.stream));
         launch_symmatu_inplace(omega_u_.get(), p_, ld_, 1e-8, R.stream);
+        enqueue_lmax(R.stream, R.blas);
       }
       if (!omega_evt_) SPB_CUDA(cudaEventCreateWithFlags(&omega_evt_, cudaEventDisableTiming));
       SPB_CUDA(cudaEventRecord(omega_evt_, R.stream));
@@ -859,6 +932,7 @@ void Engine::omega_finish() {
   SPB_CUDA(cudaMemcpy2DAsync(omega_diag_raw_.get(), sizeof(double), omega_u_.get(), (ld_ + 1) * sizeof(double),
                              sizeof(double), p_, cudaMemcpyDeviceToDevice, s));
   launch_symmatu_inplace(omega_u_.get(), p_, ld_, 1e-8, s);                 // symmatu + the ridge of :574
+  enqueue_lmax(s, R.blas);
   clock_.end(s);
   SPB_CUDA(cudaStreamSynchronize(s));
   omega_tmp_.reset();
@@ -887,6 +961,8 @@ void Engine::fold_prepare(int k) {
   f.Ytr.alloc((size_t)f.n_tr * p_);
   SPB_CUDA(cudaMemcpyAsync(rows.get(), f.rows_tr.data(), sizeof(int) * f.n_tr, cudaMemcpyHostToDevice, s));
   launch_gather_rows(dY_.get(), n_, p_, rows.get(), f.n_tr, f.Ytr.get(), s);
+  f.Ytt.alloc((size_t)f.n_tr * p_);
+  launch_transpose(f.Ytr.get(), f.n_tr, p_, f.Ytt.get(), s);                // p x n_tr
   SPB_CUDA(cudaStreamSynchronize(s));
   if (f.n_va > 0) {
     f.Yva.alloc((size_t)f.n_va * p_);
@@ -921,10 +997,33 @@ void Engine::ensure_gram(Lane& L, int k) {
 }
 
 void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double rho, ChainState& st,
-                       double* buf, bool have) {
+                       double* buf, bool have, int expected_iters) {
   // spatpcaCore2 / spatpcaCore2p (:150-222).  The reference rebuilds the inverse on every call (:165);
-  // here a call may reuse the identical matrix built earlier for the same (fold, tau1).
+  // here a call may reuse the identical matrix built earlier for the same (fold, tau1) -- or, when the system is
+  // well conditioned and serves few iterations, never build it: the matrix-free kernel solves with it by CG.
   cudaStream_t s = L.res->stream;
+  if (!have && core2_matrix_free(fold, tau1, rho, expected_iters)) {
+    wait_omega(L);
+    if (L.next_slot >= slot_cap_) flush_lane(L);
+    CgCall c;
+    c.omega_u = omega_u_.get(); c.ld = ld_; c.p = p_; c.K = K_;
+    if (fold < 0) { c.Ytr = dY_.get(); c.Yt = dYt_.get(); c.n_tr = n_; }
+    else { c.Ytr = folds_[fold].Ytr.get(); c.Yt = folds_[fold].Ytt.get(); c.n_tr = folds_[fold].n_tr; }
+    c.c_omega = 2.0 * tau1; c.c_gram = 2.0; c.rho = rho; c.maxit = maxit_; c.tol = tol_;
+    c.cg_tol = cg_tol_; c.cg_cap = 2000;
+    c.Phi = st.Phi.get(); c.C = st.C.get(); c.L2 = st.L2.get();
+    c.stat_slot = L.stat_slots.get() + (size_t)L.next_slot * 4;
+    c.err_slot = L.err_slots.get() + L.next_slot;
+    {
+      Scoped sc(L.clock, PH_ADMM, s);
+      SPB_CUDA(cudaMemsetAsync(c.stat_slot, 0, 4 * sizeof(int), s));
+      launch_core2_cg(c, L.admm_ws.get(), s);
+    }
+    L.pending.push_back({kind + 100, fold, idx, L.next_slot});     // + 100: solved matrix-free (flush_lane strips it)
+    L.next_slot++;
+    L.dirty = true;
+    return;
+  }
   if (buf == nullptr) {
     L.work.ensure(ld_ * (size_t)p_);
     buf = L.work.get();
@@ -1040,14 +1139,25 @@ void Engine::flush_lane(Lane& L) {
   if (L.next_slot > 0) {
     std::vector<int> st((size_t)L.next_slot * 4);
     SPB_CUDA(cudaMemcpy(st.data(), L.stat_slots.get(), sizeof(int) * st.size(), cudaMemcpyDeviceToHost));
-    bool polar_failed = false;
+    bool polar_failed = false, cg_failed = false, not_posdef = false;
     for (auto& r : L.pending) {
       int iters = st[(size_t)r.slot * 4 + 0];
-      if (st[(size_t)r.slot * 4 + 1] != 0) polar_failed = true;
-      log_.push_back(r.kind); log_.push_back(r.fold); log_.push_back(r.idx); log_.push_back(iters);
+      const int status = st[(size_t)r.slot * 4 + 1];
+      if (status == SPB_ERR_NOT_POSDEF) not_posdef = true;
+      else if (status == SPB_ERR_INTERNAL) cg_failed = true;
+      else if (status != 0) polar_failed = true;
+      int kind = r.kind;
+      if (kind >= 100) {                                     // matrix-free call: [3] = matrix passes
+        kind -= 100;
+        stats_.n_cg_calls++;
+        stats_.cg_passes += st[(size_t)r.slot * 4 + 3];
+      }
+      log_.push_back(kind); log_.push_back(r.fold); log_.push_back(r.idx); log_.push_back(iters);
     }
     L.pending.clear();
     L.next_slot = 0;
+    if (not_posdef) throw Error(SPB_ERR_NOT_POSDEF, "inv_sympd(): matrix is singular or not positive definite");
+    if (cg_failed) throw Error(SPB_ERR_INTERNAL, "matrix-free Core2: conjugate gradients did not converge");
     if (polar_failed)
       throw Error(SPB_ERR_POLAR, "svd_econ(): the p x K iterate is rank deficient, Stiefel projection undefined");
   }
@@ -1092,13 +1202,14 @@ void Engine::enqueue_stage1(int k, int step) {
     const int i = step;
     double* buf = nullptr;
     bool have = false;
-    if (cache_inverses_) {
+    const bool kept = cache_inverses_ && f.inv_valid[i] != 0;     // built by an earlier run on this engine (other K)
+    if (cache_inverses_ && (kept || !core2_matrix_free(k, tau1_[i], f.rho, 3))) {
       f.inv_cache[i].ensure(ld_ * (size_t)p_);
       buf = f.inv_cache[i].get();
-      have = f.inv_valid[i] != 0;              // built by an earlier run on this engine (other K)
+      have = kept;
       f.inv_valid[i] = 1;
     }
-    run_core2(L, 2, k, i, tau1_[i], f.rho, ch, buf, have);
+    run_core2(L, 2, k, i, tau1_[i], f.rho, ch, buf, have, 3);     // warm start: 1-5 iterations
     launch_loss(L, f, ch.Phi.get(), scores + i);
     return;
   }
@@ -1174,10 +1285,11 @@ void Engine::stage1_full(int index1) {
     if (index1 > 0) {                                                         // :598-599
       double* buf = nullptr;
       bool have = false;
-      if (cache_inverses_) {
+      const bool kept = cache_inverses_ && full_inv2_index_ == index1;
+      if (cache_inverses_ && (kept || !core2_matrix_free(-1, tau1_[index1], rho_full_, 8))) {
         full_inv2_.ensure(ld_ * (size_t)p_);
         buf = full_inv2_.get();
-        have = (full_inv2_index_ == index1);
+        have = kept;
         full_inv2_index_ = index1;
       }
       run_core2(L, 20, -1, index1, tau1_[index1], rho_full_, full_, buf, have);
@@ -1335,12 +1447,15 @@ void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, 
     SPB_REQUIRE(folds_[folds[f]].prepared, "stage 1 must run before stage 3 for every fold");
   }
   const int ng = (int)gamma_.size();
-  // folds sharing a lane share its chain buffers: refit + loss one lane-round at a time
-  for (int f0 = 0; f0 < nfolds; f0 += n_fold_lanes_) {
-    const int f1 = std::min(nfolds, f0 + n_fold_lanes_);
-    for (int f = f0; f < f1; ++f) enqueue_stage3_refit(folds[f], index1, index2);
-    for (int f = f0; f < f1; ++f) {
-      const int k = folds[f];
+  // folds sharing a lane share its chain buffers: refit + loss one lane-round at a time.  The rounds come
+  // from lane_rounds() -- a fold's lane is k % n_fold_lanes_, NOT its position in the caller's list, so a
+  // strided list such as [0, 2, 4] with 2 lanes must not put folds 0 and 2 into the same round.
+  std::map<int, int> row_of;
+  for (int f = 0; f < nfolds; ++f) row_of[folds[f]] = f;
+  for (const auto& round : lane_rounds(folds, nfolds)) {
+    for (int k : round) enqueue_stage3_refit(k, index1, index2);
+    for (int k : round) {
+      const int f = row_of[k];
       Lane& L = lane_of(k);
       flush_lane(L);
       FoldData& fd = folds_[k];

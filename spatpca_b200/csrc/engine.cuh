@@ -95,6 +95,7 @@ struct FoldData {
   int n_tr = 0, n_va = 0;
   std::vector<int> rows_tr, rows_va;
   DevBuf<double> Ytr, Yva;        // n_tr x p, n_va x p
+  DevBuf<double> Ytt;             // p x n_tr: transpose of Ytr (the matrix-free Core2 kernel reads both layouts)
   DevBuf<double> V;               // leading right singular vectors of Ytr (p x kcap), the PCA start for any K
   int kcap = 0;
   DevBuf<double> Phi0, L20;       // Phi_cv / Lambd2_cv slices of the reference (:569)
@@ -118,7 +119,7 @@ struct Lane {
   DevBuf<double> work, gram;       // assembled system -> inverse; Gram matrix of `gram_owner`
   int gram_owner = -2;
   ChainState chain;
-  DevBuf<char> admm_ws;
+  DevBuf<char> admm_ws;            // sized for the matrix-free Core2 kernel too (cg_workspace_bytes)
   DevBuf<double> lossW, loss_scratch;
   DevBuf<int> stat_slots;
   DevBuf<double> err_slots;
@@ -154,7 +155,7 @@ class Engine {
   // (fold, tau1 index) inverses as separately schedulable jobs: they depend on Omega, G_k, rho_k and
   // tau1[i] only -- not on the ADMM iterates -- so any GPU can build them and ship them to the fold's
   // home GPU.  Require the stage-1 inverse cache (memory permitting).
-  bool can_share_inverses() const { return cache_inverses_; }
+  bool can_share_inverses();      // false when stage 1 runs matrix-free (there is no inverse to share)
   void prepare_fold(int k) { fold_prepare(k); }
   void* inverse_buffer(int k, int i, long long* bytes);   // device buffer of inverse (k, tau1[i]), allocated on demand
   void build_inverse(int k, int i);                        // enqueue on fold k's lane
@@ -220,7 +221,13 @@ class Engine {
   // buf: matrix buffer to build the inverse in (nullptr: the lane's work buffer);
   // have: buf already holds inv_sympd(2(tau1 Omega - G) + rho I) for this (fold, tau1)
   void run_core2(Lane& L, int kind, int fold, int idx, double tau1, double rho, ChainState& st,
-                 double* buf = nullptr, bool have = false);
+                 double* buf = nullptr, bool have = false, int expected_iters = 8);
+  // Matrix-free Core2 (conjugate gradients, admm_kernels.cu) or the factored path?  Decided per call from a
+  // bound on cond(c_omega Omega_u + rho I - c_gram Ytr'Ytr) and the iterations the call is expected to run.
+  bool use_cg(double c_omega, double rho, double gram_top, int expected_iters);
+  bool core2_matrix_free(int fold, double tau1, double rho, int expected_iters);   // the decision run_core2 takes
+  double omega_lmax();                           // power-iteration estimate of lambda_max(Omega_u) (host; waits for Omega)
+  void enqueue_lmax(cudaStream_t s, cublasHandle_t blas);
   double* cached_inverse(FoldData& f, int index1);   // stage-1 inverse of the selected tau1, or nullptr
   void drop_cached_inverses(FoldData& f, int keep);
   void run_core3(Lane& L, int kind, int fold, int idx, const double* tinv, double tau2, double rho, ChainState& st);
@@ -247,6 +254,12 @@ class Engine {
   DeviceCtx& ctx_;
 
   DevBuf<double> dY_, dX_;
+  DevBuf<double> dYt_;                           // p x n: transpose of Y (full-data matrix-free Core2p)
+  DevBuf<double> lmax_vec_, lmax_out_;           // power iteration: 2 p-vectors, norms
+  double lmax_ = -1.0;                           // < 0: not read back yet
+  bool lmax_enqueued_ = false;
+  int cg_mode_ = 0;                              // SPB_CORE2: 0 = auto, 1 = always matrix-free (K <= 8), 2 = never
+  double cg_tol_ = 1e-14;                        // SPB_CG_TOL
   std::vector<double> nk_;
   DevBuf<double> omega_u_;                       // symmatu(Omega) + 1e-8 I
   DevBuf<double> omega_diag_raw_;                // diagonal before the ridge (for get_omega)

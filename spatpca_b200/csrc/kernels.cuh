@@ -62,6 +62,9 @@ void launch_lambda_init_host(const double* Phi, int p, int K, const double* coef
 void launch_scale_copy(const double* src, double alpha, double* dst, size_t n, cudaStream_t s);
 // sticky device-side status: if (*info != 0) *flag = code (first failure wins)
 void launch_check_info(const int* info, int* flag, int code, cudaStream_t s);
+// power iteration on a symmetric matrix: fixed start vector; x <- y / |y| with |y| stored to norm_out[0]
+void launch_power_init(double* x, int p, cudaStream_t s);
+void launch_power_normalize(const double* y, int p, double* x, double* norm_out, cudaStream_t s);
 // B = Phi * Q  (p x K times K x K, Q on device)
 void launch_small_rmul(const double* Phi, int p, int K, const double* Q_dev, double* out, cudaStream_t s);
 
@@ -109,6 +112,31 @@ int admm_num_segments(int p, int K);
 // {kind (0 = single fused phase, 1 = FWD, 2 = BWD), row0, nrows, col0, ncols, fin0, fin1, segments}; returns the
 // number of phases.  Host-only (tests check that the rectangles tile the matrix and solve the system).
 int admm_phase_plan(int p, int K, const Blocking& blk, int* out, int cap);
+
+// ---- matrix-free spatpcaCore2 (admm_kernels.cu): conjugate gradients on the ADMM system ------------
+// A = c_omega * Omega_u + rho I - c_gram * Ytr'Ytr is applied, never factored: every CG step streams Omega_u
+// once and uses the L2-resident data block for the rank-n_tr part.  The whole call (CG solves, Stiefel
+// projection, dual update, stopping rule) is one cooperative launch, like launch_admm.
+constexpr int kCgMaxK = 8;
+struct CgCall {
+  const double* omega_u;   // p x p symmetric, full storage (symmatu(Omega) + 1e-8 I)
+  size_t ld;
+  int p, K;
+  const double* Ytr;       // n_tr x p (ld n_tr)
+  const double* Yt;        // p x n_tr (ld p)
+  int n_tr;
+  double c_omega, c_gram;  // spatpcaCore2: 2 tau1 and 2 (:164)
+  double rho;
+  int maxit;
+  double tol;
+  double cg_tol;           // relative residual per column (default 1e-14)
+  int cg_cap;              // CG steps per solve before the call is failed
+  double *Phi, *C, *L2;    // p x K; Phi is the warm start of the first solve
+  int* stat_slot;          // device: {iterations, status, polar steps, matrix passes}
+  double* err_slot;
+};
+size_t cg_workspace_bytes(int p, int K, int n_tr);
+void launch_core2_cg(const CgCall& c, void* ws, cudaStream_t s);
 
 // ---- losses (loss_kernels.cu) --------------------------------------------------
 // W (m x K) <- Ymat (m x p) * Phi (p x K); scratch must hold cvloss_scratch_doubles(m, p, K)

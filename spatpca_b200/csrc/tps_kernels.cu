@@ -293,6 +293,36 @@ __global__ void tps_eval_kernel(const double* __restrict__ xnew, int pnew,
   out[idx] = v;
 }
 
+// ---- power iteration for lambda_max(Omega_u): start vector and normalisation (one CTA) ----------------
+__global__ void power_init_kernel(double* x, int p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p) return;
+  unsigned int h = (unsigned int)i * 2654435761u + 0x9e3779b9u;      // fixed pseudo-random signs and magnitudes
+  h ^= h >> 15; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  x[i] = ((double)(h & 0xffffffu) / 16777216.0 - 0.5) * rsqrt((double)p);
+}
+// x <- y / |y|, norm_out[it] <- |y|   (deterministic tree; p is small against one CTA's throughput)
+__global__ void __launch_bounds__(1024) power_normalize_kernel(const double* __restrict__ y, int p, double* __restrict__ x,
+                                                               double* __restrict__ norm_out) {
+  __shared__ double red[32];
+  __shared__ double nrm;
+  double t = 0.0;
+  for (int i = threadIdx.x; i < p; i += 1024) t = fma(y[i], y[i], t);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) { nrm = sqrt(v); *norm_out = nrm; }
+  }
+  __syncthreads();
+  const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+  for (int i = threadIdx.x; i < p; i += 1024) x[i] = y[i] * inv;
+}
+
 }  // namespace
 
 void launch_tps_fill(const double* x_dev, int p, int d, double* L, size_t ld, double ridge,
@@ -391,6 +421,18 @@ void launch_small_rmul(const double* Phi, int p, int K, const double* Q_dev, dou
                        cudaStream_t s) {
   size_t total = (size_t)p * K;
   small_rmul_kernel<<<ceil_div(total, 256), 256, 0, s>>>(Phi, p, K, Q_dev, out);
+  count_launch();
+  SPB_CUDA(cudaGetLastError());
+}
+
+void launch_power_init(double* x, int p, cudaStream_t s) {
+  power_init_kernel<<<ceil_div(p, 256), 256, 0, s>>>(x, p);
+  count_launch();
+  SPB_CUDA(cudaGetLastError());
+}
+
+void launch_power_normalize(const double* y, int p, double* x, double* norm_out, cudaStream_t s) {
+  power_normalize_kernel<<<1, 1024, 0, s>>>(y, p, x, norm_out);
   count_launch();
   SPB_CUDA(cudaGetLastError());
 }

@@ -322,6 +322,26 @@ def admm_system(omega, G, tau1, rho, scale, blocks, mode, C_, Lambda2, maxit, to
     return Phi, Rm, Cm, L1, L2, it.value
 
 
+def core2_matrix_free(omega, Ytr, tau1, rho, Phi0, C_, Lambda2, maxit, tol, cg_tol=0.0):
+    """spatpcaCore2 without inv_sympd (spb_core2_matrix_free): returns (Phi, C, Lambda2, iterations, matrix passes)."""
+    lib = _lib.load()
+    om, yt = fmat(omega), fmat(Ytr)
+    Ph, Cm, L2 = fmat(Phi0).copy(order="F"), fmat(C_).copy(order="F"), fmat(Lambda2).copy(order="F")
+    p, K = Cm.shape
+    it, ps = C.c_int(0), C.c_int(0)
+    check(lib.spb_core2_matrix_free(ptr(om), ptr(yt), yt.shape[0], p, K, float(tau1), float(rho), int(maxit),
+                                    float(tol), float(cg_tol), ptr(Ph), ptr(Cm), ptr(L2), C.byref(it), C.byref(ps)))
+    return Ph, Cm, L2, it.value, ps.value
+
+
+def bench_core2_cg(p, K, n_tr, iters, repeats=3):
+    lib = _lib.load()
+    out = np.zeros(1)
+    ps = C.c_int(0)
+    check(lib.spb_bench_core2_cg(int(p), int(K), int(n_tr), int(iters), int(repeats), ptr(out), C.byref(ps)))
+    return float(out[0]), ps.value
+
+
 def default_blocks(p):
     return check(_lib.load().spb_default_blocks(int(p)))
 

@@ -38,7 +38,7 @@ def test_ctypes_table_mirrors_header():
     from spatpca_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
-    assert lib.spb_abi_version() == 1
+    assert lib.spb_abi_version() == 2
 
 
 def test_header_cites_reference_interfaces():

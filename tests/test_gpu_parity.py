@@ -98,6 +98,24 @@ def test_spatial_prediction_eigenvalues(sp, seq_1d):   # test-SpatPCA.R:52-88, 1
     assert sp.spatialPrediction(f.eigenfn, f.detrended_Y, 5, f.eigenfn)["eigenvalue"].sum() - 0.1066821 <= 1e-6
 
 
+@pytest.mark.parametrize("p,K,n,p_new,gamma", [(60, 3, 40, 25, 0.05), (200, 5, 30, 200, 0.5), (130, 2, 50, 7, 0.0)])
+def test_spatial_prediction_outputs_vs_oracle(sp, p, K, n, p_new, gamma):
+    """`prediction` and `estimated_covariance` (:764-769), with p_new != p and a gamma that keeps eigenvalues alive."""
+    rng = np.random.default_rng(1000 + p)
+    load = np.linalg.qr(rng.normal(size=(p, K)))[0]
+    Y = (rng.normal(size=(n, K)) * np.linspace(5, 2, K)) @ load.T + 0.3 * rng.normal(size=(n, p))
+    phi = load + 0.01 * rng.normal(size=(p, K))
+    phi_new = rng.normal(size=(p_new, K))
+    got = sp.spatialPrediction(phi, Y, gamma, phi_new)
+    want = ref.spatial_prediction(phi, Y, gamma, phi_new)
+    assert np.count_nonzero(want["eigenvalue"]) > 0
+    np.testing.assert_allclose(got["eigenvalue"], np.ravel(want["eigenvalue"]), rtol=1e-10, atol=1e-12)
+    assert abs(got["error"] - float(want["error"])) <= 1e-10 * abs(float(want["error"]))
+    for key in ("estimated_covariance", "prediction"):
+        assert got[key].shape == want[key].shape
+        assert np.max(np.abs(got[key] - want[key])) / np.max(np.abs(want[key])) <= 1e-9, key
+
+
 def test_predict_shapes(sp, seq_1d):                   # test-SpatPCA.R:138-146
     xn = r_seq_len(6, 7, 4).reshape(-1, 1)
     assert sp.predict(seq_1d["cv_1D"], xn).shape[1] == 4
@@ -278,6 +296,67 @@ def test_factored_matches_explicit_and_is_reproducible(sp):
     assert a[5] == b[5] == e[5] == 30
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and np.array_equal(a[4], b[4])
     assert np.max(np.abs(a[0] - e[0])) / np.max(np.abs(e[0])) <= 1e-11
+
+
+# Matrix-free Core2 (conjugate gradients inside the persistent kernel, no inv_sympd) against the oracle's explicit
+# inverse: identical iteration counts, iterates to 1e-10, for ragged sizes, every K instance and warm / cold starts.
+@pytest.mark.parametrize("p,K,tau1,n", [(64, 1, 0.01, 40), (300, 3, 0.01, 40), (1000, 5, 0.01, 40), (513, 8, 0.1, 70),
+                                        (1537, 5, 1.0, 300), (2100, 2, 0.001, 33), (4100, 5, 0.1, 160)])
+def test_core2_matrix_free_vs_oracle(sp, p, K, tau1, n):
+    from spatpca_b200 import engine as eng
+    Yt, G, Om, rho, Phi0, L20 = _spd_problem(p, K, 17 * p + K, n=n)
+    tr = ref.Trace()
+    wPhi, wC, wL2 = ref.core2(G, None, Phi0, L20, Om, tau1, rho, 100, 1e-4, tr)
+    gPhi, gC, gL2, it, passes = eng.core2_matrix_free(Om, Yt, tau1, rho, Phi0, Phi0, L20, 100, 1e-4)
+    assert it == tr.calls[0][3]
+    assert passes >= 2 * it
+    for g, w in ((gPhi, wPhi), (gC, wC), (gL2, wL2)):
+        assert np.max(np.abs(g - w)) / np.max(np.abs(w)) <= 1e-10
+    # a second, warm-started call (the next tau1 of a path, :329-332) from the oracle's own state
+    tr2 = ref.Trace()
+    w2 = ref.core2(G, wPhi, wC, wL2, Om, 3.0 * tau1, rho, 100, 1e-4, tr2)
+    g2 = eng.core2_matrix_free(Om, Yt, 3.0 * tau1, rho, wPhi, wC, wL2, 100, 1e-4)
+    assert g2[3] == tr2.calls[0][3]
+    for g, w in zip(g2[:3], w2):
+        assert np.max(np.abs(g - w)) / np.max(np.abs(w)) <= 1e-10
+
+
+def test_core2_matrix_free_forced_and_reproducible(sp):
+    """thr = 0: exactly maxit iterations; two runs are bitwise equal (fixed-shape reductions, no atomics on data)."""
+    from spatpca_b200 import engine as eng
+    Yt, G, Om, rho, Phi0, L20 = _spd_problem(1300, 4, 777, n=50)
+    tr = ref.Trace()
+    want = ref.core2(G, None, Phi0, L20, Om, 0.05, rho, 12, 0.0, tr)
+    a = eng.core2_matrix_free(Om, Yt, 0.05, rho, Phi0, Phi0, L20, 12, 0.0)
+    b = eng.core2_matrix_free(Om, Yt, 0.05, rho, Phi0, Phi0, L20, 12, 0.0)
+    assert a[3] == b[3] == 12 == tr.calls[0][3]
+    for x, y in zip(a[:3], b[:3]):
+        assert np.array_equal(x, y)
+    assert np.max(np.abs(a[0] - want[0])) / np.max(np.abs(want[0])) <= 1e-10
+
+
+def test_core2_matrix_free_rejects_indefinite_system(sp):
+    """rho far below the Gram matrix's top eigenvalue: inv_sympd fails in the reference, r.Ar <= 0 here."""
+    from spatpca_b200 import engine as eng, SpatpcaError
+    Yt, G, Om, rho, Phi0, L20 = _spd_problem(300, 2, 5)
+    with pytest.raises(SpatpcaError):
+        eng.core2_matrix_free(Om, Yt, 0.01, rho * 1e-3, Phi0, Phi0, L20, 5, 1e-4)
+
+
+@pytest.mark.parametrize("name", ["irregular2d_small", "grid3d_small"])
+def test_cv_matrix_free_forced_vs_oracle(sp, name, monkeypatch):
+    """SPB_CORE2=cg: every spatpcaCore2 / Core2p call of the job runs matrix-free (the automatic choice only does so
+    from p = 2048 on); same gates as the factored path, and SPB_CORE2=factor gives the same selections."""
+    case = make_case(name)
+    monkeypatch.setenv("SPB_CORE2", "cg")
+    got, want, tr = run_both(sp, case)
+    assert_cv_parity(got, want)
+    assert got["stats"]["n_cg_calls"] > 0 and got["stats"]["cg_passes"] > 0
+    assert got["stats"]["admm_iters"] == tr.admm_iters
+    monkeypatch.setenv("SPB_CORE2", "factor")
+    fac = _run_cv(sp, case)
+    assert fac["stats"]["n_cg_calls"] == 0
+    assert_cv_parity(fac, want)
 
 
 @pytest.mark.parametrize("m,p,K", [(1, 10, 1), (20, 50, 2), (40, 1000, 5), (100, 333, 8), (7, 4097, 3)])
@@ -650,3 +729,122 @@ def test_core3_odd_sizes(sp, p, K):
     assert got[5] == tr.calls[0][3]
     for g, w in zip(got[:5], want):
         assert np.max(np.abs(g - w)) / max(np.max(np.abs(w)), 1e-300) <= 1e-10
+
+
+def test_stage3_strided_fold_list_with_two_lanes(sp, monkeypatch):
+    """A rank's fold list is strided (k % world == rank): with fewer lanes than folds two of them share a lane and
+    its chain buffers.  Stage 3 must run them one after the other (it grouped folds by list position)."""
+    case = make_case("grid3d_small")
+    M = case["M"]
+    mk = lambda: sp.Engine(case["x"].shape[0], case["x"].shape[1], case["Y"].shape[0], M, case["K"], case["tau1"],
+                           case["tau2"], case["gamma"], 100, 1e-4, case["l2"])
+
+    def run(folds_groups):
+        e = mk()
+        e.upload(case["x"], case["Y"], case["nk"])
+        e.prepare()
+        r1 = {}
+        for g in folds_groups:
+            r1.update(e.stage1_folds(g))
+        i1, _ = sp.select_index(np.array([r1[k] for k in range(M)]))
+        r2 = {}
+        for g in folds_groups:
+            r2.update(e.stage2_folds(g, i1))
+        i2, _ = sp.select_index(np.array([r2[k] for k in range(M)]))
+        r3 = {}
+        for g in folds_groups:
+            r3.update(e.stage3_folds(g, i1, i2))
+        e.close()
+        return np.array([r3[k] for k in range(M)])
+
+    base = run([list(range(M))])
+    monkeypatch.setenv("SPB_LANES", "2")
+    strided = run([[0, 2, 4], [1, 3]])
+    assert np.array_equal(base, strided)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs at full size (C2, C3, C4) against the oracle, in the driver-run suite
+# ---------------------------------------------------------------------------------------------
+def _full_config(sp, name):
+    case = make_case(name)
+    got, want, tr = run_both(sp, case)
+    return case, got, want, tr
+
+
+@pytest.mark.parametrize("name", ["C2", "C2_tau2"])
+def test_cv_config2_full(sp, name):
+    """BASELINE config 2: 30 x 30 grid, p = 900, n = 100, K = 3, default tau1 grid (and the vignette's tau2 grid)."""
+    case, got, want, tr = _full_config(sp, name)
+    assert_cv_parity(got, want)
+    assert got["stats"]["n_admm_calls"] == len(tr.calls)
+    assert got["stats"]["admm_iters"] == tr.admm_iters
+
+
+@pytest.fixture(scope="module")
+def c3_runs(sp):
+    return _full_config(sp, "C3")
+
+
+def test_cv_config3_full(sp, c3_runs):
+    """BASELINE config 3: p = 4096 irregular 2-D, n = 200, K = 5, 10 x 10 x 11 grids (oracle: ~40 s of CPU)."""
+    case, got, want, tr = c3_runs
+    assert_cv_parity(got, want)
+    assert got["stats"]["n_admm_calls"] == len(tr.calls)
+    assert got["stats"]["admm_iters"] == tr.admm_iters
+
+
+def _injected(sp, case, om):
+    e = sp.Engine(case["x"].shape[0], case["x"].shape[1], case["Y"].shape[0], case["M"], case["K"],
+                  case["tau1"], case["tau2"], case["gamma"], 100, 1e-4, case["l2"])
+    try:
+        e.set_omega(om)
+        e.upload(case["x"], case["Y"], case["nk"])
+        e.prepare()
+        M = case["M"]
+        folds = list(range(M))
+        r1 = e.stage1_folds(folds)
+        i1, s1 = sp.select_index(np.array([r1[k] for k in folds]))
+        e.stage1_full(i1)
+        r2 = e.stage2_folds(folds, i1)
+        i2, s2 = sp.select_index(np.array([r2[k] for k in folds]))
+        e.stage2_full(i1, i2)
+        r3 = e.stage3_folds(folds, i1, i2)
+        i3, s3 = sp.select_index(np.array([r3[k] for k in folds]))
+        return dict(s1=s1, s2=s2, s3=s3, phi=e.get_eigenfn(), idx=(i1, i2, i3), log=e.call_log())
+    finally:
+        e.close()
+
+
+def test_cv_config3_injected_omega(sp, c3_runs):
+    """The same job with the ORACLE's Omega on both sides: everything after thinPlateSplineMatrix to 1e-10."""
+    case, _, want, tr = c3_runs
+    r = _injected(sp, case, want["aux"]["omega"])
+    np.testing.assert_allclose(r["s1"], want["cv_score_tau1"], rtol=1e-11)
+    np.testing.assert_allclose(r["s2"], want["cv_score_tau2"], rtol=1e-11)
+    np.testing.assert_allclose(r["s3"], want["cv_score_gamma"], rtol=1e-11)
+    assert eig_err(r["phi"], want["estimated_eigenfn"]) <= 1e-10
+    assert sum(c[3] for c in r["log"]) == tr.admm_iters
+
+
+@pytest.fixture(scope="module")
+def c4_runs(sp):
+    return _full_config(sp, "C4")
+
+
+def test_cv_config4_full(sp, c4_runs):
+    """BASELINE config 4, the headline: p = 10 000, n = 200, K = 5, 11 x 11 x 11 grids (oracle: ~3 min of CPU)."""
+    case, got, want, tr = c4_runs
+    assert_cv_parity(got, want)
+    assert got["stats"]["n_admm_calls"] == len(tr.calls)
+    assert got["stats"]["admm_iters"] == tr.admm_iters
+
+
+def test_cv_config4_injected_omega(sp, c4_runs):
+    case, _, want, tr = c4_runs
+    r = _injected(sp, case, want["aux"]["omega"])
+    np.testing.assert_allclose(r["s1"], want["cv_score_tau1"], rtol=1e-11)
+    np.testing.assert_allclose(r["s2"], want["cv_score_tau2"], rtol=1e-11)
+    np.testing.assert_allclose(r["s3"], want["cv_score_gamma"], rtol=1e-11)
+    assert eig_err(r["phi"], want["estimated_eigenfn"]) <= 1e-10
+    assert sum(c[3] for c in r["log"]) == tr.admm_iters
