@@ -113,6 +113,15 @@ def make_workload(name):
     return c, cfg
 
 
+def parallelism_note(M, world):
+    """Part of `config` in BOTH arms (the reference arm runs the same job on the host cores of rank 0)."""
+    if world <= 1:
+        return "one GPU: folds run concurrently on per-fold streams"
+    from spatpca_b200 import distributed as D
+    return (f"folds sharded over {world} rank(s), full-data fit on rank {D.full_fit_owner(M, world)}; Omega built in "
+            "column blocks (one per rank) exchanged by NCCL broadcast; CV scores all-gathered per stage")
+
+
 def run_job_resident(sp, case, coll=None):
     """One spatpcaCV job with the inputs already in HBM: returns (seconds, result, stats)."""
     import torch
@@ -183,6 +192,24 @@ def reference_inverse_count(case, index):
     return cnt
 
 
+def pin_blas_threads():
+    """All host cores for the oracle's BLAS/LAPACK, whatever the launcher exported (torchrun forces
+    OMP_NUM_THREADS=1, which made the round-1 reference arm run on one core).  Returns the thread count in use."""
+    try:
+        want = len(os.sched_getaffinity(0))
+    except Exception:
+        want = os.cpu_count() or 1
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=want, user_api="blas")
+        nums = [d.get("num_threads", 1) for d in threadpoolctl.threadpool_info() if d.get("user_api") == "blas"]
+        if nums:
+            return int(max(nums))
+    except Exception:
+        pass
+    return want
+
+
 def cpu_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -194,37 +221,50 @@ def cpu_threads():
     return os.cpu_count() or 1
 
 
+def oracle_full_job(case):
+    """The reference's whole spatpcaCV job (oracle port) on the host: returns (seconds, result, trace)."""
+    from oracle import spatpca_ref as ref
+    tr = ref.Trace()
+    t0 = time.perf_counter()
+    res = ref.spatpca_cv(case["x"], case["Y"], case["M"], case["K"], case["tau1"], case["tau2"], case["gamma"],
+                         case["nk"], 100, 1e-4, case["l2"], trace=tr)
+    return time.perf_counter() - t0, res, tr
+
+
 def reference_arm(args, rank, world):
-    """`--impl reference`: the reference's CPU path (the oracle port; the reference itself needs R +
-    RcppArmadillo, absent here) on the host cores, on a bounded sample of the same workload."""
+    """`--impl reference`: the reference's CPU path on the host cores of rank 0 -- the oracle port, because the
+    reference itself needs R + RcppArmadillo (absent in this image).  It runs the SAME configuration as the GPU arm:
+    complete spatpcaCV jobs (Omega, all 62 inv_sympd, every ADMM call, all losses, the selections).  One job takes
+    minutes at C4, so the arm runs jobs until `--steps` are done or REF_BUDGET_S (default 240 s) is spent -- at least
+    one complete job -- and reports the steps it really timed."""
     if rank != 0:
         return 0
-    from oracle import spatpca_ref as ref
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(os.cpu_count() or 1))
+    cores = pin_blas_threads()
     case, cfg = make_workload(args.config)
-    p = cfg["p"]
-    t0 = time.perf_counter()
-    om = ref.thin_plate_spline_matrix(case["x"])          # untimed set-up of the sample (reported)
-    om[np.diag_indices(p)] += 1e-8
-    t_omega = time.perf_counter() - t0
-    for _ in range(args.warmup):
-        cpu_sample(case, om)
-    times, iters = [], 0
-    for _ in range(args.steps):
-        dt, it, _ = cpu_sample(case, om)
+    cfg["parallelism"] = parallelism_note(case["M"], world)
+    budget = float(os.environ.get("REF_BUDGET_S", "240"))
+    t_start = time.perf_counter()
+    times, iters, res, tr = [], 0, None, None
+    while len(times) < max(1, args.steps):
+        dt, res, tr = oracle_full_job(case)
         times.append(dt)
-        iters = it
+        iters = tr.admm_iters
+        if time.perf_counter() - t_start + dt > budget:
+            break
     mean_t = float(np.mean(times))
     value = iters / mean_t
-    cores = cpu_threads()
-    sample = ("fold 0 of stage 1 restricted to tau1[{0,5}]: SVD start + Gram matrix + 1 inv_sympd + its "
-              f"{iters} ADMM iterations + 2 hold-out losses at p={p}; Omega built once on the CPU before the "
-              f"timed steps ({t_omega:.1f} s, untimed)")
+    sample = (f"{len(times)} complete spatpcaCV job(s) of this configuration on {cores} BLAS threads "
+              f"({mean_t:.1f} s per job, {iters} ADMM iterations in {len(tr.calls)} calls; no warm-up: every job is cold); "
+              f"phases of the last job (s): " + ", ".join(f"{k}={v:.1f}" for k, v in sorted(tr.phase_s.items())))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_t * 1e3, "higher_is_better": True,
+        "steps": len(times), "warmup": 0, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": mean_t * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "omega_s": t_omega},
+        "wall_s": mean_t, "admm_iters": iters, "admm_calls": len(tr.calls),
+        "selected": [res["selected_tau1"], res["selected_tau2"], res["selected_gamma"]],
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -259,6 +299,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="C4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-forced", action="store_true", help="skip the forced-iteration leg (thr = 0)")
+    ap.add_argument("--forced-maxit", type=int, default=100)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -284,9 +326,7 @@ def main():
         coll = D.TorchCollective(torch.device("cuda", local_rank))
 
     case, cfg = make_workload(args.config)
-    cfg["parallelism"] = (f"folds sharded over {world} rank(s), full-data fit on rank {D.full_fit_owner(case['M'], world)}; "
-                          "stage-1 (fold, tau1) systems spread over all ranks and shipped to the fold's rank by NCCL "
-                          "send/recv; Omega built in column blocks (one per rank) exchanged by NCCL broadcast" if world > 1 else "one GPU: folds run concurrently on per-fold streams")
+    cfg["parallelism"] = parallelism_note(case["M"], world)
     p, K = cfg["p"], cfg["K"]
     hbm_peak, peak_src = load_peaks()
 
@@ -375,43 +415,108 @@ def main():
         dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant own kernel: the persistent ADMM kernel (HBM-bound) ----
-    # Timed alone with CUDA events on the library's stream, 10 forced Core3 iterations per launch, averaged
-    # over 3 launches after a warm-up launch.  The kernel applies a system either as an explicit inverse
-    # (one matrix-stream phase) or as a block U'DU factor (2m - 1 phases over the same 8 p^2 bytes); the
-    # headline figure is the mode the job uses for the tau2-path systems (stages 2-3, where ~70 % of the
-    # job's ADMM iterations run), the other modes are listed beside it.
+    # ---- rooflines (all timed in THIS run with CUDA events on the library's stream; peaks: MEASURED_PEAKS.json) ----
+    # (1) headline = the own kernel with the largest share of the timed step.  Since round 2 that is the
+    #     matrix-free Core2 kernel (cg_core2_kernel): every stage-1 system and the cold Core2 calls are solved by
+    #     conjugate gradients inside one persistent launch, each CG step streaming Omega_u once.  HBM-bound:
+    #     algorithmic bytes per matrix pass = 8 p^2 (Omega_u) + 16 n_tr p (Ytr and its transpose, for the
+    #     rank-n_tr part) + ~96 p K (the p x K vectors of a CG step).  Probe: a synthetic system of the job's size
+    #     and conditioning (cond ~1.6) in device memory, 4 forced ADMM iterations per launch.
+    n_tr = int(round(cfg["n"] * (cfg["M"] - 1) / cfg["M"]))
+    roof_admm_iters = 4
+    cg_ms, cg_passes = eng_mod.bench_core2_cg(p, K, n_tr, roof_admm_iters, 3) if K <= 8 else (None, 0)
+    cg_bytes_pass = 8.0 * p * p + 16.0 * n_tr * p + 96.0 * p * K
+    # (2) the persistent ADMM kernel on explicit / factored systems (the tau2-path systems of stages 2-3 and every
+    #     system the matrix-free kernel is not chosen for): 8 p^2 + 72 p K bytes per Core3 iteration
     roof_iters = 10
     alg_bytes_iter = 8.0 * p * p + 72.0 * p * K                     # SURVEY.md section 8d, U-iter (Core3)
     m_path, m_stage1 = eng_mod.default_path_blocks(p), eng_mod.default_blocks(p)
     modes = {}
     for label, m in (("path_systems", m_path), ("stage1_systems", m_stage1), ("explicit_inverse", 1)):
         ms = eng_mod.bench_admm_blocks(p, K, 3, roof_iters, 3, m)
-        modes[label] = {"blocks": m, "phases": 2 * m - 1, "us_per_iteration": ms * 1e3,
-                        "achieved_gbs": alg_bytes_iter / (ms * 1e-3) / 1e9,
+        modes[label] = {"kernel": "admm_persistent_kernel<K>", "blocks": m, "phases": 2 * m - 1,
+                        "us_per_iteration": ms * 1e3, "achieved_gbs": alg_bytes_iter / (ms * 1e-3) / 1e9,
                         "frac": alg_bytes_iter / (ms * 1e-3) / 1e9 / hbm_peak}
-    ms_iter = modes["path_systems"]["us_per_iteration"] * 1e-3
-    achieved = alg_bytes_iter / (ms_iter * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_admm_traffic.json")
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_cg_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        by_blocks = tj.get("dram_bytes_per_iteration_by_blocks", {})
-        if tj.get("p") == p and tj.get("K") == K and str(m_path) in by_blocks:
-            traffic = by_blocks[str(m_path)] * roof_iters
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic,
-                "kernel": "admm_persistent_kernel<K>, %d-block factor (one launch = %d Core3 iterations)" % (m_path, roof_iters),
-                "algorithmic_bytes_per_launch": alg_bytes_iter * roof_iters, "ms_per_launch": ms_iter * roof_iters,
-                "peak_source": peak_src, "modes": modes}
-    # second bound: the p^3 work against the FP64 GEMM rate measured in the same run
+        if tj.get("p") == p and tj.get("K") == K and tj.get("dram_bytes_per_pass"):
+            traffic = tj["dram_bytes_per_pass"] * cg_passes
+            traffic_src = "imported: ncu --set full capture of the same probe, " + tj.get("source", "profiles/r02_cg_traffic.json")
+    # in the job: algorithmic bytes of every ADMM / matrix-free launch of the timed job over the sum of their
+    # event-timed durations (per-launch CUDA events on each lane's stream; lanes share the GPU, so a launch's
+    # duration includes waiting for SMs held by other lanes' kernels -- a lower bound on the kernels' own rate)
+    ms_kernels = float(stats["ms_admm"]) + float(stats.get("ms_cg", 0.0))
+    in_job = {"algorithmic_bytes": float(stats.get("admm_bytes", 0.0)), "ms_launches_summed": ms_kernels,
+              "ms_matrix_free": float(stats.get("ms_cg", 0.0)), "ms_factored": float(stats["ms_admm"]),
+              "matrix_free_calls": int(stats.get("n_cg_calls", 0)), "matrix_passes": int(stats.get("cg_passes", 0)),
+              "achieved_gbs": (float(stats.get("admm_bytes", 0.0)) / (ms_kernels * 1e-3) / 1e9) if ms_kernels > 0 else None}
+    if in_job["achieved_gbs"]:
+        in_job["frac"] = in_job["achieved_gbs"] / hbm_peak
+    if cg_ms:
+        achieved = cg_bytes_pass * cg_passes / (cg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "kernel": "cg_core2_kernel<K> (matrix-free spatpcaCore2: one launch = %d ADMM iterations = %d matrix passes)"
+                              % (roof_admm_iters, cg_passes),
+                    "algorithmic_bytes_per_launch": cg_bytes_pass * cg_passes, "ms_per_launch": cg_ms,
+                    "us_per_matrix_pass": cg_ms * 1e3 / max(cg_passes, 1),
+                    "peak_source": peak_src, "modes": modes, "in_job": in_job}
+    else:
+        ms_iter = modes["path_systems"]["us_per_iteration"] * 1e-3
+        achieved = alg_bytes_iter / (ms_iter * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": None, "kernel": "admm_persistent_kernel<K>, %d-block factor (one launch = %d Core3 iterations)" % (m_path, roof_iters),
+                    "algorithmic_bytes_per_launch": alg_bytes_iter * roof_iters, "ms_per_launch": ms_iter * roof_iters,
+                    "peak_source": peak_src, "modes": modes, "in_job": in_job}
+    # (3) the p^3 work (Omega build, the remaining SPD factorisations) against the FP64 GEMM rate of the same run
     dgemm_tf = eng_mod.bench_dgemm(8192, 2)
     inv_ms = eng_mod.bench_inverse(p, 2)
     fac_ms = eng_mod.bench_factor(p, 2, m_stage1)
-    fp64 = {"dgemm_8192_tflops": dgemm_tf, "inverse_ms": inv_ms, "inverse_tflops_p3": (float(p) ** 3) / (inv_ms * 1e-3) / 1e12,
-            "inverse_frac_of_dgemm": (float(p) ** 3) / (inv_ms * 1e-3) / 1e12 / dgemm_tf,
-            "factor_blocks": m_stage1, "factor_ms": fac_ms}
+    fac2_ms = eng_mod.bench_factor(p, 2, m_path)
+    p3 = float(p) ** 3
+    fac_flops = lambda m: p3 if m <= 1 else p3 / 3 + p3 / m + p3 / (m * m)
+    fp64 = {"dgemm_8192_tflops": dgemm_tf, "inverse_ms": inv_ms, "inverse_tflops_p3": p3 / (inv_ms * 1e-3) / 1e12,
+            "inverse_frac_of_dgemm": p3 / (inv_ms * 1e-3) / 1e12 / dgemm_tf,
+            "factor_blocks": m_stage1, "factor_ms": fac_ms,
+            "factor_frac_of_dgemm": fac_flops(m_stage1) / (fac_ms * 1e-3) / 1e12 / dgemm_tf,
+            "path_factor_blocks": m_path, "path_factor_ms": fac2_ms,
+            "path_factor_frac_of_dgemm": fac_flops(m_path) / (fac2_ms * 1e-3) / 1e12 / dgemm_tf,
+            "job": {"p3_flops": float(stats.get("p3_flops", 0.0)), "n_factorisations": int(stats["n_inverses"]),
+                    "ms_omega": float(stats["ms_omega"]), "ms_factorisations_summed": float(stats["ms_inverse"]),
+                    "omega_frac_of_dgemm": ((2.0 / 3 + 5.0) * p3 / (float(stats["ms_omega"]) * 1e-3) / 1e12 / dgemm_tf)
+                    if stats["ms_omega"] > 0 else None}}
+
+    # ---- forced-iteration mode (SURVEY 8d mode ii: thr = 0, every ADMM call runs exactly maxit iterations): the
+    # deterministic-denominator figure of BASELINE.json's "ADMM iters/s"; HBM floor = peak / (8 p^2 + 72 p K) ----
+    forced = None
+    if world == 1 and not args.no_forced:
+        fm = args.forced_maxit
+        cf = dict(case)
+        e = sp.Engine(cf["x"].shape[0], cf["x"].shape[1], cf["Y"].shape[0], cf["M"], cf["K"], cf["tau1"], cf["tau2"],
+                      cf["gamma"], fm, 0.0, cf["l2"])
+        e.upload(cf["x"], cf["Y"], cf["nk"])
+        cf["_engine"] = e
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        D.prepare_sharded(e, D.Collective())
+        D.run_sharded(e, sp.select_index, D.Collective(), cf["M"], len(cf["tau1"]), len(cf["tau2"]), len(cf["gamma"]),
+                      cf["tau1"], cf["tau2"], cf["gamma"])
+        torch.cuda.synchronize()
+        dtf = time.perf_counter() - t0
+        stf = e.stats()
+        e.close()
+        floor = hbm_peak * 1e9 / alg_bytes_iter
+        forced = {"maxit": fm, "thr": 0.0, "wall_s": dtf, "admm_iters": int(stf["admm_iters"]),
+                  "admm_calls": int(stf["n_admm_calls"]), "iters_per_s": stf["admm_iters"] / dtf,
+                  "hbm_floor_iters_per_s": floor, "frac_of_hbm_floor": stf["admm_iters"] / dtf / floor,
+                  "ms_admm_summed": float(stf["ms_admm"]) + float(stf.get("ms_cg", 0.0)),
+                  "iters_per_s_kernel_time": (stf["admm_iters"] / ((float(stf["ms_admm"]) + float(stf.get("ms_cg", 0.0))) * 1e-3))
+                  if stf["ms_admm"] + stf.get("ms_cg", 0.0) > 0 else None,
+                  "note": "whole job incl. Omega and factorisations; with thr = 0 every call is expected to run maxit "
+                          "iterations, so the cost model keeps the factored path"}
 
     # ---- CPU baseline on a bounded sample (oracle port, host cores) ----
     cpu = None
@@ -434,8 +539,10 @@ def main():
         "dtype": "f64", "data": "synthetic", "config": cfg,
         "wall_s": t_job, "admm_iters": iters_job, "admm_calls": int(stats["n_admm_calls"]),
         "selected": [res["selected_tau1"], res["selected_tau2"], res["selected_gamma"]],
-        "phases_ms_rank0": {k: stats[k] for k in ("ms_omega", "ms_prologue", "ms_inverse", "ms_admm", "ms_cv_loss", "ms_gamma")},
-        "roofline": roofline, "fp64": fp64, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_job,
+        "phases_ms_rank0": {k: stats[k] for k in ("ms_omega", "ms_prologue", "ms_inverse", "ms_admm", "ms_cg", "ms_cv_loss", "ms_gamma")},
+        "n_factorisations": int(stats["n_inverses"]), "matrix_free_calls": int(stats.get("n_cg_calls", 0)),
+        "roofline": roofline, "fp64": fp64, "forced_iterations": forced, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": launches_job,
         "clocks": clocks,
     }
     emit(line)

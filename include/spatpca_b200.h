@@ -114,6 +114,10 @@ typedef struct spb_cv_stats {
   int       gpu_launches;     /* kernels of this library launched (library calls not counted) */
   int       n_cg_calls;       /* spatpcaCore2/2p calls solved matrix-free (conjugate gradients, no inv_sympd) */
   long long cg_passes;        /* p x p matrix passes streamed by those calls                                   */
+  double    ms_cg;            /* matrix-free Core2 kernel (device time, not included in ms_admm)               */
+  double    admm_bytes;       /* algorithmic bytes of all ADMM / matrix-free launches (8p^2 + 72pK per
+                                 Core3 iteration, 8p^2 + 40pK per Core2 iteration, 8p^2 + 16 n_tr p per CG pass) */
+  double    p3_flops;         /* flop of the p^3 work enqueued: Omega build + SPD factorisations                */
 } spb_cv_stats;
 
 /*
@@ -225,6 +229,11 @@ SPB_API int spb_engine_sync(spb_engine* e);
 SPB_API int spb_engine_omega_begin(spb_engine* e, int* needed);
 SPB_API int spb_engine_omega_solve_cols(spb_engine* e, int c0, int c1);
 SPB_API int spb_engine_omega_product_cols(spb_engine* e, int c0, int c1);
+/* Refined build (the default, csrc/omega_refine.cu): between the exchange of buffer 0 (X0 = A^-1 columns) and
+ * omega_product_cols, every rank forms the exactly-split residual and the Newton-Schulz correction of its own
+ * columns (*active = 1) and the corrected columns (buffer 2) are exchanged.  With SPB_OMEGA_REFINE=0 this is
+ * a no-op (*active = 0) and buffer 2 is empty.                                                              */
+SPB_API int spb_engine_omega_refine_cols(spb_engine* e, int c0, int c1, int* active);
 SPB_API int spb_engine_omega_buffer(spb_engine* e, int which, int c0, int c1, void** dev_ptr, long long* bytes);
 SPB_API int spb_engine_omega_sync(spb_engine* e);
 SPB_API int spb_engine_omega_finish(spb_engine* e);

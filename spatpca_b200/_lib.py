@@ -37,7 +37,8 @@ class CvStats(C.Structure):
         ("ms_omega", C.c_double), ("ms_prologue", C.c_double), ("ms_inverse", C.c_double),
         ("ms_admm", C.c_double), ("ms_cv_loss", C.c_double), ("ms_gamma", C.c_double),
         ("bytes_h2d", C.c_longlong), ("bytes_d2h", C.c_longlong), ("gpu_launches", C.c_int),
-        ("n_cg_calls", C.c_int), ("cg_passes", C.c_longlong),
+        ("n_cg_calls", C.c_int), ("cg_passes", C.c_longlong), ("ms_cg", C.c_double), ("admm_bytes", C.c_double),
+        ("p3_flops", C.c_double),
     ]
 
     def as_dict(self):
@@ -90,6 +91,7 @@ SIGNATURES = {
     "spb_engine_omega_begin": (C.c_int, [_vp, _ip]),
     "spb_engine_omega_solve_cols": (C.c_int, [_vp, C.c_int, C.c_int]),
     "spb_engine_omega_product_cols": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "spb_engine_omega_refine_cols": (C.c_int, [_vp, C.c_int, C.c_int, _ip]),
     "spb_engine_omega_buffer": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]),
     "spb_engine_omega_sync": (C.c_int, [_vp]),
     "spb_engine_omega_finish": (C.c_int, [_vp]),

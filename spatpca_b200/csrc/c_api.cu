@@ -309,6 +309,9 @@ int spb_engine_omega_solve_cols(spb_engine* e, int c0, int c1) { SPB_ENGINE_CALL
 int spb_engine_omega_product_cols(spb_engine* e, int c0, int c1) {
   SPB_ENGINE_CALL(e->impl->omega_product_cols(c0, c1));
 }
+int spb_engine_omega_refine_cols(spb_engine* e, int c0, int c1, int* active) {
+  SPB_ENGINE_CALL(SPB_REQUIRE(active != nullptr, "NULL output"); *active = e->impl->omega_refine_cols(c0, c1) ? 1 : 0);
+}
 int spb_engine_omega_buffer(spb_engine* e, int which, int c0, int c1, void** dev_ptr, long long* bytes) {
   SPB_ENGINE_CALL(SPB_REQUIRE(dev_ptr != nullptr, "NULL output"); *dev_ptr = e->impl->omega_buffer(which, c0, c1, bytes));
 }

@@ -301,6 +301,15 @@ void host_jacobi_eigh(int K, std::vector<double>& A, std::vector<double>& evals,
   }
 }
 
+// flop of one SPD system in the form the job holds it: explicit inverse p^3, m-block U'DU factor p^3/3 + p^3/m + p^3/m^2
+// LU 2/3 + solve for [I; 0] 2 + E Lp 2 + upper half of Lp'(E Lp) 1   (x p^3)
+static double omega_flops(int p) { return (2.0 / 3.0 + 2.0 + 2.0 + 1.0) * (double)p * p * p; }
+static double factor_flops(int p, const Blocking& b) {
+  const double p3 = (double)p * p * p;
+  if (b.m <= 1) return p3;
+  return p3 / 3.0 + p3 / b.m + p3 / ((double)b.m * b.m);
+}
+
 double water_filling(const std::vector<double>& d, double total, double tv, double g, int p, int K) {
   // noise level of reference :499-519 / :743-760; d = descending eigenvalues of Phi' S Phi
   int tempL = K;
@@ -328,8 +337,17 @@ double water_filling(const std::vector<double>& d, double total, double tv, doub
 // ---------------------------------------------------------------------------------------
 // static building blocks
 // ---------------------------------------------------------------------------------------
+bool Engine::omega_refine_enabled() {
+  static const bool on = [] { const char* e = std::getenv("SPB_OMEGA_REFINE"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 void Engine::build_omega_raw(OmegaRes& R, int* flag, const double* x_dev, int p, int d, double* omega_dev,
                              size_t ld, bool upper_only, OmegaTemps& tmp) {
+  if (omega_refine_enabled()) {
+    build_omega_refined(R, flag, x_dev, p, d, omega_dev, ld, upper_only, tmp);
+    return;
+  }
   // thinPlateSplineMatrix (:58-76): Lp = top-left block of inv(L + 1e-8 I) by LU with partial
   // pivoting (the reference's dgetrf/dgetri class; here getrf + getrs on [I_p; 0]); Omega = Lp'(E Lp).
   const int q = p + d + 1;
@@ -804,6 +822,7 @@ void Engine::prepare() {
       {
         Scoped so(clock_, PH_OMEGA, R.stream);
         build_omega_raw(R, ctx_.flag.get(), dX_.get(), p_, d_, omega_u_.get(), ld_, true, *omega_tmp_);   // :574
+        stats_.p3_flops += omega_refine_enabled() ? omega_refined_flops(p_) : omega_flops(p_);
         SPB_CUDA(cudaMemcpy2DAsync(omega_diag_raw_.get(), sizeof(double), omega_u_.get(),
                                    (ld_ + 1) * sizeof(double), sizeof(double), p_, cudaMemcpyDeviceToDevice,
                                    R.stream));
@@ -818,7 +837,7 @@ void Engine::prepare() {
       // (C5: 38 GB) finish the build here instead so that the lanes can have it
       size_t free_b = 0, total_b = 0;
       SPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-      if (3.0 * (double)ld_ * p_ * sizeof(double) > 0.15 * (double)free_b) finish_omega();
+      if ((omega_refine_enabled() ? 5.0 : 3.0) * (double)ld_ * p_ * sizeof(double) > 0.15 * (double)free_b) finish_omega();
     } else {
       // all taus are zero but a grid has several entries: Omega = I (:578); tau * Omega vanishes.
       launch_set_identity(omega_u_.get(), p_, p_, ld_, s);
@@ -847,6 +866,7 @@ bool Engine::omega_begin() {
   SPB_REQUIRE(dX_.get() != nullptr, "upload() must be called before omega_begin()");
   const bool need_omega = any_tau_ || tau1_.size() > 1 || tau2_.size() > 1;
   if (!need_omega || !any_tau_ || omega_ready_) return false;
+  if (omega_refine_enabled()) return omega_begin_refined();
   OmegaRes& R = ctx_.omega();
   cudaStream_t s = R.stream;
   SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
@@ -876,10 +896,11 @@ bool Engine::omega_begin() {
 void Engine::omega_solve_cols(int c0, int c1) {
   SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
   SPB_REQUIRE(c0 >= 0 && c0 <= c1 && c1 <= p_, "column range out of bounds");
-  if (c0 == c1) return;
   OmegaRes& R = ctx_.omega();
   const int q = p_ + d_ + 1;
   const size_t ldq = padded_ld(q);
+  if (omega_refine_enabled() && c1 == p_) c1 = q;       // refined build: the last block's owner also solves the border columns
+  if (c0 == c1) return;
   clock_.begin(PH_OMEGA, R.stream);
   SPB_CUSOLVER(cusolverDnDgetrs(R.solver, CUBLAS_OP_N, q, c1 - c0, omega_tmp_->L.get(), (int)ldq, R.ipiv.get(),
                                 omega_tmp_->Bm.get() + (size_t)c0 * ldq, (int)ldq, R.info.get()));
@@ -889,6 +910,7 @@ void Engine::omega_solve_cols(int c0, int c1) {
 void Engine::omega_product_cols(int c0, int c1) {
   SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
   SPB_REQUIRE(c0 >= 0 && c0 <= c1 && c1 <= p_, "column range out of bounds");
+  if (omega_refine_enabled()) { omega_product_cols_refined(c0, c1); return; }
   OmegaRes& R = ctx_.omega();
   cudaStream_t s = R.stream;
   const int q = p_ + d_ + 1;
@@ -912,11 +934,14 @@ void Engine::omega_product_cols(int c0, int c1) {
 void* Engine::omega_buffer(int which, int c0, int c1, long long* bytes) {
   SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
   SPB_REQUIRE(c0 >= 0 && c0 <= c1 && c1 <= p_, "column range out of bounds");
-  SPB_REQUIRE(which == 0 || which == 1, "which must be 0 (Lp) or 1 (Omega)");
+  SPB_REQUIRE(which >= 0 && which <= 2, "which must be 0 (X0 / Lp), 1 (Omega) or 2 (refined X1)");
   const size_t ldq = padded_ld(p_ + d_ + 1);
-  if (which == 0) {
-    if (bytes) *bytes = (long long)((size_t)(c1 - c0) * ldq * sizeof(double));
-    return omega_tmp_->Bm.get() + (size_t)c0 * ldq;
+  if (which == 0 || which == 2) {
+    const bool refined = omega_refine_enabled();
+    if (which == 2 && !refined) { if (bytes) *bytes = 0; return nullptr; }
+    const int c1e = (refined && c1 == p_) ? p_ + d_ + 1 : c1;
+    if (bytes) *bytes = (long long)((size_t)(c1e - c0) * ldq * sizeof(double));
+    return (which == 0 ? omega_tmp_->Bm.get() : omega_tmp_->C2.get()) + (size_t)c0 * ldq;
   }
   if (bytes) *bytes = (long long)((size_t)(c1 - c0) * ld_ * sizeof(double));
   return omega_u_.get() + (size_t)c0 * ld_;
@@ -1015,11 +1040,11 @@ void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double
     c.stat_slot = L.stat_slots.get() + (size_t)L.next_slot * 4;
     c.err_slot = L.err_slots.get() + L.next_slot;
     {
-      Scoped sc(L.clock, PH_ADMM, s);
+      Scoped sc(L.clock, PH_CG, s);
       SPB_CUDA(cudaMemsetAsync(c.stat_slot, 0, 4 * sizeof(int), s));
       launch_core2_cg(c, L.admm_ws.get(), s);
     }
-    L.pending.push_back({kind + 100, fold, idx, L.next_slot});     // + 100: solved matrix-free (flush_lane strips it)
+    L.pending.push_back({kind + 100, fold, idx, L.next_slot, c.n_tr});     // + 100: solved matrix-free (flush_lane strips it)
     L.next_slot++;
     L.dirty = true;
     return;
@@ -1035,6 +1060,7 @@ void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double
     Scoped sc(L.clock, PH_INVERSE, s);
     spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, tau1, rho, 2.0, buf, ld_, blocks_);
     stats_.n_inverses++;
+    stats_.p3_flops += factor_flops(p_, blocks_);
   }
   if (L.next_slot >= slot_cap_) flush_lane(L);
   AdmmCall c;
@@ -1048,7 +1074,7 @@ void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double
     SPB_CUDA(cudaMemsetAsync(c.stat_slot, 0, 4 * sizeof(int), s));
     if (maxit_ > 0) launch_admm(c, L.admm_ws.get(), s);
   }
-  L.pending.push_back({kind, fold, idx, L.next_slot});
+  L.pending.push_back({kind, fold, idx, L.next_slot, 0});
   L.next_slot++;
   L.dirty = true;
 }
@@ -1092,6 +1118,7 @@ void Engine::build_inverse(int k, int i) {
     Scoped sc(L.clock, PH_INVERSE, L.res->stream);
     spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, tau1_[i], f.rho, 2.0, buf, ld_, blocks_);
     stats_.n_inverses++;
+    stats_.p3_flops += factor_flops(p_, blocks_);
   }
   f.inv_valid[i] = 1;
   L.dirty = true;
@@ -1117,7 +1144,7 @@ void Engine::run_core3(Lane& L, int kind, int fold, int idx, const double* tinv,
     SPB_CUDA(cudaMemsetAsync(c.stat_slot, 0, 4 * sizeof(int), s));
     if (maxit_ > 0) launch_admm(c, L.admm_ws.get(), s);
   }
-  L.pending.push_back({kind, fold, idx, L.next_slot});
+  L.pending.push_back({kind, fold, idx, L.next_slot, 0});
   L.next_slot++;
   L.dirty = true;
 }
@@ -1147,10 +1174,15 @@ void Engine::flush_lane(Lane& L) {
       else if (status == SPB_ERR_INTERNAL) cg_failed = true;
       else if (status != 0) polar_failed = true;
       int kind = r.kind;
+      const double pp8 = 8.0 * (double)p_ * (double)p_, pk8 = 8.0 * (double)p_ * (double)K_;
       if (kind >= 100) {                                     // matrix-free call: [3] = matrix passes
         kind -= 100;
+        const int passes = st[(size_t)r.slot * 4 + 3];
         stats_.n_cg_calls++;
-        stats_.cg_passes += st[(size_t)r.slot * 4 + 3];
+        stats_.cg_passes += passes;
+        stats_.admm_bytes += passes * (pp8 + 16.0 * (double)r.n_tr * (double)p_) + iters * 5.0 * pk8;
+      } else {
+        stats_.admm_bytes += iters * (pp8 + (kind == 3 ? 9.0 : 5.0) * pk8);   // 8p^2 + 72pK / 40pK
       }
       log_.push_back(kind); log_.push_back(r.fold); log_.push_back(r.idx); log_.push_back(iters);
     }
@@ -1341,6 +1373,7 @@ void Engine::enqueue_stage2(int k, int index1, int step) {
     spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, f.rho, 1.0, f.tinv.get(),
                 ld_, blocks_path_);                                           // :397
     stats_.n_inverses++;
+    stats_.p3_flops += factor_flops(p_, blocks_path_);
     f.tinv_index = tag1;
   }
 }
@@ -1388,6 +1421,7 @@ double* Engine::full_tempinv(int index1) {
     spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, rho_full_, 1.0, tbuf,
                 ld_, blocks_path_);                                           // :661, :673
     stats_.n_inverses++;
+    stats_.p3_flops += factor_flops(p_, blocks_path_);
   }
   return tbuf;
 }
@@ -1480,7 +1514,7 @@ void Engine::get_eigenfn(double* out) {
 
 void Engine::get_stats(spb_cv_stats* st) {
   flush();
-  double ms[PH_COUNT], sum[PH_COUNT] = {0, 0, 0, 0, 0, 0};
+  double ms[PH_COUNT], sum[PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
   clock_.collect(ms);
   for (int i = 0; i < PH_COUNT; ++i) sum[i] = ms[i];
   for (auto& L : lanes_) {
@@ -1494,6 +1528,7 @@ void Engine::get_stats(spb_cv_stats* st) {
   stats_.ms_admm = sum[PH_ADMM];
   stats_.ms_cv_loss = sum[PH_CVLOSS];
   stats_.ms_gamma = sum[PH_GAMMA];
+  stats_.ms_cg = sum[PH_CG];
   stats_.n_admm_calls = (int)(log_.size() / 4);
   long long it = 0;
   for (size_t i = 0; i < log_.size(); i += 4) it += log_[i + 3];

@@ -10,7 +10,7 @@
 
 namespace spb {
 
-enum Phase { PH_OMEGA = 0, PH_PROLOGUE, PH_INVERSE, PH_ADMM, PH_CVLOSS, PH_GAMMA, PH_COUNT };
+enum Phase { PH_OMEGA = 0, PH_PROLOGUE, PH_INVERSE, PH_ADMM, PH_CVLOSS, PH_GAMMA, PH_CG, PH_COUNT };
 
 // Where work is enqueued: a stream with its own cuBLAS handle and inverse workspace.
 struct Exec {
@@ -41,6 +41,7 @@ struct OmegaRes {
 // temporaries of one build; must outlive the enqueued work
 struct OmegaTemps {
   DevBuf<double> L, Bm, T1;
+  DevBuf<double> C1, C2, vec;     // refined build only (omega_refine.cu)
 };
 
 // Per-thread, per-device CUDA context (stream + library handles + solver workspaces).
@@ -82,7 +83,7 @@ class PhaseClock {
   struct Span { Phase ph; cudaEvent_t a, b; };
   std::vector<Span> spans_;
   int open_ = -1;
-  double acc_[PH_COUNT] = {0, 0, 0, 0, 0, 0};
+  double acc_[PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 struct ChainState {              // ADMM iterate of one chain (p x K each)
@@ -108,7 +109,7 @@ struct FoldData {
   double tv = 0.0;                // trace(Ytr'Ytr) / n_tr
 };
 
-struct CallRec { int kind, fold, idx, slot; };
+struct CallRec { int kind, fold, idx, slot, n_tr; };
 
 // One independent chain of work (a fold's tau path, or the full-data fit): its own stream, cuBLAS
 // handle and working set, so that the latency-bound parts of one chain (leaf inverses, small
@@ -169,7 +170,10 @@ class Engine {
   bool omega_begin();
   void omega_solve_cols(int c0, int c1);
   void omega_product_cols(int c0, int c1);
-  void* omega_buffer(int which, int c0, int c1, long long* bytes);   // which: 0 = Lp columns, 1 = Omega columns
+  // refined build only (returns false and does nothing otherwise): residual + Newton-Schulz correction of this rank's
+  // columns; runs between the exchange of buffer 0 (X0) and the exchange of buffer 2 (X1)
+  bool omega_refine_cols(int c0, int c1);
+  void* omega_buffer(int which, int c0, int c1, long long* bytes);   // which: 0 = X0 / Lp columns, 1 = Omega columns, 2 = refined X1 columns
   void omega_stream_sync();
   void omega_finish();
   // Re-run with another number of eigenfunctions on the same data and grids (the K-selection loop of
@@ -198,6 +202,11 @@ class Engine {
   // drained).  upper_only: only the tiles on / above the diagonal of the final product are formed.
   static void build_omega_raw(OmegaRes& R, int* flag, const double* x_dev, int p, int d, double* omega_dev,
                               size_t ld, bool upper_only, OmegaTemps& tmp);
+  // the same matrix with this side's rounding error removed (omega_refine.cu): LU + one Newton-Schulz step on an
+  // exactly formed residual + the cancellation-free product; the default (SPB_OMEGA_REFINE=0: the plain pipeline)
+  static void build_omega_refined(OmegaRes& R, int* flag, const double* x_dev, int p, int d, double* omega_dev,
+                                  size_t ld, bool upper_only, OmegaTemps& tmp);
+  static bool omega_refine_enabled();
   // blk.m == 1: explicit inverse; blk.m > 1: block U'DU factor for the multi-phase ADMM stream
   static void spd_inverse(const Exec& ex, const double* omega_u, size_t ldo, const double* G,
                           size_t ldg, int p, double tau1, double rho, double scale, double* out,
@@ -268,6 +277,8 @@ class Engine {
   cudaEvent_t omega_evt_ = nullptr;
   std::unique_ptr<OmegaTemps> omega_tmp_;
   bool omega_cols_open_ = false;                 // between omega_begin() and omega_finish()
+  bool omega_begin_refined();
+  void omega_product_cols_refined(int c0, int c1);
   void wait_omega(Lane& L);                      // first use of Omega on a lane: wait for the build
   void finish_omega();                           // host wait + release of the temporaries
   std::vector<FoldData> folds_;
@@ -304,6 +315,8 @@ void gemm_upper_tn(cublasHandle_t blas, int n, int k, double alpha, const double
                    size_t ldb, double* C, size_t ldc);
 // block U'DU factor for the multi-phase ADMM stream (blk.m == 1: the explicit inverse)
 void spd_factor_blocked(const Exec& ex, double* A, int n, size_t ld, double* workspace, const Blocking& blk);
+
+double omega_refined_flops(int p);
 
 // small host helpers (host_math.cpp-like, defined in engine.cu)
 void host_jacobi_eigh(int K, std::vector<double>& A /*K x K col-major, destroyed*/,

@@ -1,0 +1,290 @@
+// thinPlateSplineMatrix (reference src/RcppSpatPCA.cpp:58-76) to the accuracy of the INPUT, not of the LU.
+//
+// The bordered system  A = [[E + 1e-8 I, T], [T', 1e-8 I]]  has cond ~1e8 (p = 1000) .. 1e10 (p = 10 000) on
+// irregular sites, so any FP64 LU -- LAPACK's dgetrf/dgetri in the reference, cuSOLVER's here -- returns
+// Lp = (A^-1)[0:p, 0:p] with a forward error of a few 1e-11 .. 1e-9 relative, and the reference's product
+// Omega = Lp' (E Lp) adds as much again through cancellation (E Lp = I - 1e-8 Lp - T M').  Two such pipelines
+// differ from each other by MORE than either differs from the exact result; measured against an 80-bit
+// refinement (profiles/r02_omega_threeway.md): cuSOLVER + cuBLAS 1.1e-10, the oracle's LAPACK 5.8e-11, each other
+// 9.5e-11 at p = 2000 -- and at p = 10 000 that difference alone pushed the eigenfunctions to 1.07e-8 of the
+// oracle's, over the 1e-8 parity bar.  The only way under the bar is to remove this side's share of the error:
+//
+//   1. X0 = A^-1 by LU with partial pivoting (the reference's algorithm class), symmetrised.
+//   2. One Newton-Schulz step  X1 = X0 + X0 (I - A X0)  with the residual formed EXACTLY where it matters:
+//      A and X0 are split into a head of beta = (53 - ceil(log2 q)) / 2 bits per row / column exponent and a
+//      tail (Ozaki splitting), so that the head product A1 X1 is free of rounding in FP64 DMMA arithmetic
+//      (every partial sum is representable) and the two tail products carry 2^-beta of the usual GEMM error:
+//          I - A X0 = (I - A1 X1) - (A1 X2 + A2 X0)        three DGEMMs, error ~1e-6 of a plain FP64 residual.
+//   3. Omega from the identities of the exact inverse  (E + eps I) Lp + T M' = I,  T' Lp + eps M' = 0:
+//          Lp' E Lp = Lp - eps Lp Lp + eps M M'             one symmetric product, no cancellation,
+//      instead of the reference's two products (mathematically the same matrix; with Lp accurate to ~1e-15 it is
+//      accurate to ~1e-14, while Lp' (E Lp) in FP64 keeps ~3e-11 even for an exactly rounded Lp).
+//
+// Flop count: LU 2/3 + solve 2 + residual 6 + correction 1 + product 1 = 10.7 p^3 (the unrefined pipeline: 5.7).
+// What remains between this path and the oracle is the ORACLE's own rounding error.
+#include <cmath>
+
+#include "engine.cuh"
+
+namespace spb {
+
+namespace {
+
+// column-wise max |a| of a (rows x cols) matrix -> out[cols]; one block per column
+__global__ void __launch_bounds__(256) col_absmax_kernel(const double* __restrict__ A, size_t ld, int rows,
+                                                         double* __restrict__ out) {
+  __shared__ double red[8];
+  const double* col = A + (size_t)blockIdx.x * ld;
+  double m = 0.0;
+  for (int i = threadIdx.x; i < rows; i += 256) m = fmax(m, fabs(col[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmax(m, red[w]);
+    out[blockIdx.x] = m;
+  }
+}
+
+// sigma[t] = 1.5 * 2^(52 + e - beta) with max[t] < 2^e: (a + sigma) - sigma rounds a to a multiple of 2^(e - beta)
+__global__ void split_sigma_kernel(const double* __restrict__ mx, int n, int beta, double* __restrict__ sigma) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double m = mx[t];
+  if (!(m > 0.0) || !(m < 1e300)) { sigma[t] = 0.0; return; }
+  int e;
+  frexp(m, &e);                                   // m = f * 2^e, f in [0.5, 1)
+  sigma[t] = ldexp(1.5, 52 + e - beta);
+}
+
+// out = head(src) (tail == 0) or src - head(src) (tail == 1); the exponent is per row (by_row) or per column.
+// out may alias src.
+__global__ void __launch_bounds__(128) split_kernel(const double* __restrict__ src, size_t lds, int rows, int cols,
+                                                    const double* __restrict__ sigma, int by_row, int tail,
+                                                    double* __restrict__ out, size_t ldo) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int j0 = blockIdx.y * 8;
+  if (i >= rows) return;
+  const double srow = by_row ? sigma[i] : 0.0;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = j0 + jj;
+    if (j >= cols) break;
+    const double s = by_row ? srow : sigma[j];
+    const double a = src[(size_t)j * lds + i];
+    const double hi = (s == 0.0) ? 0.0 : __dsub_rn(__dadd_rn(a, s), s);
+    out[(size_t)j * ldo + i] = tail ? __dsub_rn(a, hi) : hi;
+  }
+}
+
+// C1 <- C1 - C2
+__global__ void __launch_bounds__(128) sub_inplace_kernel(double* __restrict__ C1, const double* __restrict__ C2,
+                                                          size_t ld, int rows, int cols) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int j0 = blockIdx.y * 8;
+  if (i >= rows) return;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = j0 + jj;
+    if (j >= cols) break;
+    const size_t o = (size_t)j * ld + i;
+    C1[o] = __dsub_rn(C1[o], C2[o]);
+  }
+}
+
+// C[:, c0 + j] <- e_{c0 + j} for j in [0, nc)
+__global__ void __launch_bounds__(128) unit_cols_kernel(double* __restrict__ C, size_t ld, int rows, int c0, int nc) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int j0 = blockIdx.y * 8;
+  if (i >= rows) return;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = j0 + jj;
+    if (j >= nc) break;
+    C[(size_t)(c0 + j) * ld + i] = (i == c0 + j) ? 1.0 : 0.0;
+  }
+}
+
+int split_bits(int q) {
+  int lg = 0;
+  while ((1 << lg) < q) ++lg;
+  return (53 - lg) / 2;
+}
+
+}  // namespace
+
+double omega_refined_flops(int p) { return (2.0 / 3.0 + 2.0 + 6.0 + 1.0 + 1.0) * (double)p * p * p; }
+
+void Engine::build_omega_refined(OmegaRes& R, int* flag, const double* x_dev, int p, int d, double* omega_dev,
+                                 size_t ld, bool upper_only, OmegaTemps& tmp) {
+  const int q = p + d + 1;
+  const size_t ldq = padded_ld(q);
+  const size_t qq = ldq * (size_t)q;
+  tmp.L.ensure(qq);        // A -> LU factors -> head / tail of A
+  tmp.Bm.ensure(qq);       // X0 (symmetrised)
+  tmp.T1.ensure(qq);       // head / tail of X0
+  tmp.C1.ensure(qq);       // I - A1 X1 -> residual
+  tmp.C2.ensure(qq);       // A1 X2 + A2 X0 -> X1
+  tmp.vec.ensure(4 * (size_t)q);
+  double *A = tmp.L.get(), *X0 = tmp.Bm.get(), *S2 = tmp.T1.get(), *C1 = tmp.C1.get(), *C2 = tmp.C2.get();
+  double *mxA = tmp.vec.get(), *sgA = mxA + q, *mxX = sgA + q, *sgX = mxX + q;
+  cudaStream_t s = R.stream;
+  const double one = 1.0, zero = 0.0, mone = -1.0;
+  const dim3 g2(ceil_div(q, 128), ceil_div(q, 8));
+
+  // 1. X0 = A^-1 by LU with partial pivoting, all q columns (the border block M is needed by step 3)
+  launch_tps_fill(x_dev, p, d, A, ldq, 1e-8, true, s);
+  launch_set_identity(X0, q, q, ldq, s);
+  int lwork = 0;
+  SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(R.solver, q, q, A, (int)ldq, &lwork));
+  R.ipiv.ensure(q);
+  R.work.ensure((size_t)lwork);
+  SPB_CUSOLVER(cusolverDnDgetrf(R.solver, q, q, A, (int)ldq, R.work.get(), R.ipiv.get(), R.info.get()));
+  launch_check_info(R.info.get(), flag, SPB_ERR_SINGULAR, s);
+  SPB_CUSOLVER(cusolverDnDgetrs(R.solver, CUBLAS_OP_N, q, q, A, (int)ldq, R.ipiv.get(), X0, (int)ldq, R.info.get()));
+  launch_symmatu_inplace(X0, q, ldq, 0.0, s);                  // the exact inverse is symmetric: keep the upper triangle
+
+  // 2. residual of the symmetrised X0 with an exact head product
+  const int beta = split_bits(q);
+  launch_tps_fill(x_dev, p, d, A, ldq, 1e-8, true, s);         // A again (the LU overwrote it)
+  col_absmax_kernel<<<q, 256, 0, s>>>(A, ldq, q, mxA);         // A is symmetric: column maxima = row maxima
+  col_absmax_kernel<<<q, 256, 0, s>>>(X0, ldq, q, mxX);
+  split_sigma_kernel<<<ceil_div(q, 256), 256, 0, s>>>(mxA, q, beta, sgA);
+  split_sigma_kernel<<<ceil_div(q, 256), 256, 0, s>>>(mxX, q, beta, sgX);
+  split_kernel<<<g2, 128, 0, s>>>(A, ldq, q, q, sgA, 1, 0, A, ldq);      // A  <- A1 (head, per row)
+  split_kernel<<<g2, 128, 0, s>>>(X0, ldq, q, q, sgX, 0, 0, S2, ldq);    // S2 <- X1 (head, per column)
+  launch_set_identity(C1, q, q, ldq, s);
+  count_launch(6);
+  SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, q, q, &mone, A, (int)ldq, S2, (int)ldq, &one, C1,
+                         (int)ldq));                                     // C1 = I - A1 X1   (exact)
+  split_kernel<<<g2, 128, 0, s>>>(X0, ldq, q, q, sgX, 0, 1, S2, ldq);    // S2 <- X2 = X0 - X1
+  SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, q, q, &one, A, (int)ldq, S2, (int)ldq, &zero, C2,
+                         (int)ldq));                                     // C2 = A1 X2
+  launch_tps_fill(x_dev, p, d, A, ldq, 1e-8, true, s);
+  split_kernel<<<g2, 128, 0, s>>>(A, ldq, q, q, sgA, 1, 1, A, ldq);      // A  <- A2 = A - A1
+  SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, q, q, &one, A, (int)ldq, X0, (int)ldq, &one, C2,
+                         (int)ldq));                                     // C2 += A2 X0
+  sub_inplace_kernel<<<g2, 128, 0, s>>>(C1, C2, ldq, q, q);              // C1 = I - A X0
+  count_launch(3);
+
+  // 3. X1 = X0 + X0 (I - A X0): tiles on / above the diagonal only (X0 symmetric => X0 R = X0' R is symmetric)
+  SPB_CUDA(cudaMemcpyAsync(C2, X0, sizeof(double) * qq, cudaMemcpyDeviceToDevice, s));
+  gemm_upper_tn(R.blas, q, q, 1.0, X0, ldq, C1, ldq, C2, ldq);
+  launch_symmatu_inplace(C2, q, ldq, 0.0, s);                            // full Lp for the product below
+
+  // 4. Omega = Lp - eps Lp Lp + eps M M'  (upper tiles; Lp = C2[0:p, 0:p], M = C2[0:p, p:q])
+  SPB_CUDA(cudaMemcpy2DAsync(omega_dev, ld * sizeof(double), C2, ldq * sizeof(double), (size_t)p * sizeof(double), p,
+                             cudaMemcpyDeviceToDevice, s));
+  gemm_upper_tn(R.blas, p, p, -1e-8, C2, ldq, C2, ldq, omega_dev, ld);
+  const double eps = 1e-8;
+  SPB_CUBLAS(cublasDsyrk(R.blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, p, d + 1, &eps, C2 + (size_t)p * ldq, (int)ldq,
+                         &one, omega_dev, (int)ld));
+  if (!upper_only) launch_symmatu_inplace(omega_dev, p, ld, 0.0, s);     // the exported matrix: symmetric
+  SPB_CUDA(cudaGetLastError());
+}
+
+// ---- the same build in column blocks, for the ranks of a multi-GPU job ----------------
+// Replicated: the LU (2/3 p^3) and the O(p^2) passes (symmetrisation, splitting).  Split by columns: the solves,
+// the three residual products, the correction and the final product -- 10 p^3 / N per rank.  Three exchanges of
+// p^2 doubles (X0, X1, Omega), each one NCCL broadcast per owner straight from / into these buffers.
+bool Engine::omega_begin_refined() {
+  OmegaRes& R = ctx_.omega();
+  cudaStream_t s = R.stream;
+  SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
+  const int q = p_ + d_ + 1;
+  const size_t ldq = padded_ld(q), qq = ldq * (size_t)q;
+  omega_u_.alloc(ld_ * (size_t)p_);
+  omega_diag_raw_.alloc(p_);
+  omega_tmp_.reset(new OmegaTemps());
+  OmegaTemps& T = *omega_tmp_;
+  T.L.ensure(qq); T.Bm.ensure(qq); T.T1.ensure(qq); T.C1.ensure(qq); T.C2.ensure(qq); T.vec.ensure(4 * (size_t)q);
+  clock_.begin(PH_OMEGA, s);
+  launch_tps_fill(dX_.get(), p_, d_, T.L.get(), ldq, 1e-8, true, s);
+  launch_set_identity(T.Bm.get(), q, q, ldq, s);
+  int lwork = 0;
+  SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(R.solver, q, q, T.L.get(), (int)ldq, &lwork));
+  R.ipiv.ensure(q);
+  R.work.ensure((size_t)lwork);
+  SPB_CUSOLVER(cusolverDnDgetrf(R.solver, q, q, T.L.get(), (int)ldq, R.work.get(), R.ipiv.get(), R.info.get()));
+  launch_check_info(R.info.get(), ctx_.flag.get(), SPB_ERR_SINGULAR, s);
+  clock_.end(s);
+  stats_.p3_flops += omega_refined_flops(p_);
+  omega_cols_open_ = true;
+  return true;
+}
+
+bool Engine::omega_refine_cols(int c0, int c1) {
+  SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
+  SPB_REQUIRE(c0 >= 0 && c0 <= c1 && c1 <= p_, "column range out of bounds");
+  if (!omega_refine_enabled()) return false;
+  OmegaRes& R = ctx_.omega();
+  cudaStream_t s = R.stream;
+  const int q = p_ + d_ + 1;
+  const size_t ldq = padded_ld(q);
+  const int c1e = (c1 == p_) ? q : c1;                 // the owner of the last block also owns the border columns
+  const int nc = c1e - c0;
+  OmegaTemps& T = *omega_tmp_;
+  double *A = T.L.get(), *X0 = T.Bm.get(), *S2 = T.T1.get(), *C1 = T.C1.get(), *C2 = T.C2.get();
+  double *mxA = T.vec.get(), *sgA = mxA + q, *mxX = sgA + q, *sgX = mxX + q;
+  const double one = 1.0, zero = 0.0, mone = -1.0;
+  const dim3 gfull(ceil_div(q, 128), ceil_div(q, 8));
+  clock_.begin(PH_OMEGA, s);
+  launch_symmatu_inplace(X0, q, ldq, 0.0, s);
+  const int beta = split_bits(q);
+  launch_tps_fill(dX_.get(), p_, d_, A, ldq, 1e-8, true, s);
+  col_absmax_kernel<<<q, 256, 0, s>>>(A, ldq, q, mxA);
+  col_absmax_kernel<<<q, 256, 0, s>>>(X0, ldq, q, mxX);
+  split_sigma_kernel<<<ceil_div(q, 256), 256, 0, s>>>(mxA, q, beta, sgA);
+  split_sigma_kernel<<<ceil_div(q, 256), 256, 0, s>>>(mxX, q, beta, sgX);
+  split_kernel<<<gfull, 128, 0, s>>>(A, ldq, q, q, sgA, 1, 0, A, ldq);                       // A <- A1
+  count_launch(5);
+  if (nc > 0) {
+    const dim3 gc(ceil_div(q, 128), ceil_div(nc, 8));
+    const size_t o = (size_t)c0 * ldq;
+    split_kernel<<<gc, 128, 0, s>>>(X0 + o, ldq, q, nc, sgX + c0, 0, 0, S2 + o, ldq);        // X1 columns
+    unit_cols_kernel<<<gc, 128, 0, s>>>(C1, ldq, q, c0, nc);
+    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, nc, q, &mone, A, (int)ldq, S2 + o, (int)ldq, &one,
+                           C1 + o, (int)ldq));                                                // I - A1 X1 (exact)
+    split_kernel<<<gc, 128, 0, s>>>(X0 + o, ldq, q, nc, sgX + c0, 0, 1, S2 + o, ldq);        // X2 columns
+    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, nc, q, &one, A, (int)ldq, S2 + o, (int)ldq, &zero,
+                           C2 + o, (int)ldq));                                                // A1 X2
+    launch_tps_fill(dX_.get(), p_, d_, A, ldq, 1e-8, true, s);
+    split_kernel<<<gfull, 128, 0, s>>>(A, ldq, q, q, sgA, 1, 1, A, ldq);                     // A <- A2
+    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, nc, q, &one, A, (int)ldq, X0 + o, (int)ldq, &one,
+                           C2 + o, (int)ldq));                                                // + A2 X0
+    sub_inplace_kernel<<<gc, 128, 0, s>>>(C1 + o, C2 + o, ldq, q, nc);                       // residual columns
+    count_launch(5);
+    SPB_CUDA(cudaMemcpyAsync(C2 + o, X0 + o, sizeof(double) * ldq * nc, cudaMemcpyDeviceToDevice, s));
+    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, nc, q, &one, X0, (int)ldq, C1 + o, (int)ldq, &one,
+                           C2 + o, (int)ldq));                                                // X1 = X0 + X0 R
+  }
+  clock_.end(s);
+  SPB_CUDA(cudaGetLastError());
+  return true;
+}
+
+void Engine::omega_product_cols_refined(int c0, int c1) {
+  OmegaRes& R = ctx_.omega();
+  cudaStream_t s = R.stream;
+  const int q = p_ + d_ + 1;
+  const size_t ldq = padded_ld(q);
+  double* X1 = omega_tmp_->C2.get();
+  clock_.begin(PH_OMEGA, s);
+  launch_symmatu_inplace(X1, q, ldq, 0.0, s);
+  if (c1 > c0) {
+    const int nc = c1 - c0;
+    const double one = 1.0, eps = 1e-8, meps = -1e-8;
+    double* out = omega_u_.get() + (size_t)c0 * ld_;
+    // rows 0 .. c1-1 of these columns cover the upper triangle, which is all that is used downstream
+    SPB_CUDA(cudaMemcpy2DAsync(out, ld_ * sizeof(double), X1 + (size_t)c0 * ldq, ldq * sizeof(double),
+                               (size_t)c1 * sizeof(double), nc, cudaMemcpyDeviceToDevice, s));
+    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_T, CUBLAS_OP_N, c1, nc, p_, &meps, X1, (int)ldq, X1 + (size_t)c0 * ldq,
+                           (int)ldq, &one, out, (int)ld_));                                   // - eps Lp Lp
+    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_T, c1, nc, d_ + 1, &eps, X1 + (size_t)p_ * ldq, (int)ldq,
+                           X1 + (size_t)p_ * ldq + c0, (int)ldq, &one, out, (int)ld_));       // + eps M M'
+  }
+  clock_.end(s);
+}
+
+}  // namespace spb

@@ -151,15 +151,18 @@ def omega_columns(p: int, world: int):
 
 def prepare_sharded(engine, coll: Collective):
     """`engine.prepare()` with thinPlateSplineMatrix (:58-76) shared by the ranks: the LU of the bordered
-    system is replicated, the p solves and the two p^3 products are split by columns, and the column
-    blocks travel by NCCL broadcast (2 x 8 p^2 bytes in total).  With one rank, or an engine without the
-    column API, this is `engine.prepare()`."""
+    system is replicated, the solves, the residual / correction products of the refinement and the final
+    product are split by columns, and the column blocks travel by NCCL broadcast (3 x 8 p^2 bytes in total).
+    With one rank, or an engine without the column API, this is `engine.prepare()`."""
     if coll.world > 1 and hasattr(engine, "omega_begin") and engine.omega_begin():
         cols = omega_columns(engine.p, coll.world)
         c0, c1 = cols[coll.rank]
         engine.omega_solve_cols(c0, c1)
         engine.omega_sync()
         coll.broadcast_buffers([(r, engine.omega_buffer(0, a, b)) for r, (a, b) in enumerate(cols)])
+        if engine.omega_refine_cols(c0, c1):     # refined build: residual + correction of this rank's columns
+            engine.omega_sync()
+            coll.broadcast_buffers([(r, engine.omega_buffer(2, a, b)) for r, (a, b) in enumerate(cols)])
         engine.omega_product_cols(c0, c1)
         engine.omega_sync()
         coll.broadcast_buffers([(r, engine.omega_buffer(1, a, b)) for r, (a, b) in enumerate(cols)])

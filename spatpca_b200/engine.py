@@ -225,6 +225,11 @@ class Engine:
     def omega_solve_cols(self, c0, c1):
         check(self._lib.spb_engine_omega_solve_cols(self._h, int(c0), int(c1)))
 
+    def omega_refine_cols(self, c0, c1) -> bool:
+        active = C.c_int(0)
+        check(self._lib.spb_engine_omega_refine_cols(self._h, int(c0), int(c1), C.byref(active)))
+        return bool(active.value)
+
     def omega_product_cols(self, c0, c1):
         check(self._lib.spb_engine_omega_product_cols(self._h, int(c0), int(c1)))
 

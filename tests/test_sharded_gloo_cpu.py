@@ -29,6 +29,7 @@ class OracleBackedEngine:
     # ---- Omega in column blocks (stand-ins: one double per column, tagged by the owner's column index) ----
     def omega_begin(self):
         self.lp = self.torch.full((self.p,), -1.0, dtype=self.torch.float64)
+        self.x1 = self.torch.full((self.p,), -1.0, dtype=self.torch.float64)
         self.om = self.torch.full((self.p,), -1.0, dtype=self.torch.float64)
         self.asked.append(("omega_begin",))
         return True
@@ -37,14 +38,21 @@ class OracleBackedEngine:
         self.lp[c0:c1] = self.torch.arange(c0, c1, dtype=self.torch.float64)
         self.asked.append(("omega_solve", c0, c1))
 
-    def omega_product_cols(self, c0, c1):
-        # the product needs every column of Lp, i.e. the other ranks' blocks must have arrived
+    def omega_refine_cols(self, c0, c1):
+        # the residual / correction of a block needs every column of X0: the other ranks' blocks must have arrived
         assert bool((self.lp == self.torch.arange(self.p, dtype=self.torch.float64)).all())
+        self.x1[c0:c1] = 3.0 * self.torch.arange(c0, c1, dtype=self.torch.float64)
+        self.asked.append(("omega_refine", c0, c1))
+        return True
+
+    def omega_product_cols(self, c0, c1):
+        # the product needs every corrected column, i.e. the second exchange must have happened
+        assert bool((self.x1 == 3.0 * self.torch.arange(self.p, dtype=self.torch.float64)).all())
         self.om[c0:c1] = 2.0 * self.torch.arange(c0, c1, dtype=self.torch.float64)
         self.asked.append(("omega_product", c0, c1))
 
     def omega_buffer(self, which, c0, c1):
-        return (self.lp if which == 0 else self.om)[c0:c1]
+        return {0: self.lp, 1: self.om, 2: self.x1}[which][c0:c1]
 
     def omega_sync(self):
         pass
@@ -154,6 +162,7 @@ def _worker(rank, world, port, out_dir):
     # Omega: this rank solved and multiplied exactly its own column block, then prepare() ran
     c0, c1 = D.omega_columns(eng.p, world)[rank]
     ok &= ("omega_solve", c0, c1) in eng.asked and ("omega_product", c0, c1) in eng.asked
+    ok &= ("omega_refine", c0, c1) in eng.asked
     ok &= sum(1 for a in eng.asked if a[0] == "omega_solve") == 1 and ("prepare",) in eng.asked
     # the inverse jobs were spread as planned, and each rank built exactly its share
     jobs, owner = D.plan_inverse_jobs(case["M"], len(case["tau1"]), world)
