@@ -289,6 +289,21 @@ SPB_API int spb_admm_system(const double* omega, const double* G, int p,
 SPB_API int spb_core2_matrix_free(const double* omega, const double* Ytr, int n_tr, int p, int K,
                           double tau1, double rho, int maxit, double tol, double cg_tol,
                           double* Phi, double* C, double* Lambda2, int* iters, int* passes);
+/* U (p x nc) = A (p x p, symmetric) * V (p x nc), 1 <= nc <= 32, on the TMA-fed FP64 DMMA stream that the
+ * fold-batched matrix-free Core2 is built on (csrc/tma_dmma.cuh): kernel-level parity entry.                 */
+SPB_API int spb_dmma_matvec(const double* A, int p, const double* V, int nc, double* U);
+/* the same stream on a synthetic matrix in device memory: device time per pass (ms, mean of `repeats`)      */
+SPB_API int spb_bench_dmma_matvec(int p, int nc, int repeats, double* ms_per_pass);
+/* F matrix-free spatpcaCore2 problems in lock-step on the DMMA stream (csrc/batched_cg.cu): problem f leaves out the
+ * rows of Y with nk == fold_ids[f] (0: none), uses rho[f], and is solved for tau1[0..nsteps) one after the other
+ * with its state (Phi, C, Lambda2: F blocks of p x K) carried -- the tau1 path of one stage for all folds in ONE
+ * launch.  iters: nsteps x F (row = step); snap (may be NULL): Phi after every step, nsteps x F x (p x K).
+ * spb_core2_batched_supported: 1 if this (p, n, K, F) fits the kernel on the current device, else 0.            */
+SPB_API int spb_core2_batched(const double* omega, const double* Y, const double* nk, int p, int n, int K, int F,
+                      const int* fold_ids, const double* rho, const double* tau1, int nsteps, int maxit,
+                      double tol, double cg_tol, double* Phi, double* C, double* Lambda2, int* iters,
+                      double* snap, int* passes);
+SPB_API int spb_core2_batched_supported(int p, int n, int K, int F);
 /* block count the library uses for systems of order p (1 = explicit inverse) */
 SPB_API int spb_default_blocks(int p);
 /* the same for the systems reused along a whole tau2 path (tempinv, :397)    */

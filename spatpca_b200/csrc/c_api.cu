@@ -658,6 +658,69 @@ int spb_core2_matrix_free(const double* omega, const double* Ytr, int n_tr, int 
   });
 }
 
+int spb_core2_batched(const double* omega, const double* Y, const double* nk, int p, int n, int K, int F,
+                      const int* fold_ids, const double* rho, const double* tau1, int nsteps, int maxit, double tol,
+                      double cg_tol, double* Phi, double* C, double* Lambda2, int* iters, double* snap, int* passes) {
+  return guarded([&] {
+    SPB_REQUIRE(omega && Y && nk && fold_ids && rho && tau1 && Phi && C && Lambda2 && iters, "NULL argument");
+    SPB_REQUIRE(p >= 1 && n >= 1 && K >= 1 && F >= 1 && nsteps >= 1 && maxit >= 1, "invalid size");
+    SPB_REQUIRE(batched_core2_supported(p, n, K, F), "batched Core2: unsupported problem shape on this device");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    const size_t ld = padded_ld(p), pk = (size_t)p * K;
+    DevBuf<double> om(ld * (size_t)p), dY((size_t)n * p), dYt((size_t)n * p), st(3 * pk * F),
+        dsnap(snap ? (size_t)nsteps * F * pk : 1);
+    DevBuf<int> dnk(n), dit((size_t)nsteps * F), dstat(2);
+    DevBuf<char> ws(batched_core2_workspace_bytes(p, n, K, F));
+    upload_square(omega, p, om.get(), ld, s);
+    launch_symmatu_inplace(om.get(), p, ld, 0.0, s);
+    SPB_CUDA(cudaMemcpyAsync(dY.get(), Y, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, s));
+    launch_transpose(dY.get(), n, p, dYt.get(), s);
+    std::vector<int> nki(n);
+    for (int r = 0; r < n; ++r) nki[r] = (int)nk[r];
+    SPB_CUDA(cudaMemcpyAsync(dnk.get(), nki.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(st.get(), Phi, sizeof(double) * pk * F, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(st.get() + pk * F, C, sizeof(double) * pk * F, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemcpyAsync(st.get() + 2 * pk * F, Lambda2, sizeof(double) * pk * F, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaMemsetAsync(dit.get(), 0, sizeof(int) * nsteps * F, s));
+    SPB_CUDA(cudaMemsetAsync(dstat.get(), 0, 2 * sizeof(int), s));
+    BatchedCore2Call c;
+    c.omega_u = om.get(); c.ld = ld; c.p = p; c.n = n; c.K = K; c.F = F;
+    c.Y = dY.get(); c.Yt = dYt.get(); c.nk = dnk.get();
+    for (int f = 0; f < 8; ++f) {
+      c.fold_id[f] = f < F ? fold_ids[f] : 0;
+      c.rho[f] = f < F ? rho[f] : 1.0;
+      c.Phi[f] = f < F ? st.get() + (size_t)f * pk : nullptr;
+      c.C[f] = f < F ? st.get() + pk * F + (size_t)f * pk : nullptr;
+      c.L2[f] = f < F ? st.get() + 2 * pk * F + (size_t)f * pk : nullptr;
+    }
+    c.nsteps = nsteps; c.tau1 = tau1; c.maxit = maxit; c.tol = tol;
+    c.cg_tol = cg_tol > 0.0 ? cg_tol : 1e-14; c.cg_cap = 2000;
+    c.snap = snap ? dsnap.get() : nullptr; c.iters_out = dit.get(); c.status_out = dstat.get();
+    launch_batched_core2(c, ws.get(), s);
+    int sth[2] = {0, 0};
+    SPB_CUDA(cudaMemcpyAsync(sth, dstat.get(), sizeof(sth), cudaMemcpyDeviceToHost, s));
+    SPB_CUDA(cudaMemcpyAsync(iters, dit.get(), sizeof(int) * nsteps * F, cudaMemcpyDeviceToHost, s));
+    SPB_CUDA(cudaMemcpyAsync(Phi, st.get(), sizeof(double) * pk * F, cudaMemcpyDeviceToHost, s));
+    SPB_CUDA(cudaMemcpyAsync(C, st.get() + pk * F, sizeof(double) * pk * F, cudaMemcpyDeviceToHost, s));
+    SPB_CUDA(cudaMemcpyAsync(Lambda2, st.get() + 2 * pk * F, sizeof(double) * pk * F, cudaMemcpyDeviceToHost, s));
+    if (snap)
+      SPB_CUDA(cudaMemcpyAsync(snap, dsnap.get(), sizeof(double) * (size_t)nsteps * F * pk, cudaMemcpyDeviceToHost, s));
+    ctx.sync_and_check();
+    if (passes) *passes = sth[1];
+    if (sth[0] == SPB_ERR_NOT_POSDEF) throw Error(SPB_ERR_NOT_POSDEF, "inv_sympd(): matrix is singular or not positive definite");
+    if (sth[0] == SPB_ERR_INTERNAL) throw Error(SPB_ERR_INTERNAL, "matrix-free Core2: conjugate gradients did not converge");
+    if (sth[0] != 0)
+      throw Error(SPB_ERR_POLAR, "svd_econ(): the p x K iterate is rank deficient, Stiefel projection undefined");
+  });
+}
+
+int spb_core2_batched_supported(int p, int n, int K, int F) {
+  int v = 0;
+  int rc = guarded([&] { DeviceCtx::get(); v = batched_core2_supported(p, n, K, F) ? 1 : 0; });
+  return rc < 0 ? rc : v;
+}
+
 int spb_default_blocks(int p) {
   int m = -1;
   int rc = guarded([&] {
@@ -913,6 +976,53 @@ int spb_bench_core2_cg(int p, int K, int n_tr, int iters, int repeats, double* m
     cudaEventDestroy(e1);
     *ms_per_launch = sum_ms / repeats;
     if (passes_per_launch) *passes_per_launch = passes;
+  });
+}
+
+int spb_dmma_matvec(const double* A, int p, const double* V, int nc, double* U) {
+  return guarded([&] {
+    SPB_REQUIRE(A && V && U && p >= 1 && nc >= 1 && nc <= 32, "invalid argument");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    const size_t ld = padded_ld(p);
+    DevBuf<double> dA(ld * (size_t)p), dV(ld * (size_t)nc), dU((size_t)p * nc);
+    upload_square(A, p, dA.get(), ld, s);
+    SPB_CUDA(cudaMemsetAsync(dV.get(), 0, sizeof(double) * ld * nc, s));
+    SPB_CUDA(cudaMemcpy2DAsync(dV.get(), ld * sizeof(double), V, (size_t)p * sizeof(double), (size_t)p * sizeof(double), nc,
+                               cudaMemcpyHostToDevice, s));
+    launch_dmma_matvec(dA.get(), ld, p, dV.get(), ld, nc, dU.get(), s);
+    SPB_CUDA(cudaMemcpyAsync(U, dU.get(), sizeof(double) * (size_t)p * nc, cudaMemcpyDeviceToHost, s));
+    ctx.sync_and_check();
+  });
+}
+
+int spb_bench_dmma_matvec(int p, int nc, int repeats, double* ms_per_pass) {
+  return guarded([&] {
+    SPB_REQUIRE(p >= 1 && nc >= 1 && nc <= 32 && repeats >= 1 && ms_per_pass, "invalid argument");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    const size_t ld = padded_ld(p);
+    DevBuf<double> dA(ld * (size_t)p), dV(ld * (size_t)nc), dU((size_t)p * nc);
+    SPB_CUDA(cudaMemsetAsync(dA.get(), 0, sizeof(double) * ld * p, s));
+    bench_fill_kernel<<<ceil_div((long long)p * p, 256), 256, 0, s>>>(dA.get(), ld, p, 0.1, 0.03);
+    bench_sign_kernel<<<ceil_div((long long)ld * nc, 256), 256, 0, s>>>(dV.get(), ld * (size_t)nc, 1.0);
+    count_launch(2);
+    cudaEvent_t e0, e1;
+    SPB_CUDA(cudaEventCreate(&e0));
+    SPB_CUDA(cudaEventCreate(&e1));
+    double sum = 0.0;
+    for (int r = 0; r < repeats + 2; ++r) {
+      SPB_CUDA(cudaEventRecord(e0, s));
+      launch_dmma_matvec(dA.get(), ld, p, dV.get(), ld, nc, dU.get(), s);
+      SPB_CUDA(cudaEventRecord(e1, s));
+      ctx.sync_and_check();
+      float ms = 0.f;
+      SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (r > 1) sum += (double)ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_pass = sum / repeats;
   });
 }
 

@@ -138,6 +138,37 @@ struct CgCall {
 size_t cg_workspace_bytes(int p, int K, int n_tr);
 void launch_core2_cg(const CgCall& c, void* ws, cudaStream_t s);
 
+// ---- TMA-fed FP64 DMMA matrix stream (batched_cg.cu, tma_dmma.cuh) ---------------------------------
+// U (p x nc, ld = p) = A (p x p symmetric, full storage) * V (p x nc), 1 <= nc <= 32; device pointers
+void launch_dmma_matvec(const double* A, size_t ld, int p, const double* V, size_t ldv, int nc, double* U,
+                        cudaStream_t s);
+
+// ---- fold-batched matrix-free spatpcaCore2 (batched_cg.cu): F problems in lock-step on the DMMA stream --------
+struct BatchedCore2Call {
+  const double* omega_u;     // p x p symmetric, full storage
+  size_t ld;
+  int p, n, K, F;            // F problems of K columns each, F * K <= 32, K <= 8
+  const double* Y;           // n x p (ld n): ALL rows of the data
+  const double* Yt;          // p x n (ld p)
+  const int* nk;             // n fold ids (device)
+  int fold_id[8];            // problem f leaves out the rows with nk == fold_id[f] (0: none, i.e. the full-data fit)
+  double rho[8];
+  double* Phi[8];            // per problem, p x K (ld p): warm start in, last iterate out
+  double* C[8];
+  double* L2[8];
+  int nsteps;                // grid values solved one after the other, state carried (the tau1 path, :329-332)
+  const double* tau1;        // host, nsteps values
+  int maxit;
+  double tol, cg_tol;
+  int cg_cap;
+  double* snap;              // device, nsteps x F x (p x K): Phi after every step (may be nullptr)
+  int* iters_out;            // device, nsteps x F
+  int* status_out;           // device, {status, matrix passes}
+};
+bool batched_core2_supported(int p, int n, int K, int F);
+size_t batched_core2_workspace_bytes(int p, int n, int K, int F);
+void launch_batched_core2(const BatchedCore2Call& c, void* ws, cudaStream_t s);
+
 // ---- losses (loss_kernels.cu) --------------------------------------------------
 // W (m x K) <- Ymat (m x p) * Phi (p x K); scratch must hold cvloss_scratch_doubles(m, p, K)
 size_t yphi_scratch_doubles(int m, int p, int K);

@@ -347,6 +347,54 @@ def bench_core2_cg(p, K, n_tr, iters, repeats=3):
     return float(out[0]), ps.value
 
 
+def dmma_matvec(A, V):
+    """U = A V on the TMA-fed DMMA stream (A symmetric p x p, V p x nc, nc <= 32)."""
+    lib = _lib.load()
+    Am, Vm = fmat(A), fmat(V)
+    p, nc = Vm.shape
+    U = np.empty((p, nc), order="F")
+    check(lib.spb_dmma_matvec(ptr(Am), p, ptr(Vm), nc, ptr(U)))
+    return U
+
+
+def bench_dmma_matvec(p, nc, repeats=5):
+    lib = _lib.load()
+    out = np.zeros(1)
+    check(lib.spb_bench_dmma_matvec(int(p), int(nc), int(repeats), ptr(out)))
+    return float(out[0])
+
+
+def core2_batched_supported(p, n, K, F) -> bool:
+    return check(_lib.load().spb_core2_batched_supported(int(p), int(n), int(K), int(F))) == 1
+
+
+def core2_batched(omega, Y, nk, fold_ids, rho, tau1, Phi0, C0, L20, maxit, tol, cg_tol=0.0, snapshots=True):
+    """F matrix-free spatpcaCore2 problems in lock-step along a tau1 path (spb_core2_batched).
+    Phi0 / C0 / L20: lists of F (p x K) arrays.  Returns dict(Phi, C, L2: lists; iters: nsteps x F; snap; passes)."""
+    lib = _lib.load()
+    om, Ym, nkf = fmat(omega), fmat(Y), fvec(nk)
+    n, p = Ym.shape
+    F = len(Phi0)
+    K = np.asarray(Phi0[0]).shape[1]
+    pack = lambda xs: np.ascontiguousarray(np.concatenate([np.asfortranarray(x).ravel(order="F") for x in xs]))
+    Ph, Cm, L2 = pack(Phi0), pack(C0), pack(L20)
+    t1 = fvec(tau1)
+    ns = len(t1)
+    fid = np.ascontiguousarray(np.asarray(fold_ids, dtype=np.int32))
+    rh = fvec(rho)
+    it = np.zeros(ns * F, dtype=np.int32)
+    snap = np.zeros(ns * F * p * K) if snapshots else None
+    ps = C.c_int(0)
+    check(lib.spb_core2_batched(ptr(om), ptr(Ym), ptr(nkf), p, n, K, F, fid.ctypes.data_as(C.POINTER(C.c_int)), ptr(rh),
+                                ptr(t1), ns, int(maxit), float(tol), float(cg_tol), ptr(Ph), ptr(Cm), ptr(L2),
+                                it.ctypes.data_as(C.POINTER(C.c_int)), ptr(snap) if snapshots else None, C.byref(ps)))
+    unpack = lambda v: [v[f * p * K:(f + 1) * p * K].reshape((p, K), order="F") for f in range(F)]
+    out = dict(Phi=unpack(Ph), C=unpack(Cm), L2=unpack(L2), iters=it.reshape(ns, F), passes=ps.value)
+    if snapshots:
+        out["snap"] = snap.reshape(ns, F, K, p).transpose(0, 1, 3, 2)
+    return out
+
+
 def default_blocks(p):
     return check(_lib.load().spb_default_blocks(int(p)))
 

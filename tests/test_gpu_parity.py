@@ -347,6 +347,63 @@ def test_core2_matrix_free_rejects_indefinite_system(sp):
         eng.core2_matrix_free(Om, Yt, 0.01, rho * 1e-3, Phi0, Phi0, L20, 5, 1e-4)
 
 
+@pytest.mark.parametrize("p,K,M,n", [(300, 2, 3, 40), (1000, 5, 5, 60), (2100, 3, 5, 45), (4100, 5, 5, 200), (700, 8, 4, 50)])
+def test_core2_batched_path_vs_oracle(sp, p, K, M, n):
+    """The folds of a stage in lock-step on the TMA-fed DMMA stream: a tau1 path of 4 values, warm starts carried,
+    against the oracle's spatpcaCore2 per fold (explicit inv_sympd): identical iteration counts per (step, fold),
+    every snapshot of Phi to 1e-10."""
+    from spatpca_b200 import engine as eng
+    if not eng.core2_batched_supported(p, n, K, M):
+        pytest.skip("shape not supported by the batched kernel on this device")
+    rng = np.random.default_rng(31 * p + K)
+    x = rng.uniform(0, 1, size=(p, 2))
+    Om = ref.thin_plate_spline_matrix(x)
+    Om[np.diag_indices(p)] += 1e-8
+    load = np.linalg.qr(rng.normal(size=(p, K)))[0]
+    Y = (rng.normal(size=(n, K)) * np.linspace(30, 10, K)) @ load.T + rng.normal(size=(n, p))
+    nk = rng.permutation(np.resize(np.arange(1, M + 1), n)).astype(float)
+    tau1 = np.array([1e-4, 1e-2, 0.1, 1.0])
+    starts, rhos = [], []
+    want_snap, want_it = [], []
+    for k in range(M):
+        Ytr = Y[nk != k + 1]
+        _, rho, Phi0, L20 = ref.pca_init(Ytr, K)
+        starts.append((Phi0, L20))
+        rhos.append(rho)
+        G = np.asfortranarray(Ytr.T @ Ytr)
+        Phi, Cc, L2 = Phi0, Phi0, L20
+        snaps, its = [], []
+        for t in tau1:
+            tr = ref.Trace()
+            Phi, Cc, L2 = ref.core2(G, Phi, Cc, L2, Om, t, rho, 100, 1e-4, tr)
+            snaps.append(Phi)
+            its.append(tr.calls[0][3])
+        want_snap.append(snaps)
+        want_it.append(its)
+    got = eng.core2_batched(Om, Y, nk, list(range(1, M + 1)), rhos, tau1, [s[0] for s in starts], [s[0] for s in starts],
+                            [s[1] for s in starts], 100, 1e-4)
+    assert got["iters"].tolist() == np.array(want_it).T.tolist()
+    for k in range(M):
+        for i in range(len(tau1)):
+            w = want_snap[k][i]
+            assert np.max(np.abs(got["snap"][i, k] - w)) / np.max(np.abs(w)) <= 1e-10, (k, i)
+    assert got["passes"] > 0
+
+
+@pytest.mark.parametrize("p,nc", [(64, 3), (1003, 25), (2500, 32), (4100, 12), (777, 17), (10000, 25)])
+def test_dmma_stream_vs_numpy(sp, p, nc):
+    """U = A V on the TMA + DMMA stream (csrc/tma_dmma.cuh) against NumPy: swizzled tiles, fragment permutations,
+    ragged edges (p not a multiple of 8 / 64), every vector-tile count."""
+    from spatpca_b200 import engine as eng
+    rng = np.random.default_rng(p + nc)
+    A = rng.normal(size=(p, p))
+    A = A + A.T
+    V = rng.normal(size=(p, nc))
+    U = eng.dmma_matvec(A, V)
+    W = A @ V
+    assert np.max(np.abs(U - W)) / np.max(np.abs(W)) <= 1e-13
+
+
 @pytest.mark.parametrize("name", ["irregular2d_small", "grid3d_small"])
 def test_cv_matrix_free_forced_vs_oracle(sp, name, monkeypatch):
     """SPB_CORE2=cg: every spatpcaCore2 / Core2p call of the job runs matrix-free (the automatic choice only does so
