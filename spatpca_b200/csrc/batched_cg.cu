@@ -155,7 +155,8 @@ constexpr int kMaxF = 8;
 constexpr int kMaxSteps = 64;
 
 struct BcgParams {
-  StreamGeom g;
+  StreamGeom g;                    // the Omega_u stream
+  StreamGeom gy;                   // the same column block of Y (n rows): z = Y[:, J]' S on the same DMMA pipeline
   int p, n, K, F, NC;
   size_t ldv;                      // leading dimension of the p x NCP work vectors
   int nblk;
@@ -179,7 +180,14 @@ struct BcgParams {
   double *Xg, *Rg, *Pg, *Qg, *Bg, *Cg, *L2g;
   double *part_ru, *part_gam, *Spart, *Sred, *gram_part, *norm_part;
   unsigned int* bar;
+  unsigned long long* dbg;         // optional globaltimer stamps of CTA 0 (performance debugging), or nullptr
 };
+
+__device__ __forceinline__ unsigned long long gtimer_b() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void grid_barrier_b(unsigned int* counter, unsigned int& gen) {
   __syncthreads();
@@ -340,8 +348,6 @@ __device__ __forceinline__ void column_sums(const double* tmp, int J, int Jv, in
 struct BcgState {                 // identical in every CTA (computed redundantly from the reduced partials)
   double gam[32], gam_old[32], alpha[32], alpha_old[32], beta[32], bn[32], ss[32], ru[32];
   double rho[kMaxF], rinv[kMaxF], err[kMaxF];
-  double Pm[kMaxF][64];
-  double polw[kMaxF][4][64];      // per-fold scratch of the polar step: G, Y, Z, M
   double red[64];
   int frozen[32], fresh[32];
   int active[kMaxF], its[kMaxF];
@@ -351,7 +357,8 @@ struct BcgState {                 // identical in every CTA (computed redundantl
 template <int MT, int NTM>
 __global__ void __launch_bounds__(tmx::Shape<MT>::kThreads, 1)
 batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapX,
-                     const __grid_constant__ CUtensorMap mapR, BcgParams P) {
+                     const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapY,
+                     const __grid_constant__ CUtensorMap mapS, BcgParams P) {
   using S = Shape<MT>;
   constexpr int NTH = S::kThreads;
   extern __shared__ unsigned char dyn_raw[];
@@ -362,14 +369,16 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   uint64_t* full = reinterpret_cast<uint64_t*>(ring_end);
   uint64_t* empty = full + P.g.NS;
   BcgState& st = *reinterpret_cast<BcgState*>(empty + P.g.NS);
-  // the ring doubles as the scratch of the row phases (no TMA is in flight then)
   const int J = P.g.J, NC = P.NC, K = P.K, F = P.F, n = P.n, p = P.p;
-  double* us = reinterpret_cast<double*>(sA);                    // [NCP][J]  U = Omega_u v
-  double* Ssm = us + (size_t)S::NCP * J;                         // [NC][n]   S = Y r (masked, reduced)
-  double* zsm = Ssm + (size_t)NC * n;                            // [NC][J]   Yt S
-  double* vsm = zsm + (size_t)NC * J;                            // [NC][J]   rows of the vector whose S partial is formed
+  // U = Omega_u v must survive the DMMA mini-pass that forms z, so it has its own tile; everything else that the row
+  // phases use aliases the ring (no TMA is in flight while it is live)
+  double* us = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(&st) + ((sizeof(BcgState) + 15) & ~size_t(15)));  // [NCP][J]
+  double* zsm = reinterpret_cast<double*>(sA);                   // [NCP][J]  Y[:, J]' S (output of the mini-pass)
+  double* vsm = zsm + (size_t)S::NCP * J;                        // [NC][J]   rows of the vector whose S partial is formed
   double* tmp0 = vsm + (size_t)NC * J;                           // [NC][J]
   double* tmp1 = tmp0 + (size_t)NC * J;                          // [NC][J]
+  double* Pm = tmp1 + (size_t)NC * J;                            // [F][64]     (T'T)^(-1/2) per problem
+  double* polw = Pm + (size_t)kMaxF * 64;                        // [F][4][64]  scratch of the polar step: G, Y, Z, M
   const int tid = threadIdx.x;
   const int j0 = blockIdx.x * J;
   const int Jv = min(J, p - j0);
@@ -399,7 +408,11 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     P.Rg[dst] = 0.0;
   }
   unsigned int it = 0, bar_gen = 0;
-  int passes = 0;
+  int passes = 0, dbg_n = 0;
+  auto stamp = [&]() {
+    if (P.dbg != nullptr && blockIdx.x == 0 && tid == 0 && dbg_n < 400) P.dbg[dbg_n] = gtimer_b();
+    ++dbg_n;
+  };
   fence_proxy_async();
   grid_barrier_b(P.bar, bar_gen);
 
@@ -413,7 +426,18 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       for (int k = 0; k < 8; ++k) acc[k] = 0.0;
       const double* yp = P.Y + (size_t)j0 * n + r;
       const double* vp = vsm + (size_t)f * K * J;
-      for (int j = 0; j < Jv; ++j) {
+      int j = 0;
+      for (; j + 8 <= Jv; j += 8) {                     // 8 independent L2 loads in flight per thread
+        double y[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) y[u] = __ldg(yp + (size_t)(j + u) * n);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < K) acc[k] = fma(y[u], vp[(size_t)k * J + j + u], acc[k]);
+      }
+      for (; j < Jv; ++j) {
         const double y = __ldg(yp + (size_t)j * n);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -429,47 +453,34 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const int total = n * NC;
     const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
     const int e0 = blockIdx.x * per, e1 = min(total, e0 + per);
-    for (int e = e0 + tid; e < e1; e += NTH) {
-      const int c = e / n, r = e - c * n;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int e = e0 + warp; e < e1; e += NTH / 32) {             // warp per entry, lanes over the CTAs' partials
       double t = 0.0;
-      for (int b = 0; b < P.nblk; ++b) t += __ldcg(P.Spart + (size_t)b * total + e);
-      const int fid = P.fold_id[c / K];
-      if (fid != 0 && __ldg(P.nk + r) == fid) t = 0.0;
-      __stcg(P.Sred + e, t);
+      for (int b = lane; b < P.nblk; b += 32) t += __ldcg(P.Spart + (size_t)b * total + e);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) {
+        const int c = e / n, r = e - c * n;
+        const int fid = P.fold_id[c / K];
+        if (fid != 0 && __ldg(P.nk + r) == fid) t = 0.0;
+        __stcg(P.Sred + e, t);
+      }
     }
   };
-  // Sred -> shared memory, |S_c|^2, z = Yt[J, :] S
+  // |S_c|^2 from the reduced S, and z = Y[:, J]' S on the DMMA pipeline: the same pass as the Omega_u stream with
+  // Y (n x p) as the matrix and S (n x NC) as the vectors -- the p x n contraction of the north-star
   auto load_s_and_z = [&]() {
-    for (int e = tid; e < n * NC; e += NTH) Ssm[e] = __ldcg(P.Sred + e);
-    __syncthreads();
     {
       const int warp = tid >> 5, lane = tid & 31;
       for (int c = warp; c < NC; c += NTH / 32) {
         double t = 0.0;
-        for (int r = lane; r < n; r += 32) { const double v = Ssm[(size_t)c * n + r]; t = fma(v, v, t); }
+        for (int r = lane; r < n; r += 32) { const double v = __ldcg(P.Sred + (size_t)c * n + r); t = fma(v, v, t); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
         if (lane == 0) st.ss[c] = t;
       }
     }
-    for (int e = tid; e < Jv * F; e += NTH) {
-      const int j = e % Jv, f = e / Jv;
-      double acc[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = 0.0;
-      const double* yp = P.Yt + j0 + j;
-      const double* sp = Ssm + (size_t)f * K * n;
-      for (int r = 0; r < n; ++r) {
-        const double y = __ldg(yp + (size_t)r * p);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k < K) acc[k] = fma(y, sp[(size_t)k * n + r], acc[k]);
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (k < K) zsm[(size_t)(f * K + k) * J + j] = acc[k];
-    }
-    __syncthreads();
+    dmma_stream_pass<MT, NTM>(&mapY, &mapS, P.gy, j0, sA, sV, full, empty, it, zsm);
   };
 
   for (int step = 0; step < P.nsteps; ++step) {
@@ -536,17 +547,22 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       s_slice_reduce();
       __syncthreads();
       while (!st.cg_done) {
+        stamp();                                                                        // 0: iteration start
         dmma_stream_pass<MT, NTM>(&mapA, &mapR, P.g, j0, sA, sV, full, empty, it, us);  // U = Omega_u r
         ++passes;
+        stamp();                                                                        // 1: stream done
         for (int e = tid; e < Jv * NC; e += NTH) {
           const int j = e % Jv, c = e / Jv;
           tmp0[(size_t)c * J + j] = P.Rg[(size_t)c * ldv + j0 + j] * us[(size_t)c * J + j];
         }
         __syncthreads();
         column_sums(tmp0, J, Jv, NC, P.part_ru + (size_t)blockIdx.x * 32, NTH);
+        stamp();                                                                        // 2: r.u partials
         grid_barrier_b(P.bar, bar_gen);
+        stamp();                                                                        // 3: barrier 1
         reduce_partials(P.part_ru, P.nblk, 32, NC, st.ru, NTH);
         load_s_and_z();                                   // also publishes st.ru (barriers inside)
+        stamp();                                                                        // 4: S, z
         if (tid < NC) {
           const int c = tid, f = c / K;
           double alpha = 0.0, beta = 0.0;
@@ -587,10 +603,13 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           tmp0[(size_t)c * J + j] = rn * rn;
         }
         __syncthreads();
+        stamp();                                                                        // 5: update
         column_sums(tmp0, J, Jv, NC, P.part_gam + (size_t)blockIdx.x * 64, NTH);
         s_partial();
         fence_proxy_async();
+        stamp();                                                                        // 6: S partial
         grid_barrier_b(P.bar, bar_gen);
+        stamp();                                                                        // 7: barrier 2
         reduce_partials(P.part_gam, P.nblk, 64, NC, st.red, NTH);
         __syncthreads();
         if (tid < NC && !st.frozen[tid]) {
@@ -610,6 +629,7 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         }
         s_slice_reduce();
         __syncthreads();
+        stamp();                                                                        // 8: reductions
       }
       if (st.status != 0) break;
       // ================= Stiefel projection, dual update, stopping rule (:169-179) =================
@@ -645,7 +665,7 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const int warp = tid >> 5, lane = tid & 31;
         if (warp < F && st.active[warp]) {
           const int f = warp;
-          double* G = st.polw[f][0];
+          double* G = polw + (size_t)f * 256;
           for (int e = lane; e < K * K; e += 32) {
             int a = e / K, b = e - a * K;
             if (a > b) { const int t2 = a; a = b; b = t2; }
@@ -654,7 +674,7 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             G[e] = gfull[f * KG + idx + (b - a)];
           }
           __syncwarp();
-          const int bad = warp_inv_sqrt(G, st.polw[f][1], st.polw[f][2], st.polw[f][3], st.Pm[f], K);
+          const int bad = warp_inv_sqrt(G, G + 64, G + 128, G + 192, Pm + (size_t)f * 64, K);
           if (bad && lane == 0) st.status = 1;
         }
         __syncthreads();
@@ -665,7 +685,7 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         if (st.active[f]) {
           const size_t off = (size_t)c * ldv + j0 + j;
           double cn = 0.0;
-          for (int a = 0; a < K; ++a) cn = fma(tmp0[(size_t)(f * K + a) * J + j], st.Pm[f][a * K + k], cn);
+          for (int a = 0; a < K; ++a) cn = fma(tmp0[(size_t)(f * K + a) * J + j], Pm[(size_t)f * 64 + a * K + k], cn);
           const double x = P.Xg[off], cold = P.Cg[off], l2old = P.L2g[off];
           const double dC = __dsub_rn(x, cn);
           const double l2n = __dadd_rn(l2old, __dmul_rn(st.rho[f], dC));          // :173
@@ -761,21 +781,24 @@ struct BcgHost {
 bool bcg_geometry(int p, int n, int K, int F, BcgHost& o) {
   const int NC = K * F;
   if (K < 1 || K > 8 || F < 1 || F > kMaxF || NC > 32) return false;
+  if (n % 2 != 0) return false;              // TMA strides are multiples of 16 bytes: Y (ld = n) needs an even n
   const int sms = sm_count();
   const int MT = pick_mt(NC);
   const int NT = ceil_div(ceil_div(p, 8), sms);
   if (NT > (MT == 4 ? 10 : 16)) return false;
   const size_t cap = smem_cap_for_device();
-  const size_t state = sizeof(BcgState) + 2 * 16 * sizeof(uint64_t) + 1024;
+  const int NTg = ceil_div(ceil_div(p, 8), sms);
+  const size_t us_bytes = (size_t)8 * MT * 8 * NTg * sizeof(double);
+  const size_t state = sizeof(BcgState) + 16 + us_bytes + 2 * 16 * sizeof(uint64_t) + 1024;
   try {
     o.h = make_stream_geom(p, NC, sms, state, cap);
   } catch (const Error&) {
     return false;
   }
   o.ring = o.h.smem_stream;
-  o.alias_need = ((size_t)o.h.NCP * o.h.g.J + (size_t)NC * n + 4 * (size_t)NC * o.h.g.J) * sizeof(double);
+  o.alias_need = ((size_t)o.h.NCP * o.h.g.J + 3 * (size_t)NC * o.h.g.J + (size_t)kMaxF * 320) * sizeof(double);
   if (o.alias_need > o.ring) return false;
-  o.smem = 1024 + o.ring + (size_t)2 * o.h.g.NS * sizeof(uint64_t) + sizeof(BcgState) + 64;
+  o.smem = 1024 + o.ring + (size_t)2 * o.h.g.NS * sizeof(uint64_t) + sizeof(BcgState) + 16 + us_bytes + 64;
   if (o.smem > cap) return false;
   const size_t ldv = padded_ld(p);
   o.vec = ldv * (size_t)o.h.NCP;
@@ -789,8 +812,8 @@ bool bcg_geometry(int p, int n, int K, int F, BcgHost& o) {
 }
 
 template <int MT, int NTM>
-void launch_bcg_instance(const CUtensorMap& mA, const CUtensorMap& mX, const CUtensorMap& mR, const BcgParams& P,
-                         int nblk, size_t smem, cudaStream_t s) {
+void launch_bcg_instance(const CUtensorMap& mA, const CUtensorMap& mX, const CUtensorMap& mR, const CUtensorMap& mY,
+                         const CUtensorMap& mS, const BcgParams& P, int nblk, size_t smem, cudaStream_t s) {
   int dev = 0, per_sm = 0;
   SPB_CUDA(cudaGetDevice(&dev));
   SPB_CUDA(cudaFuncSetAttribute(batched_core2_kernel<MT, NTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -799,9 +822,9 @@ void launch_bcg_instance(const CUtensorMap& mA, const CUtensorMap& mX, const CUt
   if (per_sm < 1 || nblk > per_sm * sm_count())
     throw Error(SPB_ERR_INTERNAL, "batched Core2 kernel: " + std::to_string(nblk) + " CTAs of " + std::to_string(smem) +
                                       " B shared memory are not co-resident (" + std::to_string(per_sm) + " per SM)");
-  CUtensorMap a = mA, x = mX, r = mR;
+  CUtensorMap a = mA, x = mX, r = mR, y = mY, sm = mS;
   BcgParams Pc = P;
-  void* args[] = {&a, &x, &r, &Pc};
+  void* args[] = {&a, &x, &r, &y, &sm, &Pc};
   SPB_CUDA(cudaLaunchCooperativeKernel((void*)batched_core2_kernel<MT, NTM>, dim3(nblk), dim3(tmx::Shape<MT>::kThreads),
                                        args, smem, s));
   count_launch();
@@ -827,6 +850,9 @@ void launch_batched_core2(const BatchedCore2Call& c, void* ws, cudaStream_t s) {
   const size_t ldv = padded_ld(c.p);
   BcgParams P;
   P.g = o.h.g;
+  P.gy = o.h.g;
+  P.gy.p = c.n;
+  P.gy.nchunks = ceil_div(c.n, 64);
   P.p = c.p; P.n = c.n; P.K = c.K; P.F = c.F; P.NC = c.K * c.F; P.ldv = ldv; P.nblk = o.h.nblk;
   P.nsteps = c.nsteps;
   for (int i = 0; i < kMaxSteps; ++i) P.tau1[i] = i < c.nsteps ? c.tau1[i] : 0.0;
@@ -856,21 +882,24 @@ void launch_batched_core2(const BatchedCore2Call& c, void* ws, cudaStream_t s) {
   P.norm_part = w; w += o.norm;
   P.bar = reinterpret_cast<unsigned int*>(w);
   SPB_CUDA(cudaMemsetAsync(P.bar, 0, 64, s));
+  P.dbg = c.dbg;
   const CUtensorMap mA = make_map(c.omega_u, c.p, c.p, c.ld, o.h.g.J);
   const CUtensorMap mX = make_map(P.Xg, c.p, P.NC, ldv, o.h.NCP);
   const CUtensorMap mR = make_map(P.Rg, c.p, P.NC, ldv, o.h.NCP);
+  const CUtensorMap mY = make_map(c.Y, c.n, c.p, (size_t)c.n, o.h.g.J);
+  const CUtensorMap mS = make_map(P.Sred, c.n, P.NC, (size_t)c.n, o.h.NCP);
   const int NT = o.h.g.NT;
   switch (o.h.MT) {
     case 1:
-      if (NT <= 10) launch_bcg_instance<1, 10>(mA, mX, mR, P, o.h.nblk, o.smem, s);
-      else launch_bcg_instance<1, 16>(mA, mX, mR, P, o.h.nblk, o.smem, s);
+      if (NT <= 10) launch_bcg_instance<1, 10>(mA, mX, mR, mY, mS, P, o.h.nblk, o.smem, s);
+      else launch_bcg_instance<1, 16>(mA, mX, mR, mY, mS, P, o.h.nblk, o.smem, s);
       break;
     case 2:
-      if (NT <= 10) launch_bcg_instance<2, 10>(mA, mX, mR, P, o.h.nblk, o.smem, s);
-      else launch_bcg_instance<2, 16>(mA, mX, mR, P, o.h.nblk, o.smem, s);
+      if (NT <= 10) launch_bcg_instance<2, 10>(mA, mX, mR, mY, mS, P, o.h.nblk, o.smem, s);
+      else launch_bcg_instance<2, 16>(mA, mX, mR, mY, mS, P, o.h.nblk, o.smem, s);
       break;
     default:
-      launch_bcg_instance<4, 10>(mA, mX, mR, P, o.h.nblk, o.smem, s);
+      launch_bcg_instance<4, 10>(mA, mX, mR, mY, mS, P, o.h.nblk, o.smem, s);
       break;
   }
 }

@@ -697,7 +697,24 @@ int spb_core2_batched(const double* omega, const double* Y, const double* nk, in
     c.nsteps = nsteps; c.tau1 = tau1; c.maxit = maxit; c.tol = tol;
     c.cg_tol = cg_tol > 0.0 ? cg_tol : 1e-14; c.cg_cap = 2000;
     c.snap = snap ? dsnap.get() : nullptr; c.iters_out = dit.get(); c.status_out = dstat.get();
+    const bool dbg_on = std::getenv("SPB_BCG_DBG") != nullptr;
+    DevBuf<unsigned long long> dbg(400);
+    SPB_CUDA(cudaMemsetAsync(dbg.get(), 0, sizeof(unsigned long long) * 400, s));
+    if (dbg_on) c.dbg = dbg.get();
     launch_batched_core2(c, ws.get(), s);
+    if (dbg_on) {
+      unsigned long long h[400];
+      SPB_CUDA(cudaStreamSynchronize(s));
+      SPB_CUDA(cudaMemcpy(h, dbg.get(), sizeof(h), cudaMemcpyDeviceToHost));
+      const char* names[8] = {"stream", "r.u", "barrier1", "S+z", "update", "Spartial", "barrier2", "reduce"};
+      for (int itx = 1; itx < 6; ++itx) {
+        const unsigned long long* q = h + 9 * itx;
+        if (q[8] == 0) break;
+        fprintf(stderr, "[bcg dbg] p=%d F=%d K=%d CG step %d:", p, F, K, itx);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%.1f", names[k], (double)(q[k + 1] - q[k]) * 1e-3);
+        fprintf(stderr, " total=%.1f us\n", (double)(q[8] - q[0]) * 1e-3);
+      }
+    }
     int sth[2] = {0, 0};
     SPB_CUDA(cudaMemcpyAsync(sth, dstat.get(), sizeof(sth), cudaMemcpyDeviceToHost, s));
     SPB_CUDA(cudaMemcpyAsync(iters, dit.get(), sizeof(int) * nsteps * F, cudaMemcpyDeviceToHost, s));

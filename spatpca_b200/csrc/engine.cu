@@ -604,6 +604,7 @@ Engine::Engine(int p, int d, int n, int M, int K, const double* tau1, int n1, co
     const std::string m(e);
     cg_mode_ = (m == "cg") ? 1 : ((m == "factor") ? 2 : 0);
   }
+  if (const char* e = std::getenv("SPB_BATCH")) bcg_mode_ = (std::string(e) == "0") ? 2 : 0;
   if (const char* e = std::getenv("SPB_CG_TOL")) { const double t = std::atof(e); if (t > 0.0 && t < 1e-6) cg_tol_ = t; }
   alloc_k_state();
   std::memset(&stats_, 0, sizeof(stats_));
@@ -616,7 +617,8 @@ void Engine::alloc_k_state() {
   full_.alloc(pk);
   for (auto& L : lanes_) {
     L->chain.alloc(pk);
-    L->admm_ws.alloc(std::max(admm_workspace_bytes(p_, K_), cg_workspace_bytes(p_, K_, n_)));
+    L->admm_ws.alloc(std::max({admm_workspace_bytes(p_, K_), cg_workspace_bytes(p_, K_, n_),
+                               batched_core2_workspace_bytes(p_, n_, K_, 1)}));
     L->lossW.alloc((size_t)n_ * K_);
     L->loss_scratch.alloc(yphi_scratch_doubles(n_, p_, K_) + 512);
   }
@@ -649,6 +651,7 @@ Engine::~Engine() {
   for (auto& L : lanes_) cudaStreamSynchronize(L->res->stream);
   cudaStreamSynchronize(ctx_.stream);
   if (omega_evt_) cudaEventDestroy(omega_evt_);
+  for (auto& L : lanes_) if (L->evt) cudaEventDestroy(L->evt);
 }
 
 Lane& Engine::lane_of(int fold) {
@@ -689,6 +692,12 @@ void Engine::upload(const double* sxy, const double* Y, const double* nk) {
   }
   dYt_.alloc((size_t)n_ * p_);
   launch_transpose(dY_.get(), n_, p_, dYt_.get(), ctx_.stream);             // p x n, for the matrix-free Core2p
+  {
+    std::vector<int> nki(n_);
+    for (int r = 0; r < n_; ++r) nki[r] = (int)nk[r];
+    dNk_.alloc(n_);
+    SPB_CUDA(cudaMemcpy(dNk_.get(), nki.data(), sizeof(int) * n_, cudaMemcpyHostToDevice));
+  }
   SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
   stats_.bytes_h2d += (long long)sizeof(double) * ((size_t)n_ * p_ + (size_t)p_ * d_ + n_);
   stats_.ms_h2d += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -749,7 +758,7 @@ double Engine::omega_lmax() {
   return lmax_;
 }
 
-bool Engine::use_cg(double c_omega, double rho, double gram_top, int expected_iters) {
+bool Engine::use_cg(double c_omega, double rho, double gram_top, int expected_iters, double pass_scale) {
   if (K_ > kCgMaxK || cg_mode_ == 2) return false;
   if (cg_mode_ == 1) return true;
   if (p_ < 2048) return false;                   // small systems: latency-bound, the explicit inverse wins
@@ -763,13 +772,15 @@ bool Engine::use_cg(double c_omega, double rho, double gram_top, int expected_it
   // cost model in units of one p x p matrix pass (measured on B200, profiles/): a block factorisation costs
   // ~65 + 0.0085 p passes and each ADMM iteration on it ~2.4; a CG solve costs its steps + 3 passes
   const double factor_cost = 65.0 + 0.0085 * p_ + 2.4 * expected_iters;
-  return expected_iters * (steps + 3.0) < factor_cost;
+  // pass_scale: cost of a pass per problem relative to a single-problem pass (the fold-batched DMMA stream serves F
+  // problems with one pass that takes ~2.1 single passes)
+  return expected_iters * (steps + 3.0) * pass_scale < factor_cost;
 }
 
-bool Engine::core2_matrix_free(int fold, double tau1, double rho, int expected_iters) {
+bool Engine::core2_matrix_free(int fold, double tau1, double rho, int expected_iters, double pass_scale) {
   if (maxit_ <= 0) return false;
   const double sv1 = fold < 0 ? sv_full_[0] : folds_[fold].sv[0];
-  return use_cg(2.0 * tau1, rho, 2.0 * sv1 * sv1, tol_ > 0.0 ? expected_iters : maxit_);
+  return use_cg(2.0 * tau1, rho, 2.0 * sv1 * sv1, tol_ > 0.0 ? expected_iters : maxit_, pass_scale);
 }
 
 bool Engine::can_share_inverses() {
@@ -1030,6 +1041,30 @@ void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double
   if (!have && core2_matrix_free(fold, tau1, rho, expected_iters)) {
     wait_omega(L);
     if (L.next_slot >= slot_cap_) flush_lane(L);
+    const int n_rows = fold < 0 ? n_ : folds_[fold].n_tr;
+    if (bcg_mode_ != 2 && batched_core2_supported(p_, n_rows, K_, 1)) {
+      // one problem on the TMA-fed DMMA stream (126 us per pass at p = 10 000 against 200 us of the FMA stream)
+      BatchedCore2Call b;
+      b.omega_u = omega_u_.get(); b.ld = ld_; b.p = p_; b.n = n_rows; b.K = K_; b.F = 1;
+      b.Y = fold < 0 ? dY_.get() : folds_[fold].Ytr.get();
+      b.Yt = fold < 0 ? dYt_.get() : folds_[fold].Ytt.get();
+      b.nk = dNk_.get();
+      for (int f = 0; f < 8; ++f) { b.fold_id[f] = 0; b.rho[f] = 1.0; b.Phi[f] = b.C[f] = b.L2[f] = nullptr; }
+      b.rho[0] = rho; b.Phi[0] = st.Phi.get(); b.C[0] = st.C.get(); b.L2[0] = st.L2.get();
+      b.nsteps = 1; b.tau1 = &tau1; b.maxit = maxit_; b.tol = tol_; b.cg_tol = cg_tol_; b.cg_cap = 2000;
+      b.snap = nullptr;
+      int* slot = L.stat_slots.get() + (size_t)L.next_slot * 4;
+      b.iters_out = slot; b.status_out = slot + 1;            // {iterations, status, matrix passes, -}
+      {
+        Scoped sc(L.clock, PH_CG, s);
+        SPB_CUDA(cudaMemsetAsync(slot, 0, 4 * sizeof(int), s));
+        launch_batched_core2(b, L.admm_ws.get(), s);
+      }
+      L.pending.push_back({kind + 200, fold, idx, L.next_slot, n_rows});   // + 200: passes in slot [2]
+      L.next_slot++;
+      L.dirty = true;
+      return;
+    }
     CgCall c;
     c.omega_u = omega_u_.get(); c.ld = ld_; c.p = p_; c.K = K_;
     if (fold < 0) { c.Ytr = dY_.get(); c.Yt = dYt_.get(); c.n_tr = n_; }
@@ -1077,6 +1112,93 @@ void Engine::run_core2(Lane& L, int kind, int fold, int idx, double tau1, double
   L.pending.push_back({kind, fold, idx, L.next_slot, 0});
   L.next_slot++;
   L.dirty = true;
+}
+
+void Engine::ensure_batch_buffers(int F, int nsteps) {
+  bcg_ws_.ensure(batched_core2_workspace_bytes(p_, n_, K_, F));
+  bcg_snap_.ensure((size_t)nsteps * F * p_ * K_);
+  const size_t cap_it = (size_t)(tau1_.size() + 8) * (M_ + 1) * 4, cap_st = 64;
+  if (bcg_iters_.count < cap_it) { bcg_iters_.alloc(cap_it); bcg_it_used_ = 0; }
+  if (bcg_status_.count < cap_st) { bcg_status_.alloc(cap_st); bcg_st_used_ = 0; }
+}
+
+bool Engine::run_core2_batched(const std::vector<int>& folds, const std::vector<double>& taus, const std::vector<int>& idx,
+                               int kind, int expected_iters, double** snap_out) {
+  const int F = (int)folds.size(), ns = (int)taus.size();
+  if (bcg_mode_ == 2 || cg_mode_ == 2 || F < 1 || F > 8 || ns < 1 || ns > 64 || maxit_ <= 0 || K_ > 8 || F * K_ > 32)
+    return false;
+  if (cg_mode_ != 1 && p_ < 2048) return false;
+  if (!batched_core2_supported(p_, n_, K_, F)) return false;
+  // distinct lanes (problems sharing a lane share its chain buffers) and the matrix-free policy for every problem
+  std::vector<int> lanes_seen;
+  const double tmax = *std::max_element(taus.begin(), taus.end());
+  for (int k : folds) {
+    const int li = k < 0 ? n_fold_lanes_ : k % n_fold_lanes_;
+    if (std::find(lanes_seen.begin(), lanes_seen.end(), li) != lanes_seen.end()) return false;
+    lanes_seen.push_back(li);
+    const double rho = k < 0 ? rho_full_ : folds_[k].rho;
+    if (!core2_matrix_free(k, tmax, rho, expected_iters, F > 1 ? 2.1 / F : 1.0)) return false;
+  }
+  // one workspace and one snapshot buffer: a batch that would overlap with an earlier one on another stream, or
+  // overwrite snapshots that loss kernels may still read, waits for everything enqueued so far (rare: only when
+  // folds share lanes, i.e. when device memory limits the lane count)
+  if (!batch_pending_.empty() &&
+      (bcg_it_used_ + (size_t)ns * F > bcg_iters_.count || bcg_st_used_ + 2 > bcg_status_.count ||
+       batch_stream_ != lane_of(folds[0]).res->stream || (snap_out != nullptr && snap_in_use_)))
+    flush();
+  ensure_batch_buffers(F, ns);
+  batch_stream_ = lane_of(folds[0]).res->stream;
+  if (snap_out != nullptr) snap_in_use_ = true;
+  Lane& L0 = lane_of(folds[0]);
+  cudaStream_t s = L0.res->stream;
+  wait_omega(L0);
+  // the other lanes' pending work (their starts) must be visible to the batch stream
+  for (int k : folds) {
+    Lane& L = lane_of(k);
+    if (&L == &L0) continue;
+    if (!L.evt) SPB_CUDA(cudaEventCreateWithFlags(&L.evt, cudaEventDisableTiming));
+    SPB_CUDA(cudaEventRecord(L.evt, L.res->stream));
+    SPB_CUDA(cudaStreamWaitEvent(s, L.evt, 0));
+  }
+  BatchedCore2Call c;
+  c.omega_u = omega_u_.get(); c.ld = ld_; c.p = p_; c.n = n_; c.K = K_; c.F = F;
+  c.Y = dY_.get(); c.Yt = dYt_.get(); c.nk = dNk_.get();
+  for (int f = 0; f < 8; ++f) {
+    c.fold_id[f] = 0; c.rho[f] = 1.0; c.Phi[f] = c.C[f] = c.L2[f] = nullptr;
+  }
+  for (int f = 0; f < F; ++f) {
+    const int k = folds[f];
+    ChainState& st = k < 0 ? full_ : lane_of(k).chain;
+    c.fold_id[f] = k < 0 ? 0 : k + 1;                       // nk holds 1-based fold ids (:318-319)
+    c.rho[f] = k < 0 ? rho_full_ : folds_[k].rho;
+    c.Phi[f] = st.Phi.get(); c.C[f] = st.C.get(); c.L2[f] = st.L2.get();
+  }
+  c.nsteps = ns; c.tau1 = taus.data(); c.maxit = maxit_; c.tol = tol_; c.cg_tol = cg_tol_; c.cg_cap = 2000;
+  c.snap = snap_out ? bcg_snap_.get() : nullptr;
+  c.iters_out = bcg_iters_.get() + bcg_it_used_;
+  c.status_out = bcg_status_.get() + bcg_st_used_;
+  {
+    Scoped sc(L0.clock, PH_CG, s);
+    SPB_CUDA(cudaMemsetAsync(c.iters_out, 0, sizeof(int) * (size_t)ns * F, s));
+    SPB_CUDA(cudaMemsetAsync(c.status_out, 0, 2 * sizeof(int), s));
+    launch_batched_core2(c, bcg_ws_.get(), s);
+  }
+  BatchRec rec;
+  rec.kind = kind; rec.folds = folds; rec.idx = idx; rec.it_off = bcg_it_used_; rec.st_off = bcg_st_used_; rec.n = n_;
+  batch_pending_.push_back(rec);
+  bcg_it_used_ += (size_t)ns * F;
+  bcg_st_used_ += 2;
+  // the other lanes continue after the batch
+  if (!L0.evt) SPB_CUDA(cudaEventCreateWithFlags(&L0.evt, cudaEventDisableTiming));
+  SPB_CUDA(cudaEventRecord(L0.evt, s));
+  for (int k : folds) {
+    Lane& L = lane_of(k);
+    L.dirty = true;
+    if (&L == &L0) continue;
+    SPB_CUDA(cudaStreamWaitEvent(L.res->stream, L0.evt, 0));
+  }
+  if (snap_out) *snap_out = bcg_snap_.get();
+  return true;
 }
 
 double* Engine::cached_inverse(FoldData& f, int index1) {
@@ -1175,9 +1297,10 @@ void Engine::flush_lane(Lane& L) {
       else if (status != 0) polar_failed = true;
       int kind = r.kind;
       const double pp8 = 8.0 * (double)p_ * (double)p_, pk8 = 8.0 * (double)p_ * (double)K_;
-      if (kind >= 100) {                                     // matrix-free call: [3] = matrix passes
-        kind -= 100;
-        const int passes = st[(size_t)r.slot * 4 + 3];
+      if (kind >= 100) {                                     // matrix-free call: matrix passes in [3] ([2] from the DMMA kernel)
+        const bool dmma = kind >= 200;
+        kind -= dmma ? 200 : 100;
+        const int passes = st[(size_t)r.slot * 4 + (dmma ? 2 : 3)];
         stats_.n_cg_calls++;
         stats_.cg_passes += passes;
         stats_.admm_bytes += passes * (pp8 + 16.0 * (double)r.n_tr * (double)p_) + iters * 5.0 * pk8;
@@ -1198,6 +1321,35 @@ void Engine::flush_lane(Lane& L) {
 void Engine::flush() {
   finish_omega();
   for (auto& L : lanes_) flush_lane(*L);
+  if (!batch_pending_.empty()) {
+    std::vector<int> its(bcg_it_used_), sts(bcg_st_used_);
+    SPB_CUDA(cudaMemcpy(its.data(), bcg_iters_.get(), sizeof(int) * its.size(), cudaMemcpyDeviceToHost));
+    SPB_CUDA(cudaMemcpy(sts.data(), bcg_status_.get(), sizeof(int) * sts.size(), cudaMemcpyDeviceToHost));
+    int bad = 0;
+    const double pp8 = 8.0 * (double)p_ * (double)p_, pk8 = 8.0 * (double)p_ * (double)K_;
+    for (const BatchRec& b : batch_pending_) {
+      const int F = (int)b.folds.size(), ns = (int)b.idx.size();
+      const int status = sts[b.st_off], passes = sts[b.st_off + 1];
+      if (status != 0 && bad == 0) bad = status;
+      long long iters_sum = 0;
+      for (int i = 0; i < ns; ++i)
+        for (int f = 0; f < F; ++f) {
+          const int it = its[b.it_off + (size_t)i * F + f];
+          log_.push_back(b.kind); log_.push_back(b.folds[f]); log_.push_back(b.idx[i]); log_.push_back(it);
+          iters_sum += it;
+        }
+      stats_.n_cg_calls += F * ns;
+      stats_.cg_passes += passes;
+      stats_.admm_bytes += passes * (pp8 + 16.0 * (double)b.n * (double)p_) + (double)iters_sum * 5.0 * pk8;
+    }
+    batch_pending_.clear();
+    bcg_it_used_ = bcg_st_used_ = 0;
+    snap_in_use_ = false;
+    if (bad == SPB_ERR_NOT_POSDEF) throw Error(SPB_ERR_NOT_POSDEF, "inv_sympd(): matrix is singular or not positive definite");
+    if (bad == SPB_ERR_INTERNAL) throw Error(SPB_ERR_INTERNAL, "matrix-free Core2: conjugate gradients did not converge");
+    if (bad != 0)
+      throw Error(SPB_ERR_POLAR, "svd_econ(): the p x K iterate is rank deficient, Stiefel projection undefined");
+  }
   ctx_.sync_and_check();
 }
 
@@ -1294,8 +1446,32 @@ void Engine::stage1_folds(const int* folds, int nfolds, double* rows) {
   for (int f = 0; f < nfolds; ++f) fold_prepare(folds[f]);                    // SVD starts (host-synchronous)
   for (const auto& round : lane_rounds(folds, nfolds)) {                      // tau1 paths, concurrent lanes
     for (int k : round) enqueue_stage1(k, 0);
-    for (int i = 1; i < n1; ++i)
-      for (int k : round) enqueue_stage1(k, i);
+    bool batched = false;
+    if (n1 > 1) {
+      // all folds of the round in lock-step through ONE launch of the batched matrix-free kernel (warm-started
+      // tau1 path, :329-332); the hold-out losses (:331) are taken from its per-step snapshots afterwards
+      bool fresh = true;
+      for (int k : round)
+        for (int i = 1; i < n1; ++i)
+          if (cache_inverses_ && i < (int)folds_[k].inv_valid.size() && folds_[k].inv_valid[i]) fresh = false;
+      std::vector<double> taus(tau1_.begin() + 1, tau1_.end());
+      std::vector<int> idx(n1 - 1);
+      for (int i = 1; i < n1; ++i) idx[i - 1] = i;
+      double* snap = nullptr;
+      if (fresh && run_core2_batched(round, taus, idx, 2, 3, &snap)) {
+        batched = true;
+        const size_t pk = (size_t)p_ * K_;
+        const int F = (int)round.size();
+        for (int i = 1; i < n1; ++i)
+          for (int f = 0; f < F; ++f) {
+            const int k = round[f];
+            launch_loss(lane_of(k), folds_[k], snap + ((size_t)(i - 1) * F + f) * pk, fold_scores(k) + i);
+          }
+      }
+    }
+    if (!batched)
+      for (int i = 1; i < n1; ++i)
+        for (int k : round) enqueue_stage1(k, i);
   }
   flush();
   if (n1 > 1) {
@@ -1335,7 +1511,8 @@ void Engine::stage1_full(int index1) {
 }
 
 // ---- stage 2 (:652-680) -----------------------------------------------------------------
-// step 0: Core2 at the selected tau1 and the fold's tempinv; step 1: the tau2 path
+// step 0: start of the fold's chain; step 1: Core2 at the selected tau1 (skipped when the round ran it batched);
+// step 2: Phi_cv / Lambd2_cv and the fold's tempinv; step 3: the tau2 path
 void Engine::enqueue_stage2(int k, int index1, int step) {
   FoldData& f = folds_[k];
   Lane& L = lane_of(k);
@@ -1344,21 +1521,28 @@ void Engine::enqueue_stage2(int k, int index1, int step) {
   const int n2 = (int)tau2_.size();
   const double sel1 = selected_tau1(index1);
   double* scores = fold_scores(k);
-  if (step == 1) {
+  if (step == 3) {
     for (int i = 0; i < n2; ++i) {                                            // :398-401
       run_core3(L, 3, k, i, f.tinv.get(), tau2_[i], f.rho, ch);
       launch_loss(L, f, ch.Phi.get(), scores + i);
     }
     return;
   }
-  copy_pk(s, ch.Phi.get(), f.Phi0.get());                                     // :389
-  copy_pk(s, ch.C.get(), f.Phi0.get());
-  zero_pk(s, ch.L1.get());                                                    // :390
-  copy_pk(s, ch.L2.get(), f.L20.get());                                       // :391
-  drop_cached_inverses(f, index1);
-  if (sel1 != 0.0) {                                                          // :392-393
-    double* inv = cached_inverse(f, index1);
-    run_core2(L, 2, k, 0, sel1, f.rho, ch, inv, inv != nullptr);
+  if (step == 0) {
+    copy_pk(s, ch.Phi.get(), f.Phi0.get());                                   // :389
+    copy_pk(s, ch.C.get(), f.Phi0.get());
+    zero_pk(s, ch.L1.get());                                                  // :390
+    copy_pk(s, ch.L2.get(), f.L20.get());                                     // :391
+    drop_cached_inverses(f, index1);
+    L.dirty = true;
+    return;
+  }
+  if (step == 1) {
+    if (sel1 != 0.0) {                                                        // :392-393
+      double* inv = cached_inverse(f, index1);
+      run_core2(L, 2, k, 0, sel1, f.rho, ch, inv, inv != nullptr);
+    }
+    return;
   }
   // (the kept inverse is in use on this lane's stream: it is released after stage 3's flush)
   copy_pk(s, ch.R.get(), ch.Phi.get());                                       // :394
@@ -1386,9 +1570,20 @@ void Engine::stage2_folds(const int* folds, int nfolds, int index1, double* rows
     SPB_REQUIRE(folds[f] >= 0 && folds[f] < M_, "fold index out of range");
     SPB_REQUIRE(folds_[folds[f]].prepared, "stage 1 must run before stage 2 for every fold");
   }
-  for (const auto& round : lane_rounds(folds, nfolds))
-    for (int step = 0; step < 2; ++step)
+  const double sel1 = selected_tau1(index1);
+  for (const auto& round : lane_rounds(folds, nfolds)) {
+    for (int k : round) enqueue_stage2(k, index1, 0);
+    bool batched = false;
+    if (sel1 != 0.0) {
+      bool have_inverse = false;
+      for (int k : round) have_inverse |= (cached_inverse(folds_[k], index1) != nullptr);
+      if (!have_inverse) batched = run_core2_batched(round, {sel1}, {0}, 2, 8, nullptr);   // :392-393, all folds at once
+    }
+    if (!batched)
+      for (int k : round) enqueue_stage2(k, index1, 1);
+    for (int step = 2; step < 4; ++step)
       for (int k : round) enqueue_stage2(k, index1, step);
+  }
   flush();
   SPB_REQUIRE(rows != nullptr, "cv rows pointer is NULL");
   for (int f = 0; f < nfolds; ++f)

@@ -110,6 +110,15 @@ struct FoldData {
 };
 
 struct CallRec { int kind, fold, idx, slot, n_tr; };
+// One launch of the fold-batched matrix-free Core2 kernel: its per-(step, problem) iteration counts live in device
+// memory until the next flush.
+struct BatchRec {
+  int kind;                        // call-log kind of its calls (2 or 20)
+  std::vector<int> folds;          // problem f -> fold (-1: full data)
+  std::vector<int> idx;            // step -> grid index reported in the call log
+  size_t it_off, st_off;           // offsets into bcg_iters_ / bcg_status_
+  int n;                           // rows of Y seen by the kernel (for the byte accounting)
+};
 
 // One independent chain of work (a fold's tau path, or the full-data fit): its own stream, cuBLAS
 // handle and working set, so that the latency-bound parts of one chain (leaf inverses, small
@@ -127,6 +136,7 @@ struct Lane {
   int next_slot = 0;
   std::vector<CallRec> pending;
   PhaseClock clock;
+  cudaEvent_t evt = nullptr;       // ordering between this lane and a batched launch on another stream
   bool dirty = false;              // work enqueued since the last flush
   bool omega_synced = false;       // this lane's stream already waits for the Omega build
   Exec exec(int* flag) { return Exec{res->stream, res->blas, flag, &res->inv_work}; }
@@ -233,13 +243,18 @@ class Engine {
                  double* buf = nullptr, bool have = false, int expected_iters = 8);
   // Matrix-free Core2 (conjugate gradients, admm_kernels.cu) or the factored path?  Decided per call from a
   // bound on cond(c_omega Omega_u + rho I - c_gram Ytr'Ytr) and the iterations the call is expected to run.
-  bool use_cg(double c_omega, double rho, double gram_top, int expected_iters);
-  bool core2_matrix_free(int fold, double tau1, double rho, int expected_iters);   // the decision run_core2 takes
+  bool use_cg(double c_omega, double rho, double gram_top, int expected_iters, double pass_scale = 1.0);
+  bool core2_matrix_free(int fold, double tau1, double rho, int expected_iters, double pass_scale = 1.0);   // the decision run_core2 takes
   double omega_lmax();                           // power-iteration estimate of lambda_max(Omega_u) (host; waits for Omega)
   void enqueue_lmax(cudaStream_t s, cublasHandle_t blas);
   double* cached_inverse(FoldData& f, int index1);   // stage-1 inverse of the selected tau1, or nullptr
   void drop_cached_inverses(FoldData& f, int keep);
   void run_core3(Lane& L, int kind, int fold, int idx, const double* tinv, double tau2, double rho, ChainState& st);
+  // fold-batched matrix-free Core2 (batched_cg.cu) for `folds` (each on its own lane) along `taus`: returns false
+  // (nothing enqueued) when the shape / policy does not allow it.  snap: Phi after every step, or nullptr.
+  bool run_core2_batched(const std::vector<int>& folds, const std::vector<double>& taus, const std::vector<int>& idx,
+                         int kind, int expected_iters, double** snap_out);
+  void ensure_batch_buffers(int F, int nsteps);
   void launch_loss(Lane& L, const FoldData& f, const double* Phi, double* out_dev);
   std::vector<std::vector<int>> lane_rounds(const int* folds, int nfolds) const;
   void enqueue_stage1(int k, int step);
@@ -264,6 +279,15 @@ class Engine {
 
   DevBuf<double> dY_, dX_;
   DevBuf<double> dYt_;                           // p x n: transpose of Y (full-data matrix-free Core2p)
+  DevBuf<int> dNk_;                              // fold ids of the rows of Y (device)
+  DevBuf<char> bcg_ws_;                          // workspace of the batched kernel
+  DevBuf<double> bcg_snap_;                      // snapshots of Phi: steps x problems x (p x K)
+  DevBuf<int> bcg_iters_, bcg_status_;
+  size_t bcg_it_used_ = 0, bcg_st_used_ = 0;
+  std::vector<BatchRec> batch_pending_;
+  cudaStream_t batch_stream_ = nullptr;          // stream of the batches enqueued since the last flush
+  bool snap_in_use_ = false;
+  int bcg_mode_ = 0;                             // SPB_BATCH: 0 = auto, 2 = never batch the folds
   DevBuf<double> lmax_vec_, lmax_out_;           // power iteration: 2 p-vectors, norms
   double lmax_ = -1.0;                           // < 0: not read back yet
   bool lmax_enqueued_ = false;

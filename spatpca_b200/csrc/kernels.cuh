@@ -164,6 +164,7 @@ struct BatchedCore2Call {
   double* snap;              // device, nsteps x F x (p x K): Phi after every step (may be nullptr)
   int* iters_out;            // device, nsteps x F
   int* status_out;           // device, {status, matrix passes}
+  unsigned long long* dbg = nullptr;   // optional: globaltimer stamps of CTA 0, 9 per CG step (400 slots)
 };
 bool batched_core2_supported(int p, int n, int K, int F);
 size_t batched_core2_workspace_bytes(int p, int n, int K, int F);

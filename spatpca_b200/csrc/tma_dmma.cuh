@@ -176,6 +176,7 @@ __device__ __noinline__ void dmma_stream_pass(const CUtensorMap* mapA, const CUt
       for (int nt = 0; nt < NTM; ++nt)
         if (nt < G.NT) b[nt] = *reinterpret_cast<const double2*>(ba + (size_t)nt * 1024);
       // the x halves of all tile pairs first, then the y halves: dependent MMAs on one accumulator are MT * NT apart
+      // (loading the column tiles in two halves to save fragment registers was measured: 270 -> 340 us per pass)
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
