@@ -416,16 +416,36 @@ def main():
         return 0
 
     # ---- rooflines (all timed in THIS run with CUDA events on the library's stream; peaks: MEASURED_PEAKS.json) ----
-    # (1) headline = the own kernel with the largest share of the timed step.  Since round 2 that is the
-    #     matrix-free Core2 kernel (cg_core2_kernel): every stage-1 system and the cold Core2 calls are solved by
-    #     conjugate gradients inside one persistent launch, each CG step streaming Omega_u once.  HBM-bound:
-    #     algorithmic bytes per matrix pass = 8 p^2 (Omega_u) + 16 n_tr p (Ytr and its transpose, for the
-    #     rank-n_tr part) + ~96 p K (the p x K vectors of a CG step).  Probe: a synthetic system of the job's size
-    #     and conditioning (cond ~1.6) in device memory, 4 forced ADMM iterations per launch.
-    n_tr = int(round(cfg["n"] * (cfg["M"] - 1) / cfg["M"]))
-    roof_admm_iters = 4
-    cg_ms, cg_passes = eng_mod.bench_core2_cg(p, K, n_tr, roof_admm_iters, 3) if K <= 8 else (None, 0)
-    cg_bytes_pass = 8.0 * p * p + 16.0 * n_tr * p + 96.0 * p * K
+    # (1) headline = the own kernel with the largest share of the timed step: batched_core2_kernel, the fold-batched
+    #     matrix-free spatpcaCore2 (csrc/batched_cg.cu).  All M folds of a stage advance in lock-step; every
+    #     conjugate-gradient step streams Omega_u ONCE for the M*K = 25 columns on the TMA-fed FP64 DMMA stream
+    #     (cp.async.bulk.tensor + mbarrier -> mma.sync m8n8k4), the rank-n part rides the same pipeline.  With 25
+    #     columns the product is FP64-tensor-bound (2 p^2 * 25 flop over 8 p^2 bytes = 6.25 flop/B), so the bound is
+    #     "tensor" and the peak is the FP64 GEMM rate measured in this run (cuBLAS DGEMM 8192^3: MEASURED_PEAKS.json
+    #     carries no FP64 figure).  Algorithmic flop per matrix pass: 2 p^2 M K (Omega_u) + 4 n p M K (the two p x n
+    #     contractions); bytes per pass for the HBM view: 8 p^2 + 16 n p.
+    n_all, Mf = cfg["n"], cfg["M"]
+    n_tr = int(round(n_all * (Mf - 1) / Mf))
+    roof_admm_iters = 3
+    dgemm_tf = eng_mod.bench_dgemm(8192, 2)
+    batched_ok = K <= 8 and Mf * K <= 32 and eng_mod.core2_batched_supported(p, n_all, K, Mf)
+    stream = {}
+    for label, ncols in (("single_problem", K), ("all_folds", min(32, Mf * K))):
+        try:
+            ms = eng_mod.bench_dmma_matvec(p, ncols, 5)
+        except Exception:
+            continue
+        stream[label] = {"kernel": "dmma_matvec_kernel (the TMA + DMMA stream alone, U = Omega_u V)", "columns": ncols,
+                         "us_per_pass": ms * 1e3, "hbm_gbs": 8.0 * p * p / (ms * 1e-3) / 1e9,
+                         "hbm_frac": 8.0 * p * p / (ms * 1e-3) / 1e9 / hbm_peak,
+                         "fp64_tflops": 2.0 * p * p * ncols / (ms * 1e-3) / 1e12,
+                         "fp64_frac_of_dgemm": 2.0 * p * p * ncols / (ms * 1e-3) / 1e12 / dgemm_tf}
+    cg_ms, cg_passes = (None, 0)
+    if batched_ok:
+        cg_ms, cg_passes = eng_mod.bench_core2_batched(p, n_all, K, Mf, roof_admm_iters, 3)
+    cg_flop_pass = 2.0 * p * p * Mf * K + 4.0 * n_all * p * Mf * K
+    cg_bytes_pass = 8.0 * p * p + 16.0 * n_all * p + 96.0 * p * K * Mf
+    single_ms, single_passes = eng_mod.bench_core2_cg(p, K, n_tr, 4, 3) if K <= 8 else (None, 0)
     # (2) the persistent ADMM kernel on explicit / factored systems (the tau2-path systems of stages 2-3 and every
     #     system the matrix-free kernel is not chosen for): 8 p^2 + 72 p K bytes per Core3 iteration
     roof_iters = 10
@@ -438,13 +458,14 @@ def main():
                         "us_per_iteration": ms * 1e3, "achieved_gbs": alg_bytes_iter / (ms * 1e-3) / 1e9,
                         "frac": alg_bytes_iter / (ms * 1e-3) / 1e9 / hbm_peak}
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r02_cg_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_dmma_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        if tj.get("p") == p and tj.get("K") == K and tj.get("dram_bytes_per_pass"):
+        if tj.get("p") == p and tj.get("dram_bytes_per_pass"):
             traffic = tj["dram_bytes_per_pass"] * cg_passes
-            traffic_src = "imported: ncu --set full capture of the same probe, " + tj.get("source", "profiles/r02_cg_traffic.json")
+            traffic_src = ("imported (not measured in this run): DRAM bytes per matrix pass of the ncu --set full capture of "
+                           "the same stream, " + tj.get("source", "profiles/r02_dmma_traffic.json"))
     # in the job: algorithmic bytes of every ADMM / matrix-free launch of the timed job over the sum of their
     # event-timed durations (per-launch CUDA events on each lane's stream; lanes share the GPU, so a launch's
     # duration includes waiting for SMs held by other lanes' kernels -- a lower bound on the kernels' own rate)
@@ -456,14 +477,24 @@ def main():
     if in_job["achieved_gbs"]:
         in_job["frac"] = in_job["achieved_gbs"] / hbm_peak
     if cg_ms:
-        achieved = cg_bytes_pass * cg_passes / (cg_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        achieved = cg_flop_pass * cg_passes / (cg_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": achieved / dgemm_tf,
                     "traffic": traffic, "traffic_source": traffic_src,
-                    "kernel": "cg_core2_kernel<K> (matrix-free spatpcaCore2: one launch = %d ADMM iterations = %d matrix passes)"
-                              % (roof_admm_iters, cg_passes),
-                    "algorithmic_bytes_per_launch": cg_bytes_pass * cg_passes, "ms_per_launch": cg_ms,
+                    "kernel": "batched_core2_kernel<MT=4> (fold-batched matrix-free spatpcaCore2 on the TMA-fed FP64 DMMA "
+                              "stream: one launch = %d ADMM iterations of %d problems = %d matrix passes)"
+                              % (roof_admm_iters, Mf, cg_passes),
+                    "algorithmic_flop_per_launch": cg_flop_pass * cg_passes, "ms_per_launch": cg_ms,
                     "us_per_matrix_pass": cg_ms * 1e3 / max(cg_passes, 1),
-                    "peak_source": peak_src, "modes": modes, "in_job": in_job}
+                    "us_per_matrix_pass_per_problem": cg_ms * 1e3 / max(cg_passes, 1) / Mf,
+                    "hbm_floor_us_per_single_problem_pass": 8.0 * p * p / (hbm_peak * 1e9) * 1e6,
+                    "hbm_view": {"achieved_gbs": cg_bytes_pass * cg_passes / (cg_ms * 1e-3) / 1e9,
+                                 "frac": cg_bytes_pass * cg_passes / (cg_ms * 1e-3) / 1e9 / hbm_peak},
+                    "peak_source": "FP64 GEMM rate of this run (cuBLAS DGEMM 8192^3); MEASURED_PEAKS.json has no FP64 entry",
+                    "hbm_peak": hbm_peak, "hbm_peak_source": peak_src,
+                    "stream_alone": stream,
+                    "single_problem_fma_kernel": ({"kernel": "cg_core2_kernel<K> (round-2 first cut, FMA stream; the fallback for odd n / K*M > 32)",
+                                                   "us_per_matrix_pass": single_ms * 1e3 / max(single_passes, 1)} if single_ms else None),
+                    "modes": modes, "in_job": in_job}
     else:
         ms_iter = modes["path_systems"]["us_per_iteration"] * 1e-3
         achieved = alg_bytes_iter / (ms_iter * 1e-3) / 1e9
@@ -472,7 +503,6 @@ def main():
                     "algorithmic_bytes_per_launch": alg_bytes_iter * roof_iters, "ms_per_launch": ms_iter * roof_iters,
                     "peak_source": peak_src, "modes": modes, "in_job": in_job}
     # (3) the p^3 work (Omega build, the remaining SPD factorisations) against the FP64 GEMM rate of the same run
-    dgemm_tf = eng_mod.bench_dgemm(8192, 2)
     inv_ms = eng_mod.bench_inverse(p, 2)
     fac_ms = eng_mod.bench_factor(p, 2, m_stage1)
     fac2_ms = eng_mod.bench_factor(p, 2, m_path)

@@ -329,6 +329,10 @@ SPB_API int spb_gamma_loss(const double* Phi, int p, int K,
  * device time per launch (ms, mean of `repeats` after a warm-up) and the p x p matrix passes per launch.      */
 SPB_API int spb_bench_core2_cg(int p, int K, int n_tr, int iters, int repeats, double* ms_per_launch,
                        int* passes_per_launch);
+/* The fold-batched kernel (csrc/batched_cg.cu) on the same synthetic system: F problems of K columns in lock-step,
+ * `iters` forced ADMM iterations; device time per launch and the matrix passes (each serves all F problems).   */
+SPB_API int spb_bench_core2_batched(int p, int n, int K, int F, int iters, int repeats, double* ms_per_launch,
+                            int* passes_per_launch);
 /* Runs `iters` forced iterations on a synthetic p x p system that lives in
  * device memory (identity: the bytes streamed are what matters; the iterate
  * starts from non-orthogonal columns so that every polar step does real

@@ -110,6 +110,7 @@ SIGNATURES = {
     "spb_core2_matrix_free": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                         C.c_double, C.c_double, _dp, _dp, _dp, _ip, _ip]),
     "spb_bench_core2_cg": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _ip]),
+    "spb_bench_core2_batched": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _ip]),
     "spb_dmma_matvec": (C.c_int, [_dp, C.c_int, _dp, C.c_int, _dp]),
     "spb_bench_dmma_matvec": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp]),
     "spb_core2_batched": (C.c_int, [_dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, C.c_int, C.c_int,

@@ -60,7 +60,7 @@ HostGeom make_stream_geom(int p, int nc, int sms, size_t other_smem, size_t smem
   const int CR = 64;
   int NT = ceil_div(ceil_div(p, 8), sms);
   if (NT < 1) NT = 1;
-  SPB_REQUIRE(NT <= (h.MT == 4 ? 10 : 16), "p is too large for the DMMA stream on this device");
+  SPB_REQUIRE(NT <= (h.MT == 4 ? 15 : 16), "p is too large for the DMMA stream on this device");
   h.g.p = p; h.g.NT = NT; h.g.J = 8 * NT;
   h.nblk = ceil_div(p, h.g.J);
   h.g.nchunks = ceil_div(p, CR);
@@ -96,7 +96,7 @@ dmma_matvec_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   uint64_t* empty = full + P.g.NS;
   double* us = reinterpret_cast<double*>(sA);          // aliases the ring: written after the last chunk is consumed
   if (threadIdx.x == 0) {
-    for (int s = 0; s < P.g.NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+    for (int s = 0; s < P.g.NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], S::kConsumers); }
     fence_barrier_init();
   }
   __syncthreads();
@@ -135,8 +135,13 @@ void launch_matvec_instance2(const CUtensorMap& mA, const CUtensorMap& mV, const
 template <int MT>
 void launch_matvec_instance(const CUtensorMap& mA, const CUtensorMap& mV, const MvParams& P, int nblk, size_t smem,
                             cudaStream_t s) {
-  if (P.g.NT <= 10) launch_matvec_instance2<MT, 10>(mA, mV, P, nblk, smem, s);
-  else launch_matvec_instance2<MT, tmx::Shape<MT>::kMaxNT>(mA, mV, P, nblk, smem, s);
+  if constexpr (MT == 4) {     // NTM = column tiles per warp set (3 sets)
+    if (P.g.NT <= 9) launch_matvec_instance2<MT, 3>(mA, mV, P, nblk, smem, s);
+    else launch_matvec_instance2<MT, 5>(mA, mV, P, nblk, smem, s);
+  } else {
+    if (P.g.NT <= 10) launch_matvec_instance2<MT, 10>(mA, mV, P, nblk, smem, s);
+    else launch_matvec_instance2<MT, 16>(mA, mV, P, nblk, smem, s);
+  }
 }
 
 // =============================================================================================
@@ -386,7 +391,7 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   const double rdenom = rsqrt((double)p * (double)K);
 
   if (tid == 0) {
-    for (int s = 0; s < P.g.NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+    for (int s = 0; s < P.g.NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], S::kConsumers); }
     fence_barrier_init();
     st.status = 0; st.cg_done = 0; st.cg_its = 0;
   }
@@ -785,7 +790,7 @@ bool bcg_geometry(int p, int n, int K, int F, BcgHost& o) {
   const int sms = sm_count();
   const int MT = pick_mt(NC);
   const int NT = ceil_div(ceil_div(p, 8), sms);
-  if (NT > (MT == 4 ? 10 : 16)) return false;
+  if (NT > (MT == 4 ? 15 : 16)) return false;
   const size_t cap = smem_cap_for_device();
   const int NTg = ceil_div(ceil_div(p, 8), sms);
   const size_t us_bytes = (size_t)8 * MT * 8 * NTg * sizeof(double);
@@ -899,7 +904,8 @@ void launch_batched_core2(const BatchedCore2Call& c, void* ws, cudaStream_t s) {
       else launch_bcg_instance<2, 16>(mA, mX, mR, mY, mS, P, o.h.nblk, o.smem, s);
       break;
     default:
-      launch_bcg_instance<4, 10>(mA, mX, mR, mY, mS, P, o.h.nblk, o.smem, s);
+      if (NT <= 9) launch_bcg_instance<4, 3>(mA, mX, mR, mY, mS, P, o.h.nblk, o.smem, s);
+      else launch_bcg_instance<4, 5>(mA, mX, mR, mY, mS, P, o.h.nblk, o.smem, s);
       break;
   }
 }

@@ -185,24 +185,21 @@ int spb_spatial_prediction(const double* phi, int p, int K, const double* Y, int
     launch_yphi(dY.get(), n, p, dphi.get(), K, W.get(), scr.get(), s);
     launch_small_gram(W.get(), n, K, 1.0 / (double)n, H.get(), s);                  // phi' cov phi (:729)
     launch_sumsq(dY.get(), (size_t)n * p, scr.get(), ss.get(), s);                  // trace(cov) * n (:731)
-    std::vector<double> Hh((size_t)K * K);
     double ssq = 0.0;
-    SPB_CUDA(cudaMemcpyAsync(Hh.data(), H.get(), sizeof(double) * K * K, cudaMemcpyDeviceToHost, s));
     SPB_CUDA(cudaMemcpyAsync(&ssq, ss.get(), sizeof(double), cudaMemcpyDeviceToHost, s));
     ctx.sync_and_check();
     const double tv = ssq / (double)n;
-    std::vector<double> evals, evecs;
-    host_jacobi_eigh(K, Hh, evals, evecs);
-    const double total = arma_accumulate(evals.data(), K);
-    std::vector<double> dvals(K), Qd((size_t)K * K);
-    for (int c = 0; c < K; ++c) {
-      dvals[c] = evals[K - 1 - c];
-      for (int i = 0; i < K; ++i) Qd[(size_t)c * K + i] = evecs[(size_t)(K - 1 - c) * K + i];
-    }
-    const double err = water_filling(dvals, total, tv, gamma, p, K);               // :734-760
-    std::vector<double> ev(K), Qs((size_t)K * K);
+    // eig_sym + water filling on the device (the one-warp kernel of stage 3, :729-762)
+    DevBuf<double> gdev(1), Qd_dev((size_t)K * K), lam_dev((size_t)K), err_dev(1);
+    SPB_CUDA(cudaMemcpyAsync(gdev.get(), &gamma, sizeof(double), cudaMemcpyHostToDevice, s));
+    launch_gamma_eigen(H.get(), K, tv, p, gdev.get(), 1, Qd_dev.get(), lam_dev.get(), err_dev.get(), nullptr, s);
+    std::vector<double> ev(K), Qd((size_t)K * K), Qs((size_t)K * K);
+    double err = 0.0;
+    SPB_CUDA(cudaMemcpyAsync(ev.data(), lam_dev.get(), sizeof(double) * K, cudaMemcpyDeviceToHost, s));   // :762
+    SPB_CUDA(cudaMemcpyAsync(Qd.data(), Qd_dev.get(), sizeof(double) * K * K, cudaMemcpyDeviceToHost, s));
+    SPB_CUDA(cudaMemcpyAsync(&err, err_dev.get(), sizeof(double), cudaMemcpyDeviceToHost, s));
+    ctx.sync_and_check();
     for (int k = 0; k < K; ++k) {
-      ev[k] = std::max(dvals[k] - (err + gamma), 0.0);                              // :762
       const double ratio = ev[k] / (ev[k] + err);                                   // :763-764
       for (int i = 0; i < K; ++i) Qs[(size_t)k * K + i] = Qd[(size_t)k * K + i] * ratio;
     }
@@ -1040,6 +1037,78 @@ int spb_bench_dmma_matvec(int p, int nc, int repeats, double* ms_per_pass) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *ms_per_pass = sum / repeats;
+  });
+}
+
+int spb_bench_core2_batched(int p, int n, int K, int F, int iters, int repeats, double* ms_per_launch,
+                            int* passes_per_launch) {
+  return guarded([&] {
+    SPB_REQUIRE(p >= 1 && n >= 2 && K >= 1 && F >= 1 && iters >= 1 && repeats >= 1 && ms_per_launch, "invalid argument");
+    SPB_REQUIRE(batched_core2_supported(p, n, K, F), "batched Core2: unsupported problem shape on this device");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    const size_t ld = padded_ld(p), pk = (size_t)p * K;
+    DevBuf<double> om(ld * (size_t)p), dY((size_t)n * p), dYt((size_t)n * p), st(3 * pk * F), Q0(pk);
+    DevBuf<int> dnk(n), dit(F), dstat(2);
+    DevBuf<char> ws(batched_core2_workspace_bytes(p, n, K, F));
+    // the synthetic system of spb_bench_core2_cg: rho = 1, banded Omega_u, random-sign data, cond(A) ~ 1.6
+    SPB_CUDA(cudaMemsetAsync(om.get(), 0, sizeof(double) * ld * p, s));
+    bench_fill_kernel<<<ceil_div((long long)p * p, 256), 256, 0, s>>>(om.get(), ld, p, 0.1, 0.03);
+    bench_sign_kernel<<<ceil_div((long long)n * p, 256), 256, 0, s>>>(dY.get(), (size_t)n * p, std::sqrt(0.05 / ((double)n * p)));
+    count_launch(2);
+    launch_transpose(dY.get(), n, p, dYt.get(), s);
+    std::vector<int> nki(n);
+    for (int r = 0; r < n; ++r) nki[r] = 1 + r % (F > 1 ? F : 2);
+    SPB_CUDA(cudaMemcpyAsync(dnk.get(), nki.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    std::vector<double> q0(pk, 0.0);
+    for (int k = 0; k < K; ++k) {
+      q0[(size_t)k * p + k] = 1.0;
+      if (k + 1 < p) q0[(size_t)k * p + k + 1] = 0.15;
+      if (k + 2 < p) q0[(size_t)k * p + k + 2] = 0.1;
+    }
+    SPB_CUDA(cudaMemcpyAsync(Q0.get(), q0.data(), sizeof(double) * pk, cudaMemcpyHostToDevice, s));
+    SPB_CUDA(cudaStreamSynchronize(s));
+    cudaEvent_t e0, e1;
+    SPB_CUDA(cudaEventCreate(&e0));
+    SPB_CUDA(cudaEventCreate(&e1));
+    double sum_ms = 0.0;
+    int passes = 0;
+    const double tau = 1.0;
+    for (int r = 0; r < repeats + 1; ++r) {
+      for (int f = 0; f < F; ++f) {
+        SPB_CUDA(cudaMemcpyAsync(st.get() + (size_t)f * pk, Q0.get(), sizeof(double) * pk, cudaMemcpyDeviceToDevice, s));
+        SPB_CUDA(cudaMemcpyAsync(st.get() + pk * F + (size_t)f * pk, Q0.get(), sizeof(double) * pk, cudaMemcpyDeviceToDevice, s));
+      }
+      SPB_CUDA(cudaMemsetAsync(st.get() + 2 * pk * F, 0, sizeof(double) * pk * F, s));
+      BatchedCore2Call c;
+      c.omega_u = om.get(); c.ld = ld; c.p = p; c.n = n; c.K = K; c.F = F;
+      c.Y = dY.get(); c.Yt = dYt.get(); c.nk = dnk.get();
+      for (int f = 0; f < 8; ++f) {
+        c.fold_id[f] = (f < F && F > 1) ? f + 1 : 0;
+        c.rho[f] = 1.0;
+        c.Phi[f] = f < F ? st.get() + (size_t)f * pk : nullptr;
+        c.C[f] = f < F ? st.get() + pk * F + (size_t)f * pk : nullptr;
+        c.L2[f] = f < F ? st.get() + 2 * pk * F + (size_t)f * pk : nullptr;
+      }
+      c.nsteps = 1; c.tau1 = &tau; c.maxit = iters; c.tol = -1.0; c.cg_tol = 1e-14; c.cg_cap = 2000;
+      c.snap = nullptr; c.iters_out = dit.get(); c.status_out = dstat.get();
+      SPB_CUDA(cudaEventRecord(e0, s));
+      launch_batched_core2(c, ws.get(), s);
+      SPB_CUDA(cudaEventRecord(e1, s));
+      SPB_CUDA(cudaStreamSynchronize(s));
+      int sth[2], ith[8];
+      SPB_CUDA(cudaMemcpy(sth, dstat.get(), sizeof(sth), cudaMemcpyDeviceToHost));
+      SPB_CUDA(cudaMemcpy(ith, dit.get(), sizeof(int) * F, cudaMemcpyDeviceToHost));
+      if (sth[0] != 0 || ith[0] != iters) throw Error(SPB_ERR_INTERNAL, "bench chain did not run all iterations");
+      passes = sth[1];
+      float ms = 0.f;
+      SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (r > 0) sum_ms += (double)ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_launch = sum_ms / repeats;
+    if (passes_per_launch) *passes_per_launch = passes;
   });
 }
 

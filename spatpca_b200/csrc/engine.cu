@@ -252,86 +252,12 @@ double arma_accumulate(const double* x, int n) {
   return a1 + a2;
 }
 
-void host_jacobi_eigh(int K, std::vector<double>& A, std::vector<double>& evals,
-                      std::vector<double>& evecs) {
-  // cyclic Jacobi on the upper triangle's symmetric completion; eigenvalues ascending.
-  std::vector<double> V((size_t)K * K, 0.0);
-  for (int i = 0; i < K; ++i) V[(size_t)i * K + i] = 1.0;
-  for (int a = 0; a < K; ++a)
-    for (int b = a + 1; b < K; ++b) A[(size_t)a * K + b] = A[(size_t)b * K + a] = A[(size_t)b * K + a];
-  // (col-major: element (a, b) at A[b*K + a]; upper triangle is the source, as dsyevd 'U')
-  for (int sweep = 0; sweep < 100; ++sweep) {
-    bool rotated = false;
-    for (int pp = 0; pp < K - 1; ++pp) {
-      for (int qq = pp + 1; qq < K; ++qq) {
-        double apq = A[(size_t)qq * K + pp], app = A[(size_t)pp * K + pp], aqq = A[(size_t)qq * K + qq];
-        if (apq == 0.0 || std::fabs(apq) <= 1e-17 * std::sqrt(std::fabs(app * aqq))) continue;
-        rotated = true;
-        double theta = (aqq - app) / (2.0 * apq);
-        double t = 1.0 / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-        if (theta < 0) t = -t;
-        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c, tau = s / (1.0 + c);
-        for (int i = 0; i < K; ++i) {
-          if (i != pp && i != qq) {
-            double aip = A[(size_t)pp * K + i], aiq = A[(size_t)qq * K + i];
-            double nip = aip - s * (aiq + tau * aip), niq = aiq + s * (aip - tau * aiq);
-            A[(size_t)pp * K + i] = A[(size_t)i * K + pp] = nip;
-            A[(size_t)qq * K + i] = A[(size_t)i * K + qq] = niq;
-          }
-          double vip = V[(size_t)pp * K + i], viq = V[(size_t)qq * K + i];
-          V[(size_t)pp * K + i] = vip - s * (viq + tau * vip);
-          V[(size_t)qq * K + i] = viq + s * (vip - tau * viq);
-        }
-        A[(size_t)pp * K + pp] = app - t * apq;
-        A[(size_t)qq * K + qq] = aqq + t * apq;
-        A[(size_t)qq * K + pp] = A[(size_t)pp * K + qq] = 0.0;
-      }
-    }
-    if (!rotated) break;
-  }
-  std::vector<int> order(K);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(),
-                   [&](int a, int b) { return A[(size_t)a * K + a] < A[(size_t)b * K + b]; });
-  evals.resize(K);
-  evecs.assign((size_t)K * K, 0.0);
-  for (int c = 0; c < K; ++c) {
-    evals[c] = A[(size_t)order[c] * K + order[c]];
-    for (int i = 0; i < K; ++i) evecs[(size_t)c * K + i] = V[(size_t)order[c] * K + i];
-  }
-}
-
-// flop of one SPD system in the form the job holds it: explicit inverse p^3, m-block U'DU factor p^3/3 + p^3/m + p^3/m^2
 // LU 2/3 + solve for [I; 0] 2 + E Lp 2 + upper half of Lp'(E Lp) 1   (x p^3)
 static double omega_flops(int p) { return (2.0 / 3.0 + 2.0 + 2.0 + 1.0) * (double)p * p * p; }
 static double factor_flops(int p, const Blocking& b) {
   const double p3 = (double)p * p * p;
   if (b.m <= 1) return p3;
   return p3 / 3.0 + p3 / b.m + p3 / ((double)b.m * b.m);
-}
-
-double water_filling(const std::vector<double>& d, double total, double tv, double g, int p, int K) {
-  // noise level of reference :499-519 / :743-760; d = descending eigenvalues of Phi' S Phi
-  int tempL = K;
-  double error;
-  if (d[0] > g) {
-    error = (tv - total + K * g) / (p - tempL);
-    double temp = d[tempL - 1];
-    while (temp - g < error) {
-      if (tempL == 1) {
-        error = (tv - d[0] + g) / (p - 1);
-        break;
-      }
-      total -= d[tempL - 1];
-      tempL--;
-      error = (tv - total + tempL * g) / (p - tempL);
-      temp = d[tempL - 1];
-    }
-    if (d[0] - g < error) error = tv / p;
-  } else {
-    error = tv / p;
-  }
-  return error;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -506,43 +432,42 @@ void Engine::cv_loss(cudaStream_t s, const double* Yva, int m, int p, const doub
   launch_residual_sumsq(Yva, m, p, Phi, K, W, scratch, out_dev, s);
 }
 
+void GammaWork::ensure(int p, int K, int n_tr, int ng) {
+  W.ensure((size_t)n_tr * K);
+  scr.ensure(yphi_scratch_doubles(n_tr, p, K));
+  H.ensure((size_t)K * K);
+  Q.ensure((size_t)K * K);
+  B.ensure((size_t)p * K);
+  lam.ensure((size_t)ng * K);
+  err.ensure((size_t)ng);
+  gscr.ensure(gamma_scratch_doubles(p));
+}
+
+void Engine::gamma_losses_async(cudaStream_t s, GammaWork& w, const double* Phi, int p, int K, const double* Ytr, int n_tr,
+                                double tv, const double* Yva, int n_va, const double* gamma_dev, int ng, double* out_dev) {
+  // stage-3 body for one fold (:489-523), entirely on stream `s`: H = Phi' S_tr Phi through W = Ytr Phi, its
+  // eigen-decomposition + water filling in a one-warp kernel (no host round trip), B = Phi Q, then the covariance
+  // losses of all gammas without ever forming a p x p matrix.
+  w.ensure(p, K, n_tr, ng);
+  launch_yphi(Ytr, n_tr, p, Phi, K, w.W.get(), w.scr.get(), s);
+  launch_small_gram(w.W.get(), n_tr, K, 1.0 / (double)n_tr, w.H.get(), s);
+  launch_gamma_eigen(w.H.get(), K, tv, p, gamma_dev, ng, w.Q.get(), w.lam.get(), w.err.get(), nullptr, s);
+  launch_small_rmul(Phi, p, K, w.Q.get(), w.B.get(), s);
+  for (int g0 = 0; g0 < ng; g0 += kGammaBatch) {
+    const int nb = std::min(kGammaBatch, ng - g0);
+    launch_gamma_loss(Yva, n_va, p, w.B.get(), K, w.lam.get() + (size_t)g0 * K, w.err.get() + g0, nb, w.gscr.get(),
+                      out_dev + g0, s);
+  }
+}
+
 void Engine::gamma_losses(DeviceCtx& ctx, cudaStream_t s, const double* Phi, int p, int K, const double* Ytr,
                           int n_tr, double tv, const double* Yva, int n_va, const std::vector<double>& gamma,
                           double* out_host) {
-  // stage-3 body for one fold (:489-523).  K x K eigen step and water-filling run on the host
-  // (O(K^3)); everything that touches p runs on the device, on stream `s`.
   const int ng = (int)gamma.size();
-  DevBuf<double> W((size_t)n_tr * K), scr(yphi_scratch_doubles(n_tr, p, K)), H((size_t)K * K);
-  launch_yphi(Ytr, n_tr, p, Phi, K, W.get(), scr.get(), s);
-  launch_small_gram(W.get(), n_tr, K, 1.0 / (double)n_tr, H.get(), s);
-  std::vector<double> Hh((size_t)K * K);
-  SPB_CUDA(cudaMemcpyAsync(Hh.data(), H.get(), sizeof(double) * K * K, cudaMemcpyDeviceToHost, s));
-  SPB_CUDA(cudaStreamSynchronize(s));
-  ctx.sync_and_check();
-  std::vector<double> evals, evecs;
-  host_jacobi_eigh(K, Hh, evals, evecs);                 // ascending, like eig_sym (:492)
-  const double total = arma_accumulate(evals.data(), K); // accu(transformed_eigenvalues) (:493)
-  std::vector<double> dvals(K), Qd((size_t)K * K);
-  for (int c = 0; c < K; ++c) {                          // descending order (:494-495)
-    dvals[c] = evals[K - 1 - c];
-    for (int i = 0; i < K; ++i) Qd[(size_t)c * K + i] = evecs[(size_t)(K - 1 - c) * K + i];
-  }
-  std::vector<double> errs(ng), lams((size_t)ng * K);
-  for (int g = 0; g < ng; ++g) {
-    errs[g] = water_filling(dvals, total, tv, gamma[g], p, K);
-    for (int k = 0; k < K; ++k) lams[(size_t)g * K + k] = std::max(dvals[k] - (errs[g] + gamma[g]), 0.0);  // :520
-  }
-  DevBuf<double> Qdev((size_t)K * K), B((size_t)p * K), lam_dev((size_t)ng * K), err_dev((size_t)ng),
-      out_dev((size_t)ng), gscr(gamma_scratch_doubles(p));
-  SPB_CUDA(cudaMemcpyAsync(Qdev.get(), Qd.data(), sizeof(double) * K * K, cudaMemcpyHostToDevice, s));
-  SPB_CUDA(cudaMemcpyAsync(lam_dev.get(), lams.data(), sizeof(double) * ng * K, cudaMemcpyHostToDevice, s));
-  SPB_CUDA(cudaMemcpyAsync(err_dev.get(), errs.data(), sizeof(double) * ng, cudaMemcpyHostToDevice, s));
-  launch_small_rmul(Phi, p, K, Qdev.get(), B.get(), s);
-  for (int g0 = 0; g0 < ng; g0 += kGammaBatch) {
-    const int nb = std::min(kGammaBatch, ng - g0);
-    launch_gamma_loss(Yva, n_va, p, B.get(), K, lam_dev.get() + (size_t)g0 * K, err_dev.get() + g0, nb,
-                      gscr.get(), out_dev.get() + g0, s);
-  }
+  GammaWork w;
+  DevBuf<double> gdev((size_t)ng), out_dev((size_t)ng);
+  SPB_CUDA(cudaMemcpyAsync(gdev.get(), gamma.data(), sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+  gamma_losses_async(s, w, Phi, p, K, Ytr, n_tr, tv, Yva, n_va, gdev.get(), ng, out_dev.get());
   SPB_CUDA(cudaMemcpyAsync(out_host, out_dev.get(), sizeof(double) * ng, cudaMemcpyDeviceToHost, s));
   SPB_CUDA(cudaStreamSynchronize(s));
   ctx.sync_and_check();
@@ -1681,20 +1606,29 @@ void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, 
   // strided list such as [0, 2, 4] with 2 lanes must not put folds 0 and 2 into the same round.
   std::map<int, int> row_of;
   for (int f = 0; f < nfolds; ++f) row_of[folds[f]] = f;
+  if (gamma_dev_.count < (size_t)ng) {
+    gamma_dev_.alloc(ng);
+    SPB_CUDA(cudaMemcpy(gamma_dev_.get(), gamma_.data(), sizeof(double) * ng, cudaMemcpyHostToDevice));
+  }
+  gamma_out_.ensure((size_t)M_ * ng);
   for (const auto& round : lane_rounds(folds, nfolds)) {
     for (int k : round) enqueue_stage3_refit(k, index1, index2);
     for (int k : round) {
-      const int f = row_of[k];
+      // eigen step, water filling and the covariance losses follow the refit on the fold's own stream: no host
+      // synchronisation per fold (round 1 synchronised twice per fold around a host Jacobi solve)
       Lane& L = lane_of(k);
-      flush_lane(L);
       FoldData& fd = folds_[k];
       drop_cached_inverses(fd, -1);
       Scoped sc(L.clock, PH_GAMMA, L.res->stream);
-      gamma_losses(ctx_, L.res->stream, L.chain.Phi.get(), p_, K_, fd.Ytr.get(), fd.n_tr, fd.tv, fd.Yva.get(),
-                   fd.n_va, gamma_, rows + (size_t)f * ng);
+      gamma_losses_async(L.res->stream, L.gwork, L.chain.Phi.get(), p_, K_, fd.Ytr.get(), fd.n_tr, fd.tv, fd.Yva.get(),
+                         fd.n_va, gamma_dev_.get(), ng, gamma_out_.get() + (size_t)k * ng);
+      L.dirty = true;
     }
   }
-  ctx_.sync_and_check();
+  flush();
+  for (int f = 0; f < nfolds; ++f)
+    SPB_CUDA(cudaMemcpy(rows + (size_t)f * ng, gamma_out_.get() + (size_t)folds[f] * ng, sizeof(double) * ng,
+                        cudaMemcpyDeviceToHost));
   stats_.bytes_d2h += (long long)sizeof(double) * ng * nfolds;
 }
 

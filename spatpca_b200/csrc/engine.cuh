@@ -109,6 +109,12 @@ struct FoldData {
   double tv = 0.0;                // trace(Ytr'Ytr) / n_tr
 };
 
+// device temporaries of one stage-3 evaluation (kept per lane so that the work can stay asynchronous)
+struct GammaWork {
+  DevBuf<double> W, scr, H, Q, B, lam, err, gscr;
+  void ensure(int p, int K, int n_tr, int ng);
+};
+
 struct CallRec { int kind, fold, idx, slot, n_tr; };
 // One launch of the fold-batched matrix-free Core2 kernel: its per-(step, problem) iteration counts live in device
 // memory until the next flush.
@@ -136,6 +142,7 @@ struct Lane {
   int next_slot = 0;
   std::vector<CallRec> pending;
   PhaseClock clock;
+  GammaWork gwork;                 // stage-3 temporaries
   cudaEvent_t evt = nullptr;       // ordering between this lane and a batched launch on another stream
   bool dirty = false;              // work enqueued since the last flush
   bool omega_synced = false;       // this lane's stream already waits for the Omega build
@@ -227,7 +234,11 @@ class Engine {
                         std::vector<double>& sv, double* Phi_dev);
   static void cv_loss(cudaStream_t s, const double* Yva, int m, int p, const double* Phi, int K,
                       double* W, double* scratch, double* out_dev);
-  // all-gamma covariance losses of one fold; `out_host` receives n_gamma values
+  // all-gamma covariance losses of one fold, asynchronous on `s`: eigen step and water filling on the device
+  static void gamma_losses_async(cudaStream_t s, GammaWork& w, const double* Phi, int p, int K, const double* Ytr,
+                                 int n_tr, double tv, const double* Yva, int n_va, const double* gamma_dev, int ng,
+                                 double* out_dev);
+  // the same, synchronous: `out_host` receives n_gamma values
   static void gamma_losses(DeviceCtx& ctx, cudaStream_t s, const double* Phi, int p, int K, const double* Ytr,
                            int n_tr, double tv, const double* Yva, int n_va, const std::vector<double>& gamma,
                            double* out_host);
@@ -323,6 +334,7 @@ class Engine {
   bool cache_inverses_ = false;                  // keep the (fold, tau1) inverses of stage 1 for stages 2/3
   int slot_cap_ = 0;
   DevBuf<double> loss_out_;                      // M x max_grid scores, (M+1)-th row = scratch
+  DevBuf<double> gamma_dev_, gamma_out_;         // the gamma grid on the device; M x n_gamma stage-3 losses
   DevBuf<double> prep_scratch_;
   std::vector<int> log_;                         // 4 ints per call
 
@@ -343,9 +355,6 @@ void spd_factor_blocked(const Exec& ex, double* A, int n, size_t ld, double* wor
 double omega_refined_flops(int p);
 
 // small host helpers (host_math.cpp-like, defined in engine.cu)
-void host_jacobi_eigh(int K, std::vector<double>& A /*K x K col-major, destroyed*/,
-                      std::vector<double>& evals, std::vector<double>& evecs);
 double arma_accumulate(const double* x, int n);
-double water_filling(const std::vector<double>& d, double total, double tv, double g, int p, int K);
 
 }  // namespace spb

@@ -180,6 +180,10 @@ void launch_residual_sumsq(const double* Yva, int m, int p, const double* Phi, i
                            const double* W, double* scratch, double* out, cudaStream_t s);
 // H (K x K) <- W' W * alpha
 void launch_small_gram(const double* W, int m, int K, double alpha, double* H, cudaStream_t s);
+// stage-3 eigen step on the device: eig_sym(H) sorted descending, accu(), water-filling `err` and the kept eigenvalues
+// per gamma (reference :492-520); Qd: K x K eigenvectors (descending), lam: ng x K, err: ng, dvals_out: K or nullptr
+void launch_gamma_eigen(const double* H, int K, double tv, int p, const double* gamma_dev, int ng, double* Qd,
+                        double* lam, double* err, double* dvals_out, cudaStream_t s);
 // stage-3 covariance losses for up to SPB_GAMMA_BATCH gammas per launch:
 // out[g] = || Yva'Yva / m - B diag(lam_g) B' - err_g I ||_F^2
 constexpr int kGammaBatch = 16;

@@ -305,6 +305,123 @@ void launch_residual_sumsq(const double* Yva, int m, int p, const double* Phi, i
   SPB_CUDA(cudaGetLastError());
 }
 
+// ---- stage-3 eigen step on the device (reference src/RcppSpatPCA.cpp:492-520, :729-762) ------------------------
+// One warp: cyclic Jacobi eigen-decomposition of H = Phi' S_tr Phi (K x K, upper triangle valid), eigenvalues
+// sorted as the reference does (eig_sym ascending, then reversed), accu() with Armadillo's two interleaved
+// accumulators, and per gamma the water-filling noise level `err` and the kept eigenvalues max(d - (err + gamma), 0).
+// Rotations are applied by lanes i < K; the scalar control flow (thresholds, angles) is uniform.
+namespace {
+__global__ void __launch_bounds__(32)
+gamma_eigen_kernel(const double* __restrict__ H, int K, double tv, int p, const double* __restrict__ gamma, int ng,
+                   double* __restrict__ Qd /* K x K, column c = eigenvector of the c-th LARGEST eigenvalue */,
+                   double* __restrict__ lam /* ng x K */, double* __restrict__ err /* ng */,
+                   double* __restrict__ dvals_out /* K, descending (may be nullptr) */) {
+  __shared__ double A[SPB_MAX_K * SPB_MAX_K], V[SPB_MAX_K * SPB_MAX_K], d[SPB_MAX_K];
+  __shared__ int order[SPB_MAX_K];
+  const int lane = threadIdx.x;
+  for (int e = lane; e < K * K; e += 32) {
+    const int i = e % K, j = e / K;                       // col-major (i, j); the upper triangle is the source
+    A[e] = (i <= j) ? H[(size_t)j * K + i] : H[(size_t)i * K + j];
+    V[e] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    bool rotated = false;
+    for (int pp = 0; pp < K - 1; ++pp) {
+      for (int qq = pp + 1; qq < K; ++qq) {
+        const double apq = A[qq * K + pp], app = A[pp * K + pp], aqq = A[qq * K + qq];
+        if (apq == 0.0 || fabs(apq) <= 1e-17 * sqrt(fabs(app * aqq))) continue;
+        rotated = true;
+        const double theta = (aqq - app) / (2.0 * apq);
+        double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+        if (theta < 0.0) t = -t;
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c, tau = sn / (1.0 + c);
+        double aip = 0.0, aiq = 0.0, vip = 0.0, viq = 0.0;
+        if (lane < K) {
+          aip = A[pp * K + lane]; aiq = A[qq * K + lane];
+          vip = V[pp * K + lane]; viq = V[qq * K + lane];
+        }
+        __syncwarp();
+        if (lane < K) {
+          if (lane != pp && lane != qq) {
+            const double nip = aip - sn * (aiq + tau * aip), niq = aiq + sn * (aip - tau * aiq);
+            A[pp * K + lane] = nip; A[lane * K + pp] = nip;
+            A[qq * K + lane] = niq; A[lane * K + qq] = niq;
+          }
+          V[pp * K + lane] = vip - sn * (viq + tau * vip);
+          V[qq * K + lane] = viq + sn * (vip - tau * viq);
+        }
+        if (lane == 0) {
+          A[pp * K + pp] = app - t * apq;
+          A[qq * K + qq] = aqq + t * apq;
+          A[qq * K + pp] = 0.0; A[pp * K + qq] = 0.0;
+        }
+        __syncwarp();
+      }
+    }
+    if (!rotated) break;
+  }
+  // stable ascending order of the eigenvalues, then reversed (:494-495)
+  if (lane == 0) {
+    for (int i = 0; i < K; ++i) order[i] = i;
+    for (int i = 1; i < K; ++i) {                          // insertion sort: stable
+      const int o = order[i];
+      const double v = A[o * K + o];
+      int j = i - 1;
+      while (j >= 0 && A[order[j] * K + order[j]] > v) { order[j + 1] = order[j]; --j; }
+      order[j + 1] = o;
+    }
+  }
+  __syncwarp();
+  if (lane < K) d[lane] = A[order[K - 1 - lane] * K + order[K - 1 - lane]];          // descending
+  for (int e = lane; e < K * K; e += 32) {
+    const int i = e % K, c = e / K;
+    Qd[e] = V[order[K - 1 - c] * K + i];
+  }
+  __syncwarp();
+  if (dvals_out != nullptr && lane < K) dvals_out[lane] = d[lane];
+  // accu(transformed_eigenvalues) over the ASCENDING vector with two interleaved accumulators (:493)
+  double total;
+  {
+    double a1 = 0.0, a2 = 0.0;
+    int i = 0, j = 1;
+    for (; j < K; j += 2, i += 2) { a1 += d[K - 1 - i]; a2 += d[K - 1 - (i + 1)]; }
+    if ((j - 1) < K) a1 += d[K - 1 - i];
+    total = a1 + a2;
+  }
+  for (int g = lane; g < ng; g += 32) {
+    const double gm = gamma[g];
+    // water filling (:499-519 / :743-760)
+    int tempL = K;
+    double tot = total, e;
+    if (d[0] > gm) {
+      e = (tv - tot + K * gm) / (p - tempL);
+      double temp = d[tempL - 1];
+      while (temp - gm < e) {
+        if (tempL == 1) { e = (tv - d[0] + gm) / (p - 1); break; }
+        tot -= d[tempL - 1];
+        tempL--;
+        e = (tv - tot + tempL * gm) / (p - tempL);
+        temp = d[tempL - 1];
+      }
+      if (d[0] - gm < e) e = tv / p;
+    } else {
+      e = tv / p;
+    }
+    err[g] = e;
+    for (int k = 0; k < K; ++k) lam[(size_t)g * K + k] = fmax(d[k] - (e + gm), 0.0);                  // :520
+  }
+}
+}  // namespace
+
+void launch_gamma_eigen(const double* H, int K, double tv, int p, const double* gamma_dev, int ng, double* Qd,
+                        double* lam, double* err, double* dvals_out, cudaStream_t s) {
+  SPB_REQUIRE(K >= 1 && K <= SPB_MAX_K, "K must be in 1..SPB_MAX_K");
+  gamma_eigen_kernel<<<1, 32, 0, s>>>(H, K, tv, p, gamma_dev, ng, Qd, lam, err, dvals_out);
+  count_launch();
+  SPB_CUDA(cudaGetLastError());
+}
+
 void launch_small_gram(const double* W, int m, int K, double alpha, double* H, cudaStream_t s) {
   small_gram_kernel<<<1, kT, 0, s>>>(W, m, K, alpha, H);
   count_launch();

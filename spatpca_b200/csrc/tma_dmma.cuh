@@ -46,8 +46,12 @@ struct Shape {
   static constexpr int NBX = CR / 16;                    // TMA boxes (16 rows) per chunk and operand
   static constexpr int NCP = 8 * MT;                     // vectors, padded
   static constexpr bool kDedicatedProducer = (MT < 4);
-  static constexpr int kThreads = 32 * (kConsumerWarps + (kDedicatedProducer ? 1 : 0));
-  static constexpr int kMaxNT = (MT == 4) ? 10 : 16;     // column tiles (of 8) per CTA
+  // MT = 4 (FP64-tensor-bound): 12 consumer warps = 4 row-group pairs x 3 column-tile sets, 3 warps per scheduler
+  // (ncu on the 8-warp version: DMMA pipe 62 % busy, 38 % of the stall samples `wait`, i.e. too few warps to cover
+  // the fixed issue latency of back-to-back DMMAs); lane 0 of warp 0 doubles as the TMA producer.
+  static constexpr int kConsumers = (MT == 4) ? 12 : kConsumerWarps;
+  static constexpr int kThreads = 32 * (kConsumers + (kDedicatedProducer ? 1 : 0));
+  static constexpr int kMaxNT = (MT == 4) ? 15 : 16;     // column tiles (of 8) per CTA
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -148,6 +152,83 @@ __device__ __noinline__ void dmma_stream_pass(const CUtensorMap* mapA, const CUt
     }
     const int g = lane >> 2, t = lane & 3;
     const int pg = perm8(g);
+    if constexpr (MT == 4) {
+      // warp = (row-group pair hq, column-tile set ns): row groups 2 hq and 2 hq + 1 of every chunk (= the two halves
+      // of TMA box hq), column tiles [ns * NTM, ns * NTM + NTM) of the CTA's NT, all 4 vector tiles
+      const int ns = warp % 3, hq = warp / 3;
+      const int nt0 = ns * NTM;
+      const uint32_t swz0 = (uint32_t)((t ^ pg) << 4), swz1 = (uint32_t)(((4 | t) ^ pg) << 4);
+      const uint32_t baseA = (uint32_t)hq * 128u * (uint32_t)S::NCP + (uint32_t)pg * 128u;
+      const uint32_t baseB = (uint32_t)hq * 128u * (uint32_t)G.J + (uint32_t)(nt0 * 8 + pg) * 128u;
+      double acc[4][NTM][2];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int q = 0; q < NTM; ++q) { acc[mt][q][0] = 0.0; acc[mt][q][1] = 0.0; }
+      unsigned int cit = it;
+      for (int c = 0; c < G.nchunks; ++c, ++cit) {
+        if (producer && c + D < G.nchunks) issue(c + D);
+        __syncwarp();
+        const int stage = cit % G.NS;
+        const uint32_t phase = (cit / G.NS) & 1;
+        mbar_wait(&full[stage], phase);
+        const unsigned char* va = sV + (size_t)stage * G.stageV + baseA;
+        const unsigned char* ba = sA + (size_t)stage * G.stageA + baseB;
+        double2 a0[4], a1[4], b0[NTM], b1[NTM];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          a0[mt] = *reinterpret_cast<const double2*>(va + (size_t)mt * 1024 + swz0);
+          a1[mt] = *reinterpret_cast<const double2*>(va + (size_t)mt * 1024 + swz1);
+        }
+#pragma unroll
+        for (int q = 0; q < NTM; ++q)
+          if (nt0 + q < G.NT) {
+            b0[q] = *reinterpret_cast<const double2*>(ba + (size_t)q * 1024 + swz0);
+            b1[q] = *reinterpret_cast<const double2*>(ba + (size_t)q * 1024 + swz1);
+          }
+        // four rounds over the warp's 4 x NTM accumulators: dependent MMAs are 4 * NTM apart
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int q = 0; q < NTM; ++q)
+            if (nt0 + q < G.NT) dmma(acc[mt][q][0], acc[mt][q][1], a0[mt].x, b0[q].x);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int q = 0; q < NTM; ++q)
+            if (nt0 + q < G.NT) dmma(acc[mt][q][0], acc[mt][q][1], a0[mt].y, b0[q].y);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int q = 0; q < NTM; ++q)
+            if (nt0 + q < G.NT) dmma(acc[mt][q][0], acc[mt][q][1], a1[mt].x, b1[q].x);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int q = 0; q < NTM; ++q)
+            if (nt0 + q < G.NT) dmma(acc[mt][q][0], acc[mt][q][1], a1[mt].y, b1[q].y);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+      }
+      // ---- sum the 4 row-group pairs of every tile in hq order (fixed shape) ----
+      for (int hh = 0; hh < 4; ++hh) {
+        __syncthreads();
+        if (hq == hh) {
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            double* urow = us + (size_t)(mt * 8 + pg) * G.J + t;
+#pragma unroll
+            for (int q = 0; q < NTM; ++q) {
+              if (nt0 + q < G.NT) {
+                double* o = urow + (nt0 + q) * 8;
+                if (hh == 0) { o[0] = acc[mt][q][0]; o[4] = acc[mt][q][1]; }
+                else { o[0] += acc[mt][q][0]; o[4] += acc[mt][q][1]; }
+              }
+            }
+          }
+        }
+      }
+    } else {
     const int box = warp >> 1;                               // row group `warp` of the chunk: box, half of its 16 rows
     const int x = ((warp & 1) << 2) | t;                     // 16-byte chunk (row pair) inside the box's lines
     const uint32_t sw = (uint32_t)((x ^ pg) << 4);
@@ -176,7 +257,6 @@ __device__ __noinline__ void dmma_stream_pass(const CUtensorMap* mapA, const CUt
       for (int nt = 0; nt < NTM; ++nt)
         if (nt < G.NT) b[nt] = *reinterpret_cast<const double2*>(ba + (size_t)nt * 1024);
       // the x halves of all tile pairs first, then the y halves: dependent MMAs on one accumulator are MT * NT apart
-      // (loading the column tiles in two halves to save fragment registers was measured: 270 -> 340 us per pass)
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -208,6 +288,7 @@ __device__ __noinline__ void dmma_stream_pass(const CUtensorMap* mapA, const CUt
           }
         }
       }
+    }
     }
   }
   it += (unsigned int)G.nchunks;

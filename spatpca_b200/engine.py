@@ -347,6 +347,14 @@ def bench_core2_cg(p, K, n_tr, iters, repeats=3):
     return float(out[0]), ps.value
 
 
+def bench_core2_batched(p, n, K, F, iters, repeats=3):
+    lib = _lib.load()
+    out = np.zeros(1)
+    ps = C.c_int(0)
+    check(lib.spb_bench_core2_batched(int(p), int(n), int(K), int(F), int(iters), int(repeats), ptr(out), C.byref(ps)))
+    return float(out[0]), ps.value
+
+
 def dmma_matvec(A, V):
     """U = A V on the TMA-fed DMMA stream (A symmetric p x p, V p x nc, nc <= 32)."""
     lib = _lib.load()
