@@ -57,9 +57,14 @@ BEGIN_RCPP
   // shapes of the reference's return value (:600/:649, :668/:679, :692, :697)
   NumericMatrix cv1(1, n1 > 1 ? n1 : 1), cv2(1, n2 > 1 ? n2 : 1), cv3(1, n3), eigenfn(p, K);
   double sel[3] = {0, 0, 0};
-  check(spb_cv(sxy.begin(), p, d, Y.begin(), n, M, K, tau1.begin(), n1, tau2.begin(), n2, gamma.begin(), n3,
-               nk.begin(), maxit, tol, l2.begin(), (int)l2.size(), cv1.begin(), cv2.begin(), cv3.begin(),
-               eigenfn.begin(), sel, NULL));
+  // spb_cv_session, not the stateless spb_cv: R's K-selection loop (R/SpatPCA.R:35-39) calls this entry for
+  // K = 1, 2, ... on the SAME data and grids, and the session keeps Omega, the fold SVD starts and the K-independent
+  // factorisations between such calls.  The session is keyed by the CONTENT of every argument except K (data,
+  // locations, fold ids, the three grids and their lengths, maxit, tol), so a call with anything else rebuilds;
+  // results are bitwise those of spb_cv (tests/test_gpu_parity.py::test_session_reuse_is_bitwise_identical).
+  check(spb_cv_session(sxy.begin(), p, d, Y.begin(), n, M, K, tau1.begin(), n1, tau2.begin(), n2, gamma.begin(), n3,
+                       nk.begin(), maxit, tol, l2.begin(), (int)l2.size(), cv1.begin(), cv2.begin(), cv3.begin(),
+                       eigenfn.begin(), sel, NULL));
   return List::create(Named("cv_score_tau1") = cv1, Named("cv_score_tau2") = cv2, Named("cv_score_gamma") = cv3,
                       Named("estimated_eigenfn") = eigenfn, Named("selected_tau1") = sel[0],
                       Named("selected_tau2") = sel[1], Named("selected_gamma") = sel[2]);
@@ -94,4 +99,11 @@ static const R_CallMethodDef CallEntries[] = {
 RcppExport void R_init_SpatPCA(DllInfo* dll) {
   R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
   R_useDynamicSymbols(dll, FALSE);
+}
+
+// library.dynam.unload(): give the session's device memory (Omega, cached factors) back before the DLL goes away
+RcppExport void R_unload_SpatPCA(DllInfo* dll) {
+  (void)dll;
+  spb_session_clear();
+  spb_trim_memory();
 }

@@ -11,6 +11,8 @@
 #include <stdexcept>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/spatpca_b200.h"
 
 namespace spb {
@@ -92,6 +94,15 @@ struct DevBuf {
   void release() { if (ptr) { cached_free(ptr, count * sizeof(T)); ptr = nullptr; count = 0; } }
   T* get() const { return ptr; }
   operator T*() const { return ptr; }
+};
+
+// NVTX range for the host-side span that ENQUEUES a stage (tracing); shows up in nsys / ncu
+// timelines next to the kernels it launched.  Header-only NVTX3: no link dependency, a no-op without a tool attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 // Kernel-launch counter (claimed in bench.py as `gpu_launches`): only launches of

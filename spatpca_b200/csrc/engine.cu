@@ -270,6 +270,7 @@ bool Engine::omega_refine_enabled() {
 
 void Engine::build_omega_raw(OmegaRes& R, int* flag, const double* x_dev, int p, int d, double* omega_dev,
                              size_t ld, bool upper_only, OmegaTemps& tmp) {
+  NvtxRange nvtx_range("spb::thinPlateSplineMatrix");
   if (omega_refine_enabled()) {
     build_omega_refined(R, flag, x_dev, p, d, omega_dev, ld, upper_only, tmp);
     return;
@@ -728,6 +729,7 @@ void Engine::init_lambda(cudaStream_t s, const double* Phi, const std::vector<do
 }
 
 void Engine::prepare() {
+  NvtxRange nvtx_range("spb::prepare (SVD start, Omega build enqueue)");
   SPB_REQUIRE(dY_.get() != nullptr, "upload() must be called before prepare()");
   trace(ctx_, "prepare: enter");
   cudaStream_t s = ctx_.stream;
@@ -913,6 +915,7 @@ void Engine::get_omega(double* out) {
 }
 
 void Engine::fold_prepare(int k) {
+  NvtxRange nvtx_range("spb::fold_prepare (gather, SVD start)");
   FoldData& f = folds_[k];
   if (f.prepared) return;
   trace(ctx_, "fold_prepare: enter");
@@ -1364,6 +1367,7 @@ void Engine::enqueue_stage1(int k, int step) {
 }
 
 void Engine::stage1_folds(const int* folds, int nfolds, double* rows) {
+  NvtxRange nvtx_range("spb::stage1_folds (tau1 paths)");
   SPB_REQUIRE(full_ready_, "prepare() must be called first");
   SPB_REQUIRE(folds != nullptr && nfolds >= 0, "invalid fold list");
   for (int f = 0; f < nfolds; ++f) SPB_REQUIRE(folds[f] >= 0 && folds[f] < M_, "fold index out of range");
@@ -1408,6 +1412,7 @@ void Engine::stage1_folds(const int* folds, int nfolds, double* rows) {
 }
 
 void Engine::stage1_full(int index1) {
+  NvtxRange nvtx_range("spb::stage1_full");
   SPB_REQUIRE(full_ready_, "prepare() must be called first");
   const int n1 = (int)tau1_.size();
   const double max_tau2 = *std::max_element(tau2_.begin(), tau2_.end());
@@ -1488,6 +1493,7 @@ void Engine::enqueue_stage2(int k, int index1, int step) {
 }
 
 void Engine::stage2_folds(const int* folds, int nfolds, int index1, double* rows) {
+  NvtxRange nvtx_range("spb::stage2_folds (tau2 paths)");
   const int n2 = (int)tau2_.size();
   if (n2 <= 1) return;
   SPB_REQUIRE(folds != nullptr && nfolds >= 0, "invalid fold list");
@@ -1547,6 +1553,7 @@ double* Engine::full_tempinv(int index1) {
 }
 
 void Engine::stage2_full(int index1, int index2) {
+  NvtxRange nvtx_range("spb::stage2_full");
   const int n2 = (int)tau2_.size();
   const double sel1 = selected_tau1(index1);
   const std::vector<double>* path = nullptr;
@@ -1595,6 +1602,7 @@ void Engine::enqueue_stage3_refit(int k, int index1, int index2) {
 }
 
 void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, double* rows) {
+  NvtxRange nvtx_range("spb::stage3_folds (gamma losses)");
   SPB_REQUIRE(folds != nullptr && nfolds >= 0 && rows != nullptr, "invalid fold list");
   for (int f = 0; f < nfolds; ++f) {
     SPB_REQUIRE(folds[f] >= 0 && folds[f] < M_, "fold index out of range");
