@@ -127,6 +127,11 @@ int spb_tps_matrix(const double* location, int p, int d, double* omega_out) {
     OmegaTemps tmp;
     Engine::build_omega_raw(R, ctx.flag.get(), x.get(), p, d, om.get(), ld, false, tmp);   // the full raw product (:75)
     SPB_CUDA(cudaStreamSynchronize(R.stream));
+    if (Engine::omega_refine_enabled() && !omega_build_ok(tmp)) {      // SPD route to X0 broke down: pivoted LU
+      tmp.force_lu = true;
+      Engine::build_omega_raw(R, ctx.flag.get(), x.get(), p, d, om.get(), ld, false, tmp);
+      SPB_CUDA(cudaStreamSynchronize(R.stream));
+    }
     download_square(omega_out, p, om.get(), ld, ctx.stream);
     ctx.sync_and_check();
   });

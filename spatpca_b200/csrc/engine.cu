@@ -622,7 +622,8 @@ void Engine::upload(const double* sxy, const double* Y, const double* nk) {
     std::vector<int> nki(n_);
     for (int r = 0; r < n_; ++r) nki[r] = (int)nk[r];
     dNk_.alloc(n_);
-    SPB_CUDA(cudaMemcpy(dNk_.get(), nki.data(), sizeof(int) * n_, cudaMemcpyHostToDevice));
+    SPB_CUDA(cudaMemcpyAsync(dNk_.get(), nki.data(), sizeof(int) * n_, cudaMemcpyHostToDevice, ctx_.stream));
+    SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
   }
   SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
   stats_.bytes_h2d += (long long)sizeof(double) * ((size_t)n_ * p_ + (size_t)p_ * d_ + n_);
@@ -787,14 +788,26 @@ void Engine::prepare() {
 }
 
 void Engine::wait_omega(Lane& L) {
-  if (!omega_pending_ || L.omega_synced) return;
-  SPB_CUDA(cudaStreamWaitEvent(L.res->stream, omega_evt_, 0));
-  L.omega_synced = true;
+  // The first consumer of Omega waits for the build on the HOST (it is on the critical path anyway) so that the
+  // result can be checked -- and rebuilt by the LU route if the SPD route broke down -- before anything reads it.
+  finish_omega();
 }
 
 void Engine::finish_omega() {
   if (!omega_pending_) return;
-  SPB_CUDA(cudaStreamSynchronize(ctx_.omega().stream));
+  OmegaRes& R = ctx_.omega();
+  SPB_CUDA(cudaStreamSynchronize(R.stream));
+  if (omega_tmp_ && omega_refine_enabled() && !omega_build_ok(*omega_tmp_)) {
+    // the SPD route to X0 broke down in FP64 (cond(B) ~ 1e11, e.g. one-dimensional sites): rebuild with the pivoted LU
+    omega_tmp_->force_lu = true;
+    build_omega_raw(R, ctx_.flag.get(), dX_.get(), p_, d_, omega_u_.get(), ld_, true, *omega_tmp_);
+    SPB_CUDA(cudaMemcpy2DAsync(omega_diag_raw_.get(), sizeof(double), omega_u_.get(), (ld_ + 1) * sizeof(double),
+                               sizeof(double), p_, cudaMemcpyDeviceToDevice, R.stream));
+    launch_symmatu_inplace(omega_u_.get(), p_, ld_, 1e-8, R.stream);
+    lmax_ = -1.0;
+    enqueue_lmax(R.stream, R.blas);
+    SPB_CUDA(cudaStreamSynchronize(R.stream));
+  }
   omega_tmp_.reset();
   omega_pending_ = false;
 }
@@ -837,6 +850,7 @@ void Engine::omega_solve_cols(int c0, int c1) {
   OmegaRes& R = ctx_.omega();
   const int q = p_ + d_ + 1;
   const size_t ldq = padded_ld(q);
+  if (omega_refine_enabled() && omega_x0_is_spd_) return;   // X0 was built whole by omega_begin()
   if (omega_refine_enabled() && c1 == p_) c1 = q;       // refined build: the last block's owner also solves the border columns
   if (c0 == c1) return;
   clock_.begin(PH_OMEGA, R.stream);
@@ -877,6 +891,7 @@ void* Engine::omega_buffer(int which, int c0, int c1, long long* bytes) {
   if (which == 0 || which == 2) {
     const bool refined = omega_refine_enabled();
     if (which == 2 && !refined) { if (bytes) *bytes = 0; return nullptr; }
+    if (which == 0 && refined && omega_x0_is_spd_) { if (bytes) *bytes = 0; return nullptr; }   // replicated
     const int c1e = (refined && c1 == p_) ? p_ + d_ + 1 : c1;
     if (bytes) *bytes = (long long)((size_t)(c1e - c0) * ldq * sizeof(double));
     return (which == 0 ? omega_tmp_->Bm.get() : omega_tmp_->C2.get()) + (size_t)c0 * ldq;
@@ -1615,8 +1630,12 @@ void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, 
   std::map<int, int> row_of;
   for (int f = 0; f < nfolds; ++f) row_of[folds[f]] = f;
   if (gamma_dev_.count < (size_t)ng) {
+    // stream-ordered copy + wait: a plain cudaMemcpy from pageable memory returns once the data is STAGED, and the
+    // lanes' non-blocking streams do not synchronise with the legacy stream -- the one-warp eigen kernel then read
+    // the recycled buffer's previous contents now and then (found as a flaky last-gamma score in test_cv_branches)
     gamma_dev_.alloc(ng);
-    SPB_CUDA(cudaMemcpy(gamma_dev_.get(), gamma_.data(), sizeof(double) * ng, cudaMemcpyHostToDevice));
+    SPB_CUDA(cudaMemcpyAsync(gamma_dev_.get(), gamma_.data(), sizeof(double) * ng, cudaMemcpyHostToDevice, ctx_.stream));
+    SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
   }
   gamma_out_.ensure((size_t)M_ * ng);
   for (const auto& round : lane_rounds(folds, nfolds)) {

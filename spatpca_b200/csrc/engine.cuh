@@ -41,7 +41,10 @@ struct OmegaRes {
 // temporaries of one build; must outlive the enqueued work
 struct OmegaTemps {
   DevBuf<double> L, Bm, T1;
-  DevBuf<double> C1, C2, vec;     // refined build only (omega_refine.cu)
+  DevBuf<double> C1, C2, vec, hh, resid;   // refined build only (omega_refine.cu)
+  DevBuf<int> spdflag;            // failure flag of the SPD route to X0
+  bool force_lu = false;          // take the LU route to X0 (the fallback after a failed SPD route)
+  bool used_spd = false;
 };
 
 // Per-thread, per-device CUDA context (stream + library handles + solver workspaces).
@@ -312,6 +315,7 @@ class Engine {
   cudaEvent_t omega_evt_ = nullptr;
   std::unique_ptr<OmegaTemps> omega_tmp_;
   bool omega_cols_open_ = false;                 // between omega_begin() and omega_finish()
+  bool omega_x0_is_spd_ = false;                 // column build: X0 came from the SPD route (replicated, no first exchange)
   bool omega_begin_refined();
   void omega_product_cols_refined(int c0, int c1);
   void wait_omega(Lane& L);                      // first use of Omega on a lane: wait for the build
@@ -353,6 +357,9 @@ void gemm_upper_tn(cublasHandle_t blas, int n, int k, double alpha, const double
 void spd_factor_blocked(const Exec& ex, double* A, int n, size_t ld, double* workspace, const Blocking& blk);
 
 double omega_refined_flops(int p);
+bool omega_x0_spd_enabled(int p, int d);   // X0 of the refined Omega build through the SPD part of the system (no LU)
+void omega_x0_spd(OmegaRes& R, const double* x_dev, int p, int d, double* Pbuf, double* X0, double* inv_ws, OmegaTemps& tmp);
+bool omega_build_ok(OmegaTemps& tmp);      // host check after the build has been waited for (SPD route held, residual small)
 
 // small host helpers (host_math.cpp-like, defined in engine.cu)
 double arma_accumulate(const double* x, int n);

@@ -22,7 +22,10 @@
 //
 // Flop count: LU 2/3 + solve 2 + residual 6 + correction 1 + product 1 = 10.7 p^3 (the unrefined pipeline: 5.7).
 // What remains between this path and the oracle is the ORACLE's own rounding error.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <string>
 
 #include "engine.cuh"
 
@@ -106,6 +109,92 @@ __global__ void __launch_bounds__(128) unit_cols_kernel(double* __restrict__ C, 
   }
 }
 
+// ---- X0 through the symmetric positive definite part of the bordered system ---------------------------------
+// v = Householder vector j of a geqrf-factored p x m matrix: zeros above row j, 1 at row j, the stored tail below
+__global__ void hh_vector_kernel(const double* __restrict__ V, size_t ldv, int p, int j, double* __restrict__ v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p) return;
+  v[i] = i < j ? 0.0 : (i == j ? 1.0 : V[(size_t)j * ldv + i]);
+}
+
+// Two-sided reflector H = I - tau v v' on a symmetric matrix P:  H P H = P - tau (v u' + u v'),  u = w - (tau alpha / 2) v,
+// w = P v, alpha = v'w.  One CTA: alpha, then u and vt = -tau v  (so that P += vt u' + u vt' is one dsyr2 with alpha = 1).
+__global__ void __launch_bounds__(1024) hh_prep_kernel(const double* __restrict__ v, const double* __restrict__ w,
+                                                       const double* __restrict__ tau, int p, double* __restrict__ u,
+                                                       double* __restrict__ vt) {
+  __shared__ double red[32];
+  __shared__ double alpha_s;
+  double t = 0.0;
+  for (int i = threadIdx.x; i < p; i += 1024) t = fma(v[i], w[i], t);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double x = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (threadIdx.x == 0) alpha_s = x;
+  }
+  __syncthreads();
+  const double tj = *tau;
+  const double c = 0.5 * tj * alpha_s;
+  for (int i = threadIdx.x; i < p; i += 1024) {
+    u[i] = w[i] - c * v[i];
+    vt[i] = -tj * v[i];
+  }
+}
+
+// The 2m x 2m Schur complement of the rotated bordered system and its inverse (one thread; m <= 4):
+//   S = [[F11 - C, R], [R', eps I]],  F11 = rotated block (upper valid, ridge included), C = F12 B^-1 F21, R = upper
+//   triangular factor of T.  Xs = S^-1 by Gauss-Jordan with partial pivoting.  Xs: 2m x 2m, column-major, ld 2m.
+__global__ void schur_small_kernel(const double* __restrict__ F, size_t ldf, const double* __restrict__ Cm,
+                                   const double* __restrict__ Rm, size_t ldr, int m, double eps, double* __restrict__ Xs,
+                                   int* __restrict__ flag, int code) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int n = 2 * m;
+  double A[8][16];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < 2 * n; ++j) A[i][j] = (j == n + i) ? 1.0 : 0.0;
+  for (int a = 0; a < m; ++a)
+    for (int b = 0; b < m; ++b) {
+      const double f = (a <= b) ? F[(size_t)b * ldf + a] : F[(size_t)a * ldf + b];
+      A[a][b] = f - Cm[(size_t)b * m + a];
+      const double r = (a <= b) ? Rm[(size_t)b * ldr + a] : 0.0;       // R upper triangular
+      A[a][m + b] = r;
+      A[m + b][a] = r;
+      A[m + a][m + b] = (a == b) ? eps : 0.0;
+    }
+  bool bad = false;
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r)
+      if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+    if (!(fabs(A[piv][c]) > 0.0)) { bad = true; break; }
+    if (piv != c)
+      for (int j = 0; j < 2 * n; ++j) { const double t = A[c][j]; A[c][j] = A[piv][j]; A[piv][j] = t; }
+    const double inv = 1.0 / A[c][c];
+    for (int j = 0; j < 2 * n; ++j) A[c][j] *= inv;
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      const double f = A[r][c];
+      if (f != 0.0)
+        for (int j = 0; j < 2 * n; ++j) A[r][j] = fma(-f, A[c][j], A[r][j]);
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) Xs[(size_t)j * n + i] = A[i][n + j];
+  if (bad && *flag == 0) *flag = code;
+}
+
+// dst (rows x cols, ldd) <- alpha * src (rows x cols, lds)
+__global__ void __launch_bounds__(128) scaled_copy2d_kernel(const double* __restrict__ src, size_t lds, int rows, int cols,
+                                                            double alpha, double* __restrict__ dst, size_t ldd) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= rows) return;
+  for (int j = blockIdx.y; j < cols; j += gridDim.y) dst[(size_t)j * ldd + i] = alpha * src[(size_t)j * lds + i];
+}
+
 int split_bits(int q) {
   int lg = 0;
   while ((1 << lg) < q) ++lg;
@@ -114,7 +203,119 @@ int split_bits(int q) {
 
 }  // namespace
 
-double omega_refined_flops(int p) { return (2.0 / 3.0 + 2.0 + 6.0 + 1.0 + 1.0) * (double)p * p * p; }
+// X0 = A^-1 (q x q, symmetric, full storage) WITHOUT a pivoted LU.  The TPS kernels are conditionally positive definite
+// (order 2 for r^3 and r^2 log r, order 1 for -r; T = [1 X] spans the polynomials they exclude), so in an orthonormal
+// basis Q = [Q1 Q2] with span(Q1) = span(T) the block B = Q2'(E + eps I)Q2 is symmetric POSITIVE DEFINITE and carries
+// all the p^3 work: it goes through the GEMM-rate recursive SPD inverse of spd_inverse.cu (p^3 flop at ~24 TFLOP/s:
+// 42 ms at p = 10 000) instead of cuSOLVER getrf + getrs (2.7 p^3 at 10 / 25 TFLOP/s: 145 ms).  Q is three Householder
+// reflectors (QR of T), applied to the symmetric matrix as rank-2 updates (O(p^2) each); the rest of the bordered
+// system is a 2m x 2m Schur complement (m = d + 1), solved in a one-thread kernel.  cond(B) ~ |E| / eps, the same class
+// as the bordered system, so X0 is as good a starting point for the Newton-Schulz step as the LU's (the step, with its
+// exactly formed residual against A ITSELF, is what fixes the accuracy either way).  Pbuf: q x q work (destroyed).
+void omega_x0_spd(OmegaRes& R, const double* x_dev, int p, int d, double* Pbuf, double* X0, double* inv_ws,
+                  OmegaTemps& tmp) {
+  const int m = d + 1, q = p + m, pm = p - m, n2 = 2 * m;
+  // failures of this route (a non-positive pivot: B is positive definite in exact arithmetic, but with cond(B) ~ 1e11
+  // -- one-dimensional sites -- rounding can break it) go to a flag of their own: the caller then falls back to the LU
+  tmp.spdflag.ensure(4);
+  int* flag = tmp.spdflag.get();
+  SPB_CUDA(cudaMemsetAsync(flag, 0, 4 * sizeof(int), R.stream));
+  const size_t ldq = padded_ld(q);
+  cudaStream_t s = R.stream;
+  const double one = 1.0, zero = 0.0, mone = -1.0;
+  // small buffers: T / V (p x m, ld ldq), tau (m), v, w, u, vt (p each), Gt (m x pm), Ht (m x pm), Cm (m x m), Xs (2m x 2m),
+  // Mrot (p x m, ld ldq)
+  tmp.hh.ensure((size_t)2 * m * ldq + 4 * ldq + (size_t)2 * m * ldq + 256);
+  double* Tm = tmp.hh.get();
+  double* Mrot = Tm + (size_t)m * ldq;
+  double* v = Mrot + (size_t)m * ldq;
+  double* w = v + ldq;
+  double* u = w + ldq;
+  double* vt = u + ldq;
+  double* Gt = vt + ldq;                       // m x pm, ld m
+  double* Ht = Gt + (size_t)m * ldq;           // m x pm, ld m
+  double* tau = Ht + (size_t)m * ldq;
+  double* Cm = tau + 16;
+  double* Xs = Cm + 32;
+  // 1. bordered matrix; T out of its border columns; QR of T
+  launch_tps_fill(x_dev, p, d, Pbuf, ldq, 1e-8, true, s);
+  SPB_CUDA(cudaMemcpy2DAsync(Tm, ldq * sizeof(double), Pbuf + (size_t)p * ldq, ldq * sizeof(double), (size_t)p * sizeof(double),
+                             m, cudaMemcpyDeviceToDevice, s));
+  int lw1 = 0, lw2 = 0;
+  SPB_CUSOLVER(cusolverDnDgeqrf_bufferSize(R.solver, p, m, Tm, (int)ldq, &lw1));
+  SPB_CUSOLVER(cusolverDnDormqr_bufferSize(R.solver, CUBLAS_SIDE_LEFT, CUBLAS_OP_N, p, m, m, Tm, (int)ldq, tau, Mrot, (int)ldq,
+                                           &lw2));
+  R.work.ensure((size_t)std::max(lw1, lw2));
+  SPB_CUSOLVER(cusolverDnDgeqrf(R.solver, p, m, Tm, (int)ldq, tau, R.work.get(), lw1, R.info.get()));
+  // 2. P <- Q'(E + eps I)Q on the upper triangle: reflectors 0 .. m-1
+  auto two_sided = [&](int j) {
+    hh_vector_kernel<<<ceil_div(p, 256), 256, 0, s>>>(Tm, ldq, p, j, v);
+    SPB_CUBLAS(cublasDsymv(R.blas, CUBLAS_FILL_MODE_UPPER, p, &one, Pbuf, (int)ldq, v, 1, &zero, w, 1));
+    hh_prep_kernel<<<1, 1024, 0, s>>>(v, w, tau + j, p, u, vt);
+    SPB_CUBLAS(cublasDsyr2(R.blas, CUBLAS_FILL_MODE_UPPER, p, &one, vt, 1, u, 1, Pbuf, (int)ldq));
+    count_launch(2);
+  };
+  for (int j = 0; j < m; ++j) two_sided(j);
+  // 3. B^-1 in place (B = rows / columns m .. p-1), GEMM-rate recursive SPD inverse
+  double* B = Pbuf + (size_t)m * ldq + m;
+  {
+    Exec ex{s, R.blas, flag, nullptr};
+    spd_inverse_recursive(ex, B, pm, ldq, inv_ws);
+  }
+  // 4. Gt = F12 B^-1 (m x pm), C = F12 B^-1 F21, Schur complement and its inverse
+  const double* F12 = Pbuf + (size_t)m * ldq;                      // rows 0 .. m-1, columns m .. p-1
+  SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, m, pm, pm, &one, F12, (int)ldq, B, (int)ldq, &zero, Gt, m));
+  SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_T, m, m, pm, &one, Gt, m, F12, (int)ldq, &zero, Cm, m));
+  schur_small_kernel<<<1, 1, 0, s>>>(Pbuf, ldq, Cm, Tm, ldq, m, 1e-8, Xs, flag, SPB_ERR_SINGULAR);
+  count_launch();
+  // 5. rotated inverse in place: X22 = B^-1 + G Xuu G', X12 = -Xuu G', X11 = Xuu;  Mrot = [Xul; -G Xul]
+  SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, m, pm, m, &one, Xs, n2, Gt, m, &zero, Ht, m));      // Xuu G'
+  SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_T, CUBLAS_OP_N, pm, pm, m, &one, Gt, m, Ht, m, &one, B, (int)ldq));
+  scaled_copy2d_kernel<<<dim3(1, pm < 1024 ? pm : 1024), 128, 0, s>>>(Ht, m, m, pm, -1.0, Pbuf + (size_t)m * ldq, ldq);
+  scaled_copy2d_kernel<<<dim3(1, m), 128, 0, s>>>(Xs, n2, m, m, 1.0, Pbuf, ldq);
+  scaled_copy2d_kernel<<<dim3(1, m), 128, 0, s>>>(Xs + (size_t)m * n2, n2, m, m, 1.0, Mrot, ldq);            // Xul
+  SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_T, CUBLAS_OP_N, pm, m, m, &mone, Gt, m, Xs + (size_t)m * n2, n2, &zero,
+                         Mrot + m, (int)ldq));                                                                 // -G Xul
+  count_launch(3);
+  // 6. back to the original basis: Lp0 = Q X Q' (reflectors m-1 .. 0), M0 = Q Mrot
+  for (int j = m - 1; j >= 0; --j) two_sided(j);
+  SPB_CUSOLVER(cusolverDnDormqr(R.solver, CUBLAS_SIDE_LEFT, CUBLAS_OP_N, p, m, m, Tm, (int)ldq, tau, Mrot, (int)ldq,
+                                R.work.get(), lw2, R.info.get()));
+  // 7. X0 = [[Lp0, M0], [M0', Xll]] (upper triangle, then mirrored)
+  SPB_CUDA(cudaMemcpy2DAsync(X0, ldq * sizeof(double), Pbuf, ldq * sizeof(double), (size_t)p * sizeof(double), p,
+                             cudaMemcpyDeviceToDevice, s));
+  SPB_CUDA(cudaMemcpy2DAsync(X0 + (size_t)p * ldq, ldq * sizeof(double), Mrot, ldq * sizeof(double), (size_t)p * sizeof(double),
+                             m, cudaMemcpyDeviceToDevice, s));
+  scaled_copy2d_kernel<<<dim3(1, m), 128, 0, s>>>(Xs + (size_t)m * n2 + m, n2, m, m, 1.0, X0 + (size_t)p * ldq + p, ldq);
+  count_launch();
+  launch_symmatu_inplace(X0, q, ldq, 0.0, s);
+  SPB_CUDA(cudaGetLastError());
+}
+
+// After the build's stream has been waited for: did the SPD route hold (no bad pivot) and is |I - A X0| small enough
+// for one Newton-Schulz step (error after the step ~ |I - A X0|^2)?
+bool omega_build_ok(OmegaTemps& tmp) {
+  if (tmp.spdflag.get() != nullptr && tmp.used_spd) {
+    int hf[4] = {0, 0, 0, 0};
+    SPB_CUDA(cudaMemcpy(hf, tmp.spdflag.get(), sizeof(hf), cudaMemcpyDeviceToHost));
+    if (hf[0] != 0) return false;
+  }
+  if (tmp.resid.get() != nullptr && tmp.used_spd) {
+    double r[2] = {0.0, 0.0};
+    SPB_CUDA(cudaMemcpy(r, tmp.resid.get(), sizeof(double), cudaMemcpyDeviceToHost));
+    if (!(r[0] < 1e-4)) return false;
+  }
+  return true;
+}
+
+bool omega_x0_spd_enabled(int p, int d) {
+  static const bool lu = [] { const char* e = std::getenv("SPB_OMEGA_X0"); return e && std::string(e) == "lu"; }();
+  return !lu && p >= 64 && p > 4 * (d + 1);
+}
+
+double omega_refined_flops(int p) {          // X0 1 (SPD inverse; LU + solve: 2.7) + residual 6 + correction 1 + product 1
+  return 9.0 * (double)p * p * p;
+}
 
 void Engine::build_omega_refined(OmegaRes& R, int* flag, const double* x_dev, int p, int d, double* omega_dev,
                                  size_t ld, bool upper_only, OmegaTemps& tmp) {
@@ -133,17 +334,23 @@ void Engine::build_omega_refined(OmegaRes& R, int* flag, const double* x_dev, in
   const double one = 1.0, zero = 0.0, mone = -1.0;
   const dim3 g2(ceil_div(q, 128), ceil_div(q, 8));
 
-  // 1. X0 = A^-1 by LU with partial pivoting, all q columns (the border block M is needed by step 3)
-  launch_tps_fill(x_dev, p, d, A, ldq, 1e-8, true, s);
-  launch_set_identity(X0, q, q, ldq, s);
-  int lwork = 0;
-  SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(R.solver, q, q, A, (int)ldq, &lwork));
-  R.ipiv.ensure(q);
-  R.work.ensure((size_t)lwork);
-  SPB_CUSOLVER(cusolverDnDgetrf(R.solver, q, q, A, (int)ldq, R.work.get(), R.ipiv.get(), R.info.get()));
-  launch_check_info(R.info.get(), flag, SPB_ERR_SINGULAR, s);
-  SPB_CUSOLVER(cusolverDnDgetrs(R.solver, CUBLAS_OP_N, q, q, A, (int)ldq, R.ipiv.get(), X0, (int)ldq, R.info.get()));
-  launch_symmatu_inplace(X0, q, ldq, 0.0, s);                  // the exact inverse is symmetric: keep the upper triangle
+  // 1. X0 = A^-1: through the SPD part of the system (omega_x0_spd), or by LU with partial pivoting (small p,
+  //    SPB_OMEGA_X0=lu); all q columns (the border block M is needed by step 4), symmetric
+  tmp.used_spd = !tmp.force_lu && omega_x0_spd_enabled(p, d);
+  if (tmp.used_spd) {
+    omega_x0_spd(R, x_dev, p, d, A, X0, C1, tmp);
+  } else {
+    launch_tps_fill(x_dev, p, d, A, ldq, 1e-8, true, s);
+    launch_set_identity(X0, q, q, ldq, s);
+    int lwork = 0;
+    SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(R.solver, q, q, A, (int)ldq, &lwork));
+    R.ipiv.ensure(q);
+    R.work.ensure((size_t)lwork);
+    SPB_CUSOLVER(cusolverDnDgetrf(R.solver, q, q, A, (int)ldq, R.work.get(), R.ipiv.get(), R.info.get()));
+    launch_check_info(R.info.get(), flag, SPB_ERR_SINGULAR, s);
+    SPB_CUSOLVER(cusolverDnDgetrs(R.solver, CUBLAS_OP_N, q, q, A, (int)ldq, R.ipiv.get(), X0, (int)ldq, R.info.get()));
+    launch_symmatu_inplace(X0, q, ldq, 0.0, s);                // the exact inverse is symmetric: keep the upper triangle
+  }
 
   // 2. residual of the symmetrised X0 with an exact head product
   const int beta = split_bits(q);
@@ -166,7 +373,11 @@ void Engine::build_omega_refined(OmegaRes& R, int* flag, const double* x_dev, in
   SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, q, q, &one, A, (int)ldq, X0, (int)ldq, &one, C2,
                          (int)ldq));                                     // C2 += A2 X0
   sub_inplace_kernel<<<g2, 128, 0, s>>>(C1, C2, ldq, q, q);              // C1 = I - A X0
-  count_launch(3);
+  // max |I - A X0|: the Newton-Schulz step squares it; checked on the host when the build is waited for
+  tmp.resid.ensure(2);
+  col_absmax_kernel<<<q, 256, 0, s>>>(C1, ldq, q, mxX);
+  col_absmax_kernel<<<1, 256, 0, s>>>(mxX, (size_t)q, q, tmp.resid.get());
+  count_launch(5);
 
   // 3. X1 = X0 + X0 (I - A X0): tiles on / above the diagonal only (X0 symmetric => X0 R = X0' R is symmetric)
   SPB_CUDA(cudaMemcpyAsync(C2, X0, sizeof(double) * qq, cudaMemcpyDeviceToDevice, s));
@@ -200,14 +411,26 @@ bool Engine::omega_begin_refined() {
   OmegaTemps& T = *omega_tmp_;
   T.L.ensure(qq); T.Bm.ensure(qq); T.T1.ensure(qq); T.C1.ensure(qq); T.C2.ensure(qq); T.vec.ensure(4 * (size_t)q);
   clock_.begin(PH_OMEGA, s);
-  launch_tps_fill(dX_.get(), p_, d_, T.L.get(), ldq, 1e-8, true, s);
-  launch_set_identity(T.Bm.get(), q, q, ldq, s);
-  int lwork = 0;
-  SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(R.solver, q, q, T.L.get(), (int)ldq, &lwork));
-  R.ipiv.ensure(q);
-  R.work.ensure((size_t)lwork);
-  SPB_CUSOLVER(cusolverDnDgetrf(R.solver, q, q, T.L.get(), (int)ldq, R.work.get(), R.ipiv.get(), R.info.get()));
-  launch_check_info(R.info.get(), ctx_.flag.get(), SPB_ERR_SINGULAR, s);
+  omega_x0_is_spd_ = omega_x0_spd_enabled(p_, d_);
+  if (omega_x0_is_spd_) {
+    // X0 is built whole on every rank (p^3 flop at GEMM rate, deterministic: the ranks hold identical copies, so the
+    // first exchange is not needed); only the refinement and the final product are split by columns
+    omega_x0_spd(R, dX_.get(), p_, d_, T.L.get(), T.Bm.get(), T.C1.get(), T);
+    int hf[4] = {0, 0, 0, 0};
+    SPB_CUDA(cudaStreamSynchronize(s));
+    SPB_CUDA(cudaMemcpy(hf, T.spdflag.get(), sizeof(hf), cudaMemcpyDeviceToHost));
+    if (hf[0] != 0) omega_x0_is_spd_ = false;                  // not positive definite in FP64: the LU route below
+  }
+  if (!omega_x0_is_spd_) {
+    launch_tps_fill(dX_.get(), p_, d_, T.L.get(), ldq, 1e-8, true, s);
+    launch_set_identity(T.Bm.get(), q, q, ldq, s);
+    int lwork = 0;
+    SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(R.solver, q, q, T.L.get(), (int)ldq, &lwork));
+    R.ipiv.ensure(q);
+    R.work.ensure((size_t)lwork);
+    SPB_CUSOLVER(cusolverDnDgetrf(R.solver, q, q, T.L.get(), (int)ldq, R.work.get(), R.ipiv.get(), R.info.get()));
+    launch_check_info(R.info.get(), ctx_.flag.get(), SPB_ERR_SINGULAR, s);
+  }
   clock_.end(s);
   stats_.p3_flops += omega_refined_flops(p_);
   omega_cols_open_ = true;

@@ -112,6 +112,8 @@ class TorchCollective(Collective):
         keep = []
         works = []
         for src, buf in items:
+            if not isinstance(buf, self.torch.Tensor) and buf[1] == 0:
+                continue                      # nothing to exchange for this block (e.g. a replicated X0)
             t = self._tensor(buf)
             if t.numel() == 0:
                 continue

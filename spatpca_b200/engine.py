@@ -211,7 +211,7 @@ class Engine:
         p = C.c_void_p()
         nb = C.c_longlong()
         check(self._lib.spb_engine_inverse_buffer(self._h, int(k), int(i), C.byref(p), C.byref(nb)))
-        return int(p.value), int(nb.value)
+        return int(p.value or 0), int(nb.value)
 
     def build_inverse(self, k, i):
         check(self._lib.spb_engine_build_inverse(self._h, int(k), int(i)))
@@ -237,7 +237,7 @@ class Engine:
         p = C.c_void_p()
         nb = C.c_longlong()
         check(self._lib.spb_engine_omega_buffer(self._h, int(which), int(c0), int(c1), C.byref(p), C.byref(nb)))
-        return int(p.value), int(nb.value)
+        return int(p.value or 0), int(nb.value)
 
     def omega_sync(self):
         check(self._lib.spb_engine_omega_sync(self._h))
