@@ -118,6 +118,9 @@ typedef struct spb_cv_stats {
   double    admm_bytes;       /* algorithmic bytes of all ADMM / matrix-free launches (8p^2 + 72pK per
                                  Core3 iteration, 8p^2 + 40pK per Core2 iteration, 8p^2 + 16 n_tr p per CG pass) */
   double    p3_flops;         /* flop of the p^3 work enqueued: Omega build + SPD factorisations                */
+  int       omega_route;      /* start of the Omega inverse: 0 none / plain LU, 1 SPD route, 2 pivoted LU,
+                                 3 SPD route broke down and the build was repeated with the LU                  */
+  double    omega_x0_resid;   /* max |I - A X0| of that start, before the Newton-Schulz step                     */
 } spb_cv_stats;
 
 /*

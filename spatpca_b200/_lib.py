@@ -39,6 +39,8 @@ class CvStats(C.Structure):
         ("bytes_h2d", C.c_longlong), ("bytes_d2h", C.c_longlong), ("gpu_launches", C.c_int),
         ("n_cg_calls", C.c_int), ("cg_passes", C.c_longlong), ("ms_cg", C.c_double), ("admm_bytes", C.c_double),
         ("p3_flops", C.c_double),
+        ("omega_route", C.c_int),
+        ("omega_x0_resid", C.c_double),
     ]
 
     def as_dict(self):

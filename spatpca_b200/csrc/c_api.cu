@@ -127,7 +127,10 @@ int spb_tps_matrix(const double* location, int p, int d, double* omega_out) {
     OmegaTemps tmp;
     Engine::build_omega_raw(R, ctx.flag.get(), x.get(), p, d, om.get(), ld, false, tmp);   // the full raw product (:75)
     SPB_CUDA(cudaStreamSynchronize(R.stream));
-    if (Engine::omega_refine_enabled() && !omega_build_ok(tmp)) {      // SPD route to X0 broke down: pivoted LU
+    double r0 = -1.0;
+    const bool ok = !Engine::omega_refine_enabled() || omega_build_ok(tmp, &r0);
+    if (std::getenv("SPB_TRACE")) fprintf(stderr, "[spb omega] p %d spd %d ok %d max|I - A X0| = %.3e\n", p, (int)tmp.used_spd, (int)ok, r0);
+    if (!ok) {      // SPD route to X0 broke down: pivoted LU
       tmp.force_lu = true;
       Engine::build_omega_raw(R, ctx.flag.get(), x.get(), p, d, om.get(), ld, false, tmp);
       SPB_CUDA(cudaStreamSynchronize(R.stream));

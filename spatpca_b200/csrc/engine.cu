@@ -734,20 +734,7 @@ void Engine::prepare() {
   SPB_REQUIRE(dY_.get() != nullptr, "upload() must be called before prepare()");
   trace(ctx_, "prepare: enter");
   cudaStream_t s = ctx_.stream;
-  if (!full_svd_done_) {
-    Scoped sc(clock_, PH_PROLOGUE, s);
-    kcap_full_ = std::min(std::min(n_, p_), SPB_MAX_K);
-    Vfull_.alloc((size_t)p_ * kcap_full_);
-    svd_right(ctx_, dY_.get(), n_, p_, kcap_full_, sv_full_, Vfull_.get());   // :563
-    rho_full_ = 10.0 * (sv_full_[0] * sv_full_[0]);                           // :564
-    full_svd_done_ = true;
-  }
-  if (!full_ready_) {
-    copy_pk(s, full_.Phi.get(), Vfull_.get());                                // :565 (first K columns)
-    copy_pk(s, full_.C.get(), full_.Phi.get());                               // :566
-    init_lambda(s, full_.Phi.get(), sv_full_, rho_full_, full_.L2.get());     // :567
-    full_ready_ = true;
-  }
+  // Omega first: its build (GEMM-bound, own stream) runs under the host-synchronous SVD starts below
   const bool need_omega = any_tau_ || tau1_.size() > 1 || tau2_.size() > 1;
   if (need_omega && !omega_ready_) {
     omega_u_.alloc(ld_ * (size_t)p_);
@@ -776,12 +763,28 @@ void Engine::prepare() {
       // (C5: 38 GB) finish the build here instead so that the lanes can have it
       size_t free_b = 0, total_b = 0;
       SPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-      if ((omega_refine_enabled() ? 5.0 : 3.0) * (double)ld_ * p_ * sizeof(double) > 0.15 * (double)free_b) finish_omega();
+      // 3 (plain) / 5 (refined) p x p FP64 temporaries, plus 2 x 12 INT8 planes and the int32 product
+      const double tmp_mats = !omega_refine_enabled() ? 3.0 : (omega_int8_enabled() ? 8.5 : 5.0);
+      if (tmp_mats * (double)ld_ * p_ * sizeof(double) > 0.15 * (double)free_b) finish_omega();
     } else {
       // all taus are zero but a grid has several entries: Omega = I (:578); tau * Omega vanishes.
       launch_set_identity(omega_u_.get(), p_, p_, ld_, s);
     }
     omega_ready_ = true;
+  }
+  if (!full_svd_done_) {
+    Scoped sc(clock_, PH_PROLOGUE, s);
+    kcap_full_ = std::min(std::min(n_, p_), SPB_MAX_K);
+    Vfull_.alloc((size_t)p_ * kcap_full_);
+    svd_right(ctx_, dY_.get(), n_, p_, kcap_full_, sv_full_, Vfull_.get());   // :563
+    rho_full_ = 10.0 * (sv_full_[0] * sv_full_[0]);                           // :564
+    full_svd_done_ = true;
+  }
+  if (!full_ready_) {
+    copy_pk(s, full_.Phi.get(), Vfull_.get());                                // :565 (first K columns)
+    copy_pk(s, full_.C.get(), full_.Phi.get());                               // :566
+    init_lambda(s, full_.Phi.get(), sv_full_, rho_full_, full_.L2.get());     // :567
+    full_ready_ = true;
   }
   ctx_.sync_and_check();            // the lanes read Omega and the full-data start from other streams
   trace(ctx_, "prepare: done");
@@ -797,7 +800,13 @@ void Engine::finish_omega() {
   if (!omega_pending_) return;
   OmegaRes& R = ctx_.omega();
   SPB_CUDA(cudaStreamSynchronize(R.stream));
-  if (omega_tmp_ && omega_refine_enabled() && !omega_build_ok(*omega_tmp_)) {
+  bool ok = true;
+  if (omega_tmp_ && omega_refine_enabled()) {
+    ok = omega_build_ok(*omega_tmp_, &stats_.omega_x0_resid);
+    stats_.omega_route = omega_tmp_->used_spd ? (ok ? 1 : 3) : 2;
+    if (trace_on()) fprintf(stderr, "[spb omega] route %d, max|I - A X0| = %.3e\n", stats_.omega_route, stats_.omega_x0_resid);
+  }
+  if (!ok) {
     // the SPD route to X0 broke down in FP64 (cond(B) ~ 1e11, e.g. one-dimensional sites): rebuild with the pivoted LU
     omega_tmp_->force_lu = true;
     build_omega_raw(R, ctx_.flag.get(), dX_.get(), p_, d_, omega_u_.get(), ld_, true, *omega_tmp_);

@@ -3,6 +3,7 @@
 #pragma once
 
 #include <chrono>
+#include <cstdint>
 #include <memory>
 #include <vector>
 
@@ -42,9 +43,13 @@ struct OmegaRes {
 struct OmegaTemps {
   DevBuf<double> L, Bm, T1;
   DevBuf<double> C1, C2, vec, hh, resid;   // refined build only (omega_refine.cu)
+  DevBuf<int8_t> oz_left, oz_right;        // INT8 digit planes of the refinement products (ozaki_int8.cu)
+  DevBuf<int> oz_c, oz_ea, oz_eb, oz_bad;
   DevBuf<int> spdflag;            // failure flag of the SPD route to X0
   bool force_lu = false;          // take the LU route to X0 (the fallback after a failed SPD route)
   bool used_spd = false;
+  int steps_done = 0;             // Newton-Schulz steps enqueued (residual records in `resid`)
+  int col_step = 0;               // column-split build: steps done so far
 };
 
 // Per-thread, per-device CUDA context (stream + library handles + solver workspaces).
@@ -359,7 +364,25 @@ void spd_factor_blocked(const Exec& ex, double* A, int n, size_t ld, double* wor
 double omega_refined_flops(int p);
 bool omega_x0_spd_enabled(int p, int d);   // X0 of the refined Omega build through the SPD part of the system (no LU)
 void omega_x0_spd(OmegaRes& R, const double* x_dev, int p, int d, double* Pbuf, double* X0, double* inv_ws, OmegaTemps& tmp);
-bool omega_build_ok(OmegaTemps& tmp);      // host check after the build has been waited for (SPD route held, residual small)
+bool omega_build_ok(OmegaTemps& tmp, double* resid_out = nullptr);
+int omega_refine_steps(bool spd_start);
+bool omega_int8_enabled();
+
+// ---- ozaki_int8.cu: extended-precision products on the INT8 tensor cores ----
+struct OzakiGeom {
+  size_t kq = 0;      // contraction length of one digit plane (q rounded up to 128)
+  int mp = 0, np = 0; // padded row / column counts of the product (multiples of 16)
+};
+OzakiGeom ozaki_geom(int q, int nc);
+int ozaki_env_slices(const char* name, int dflt, int lo, int hi);
+size_t ozaki_workspace_bytes(int q, int nc, int S, int Sc);
+void ozaki_transpose(cudaStream_t s, const double* src, size_t lds, int n, double* dst, size_t ldd);
+void ozaki_slice(cudaStream_t s, const double* M, size_t ld, int rows, int cols, int colsp, int S, bool reversed,
+                 int8_t* out, size_t kq, int* expo, int* bad);
+void ozaki_product(cublasHandle_t blas, cudaStream_t s, const OzakiGeom& g, const int8_t* left, int Sa,
+                   const int8_t* right, int Sb, int S, int m, int n, int* C, double* acc, size_t lda, const int* ea,
+                   const int* eb, int mode, int col0, double coef, const double* base, size_t ldb, double* out,
+                   size_t ldo, const int* bad);      // host check after the build has been waited for (SPD route held, residual small)
 
 // small host helpers (host_math.cpp-like, defined in engine.cu)
 double arma_accumulate(const double* x, int n);

@@ -23,6 +23,8 @@
 // Flop count: LU 2/3 + solve 2 + residual 6 + correction 1 + product 1 = 10.7 p^3 (the unrefined pipeline: 5.7).
 // What remains between this path and the oracle is the ORACLE's own rounding error.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <string>
@@ -32,6 +34,11 @@
 namespace spb {
 
 namespace {
+
+bool trace_on() {
+  static const bool on = [] { const char* e = std::getenv("SPB_TRACE"); return e && e[0] == '1'; }();
+  return on;
+}
 
 // column-wise max |a| of a (rows x cols) matrix -> out[cols]; one block per column
 __global__ void __launch_bounds__(256) col_absmax_kernel(const double* __restrict__ A, size_t ld, int rows,
@@ -292,25 +299,113 @@ void omega_x0_spd(OmegaRes& R, const double* x_dev, int p, int d, double* Pbuf, 
   SPB_CUDA(cudaGetLastError());
 }
 
+
+// SPB_OMEGA_RESID=dgemm keeps the refinement products in FP64 (three head/tail DGEMMs + one DGEMM); the default
+// runs them on the INT8 tensor cores (ozaki_int8.cu)
+bool omega_int8_enabled() {
+  static const bool fp64 = [] { const char* e = std::getenv("SPB_OMEGA_RESID"); return e && std::string(e) == "dgemm"; }();
+  return !fp64;
+}
+
+// Columns [c0, c0 + nc) of one Newton-Schulz step on INT8 digit planes:
+//   C1[:, cols]   = I - A X0[:, cols]              (S planes per operand, ~2^(-7 S) of rowmax * colmax)
+//   Xout[:, cols] = X0[:, cols] + X0 C1[:, cols]   (Sc planes)
+// A = T.L (the bordered matrix, symmetric, full); T.T1 is the FP64 accumulator.  X0 need NOT be symmetric: an LU
+// inverse is accurate column by column (|I - A X0| ~ 1e-8 .. 1e-6), mirroring its upper triangle mixes the columns'
+// forward errors and lifts the residual to ~cond * eps * sqrt(q) (0.1 at p = 10 000, measured) -- and the step only
+// contracts the error by the size of that residual.  The rows of X0 (left operand of the correction) are sliced from
+// a transposed copy parked in Xout (x0_symmetric: X0 itself).
+static void refine_cols_int8(OmegaRes& R, OmegaTemps& T, int q, size_t ldq, int c0, int nc, const double* X0,
+                             double* Xout, int S, bool x0_symmetric) {
+  if (nc <= 0) return;
+  const int Sc = ozaki_env_slices("SPB_OZAKI_CORR_SLICES", x0_symmetric ? 8 : 6, 2, 16);
+  const int Sm = std::max(S, Sc);
+  const OzakiGeom g = ozaki_geom(q, nc);
+  cudaStream_t s = R.stream;
+  T.oz_left.ensure((size_t)Sm * g.kq * g.mp);
+  T.oz_right.ensure((size_t)Sm * g.kq * g.np);
+  T.oz_c.ensure((size_t)g.mp * g.np);
+  T.oz_ea.ensure(g.mp);
+  T.oz_eb.ensure(g.np);
+  T.oz_bad.ensure(1);
+  SPB_CUDA(cudaMemsetAsync(T.oz_bad.get(), 0, sizeof(int), s));
+  const size_t o = (size_t)c0 * ldq;
+  const double* A = T.L.get();
+  double *acc = T.T1.get() + o, *C1 = T.C1.get() + o;
+  int8_t *left = T.oz_left.get(), *right = T.oz_right.get();
+  int *ea = T.oz_ea.get(), *eb = T.oz_eb.get(), *bad = T.oz_bad.get();
+  ozaki_slice(s, A, ldq, q, q, g.mp, S, false, left, g.kq, ea, bad);              // rows of A = its columns
+  ozaki_slice(s, X0 + o, ldq, q, nc, g.np, S, true, right, g.kq, eb, bad);
+  ozaki_product(R.blas, s, g, left, S, right, S, S, q, nc, T.oz_c.get(), acc, ldq, ea, eb, 0, c0, 0.0, nullptr, 0, C1, ldq, bad);
+  const double* X0rows = X0;
+  if (!x0_symmetric) {
+    ozaki_transpose(s, X0, ldq, q, Xout, ldq);                                    // overwritten by the epilogue below
+    X0rows = Xout;
+  }
+  ozaki_slice(s, X0rows, ldq, q, q, g.mp, Sc, false, left, g.kq, ea, bad);        // rows of X0
+  ozaki_slice(s, C1, ldq, q, nc, g.np, Sc, true, right, g.kq, eb, bad);
+  ozaki_product(R.blas, s, g, left, Sc, right, Sc, Sc, q, nc, T.oz_c.get(), acc, ldq, ea, eb, 1, c0, 1.0, X0 + o, ldq,
+                Xout + o, ldq, bad);
+}
+
+// Newton-Schulz steps of the build: ONE.  The step takes the forward error E0 of X0 to E0 A E0; a second step cannot
+// improve on that, because X1 rounded to FP64 already has a residual of ~cond * eps * sqrt(q) (measured: 0.5 at
+// p = 10 000).  SPB_OMEGA_STEPS = 2..4 (INT8 planes only, earlier steps with fewer planes) is a debugging aid.
+int omega_refine_steps(bool spd_start) {
+  static const int n = [] {
+    const char* e = std::getenv("SPB_OMEGA_STEPS");
+    return e ? std::min(4, std::max(1, std::atoi(e))) : 0;
+  }();
+  return n > 0 ? n : (spd_start ? 2 : 1);
+}
+static int refine_planes(int step, int nsteps) {
+  const int S = ozaki_env_slices("SPB_OZAKI_SLICES", 12, 4, 16);
+  const int S1 = ozaki_env_slices("SPB_OZAKI_FIRST_SLICES", 9, 4, 16);
+  return step + 1 < nsteps ? std::min(S, S1) : S;
+}
+
+// max |R| of the residual columns [0, ncols) -> resid[2 step] (columns < p: what the Lp block of the next iterate
+// depends on) and resid[2 step + 1] (all columns; the border columns carry entries ~1 / 1e-8 and are much larger)
+static void record_residual(OmegaTemps& T, cudaStream_t s, const double* C1, size_t ldq, int q, int p, int step, double* mx) {
+  T.resid.ensure(8);
+  col_absmax_kernel<<<q, 256, 0, s>>>(C1, ldq, q, mx);
+  col_absmax_kernel<<<1, 256, 0, s>>>(mx, (size_t)p, p, T.resid.get() + 2 * step);
+  col_absmax_kernel<<<1, 256, 0, s>>>(mx, (size_t)q, q, T.resid.get() + 2 * step + 1);
+  count_launch(3);
+}
+
 // After the build's stream has been waited for: did the SPD route hold (no bad pivot) and is |I - A X0| small enough
 // for one Newton-Schulz step (error after the step ~ |I - A X0|^2)?
-bool omega_build_ok(OmegaTemps& tmp) {
+bool omega_build_ok(OmegaTemps& tmp, double* resid_out) {
+  if (resid_out) *resid_out = -1.0;
+  double r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int steps = std::max(1, tmp.steps_done);
+  if (tmp.resid.get() != nullptr) {
+    SPB_CUDA(cudaMemcpy(r, tmp.resid.get(), sizeof(double) * 2 * steps, cudaMemcpyDeviceToHost));
+    if (resid_out) *resid_out = r[0];
+    if (trace_on())
+      for (int k = 0; k < steps; ++k)
+        fprintf(stderr, "[spb omega] step %d: max|I - A X| = %.3e over the Lp columns, %.3e over all\n", k, r[2 * k], r[2 * k + 1]);
+  }
   if (tmp.spdflag.get() != nullptr && tmp.used_spd) {
     int hf[4] = {0, 0, 0, 0};
     SPB_CUDA(cudaMemcpy(hf, tmp.spdflag.get(), sizeof(hf), cudaMemcpyDeviceToHost));
     if (hf[0] != 0) return false;
   }
   if (tmp.resid.get() != nullptr && tmp.used_spd) {
-    double r[2] = {0.0, 0.0};
-    SPB_CUDA(cudaMemcpy(r, tmp.resid.get(), sizeof(double), cudaMemcpyDeviceToHost));
-    if (!(r[0] < 1e-4)) return false;
+    // the SPD start must be close enough for its two steps (measured: 5e-4 at p = 10 000)
+    if (!(r[0] < 5e-3)) return false;
   }
   return true;
 }
 
+// The SPD route to X0 (omega_x0_spd) is opt-in (SPB_OMEGA_X0=spd).  Measured on B200 against an extended-precision
+// ground truth (p = 4000) and at p = 10 000: its X0 costs 49 ms instead of the LU's 149 ms, but it starts further from
+// the inverse (|I - A X0| 3e-5 .. 5e-4 against 1e-7), one Newton-Schulz step leaves 4.6e-10 in Omega where the LU start
+// reaches 1e-11, and the second step it needs (67 ms) eats most of the gain.
 bool omega_x0_spd_enabled(int p, int d) {
-  static const bool lu = [] { const char* e = std::getenv("SPB_OMEGA_X0"); return e && std::string(e) == "lu"; }();
-  return !lu && p >= 64 && p > 4 * (d + 1);
+  static const bool spd = [] { const char* e = std::getenv("SPB_OMEGA_X0"); return e && std::string(e) == "spd"; }();
+  return spd && omega_int8_enabled() && p >= 64 && p > 4 * (d + 1);
 }
 
 double omega_refined_flops(int p) {          // X0 1 (SPD inverse; LU + solve: 2.7) + residual 6 + correction 1 + product 1
@@ -349,49 +444,88 @@ void Engine::build_omega_refined(OmegaRes& R, int* flag, const double* x_dev, in
     SPB_CUSOLVER(cusolverDnDgetrf(R.solver, q, q, A, (int)ldq, R.work.get(), R.ipiv.get(), R.info.get()));
     launch_check_info(R.info.get(), flag, SPB_ERR_SINGULAR, s);
     SPB_CUSOLVER(cusolverDnDgetrs(R.solver, CUBLAS_OP_N, q, q, A, (int)ldq, R.ipiv.get(), X0, (int)ldq, R.info.get()));
-    launch_symmatu_inplace(X0, q, ldq, 0.0, s);                // the exact inverse is symmetric: keep the upper triangle
+    // the FP64 products below read X0 through its upper triangle; the INT8 step takes it as it is (see refine_cols_int8)
+    if (!omega_int8_enabled()) launch_symmatu_inplace(X0, q, ldq, 0.0, s);
   }
 
-  // 2. residual of the symmetrised X0 with an exact head product
-  const int beta = split_bits(q);
-  launch_tps_fill(x_dev, p, d, A, ldq, 1e-8, true, s);         // A again (the LU overwrote it)
-  col_absmax_kernel<<<q, 256, 0, s>>>(A, ldq, q, mxA);         // A is symmetric: column maxima = row maxima
-  col_absmax_kernel<<<q, 256, 0, s>>>(X0, ldq, q, mxX);
-  split_sigma_kernel<<<ceil_div(q, 256), 256, 0, s>>>(mxA, q, beta, sgA);
-  split_sigma_kernel<<<ceil_div(q, 256), 256, 0, s>>>(mxX, q, beta, sgX);
-  split_kernel<<<g2, 128, 0, s>>>(A, ldq, q, q, sgA, 1, 0, A, ldq);      // A  <- A1 (head, per row)
-  split_kernel<<<g2, 128, 0, s>>>(X0, ldq, q, q, sgX, 0, 0, S2, ldq);    // S2 <- X1 (head, per column)
-  launch_set_identity(C1, q, q, ldq, s);
-  count_launch(6);
-  SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, q, q, &mone, A, (int)ldq, S2, (int)ldq, &one, C1,
-                         (int)ldq));                                     // C1 = I - A1 X1   (exact)
-  split_kernel<<<g2, 128, 0, s>>>(X0, ldq, q, q, sgX, 0, 1, S2, ldq);    // S2 <- X2 = X0 - X1
-  SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, q, q, &one, A, (int)ldq, S2, (int)ldq, &zero, C2,
-                         (int)ldq));                                     // C2 = A1 X2
-  launch_tps_fill(x_dev, p, d, A, ldq, 1e-8, true, s);
-  split_kernel<<<g2, 128, 0, s>>>(A, ldq, q, q, sgA, 1, 1, A, ldq);      // A  <- A2 = A - A1
-  SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, q, q, &one, A, (int)ldq, X0, (int)ldq, &one, C2,
-                         (int)ldq));                                     // C2 += A2 X0
-  sub_inplace_kernel<<<g2, 128, 0, s>>>(C1, C2, ldq, q, q);              // C1 = I - A X0
+  auto lap = [&](const char* label) {               // SPB_TRACE=1: synchronous per-step timing
+    if (!trace_on()) return;
+    static auto last = std::chrono::steady_clock::now();
+    cudaStreamSynchronize(s);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[spb omega] %-12s +%8.3f ms\n", label, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+  };
+  lap("X0");
+  // 2 + 3. residual of the symmetrised X0 and the Newton-Schulz correction
+  const bool int8 = omega_int8_enabled();
+  const int nsteps = int8 ? omega_refine_steps(tmp.used_spd) : 1;
+  tmp.steps_done = nsteps;
+  if (int8) {
+    launch_tps_fill(x_dev, p, d, A, ldq, 1e-8, true, s);       // A again (the LU overwrote it)
+    for (int step = 0; step < nsteps; ++step) {
+      if (step > 0) {                                          // the iterate moves back into X0's buffer
+        std::swap(X0, C2);
+        launch_symmatu_inplace(X0, q, ldq, 0.0, s);
+      }
+      refine_cols_int8(R, tmp, q, ldq, 0, q, X0, C2, refine_planes(step, nsteps),     // C1 = I - A X0, C2 = X0 + X0 C1
+                       tmp.used_spd || step > 0);
+      record_residual(tmp, s, C1, ldq, q, p, step, mxX);
+    }
+  } else {
+    // 2. residual of the symmetrised X0 with an exact head product
+    const int beta = split_bits(q);
+    launch_tps_fill(x_dev, p, d, A, ldq, 1e-8, true, s);         // A again (the LU overwrote it)
+    col_absmax_kernel<<<q, 256, 0, s>>>(A, ldq, q, mxA);         // A is symmetric: column maxima = row maxima
+    col_absmax_kernel<<<q, 256, 0, s>>>(X0, ldq, q, mxX);
+    split_sigma_kernel<<<ceil_div(q, 256), 256, 0, s>>>(mxA, q, beta, sgA);
+    split_sigma_kernel<<<ceil_div(q, 256), 256, 0, s>>>(mxX, q, beta, sgX);
+    split_kernel<<<g2, 128, 0, s>>>(A, ldq, q, q, sgA, 1, 0, A, ldq);      // A  <- A1 (head, per row)
+    split_kernel<<<g2, 128, 0, s>>>(X0, ldq, q, q, sgX, 0, 0, S2, ldq);    // S2 <- X1 (head, per column)
+    launch_set_identity(C1, q, q, ldq, s);
+    count_launch(6);
+    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, q, q, &mone, A, (int)ldq, S2, (int)ldq, &one, C1,
+                           (int)ldq));                                     // C1 = I - A1 X1   (exact)
+    split_kernel<<<g2, 128, 0, s>>>(X0, ldq, q, q, sgX, 0, 1, S2, ldq);    // S2 <- X2 = X0 - X1
+    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, q, q, &one, A, (int)ldq, S2, (int)ldq, &zero, C2,
+                           (int)ldq));                                     // C2 = A1 X2
+    launch_tps_fill(x_dev, p, d, A, ldq, 1e-8, true, s);
+    split_kernel<<<g2, 128, 0, s>>>(A, ldq, q, q, sgA, 1, 1, A, ldq);      // A  <- A2 = A - A1
+    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_N, q, q, q, &one, A, (int)ldq, X0, (int)ldq, &one, C2,
+                           (int)ldq));                                     // C2 += A2 X0
+    sub_inplace_kernel<<<g2, 128, 0, s>>>(C1, C2, ldq, q, q);              // C1 = I - A X0
+  }
   // max |I - A X0|: the Newton-Schulz step squares it; checked on the host when the build is waited for
-  tmp.resid.ensure(2);
-  col_absmax_kernel<<<q, 256, 0, s>>>(C1, ldq, q, mxX);
-  col_absmax_kernel<<<1, 256, 0, s>>>(mxX, (size_t)q, q, tmp.resid.get());
-  count_launch(5);
+  if (!int8) record_residual(tmp, s, C1, ldq, q, p, 0, mxX);
 
-  // 3. X1 = X0 + X0 (I - A X0): tiles on / above the diagonal only (X0 symmetric => X0 R = X0' R is symmetric)
-  SPB_CUDA(cudaMemcpyAsync(C2, X0, sizeof(double) * qq, cudaMemcpyDeviceToDevice, s));
-  gemm_upper_tn(R.blas, q, q, 1.0, X0, ldq, C1, ldq, C2, ldq);
+  if (!int8) {
+    // 3. X1 = X0 + X0 (I - A X0): tiles on / above the diagonal only (X0 symmetric => X0 R = X0' R is symmetric)
+    SPB_CUDA(cudaMemcpyAsync(C2, X0, sizeof(double) * qq, cudaMemcpyDeviceToDevice, s));
+    gemm_upper_tn(R.blas, q, q, 1.0, X0, ldq, C1, ldq, C2, ldq);
+  }
   launch_symmatu_inplace(C2, q, ldq, 0.0, s);                            // full Lp for the product below
+  lap(int8 ? "refine int8" : "refine fp64");
 
   // 4. Omega = Lp - eps Lp Lp + eps M M'  (upper tiles; Lp = C2[0:p, 0:p], M = C2[0:p, p:q])
-  SPB_CUDA(cudaMemcpy2DAsync(omega_dev, ld * sizeof(double), C2, ldq * sizeof(double), (size_t)p * sizeof(double), p,
-                             cudaMemcpyDeviceToDevice, s));
-  gemm_upper_tn(R.blas, p, p, -1e-8, C2, ldq, C2, ldq, omega_dev, ld);
+  if (int8) {
+    // the product only enters with the weight eps: 7 planes (2^-49 of rowmax * colmax) leave < 1e-14 of Omega, and the
+    // 28 plane products take 22 ms at p = 10 000 where the FP64 upper-tile product takes 40
+    const int Sp = ozaki_env_slices("SPB_OZAKI_PROD_SLICES", 7, 3, 16);
+    const OzakiGeom g = ozaki_geom(p, p);
+    ozaki_slice(s, C2, ldq, p, p, g.mp, Sp, false, tmp.oz_left.get(), g.kq, tmp.oz_ea.get(), tmp.oz_bad.get());
+    ozaki_slice(s, C2, ldq, p, p, g.np, Sp, true, tmp.oz_right.get(), g.kq, tmp.oz_eb.get(), tmp.oz_bad.get());
+    ozaki_product(R.blas, s, g, tmp.oz_left.get(), Sp, tmp.oz_right.get(), Sp, Sp, p, p, tmp.oz_c.get(), S2, ldq,
+                  tmp.oz_ea.get(), tmp.oz_eb.get(), 1, 0, -1e-8, C2, ldq, omega_dev, ld, tmp.oz_bad.get());
+  } else {
+    SPB_CUDA(cudaMemcpy2DAsync(omega_dev, ld * sizeof(double), C2, ldq * sizeof(double), (size_t)p * sizeof(double), p,
+                               cudaMemcpyDeviceToDevice, s));
+    gemm_upper_tn(R.blas, p, p, -1e-8, C2, ldq, C2, ldq, omega_dev, ld);
+  }
   const double eps = 1e-8;
   SPB_CUBLAS(cublasDsyrk(R.blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, p, d + 1, &eps, C2 + (size_t)p * ldq, (int)ldq,
                          &one, omega_dev, (int)ld));
   if (!upper_only) launch_symmatu_inplace(omega_dev, p, ld, 0.0, s);     // the exported matrix: symmetric
+  lap("product");
   SPB_CUDA(cudaGetLastError());
 }
 
@@ -448,12 +582,27 @@ bool Engine::omega_refine_cols(int c0, int c1) {
   const int c1e = (c1 == p_) ? q : c1;                 // the owner of the last block also owns the border columns
   const int nc = c1e - c0;
   OmegaTemps& T = *omega_tmp_;
+  // one Newton-Schulz step per call; false once all steps are done (the caller exchanges the columns after each)
+  const bool int8 = omega_int8_enabled();
+  const int nsteps = int8 ? omega_refine_steps(omega_x0_is_spd_) : 1;
+  if (T.col_step >= nsteps) return false;
+  if (T.col_step > 0) std::swap(T.Bm, T.C2);           // the exchanged iterate X1 becomes this step's X0
   double *A = T.L.get(), *X0 = T.Bm.get(), *S2 = T.T1.get(), *C1 = T.C1.get(), *C2 = T.C2.get();
   double *mxA = T.vec.get(), *sgA = mxA + q, *mxX = sgA + q, *sgX = mxX + q;
   const double one = 1.0, zero = 0.0, mone = -1.0;
   const dim3 gfull(ceil_div(q, 128), ceil_div(q, 8));
   clock_.begin(PH_OMEGA, s);
-  launch_symmatu_inplace(X0, q, ldq, 0.0, s);
+  const bool x0_symmetric = !int8 || omega_x0_is_spd_ || T.col_step > 0;
+  if (x0_symmetric) launch_symmatu_inplace(X0, q, ldq, 0.0, s);
+  if (int8) {
+    launch_tps_fill(dX_.get(), p_, d_, A, ldq, 1e-8, true, s);
+    refine_cols_int8(R, T, q, ldq, c0, nc, X0, C2, refine_planes(T.col_step, nsteps), x0_symmetric);
+    ++T.col_step;
+    clock_.end(s);
+    SPB_CUDA(cudaGetLastError());
+    return true;
+  }
+  ++T.col_step;
   const int beta = split_bits(q);
   launch_tps_fill(dX_.get(), p_, d_, A, ldq, 1e-8, true, s);
   col_absmax_kernel<<<q, 256, 0, s>>>(A, ldq, q, mxA);

@@ -162,7 +162,9 @@ def prepare_sharded(engine, coll: Collective):
         engine.omega_solve_cols(c0, c1)
         engine.omega_sync()
         coll.broadcast_buffers([(r, engine.omega_buffer(0, a, b)) for r, (a, b) in enumerate(cols)])
-        if engine.omega_refine_cols(c0, c1):     # refined build: residual + correction of this rank's columns
+        # refined build: one Newton-Schulz step (residual + correction of this rank's columns) per call, the updated
+        # columns are exchanged after each; False once no step is left (or the build is not the refined one)
+        while engine.omega_refine_cols(c0, c1):
             engine.omega_sync()
             coll.broadcast_buffers([(r, engine.omega_buffer(2, a, b)) for r, (a, b) in enumerate(cols)])
         engine.omega_product_cols(c0, c1)

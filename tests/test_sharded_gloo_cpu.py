@@ -39,15 +39,23 @@ class OracleBackedEngine:
         self.asked.append(("omega_solve", c0, c1))
 
     def omega_refine_cols(self, c0, c1):
-        # the residual / correction of a block needs every column of X0: the other ranks' blocks must have arrived
-        assert bool((self.lp == self.torch.arange(self.p, dtype=self.torch.float64)).all())
-        self.x1[c0:c1] = 3.0 * self.torch.arange(c0, c1, dtype=self.torch.float64)
+        # two Newton-Schulz steps, one per call, False once none is left.  The residual / correction of a block needs
+        # every column of the current iterate: the other ranks' blocks must have arrived before each step
+        ar = self.torch.arange(self.p, dtype=self.torch.float64)
+        step = sum(1 for a in self.asked if a[0] == "omega_refine")
+        if step >= 2:
+            return False
+        if step == 0:
+            assert bool((self.lp == ar).all())
+        else:
+            assert bool((self.x1 == 3.0 * ar).all())
+        self.x1[c0:c1] = (3.0 if step == 0 else 5.0) * ar[c0:c1]
         self.asked.append(("omega_refine", c0, c1))
         return True
 
     def omega_product_cols(self, c0, c1):
         # the product needs every corrected column, i.e. the second exchange must have happened
-        assert bool((self.x1 == 3.0 * self.torch.arange(self.p, dtype=self.torch.float64)).all())
+        assert bool((self.x1 == 5.0 * self.torch.arange(self.p, dtype=self.torch.float64)).all())
         self.om[c0:c1] = 2.0 * self.torch.arange(c0, c1, dtype=self.torch.float64)
         self.asked.append(("omega_product", c0, c1))
 
@@ -162,7 +170,7 @@ def _worker(rank, world, port, out_dir):
     # Omega: this rank solved and multiplied exactly its own column block, then prepare() ran
     c0, c1 = D.omega_columns(eng.p, world)[rank]
     ok &= ("omega_solve", c0, c1) in eng.asked and ("omega_product", c0, c1) in eng.asked
-    ok &= ("omega_refine", c0, c1) in eng.asked
+    ok &= sum(1 for a in eng.asked if a == ("omega_refine", c0, c1)) == 2
     ok &= sum(1 for a in eng.asked if a[0] == "omega_solve") == 1 and ("prepare",) in eng.asked
     # the inverse jobs were spread as planned, and each rank built exactly its share
     jobs, owner = D.plan_inverse_jobs(case["M"], len(case["tau1"]), world)
