@@ -307,6 +307,14 @@ SPB_API int spb_core2_batched(const double* omega, const double* Y, const double
                       double tol, double cg_tol, double* Phi, double* C, double* Lambda2, int* iters,
                       double* snap, int* passes);
 SPB_API int spb_core2_batched_supported(int p, int n, int K, int F);
+/* The same kernel in spatpcaCore3 form (src/RcppSpatPCA.cpp:224-270): F problems at one tau1, solved for
+ * tau2[0..nsteps) one after the other with the state (Phi, R, C, Lambda1, Lambda2) carried -- the tau2 path of stage 2
+ * (:398-401) for all folds in ONE launch, matrix-free: Phi = (2 tau1 Omega - 2 Ytr'Ytr + 2 rho I)^-1 (rho (R + C) -
+ * (Lambda1 + Lambda2)) by conjugate gradients instead of the reference's tempinv product (:247).                     */
+SPB_API int spb_core3_batched(const double* omega, const double* Y, const double* nk, int p, int n, int K, int F,
+                      const int* fold_ids, const double* rho, double tau1, const double* tau2, int nsteps,
+                      int maxit, double tol, double cg_tol, double* Phi, double* R, double* C, double* Lambda1,
+                      double* Lambda2, int* iters, double* snap, int* passes);
 /* block count the library uses for systems of order p (1 = explicit inverse) */
 SPB_API int spb_default_blocks(int p);
 /* the same for the systems reused along a whole tau2 path (tempinv, :397)    */

@@ -117,6 +117,8 @@ SIGNATURES = {
     "spb_bench_dmma_matvec": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp]),
     "spb_core2_batched": (C.c_int, [_dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, C.c_int, C.c_int,
                                     C.c_double, C.c_double, _dp, _dp, _dp, _ip, _dp, _ip]),
+    "spb_core3_batched": (C.c_int, [_dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, C.c_double, _dp, C.c_int,
+                                    C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _ip]),
     "spb_core2_batched_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "spb_default_blocks": (C.c_int, [C.c_int]),
     "spb_default_path_blocks": (C.c_int, [C.c_int]),

@@ -166,7 +166,9 @@ struct BcgParams {
   size_t ldv;                      // leading dimension of the p x NCP work vectors
   int nblk;
   int nsteps;
+  int mode;                        // 2: spatpcaCore2 / 2p (steps over tau1); 3: spatpcaCore3 (steps over tau2, tau1 fixed)
   double tau1[kMaxSteps];
+  double tau2[kMaxSteps];          // mode 3
   double c_gram;
   int maxit;
   double tol, cg_tol2;
@@ -179,10 +181,13 @@ struct BcgParams {
   double* Phi[kMaxF];              // per problem p x K (ld p): in = warm start, out = last iterate
   double* C[kMaxF];
   double* L2[kMaxF];
+  double* R[kMaxF];                // mode 3
+  double* L1[kMaxF];               // mode 3
   double* snap;                    // nsteps x F x (p x K) iterates after every step (may be nullptr)
   int* iters_out;                  // nsteps x F
   int* status_out;                 // [0] status, [1] matrix passes
   double *Xg, *Rg, *Pg, *Qg, *Bg, *Cg, *L2g;
+  double *Radg, *L1g;              // mode 3: the ADMM variables R and Lambda1 (Rg is the CG residual)
   double *part_ru, *part_gam, *Spart, *Sred, *gram_part, *norm_part;
   unsigned int* bar;
   unsigned long long* dbg;         // optional globaltimer stamps of CTA 0 (performance debugging), or nullptr
@@ -353,6 +358,7 @@ __device__ __forceinline__ void column_sums(const double* tmp, int J, int Jv, in
 struct BcgState {                 // identical in every CTA (computed redundantly from the reduced partials)
   double gam[32], gam_old[32], alpha[32], alpha_old[32], beta[32], bn[32], ss[32], ru[32];
   double rho[kMaxF], rinv[kMaxF], err[kMaxF];
+  double rsys[kMaxF], thr[kMaxF];  // diagonal shift of the system (rho, or 2 rho in mode 3: Phi = (2 tau1 Omega - 2 G + 2 rho I)^-1 b); tau2 / rho
   double red[64];
   int frozen[32], fresh[32];
   int active[kMaxF], its[kMaxF];
@@ -363,7 +369,7 @@ template <int MT, int NTM>
 __global__ void __launch_bounds__(tmx::Shape<MT>::kThreads, 1)
 batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapX,
                      const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapY,
-                     const __grid_constant__ CUtensorMap mapS, BcgParams P) {
+                     const __grid_constant__ CUtensorMap mapS, const __grid_constant__ BcgParams P) {
   using S = Shape<MT>;
   constexpr int NTH = S::kThreads;
   extern __shared__ unsigned char dyn_raw[];
@@ -398,6 +404,8 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   if (tid < kMaxF) {
     st.rho[tid] = tid < F ? P.rho[tid] : 1.0;
     st.rinv[tid] = tid < F ? 1.0 / P.rho[tid] : 1.0;
+    st.rsys[tid] = (P.mode == 3 ? 2.0 : 1.0) * st.rho[tid];
+    st.thr[tid] = 0.0;
     st.active[tid] = 0; st.its[tid] = 0; st.err[tid] = 0.0;
   }
   __syncthreads();
@@ -409,7 +417,14 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     P.Xg[dst] = P.Phi[f][src];
     P.Cg[dst] = cv;
     P.L2g[dst] = l2;
-    P.Bg[dst] = __dsub_rn(__dmul_rn(st.rho[f], cv), l2);
+    if (P.mode == 3) {                                   // b = rho (R + C) - (Lambda1 + Lambda2) (:247)
+      const double rv = P.R[f][src], l1 = P.L1[f][src];
+      P.Radg[dst] = rv;
+      P.L1g[dst] = l1;
+      P.Bg[dst] = __dsub_rn(__dmul_rn(st.rho[f], __dadd_rn(rv, cv)), __dadd_rn(l1, l2));
+    } else {
+      P.Bg[dst] = __dsub_rn(__dmul_rn(st.rho[f], cv), l2);
+    }
     P.Rg[dst] = 0.0;
   }
   unsigned int it = 0, bar_gen = 0;
@@ -490,7 +505,7 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
   for (int step = 0; step < P.nsteps; ++step) {
     const double c_omega = 2.0 * P.tau1[step];
-    if (tid < F) { st.active[tid] = 1; st.its[tid] = 0; }
+    if (tid < F) { st.active[tid] = 1; st.its[tid] = 0; st.thr[tid] = (P.mode == 3) ? P.tau2[step] / st.rho[tid] : 0.0; }
     __syncthreads();
     for (int admm = 0; admm < P.maxit; ++admm) {
       int any = 0;
@@ -519,7 +534,7 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           double r = 0.0, b = 0.0;
           if (st.active[f]) {
             const double x = P.Xg[off];
-            const double w = fma(c_omega, us[(size_t)c * J + j], fma(st.rho[f], x, -P.c_gram * zsm[(size_t)c * J + j]));
+            const double w = fma(c_omega, us[(size_t)c * J + j], fma(st.rsys[f], x, -P.c_gram * zsm[(size_t)c * J + j]));
             b = P.Bg[off];
             r = b - w;
           }
@@ -573,7 +588,7 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           double alpha = 0.0, beta = 0.0;
           if (!st.frozen[c]) {
             const double gam = st.gam[c];
-            const double delta = fma(c_omega, st.ru[c], fma(st.rho[f], gam, -P.c_gram * st.ss[c]));     // r . A r
+            const double delta = fma(c_omega, st.ru[c], fma(st.rsys[f], gam, -P.c_gram * st.ss[c]));     // r . A r
             double den = delta;
             if (!st.fresh[c]) {
               beta = gam * fast_rcp(st.gam_old[c]);
@@ -592,7 +607,7 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           const double r = P.Rg[off];
           double rn = r;
           if (!st.frozen[c]) {
-            const double w = fma(c_omega, us[(size_t)c * J + j], fma(st.rho[f], r, -P.c_gram * zsm[(size_t)c * J + j]));
+            const double w = fma(c_omega, us[(size_t)c * J + j], fma(st.rsys[f], r, -P.c_gram * zsm[(size_t)c * J + j]));
             double pn = r, qn = w;
             if (!st.fresh[c]) {
               pn = fma(st.beta[c], P.Pg[off], r);
@@ -686,46 +701,66 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
       for (int e = tid; e < Jv * NC; e += NTH) {
         const int j = e % Jv, c = e / Jv, f = c / K, k = c - f * K;
-        double d0 = 0.0, d1 = 0.0;
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
         if (st.active[f]) {
           const size_t off = (size_t)c * ldv + j0 + j;
           double cn = 0.0;
           for (int a = 0; a < K; ++a) cn = fma(tmp0[(size_t)(f * K + a) * J + j], Pm[(size_t)f * 64 + a * K + k], cn);
           const double x = P.Xg[off], cold = P.Cg[off], l2old = P.L2g[off];
           const double dC = __dsub_rn(x, cn);
-          const double l2n = __dadd_rn(l2old, __dmul_rn(st.rho[f], dC));          // :173
+          const double l2n = __dadd_rn(l2old, __dmul_rn(st.rho[f], dC));          // :173, :258
           const double ec = __dsub_rn(cn, cold);
           P.Cg[off] = cn;
           P.L2g[off] = l2n;
-          P.Bg[off] = __dsub_rn(__dmul_rn(st.rho[f], cn), l2n);
           d0 = dC * dC; d1 = ec * ec;
+          if (P.mode == 3) {
+            const double rold = P.Radg[off], l1old = P.L1g[off];
+            const double a1 = __dadd_rn(div_rho_b(l1old, st.rho[f], st.rinv[f]), x);                    // :248
+            const double mag = fmax(0.0, __dsub_rn(fabs(a1), st.thr[f]));
+            const double sg = (a1 > 0.0) ? 1.0 : ((a1 < 0.0) ? -1.0 : 0.0);
+            const double rn = sg * mag;                                                                  // :249
+            const double dR = __dsub_rn(x, rn);
+            const double l1n = __dadd_rn(l1old, __dmul_rn(st.rho[f], dR));                               // :257
+            const double er = __dsub_rn(rn, rold);
+            P.Radg[off] = rn;
+            P.L1g[off] = l1n;
+            P.Bg[off] = __dsub_rn(__dmul_rn(st.rho[f], __dadd_rn(rn, cn)), __dadd_rn(l1n, l2n));
+            d2 = dR * dR; d3 = er * er;
+          } else {
+            P.Bg[off] = __dsub_rn(__dmul_rn(st.rho[f], cn), l2n);
+          }
         }
         vsm[(size_t)c * J + j] = d0;
         zsm[(size_t)c * J + j] = d1;
+        if (P.mode == 3) { us[(size_t)c * J + j] = d2; tmp1[(size_t)c * J + j] = d3; }
       }
       __syncthreads();
       {
         // per problem: sums over its K columns and this CTA's rows, fixed order (warp per (problem, norm))
         const int warp = tid >> 5, lane = tid & 31;
-        for (int e = warp; e < 2 * F; e += NTH / 32) {
-          const int f = e >> 1;
-          const double* src = (e & 1) ? zsm : vsm;
+        const int NN = (P.mode == 3) ? 4 : 2;                // norms per problem (:175-176; :261-264)
+        for (int e = warp; e < NN * F; e += NTH / 32) {
+          const int f = e / NN, v = e - f * NN;
+          const double* src = v == 0 ? vsm : (v == 1 ? zsm : (v == 2 ? us : tmp1));
           double t = 0.0;
           for (int k = 0; k < K; ++k)
             for (int j = lane; j < Jv; j += 32) t += src[(size_t)(f * K + k) * J + j];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-          if (lane == 0) __stcg(P.norm_part + (size_t)blockIdx.x * (2 * kMaxF) + e, t);
+          if (lane == 0) __stcg(P.norm_part + (size_t)blockIdx.x * (4 * kMaxF) + e, t);
         }
       }
       grid_barrier_b(P.bar, bar_gen);
-      reduce_partials(P.norm_part, P.nblk, 2 * kMaxF, 2 * F, st.red, NTH);
+      const int NN = (P.mode == 3) ? 4 : 2;
+      reduce_partials(P.norm_part, P.nblk, 4 * kMaxF, NN * F, st.red, NTH);
       __syncthreads();
       if (tid < F && st.active[tid]) {
-        const double a = st.red[2 * tid], b = st.red[2 * tid + 1];
-        const double e0 = (a > 0.0) ? (a * fast_rsqrt(a)) * rdenom : 0.0;
-        const double e1 = (b > 0.0) ? (b * fast_rsqrt(b)) * rdenom : 0.0;
-        st.err[tid] = fmax(e0, e1);
+        double emax = 0.0;
+        for (int v = 0; v < NN; ++v) {
+          const double a = st.red[NN * tid + v];
+          emax = fmax(emax, (a > 0.0) ? (a * fast_rsqrt(a)) * rdenom : 0.0);
+        }
+        st.err[tid] = emax;
         st.its[tid] = st.its[tid] + 1;
         if (st.err[tid] <= P.tol) st.active[tid] = 0;                          // stopping rule (:178)
       }
@@ -749,6 +784,7 @@ batched_core2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     P.Phi[f][dst] = P.Xg[src];
     P.C[f][dst] = P.Cg[src];
     P.L2[f][dst] = P.L2g[src];
+    if (P.mode == 3) { P.R[f][dst] = P.Radg[src]; P.L1[f][dst] = P.L1g[src]; }
   }
   if (blockIdx.x == 0 && tid == 0) { P.status_out[0] = st.status; P.status_out[1] = passes; }
 }
@@ -812,7 +848,7 @@ bool bcg_geometry(int p, int n, int K, int F, BcgHost& o) {
   o.spart = round_up((size_t)o.h.nblk * n * NC, 16);
   o.sred = round_up((size_t)n * NC, 16);
   o.gram = round_up((size_t)o.h.nblk * kMaxF * 36, 16);
-  o.norm = round_up((size_t)o.h.nblk * 2 * kMaxF, 16);
+  o.norm = round_up((size_t)o.h.nblk * 4 * kMaxF, 16);
   return true;
 }
 
@@ -845,7 +881,7 @@ bool batched_core2_supported(int p, int n, int K, int F) {
 size_t batched_core2_workspace_bytes(int p, int n, int K, int F) {
   BcgHost o;
   if (!bcg_geometry(p, n, K, F, o)) return 0;
-  return (7 * o.vec + o.part_ru + o.part_gam + o.spart + o.sred + o.gram + o.norm) * sizeof(double) + 256;
+  return (9 * o.vec + o.part_ru + o.part_gam + o.spart + o.sred + o.gram + o.norm) * sizeof(double) + 256;
 }
 
 void launch_batched_core2(const BatchedCore2Call& c, void* ws, cudaStream_t s) {
@@ -860,7 +896,11 @@ void launch_batched_core2(const BatchedCore2Call& c, void* ws, cudaStream_t s) {
   P.gy.nchunks = ceil_div(c.n, 64);
   P.p = c.p; P.n = c.n; P.K = c.K; P.F = c.F; P.NC = c.K * c.F; P.ldv = ldv; P.nblk = o.h.nblk;
   P.nsteps = c.nsteps;
+  SPB_REQUIRE(c.mode == 2 || c.mode == 3, "batched kernel: mode must be 2 (Core2) or 3 (Core3)");
+  SPB_REQUIRE(c.mode == 2 || c.tau2 != nullptr, "batched Core3: tau2 path missing");
+  P.mode = c.mode;
   for (int i = 0; i < kMaxSteps; ++i) P.tau1[i] = i < c.nsteps ? c.tau1[i] : 0.0;
+  for (int i = 0; i < kMaxSteps; ++i) P.tau2[i] = (c.mode == 3 && i < c.nsteps) ? c.tau2[i] : 0.0;
   P.c_gram = 2.0; P.maxit = c.maxit; P.tol = c.tol; P.cg_tol2 = c.cg_tol * c.cg_tol; P.cg_cap = c.cg_cap;
   for (int f = 0; f < kMaxF; ++f) {
     P.fold_id[f] = f < c.F ? c.fold_id[f] : 0;
@@ -868,6 +908,8 @@ void launch_batched_core2(const BatchedCore2Call& c, void* ws, cudaStream_t s) {
     P.Phi[f] = f < c.F ? c.Phi[f] : nullptr;
     P.C[f] = f < c.F ? c.C[f] : nullptr;
     P.L2[f] = f < c.F ? c.L2[f] : nullptr;
+    P.R[f] = (c.mode == 3 && f < c.F) ? c.R[f] : nullptr;
+    P.L1[f] = (c.mode == 3 && f < c.F) ? c.L1[f] : nullptr;
   }
   P.nk = c.nk; P.Y = c.Y; P.Yt = c.Yt;
   P.snap = c.snap; P.iters_out = c.iters_out; P.status_out = c.status_out;
@@ -879,6 +921,8 @@ void launch_batched_core2(const BatchedCore2Call& c, void* ws, cudaStream_t s) {
   P.Bg = w; w += o.vec;
   P.Cg = w; w += o.vec;
   P.L2g = w; w += o.vec;
+  P.Radg = w; w += o.vec;
+  P.L1g = w; w += o.vec;
   P.part_ru = w; w += o.part_ru;
   P.part_gam = w; w += o.part_gam;
   P.Spart = w; w += o.spart;

@@ -663,17 +663,20 @@ int spb_core2_matrix_free(const double* omega, const double* Ytr, int n_tr, int 
   });
 }
 
-int spb_core2_batched(const double* omega, const double* Y, const double* nk, int p, int n, int K, int F,
-                      const int* fold_ids, const double* rho, const double* tau1, int nsteps, int maxit, double tol,
-                      double cg_tol, double* Phi, double* C, double* Lambda2, int* iters, double* snap, int* passes) {
+// mode 2: steps over tau1[0..nsteps); mode 3: steps over tau2[0..nsteps) at tau1[0], with R and Lambda1
+static int core_batched_impl(int mode, const double* omega, const double* Y, const double* nk, int p, int n, int K, int F,
+                             const int* fold_ids, const double* rho, const double* tau1, const double* tau2, int nsteps,
+                             int maxit, double tol, double cg_tol, double* Phi, double* Rm, double* C, double* Lambda1,
+                             double* Lambda2, int* iters, double* snap, int* passes) {
   return guarded([&] {
     SPB_REQUIRE(omega && Y && nk && fold_ids && rho && tau1 && Phi && C && Lambda2 && iters, "NULL argument");
+    SPB_REQUIRE(mode == 2 || (tau2 && Rm && Lambda1), "NULL argument");
     SPB_REQUIRE(p >= 1 && n >= 1 && K >= 1 && F >= 1 && nsteps >= 1 && maxit >= 1, "invalid size");
     SPB_REQUIRE(batched_core2_supported(p, n, K, F), "batched Core2: unsupported problem shape on this device");
     DeviceCtx& ctx = DeviceCtx::get();
     cudaStream_t s = ctx.stream;
     const size_t ld = padded_ld(p), pk = (size_t)p * K;
-    DevBuf<double> om(ld * (size_t)p), dY((size_t)n * p), dYt((size_t)n * p), st(3 * pk * F),
+    DevBuf<double> om(ld * (size_t)p), dY((size_t)n * p), dYt((size_t)n * p), st(5 * pk * F),
         dsnap(snap ? (size_t)nsteps * F * pk : 1);
     DevBuf<int> dnk(n), dit((size_t)nsteps * F), dstat(2);
     DevBuf<char> ws(batched_core2_workspace_bytes(p, n, K, F));
@@ -687,6 +690,10 @@ int spb_core2_batched(const double* omega, const double* Y, const double* nk, in
     SPB_CUDA(cudaMemcpyAsync(st.get(), Phi, sizeof(double) * pk * F, cudaMemcpyHostToDevice, s));
     SPB_CUDA(cudaMemcpyAsync(st.get() + pk * F, C, sizeof(double) * pk * F, cudaMemcpyHostToDevice, s));
     SPB_CUDA(cudaMemcpyAsync(st.get() + 2 * pk * F, Lambda2, sizeof(double) * pk * F, cudaMemcpyHostToDevice, s));
+    if (mode == 3) {
+      SPB_CUDA(cudaMemcpyAsync(st.get() + 3 * pk * F, Rm, sizeof(double) * pk * F, cudaMemcpyHostToDevice, s));
+      SPB_CUDA(cudaMemcpyAsync(st.get() + 4 * pk * F, Lambda1, sizeof(double) * pk * F, cudaMemcpyHostToDevice, s));
+    }
     SPB_CUDA(cudaMemsetAsync(dit.get(), 0, sizeof(int) * nsteps * F, s));
     SPB_CUDA(cudaMemsetAsync(dstat.get(), 0, 2 * sizeof(int), s));
     BatchedCore2Call c;
@@ -698,8 +705,13 @@ int spb_core2_batched(const double* omega, const double* Y, const double* nk, in
       c.Phi[f] = f < F ? st.get() + (size_t)f * pk : nullptr;
       c.C[f] = f < F ? st.get() + pk * F + (size_t)f * pk : nullptr;
       c.L2[f] = f < F ? st.get() + 2 * pk * F + (size_t)f * pk : nullptr;
+      c.R[f] = (mode == 3 && f < F) ? st.get() + 3 * pk * F + (size_t)f * pk : nullptr;
+      c.L1[f] = (mode == 3 && f < F) ? st.get() + 4 * pk * F + (size_t)f * pk : nullptr;
     }
-    c.nsteps = nsteps; c.tau1 = tau1; c.maxit = maxit; c.tol = tol;
+    std::vector<double> t1rep(nsteps, tau1[0]);
+    c.mode = mode;
+    c.nsteps = nsteps; c.tau1 = mode == 3 ? t1rep.data() : tau1; c.tau2 = mode == 3 ? tau2 : nullptr;
+    c.maxit = maxit; c.tol = tol;
     c.cg_tol = cg_tol > 0.0 ? cg_tol : 1e-14; c.cg_cap = 2000;
     c.snap = snap ? dsnap.get() : nullptr; c.iters_out = dit.get(); c.status_out = dstat.get();
     const bool dbg_on = std::getenv("SPB_BCG_DBG") != nullptr;
@@ -726,6 +738,10 @@ int spb_core2_batched(const double* omega, const double* Y, const double* nk, in
     SPB_CUDA(cudaMemcpyAsync(Phi, st.get(), sizeof(double) * pk * F, cudaMemcpyDeviceToHost, s));
     SPB_CUDA(cudaMemcpyAsync(C, st.get() + pk * F, sizeof(double) * pk * F, cudaMemcpyDeviceToHost, s));
     SPB_CUDA(cudaMemcpyAsync(Lambda2, st.get() + 2 * pk * F, sizeof(double) * pk * F, cudaMemcpyDeviceToHost, s));
+    if (mode == 3) {
+      SPB_CUDA(cudaMemcpyAsync(Rm, st.get() + 3 * pk * F, sizeof(double) * pk * F, cudaMemcpyDeviceToHost, s));
+      SPB_CUDA(cudaMemcpyAsync(Lambda1, st.get() + 4 * pk * F, sizeof(double) * pk * F, cudaMemcpyDeviceToHost, s));
+    }
     if (snap)
       SPB_CUDA(cudaMemcpyAsync(snap, dsnap.get(), sizeof(double) * (size_t)nsteps * F * pk, cudaMemcpyDeviceToHost, s));
     ctx.sync_and_check();
@@ -735,6 +751,21 @@ int spb_core2_batched(const double* omega, const double* Y, const double* nk, in
     if (sth[0] != 0)
       throw Error(SPB_ERR_POLAR, "svd_econ(): the p x K iterate is rank deficient, Stiefel projection undefined");
   });
+}
+
+int spb_core2_batched(const double* omega, const double* Y, const double* nk, int p, int n, int K, int F,
+                      const int* fold_ids, const double* rho, const double* tau1, int nsteps, int maxit, double tol,
+                      double cg_tol, double* Phi, double* C, double* Lambda2, int* iters, double* snap, int* passes) {
+  return core_batched_impl(2, omega, Y, nk, p, n, K, F, fold_ids, rho, tau1, nullptr, nsteps, maxit, tol, cg_tol, Phi,
+                           nullptr, C, nullptr, Lambda2, iters, snap, passes);
+}
+
+int spb_core3_batched(const double* omega, const double* Y, const double* nk, int p, int n, int K, int F,
+                      const int* fold_ids, const double* rho, double tau1, const double* tau2, int nsteps, int maxit,
+                      double tol, double cg_tol, double* Phi, double* R, double* C, double* Lambda1, double* Lambda2,
+                      int* iters, double* snap, int* passes) {
+  return core_batched_impl(3, omega, Y, nk, p, n, K, F, fold_ids, rho, &tau1, tau2, nsteps, maxit, tol, cg_tol, Phi, R, C,
+                           Lambda1, Lambda2, iters, snap, passes);
 }
 
 int spb_core2_batched_supported(int p, int n, int K, int F) {

@@ -531,6 +531,7 @@ Engine::Engine(int p, int d, int n, int M, int K, const double* tau1, int n1, co
     cg_mode_ = (m == "cg") ? 1 : ((m == "factor") ? 2 : 0);
   }
   if (const char* e = std::getenv("SPB_BATCH")) bcg_mode_ = (std::string(e) == "0") ? 2 : 0;
+  if (const char* e = std::getenv("SPB_CORE3")) core3_mode_ = (std::string(e) == "factor") ? 2 : 0;
   if (const char* e = std::getenv("SPB_CG_TOL")) { const double t = std::atof(e); if (t > 0.0 && t < 1e-6) cg_tol_ = t; }
   alloc_k_state();
   std::memset(&stats_, 0, sizeof(stats_));
@@ -559,6 +560,7 @@ void Engine::reset_k(int K) {
   for (auto& f : folds_) SPB_REQUIRE(K <= std::min(f.n_tr, p_), "K must not exceed min(training rows, p)");
   flush();
   K_ = K;
+  if (!cache_inverses_) for (auto& f : folds_) f.tinv_valid = false;
   alloc_k_state();
   full_ready_ = false;                          // prepare() re-derives the full-data start for the new K
   log_.clear();
@@ -708,6 +710,13 @@ bool Engine::core2_matrix_free(int fold, double tau1, double rho, int expected_i
   if (maxit_ <= 0) return false;
   const double sv1 = fold < 0 ? sv_full_[0] : folds_[fold].sv[0];
   return use_cg(2.0 * tau1, rho, 2.0 * sv1 * sv1, tol_ > 0.0 ? expected_iters : maxit_, pass_scale);
+}
+
+bool Engine::core3_matrix_free(int fold, double tau1, double rho, int expected_iters, double pass_scale) {
+  // spatpcaCore3's system (:247 with tempinv of :397) is 2 tau1 Omega - 2 G + 2 rho I: twice Core2's shift
+  if (maxit_ <= 0) return false;
+  const double sv1 = fold < 0 ? sv_full_[0] : folds_[fold].sv[0];
+  return use_cg(2.0 * tau1, 2.0 * rho, 2.0 * sv1 * sv1, tol_ > 0.0 ? expected_iters : maxit_, pass_scale);
 }
 
 bool Engine::can_share_inverses() {
@@ -1074,23 +1083,34 @@ void Engine::ensure_batch_buffers(int F, int nsteps) {
   if (bcg_status_.count < cap_st) { bcg_status_.alloc(cap_st); bcg_st_used_ = 0; }
 }
 
-bool Engine::run_core2_batched(const std::vector<int>& folds, const std::vector<double>& taus, const std::vector<int>& idx,
-                               int kind, int expected_iters, double** snap_out) {
-  const int F = (int)folds.size(), ns = (int)taus.size();
+bool Engine::batch_eligible(const std::vector<int>& folds, int ns, double tau1_max, int expected_iters, int mode) {
+  const int F = (int)folds.size();
   if (bcg_mode_ == 2 || cg_mode_ == 2 || F < 1 || F > 8 || ns < 1 || ns > 64 || maxit_ <= 0 || K_ > 8 || F * K_ > 32)
     return false;
+  if (mode == 3 && core3_mode_ == 2) return false;
   if (cg_mode_ != 1 && p_ < 2048) return false;
   if (!batched_core2_supported(p_, n_, K_, F)) return false;
   // distinct lanes (problems sharing a lane share its chain buffers) and the matrix-free policy for every problem
   std::vector<int> lanes_seen;
-  const double tmax = *std::max_element(taus.begin(), taus.end());
   for (int k : folds) {
     const int li = k < 0 ? n_fold_lanes_ : k % n_fold_lanes_;
     if (std::find(lanes_seen.begin(), lanes_seen.end(), li) != lanes_seen.end()) return false;
     lanes_seen.push_back(li);
     const double rho = k < 0 ? rho_full_ : folds_[k].rho;
-    if (!core2_matrix_free(k, tmax, rho, expected_iters, F > 1 ? 2.1 / F : 1.0)) return false;
+    const double scale = F > 1 ? 2.1 / F : 1.0;
+    const bool ok = mode == 3 ? core3_matrix_free(k, tau1_max, rho, expected_iters, scale)
+                              : core2_matrix_free(k, tau1_max, rho, expected_iters, scale);
+    if (!ok) return false;
   }
+  return true;
+}
+
+bool Engine::run_core2_batched(const std::vector<int>& folds, const std::vector<double>& taus, const std::vector<int>& idx,
+                               int kind, int expected_iters, double** snap_out, int mode, double fixed_tau1) {
+  const int F = (int)folds.size(), ns = (int)taus.size();
+  if (ns < 1) return false;
+  const double tmax = mode == 3 ? fixed_tau1 : *std::max_element(taus.begin(), taus.end());
+  if (!batch_eligible(folds, ns, tmax, expected_iters, mode)) return false;
   // one workspace and one snapshot buffer: a batch that would overlap with an earlier one on another stream, or
   // overwrite snapshots that loss kernels may still read, waits for everything enqueued so far (rare: only when
   // folds share lanes, i.e. when device memory limits the lane count)
@@ -1124,8 +1144,12 @@ bool Engine::run_core2_batched(const std::vector<int>& folds, const std::vector<
     c.fold_id[f] = k < 0 ? 0 : k + 1;                       // nk holds 1-based fold ids (:318-319)
     c.rho[f] = k < 0 ? rho_full_ : folds_[k].rho;
     c.Phi[f] = st.Phi.get(); c.C[f] = st.C.get(); c.L2[f] = st.L2.get();
+    if (mode == 3) { c.R[f] = st.R.get(); c.L1[f] = st.L1.get(); }
   }
-  c.nsteps = ns; c.tau1 = taus.data(); c.maxit = maxit_; c.tol = tol_; c.cg_tol = cg_tol_; c.cg_cap = 2000;
+  const std::vector<double> t1rep(ns, fixed_tau1);
+  c.mode = mode;
+  c.nsteps = ns; c.tau1 = mode == 3 ? t1rep.data() : taus.data(); c.tau2 = mode == 3 ? taus.data() : nullptr;
+  c.maxit = maxit_; c.tol = tol_; c.cg_tol = cg_tol_; c.cg_cap = 2000;
   c.snap = snap_out ? bcg_snap_.get() : nullptr;
   c.iters_out = bcg_iters_.get() + bcg_it_used_;
   c.status_out = bcg_status_.get() + bcg_st_used_;
@@ -1292,7 +1316,7 @@ void Engine::flush() {
         }
       stats_.n_cg_calls += F * ns;
       stats_.cg_passes += passes;
-      stats_.admm_bytes += passes * (pp8 + 16.0 * (double)b.n * (double)p_) + (double)iters_sum * 5.0 * pk8;
+      stats_.admm_bytes += passes * (pp8 + 16.0 * (double)b.n * (double)p_) + (double)iters_sum * (b.kind == 3 ? 9.0 : 5.0) * pk8;
     }
     batch_pending_.clear();
     bcg_it_used_ = bcg_st_used_ = 0;
@@ -1461,7 +1485,11 @@ void Engine::stage1_full(int index1) {
     if (sel != 0.0 && max_tau2 == 0.0) run_core2(L, 20, -1, 0, sel, rho_full_, full_); // :605
   }
   const bool stage2_needs_tempinv = tau2_.size() > 1 || tau2_[0] > 0.0;       // the cases in which stage2_full() works
-  if (cache_inverses_ && stage2_needs_tempinv) full_tempinv(index1);
+  // early, so that it overlaps with the folds' stage 2 -- unless stage2_full() will run matrix-free
+  const int path_len = tau2_.size() > 1 ? (int)tau2_.size() : (int)l2_.size();
+  if (cache_inverses_ && stage2_needs_tempinv &&
+      !batch_eligible({-1}, std::min(path_len, 64), selected_tau1(index1), 2 * path_len, 3))
+    full_tempinv(index1);
 }
 
 // ---- stage 2 (:652-680) -----------------------------------------------------------------
@@ -1476,6 +1504,7 @@ void Engine::enqueue_stage2(int k, int index1, int step) {
   const double sel1 = selected_tau1(index1);
   double* scores = fold_scores(k);
   if (step == 3) {
+    ensure_fold_tempinv(k, index1);
     for (int i = 0; i < n2; ++i) {                                            // :398-401
       run_core3(L, 3, k, i, f.tinv.get(), tau2_[i], f.rho, ch);
       launch_loss(L, f, ch.Phi.get(), scores + i);
@@ -1502,18 +1531,25 @@ void Engine::enqueue_stage2(int k, int index1, int step) {
   copy_pk(s, ch.R.get(), ch.Phi.get());                                       // :394
   copy_pk(s, f.Phi0.get(), ch.Phi.get());                                     // :395
   copy_pk(s, f.L20.get(), ch.L2.get());                                       // :396
+}
+
+void Engine::ensure_fold_tempinv(int k, int index1) {
+  FoldData& f = folds_[k];
+  Lane& L = lane_of(k);
+  cudaStream_t s = L.res->stream;
+  const double sel1 = selected_tau1(index1);
   const int tag1 = ((int)tau1_.size() > 1) ? index1 : 0;
-  if (!(cache_inverses_ && f.tinv.get() != nullptr && f.tinv_index == tag1)) {
-    ensure_gram(L, k);
-    wait_omega(L);
-    Scoped sc(L.clock, PH_INVERSE, s);
-    f.tinv.ensure(ld_ * (size_t)p_);
-    spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, f.rho, 1.0, f.tinv.get(),
-                ld_, blocks_path_);                                           // :397
-    stats_.n_inverses++;
-    stats_.p3_flops += factor_flops(p_, blocks_path_);
-    f.tinv_index = tag1;
-  }
+  if (f.tinv.get() != nullptr && f.tinv_index == tag1 && f.tinv_valid) return;
+  ensure_gram(L, k);
+  wait_omega(L);
+  Scoped sc(L.clock, PH_INVERSE, s);
+  f.tinv.ensure(ld_ * (size_t)p_);
+  spd_inverse(L.exec(ctx_.flag.get()), omega_u_.get(), ld_, L.gram.get(), ld_, p_, sel1, f.rho, 1.0, f.tinv.get(),
+              ld_, blocks_path_);                                             // :397
+  stats_.n_inverses++;
+  stats_.p3_flops += factor_flops(p_, blocks_path_);
+  f.tinv_index = tag1;
+  f.tinv_valid = true;
 }
 
 void Engine::stage2_folds(const int* folds, int nfolds, int index1, double* rows) {
@@ -1536,8 +1572,23 @@ void Engine::stage2_folds(const int* folds, int nfolds, int index1, double* rows
     }
     if (!batched)
       for (int k : round) enqueue_stage2(k, index1, 1);
-    for (int step = 2; step < 4; ++step)
-      for (int k : round) enqueue_stage2(k, index1, step);
+    for (int k : round) enqueue_stage2(k, index1, 2);
+    // the tau2 path (:398-401) of all folds of the round in ONE launch of the matrix-free kernel -- no tempinv (:397)
+    // is ever formed; the hold-out losses (:400) are taken from the per-step snapshots.  Otherwise: factor + Core3.
+    std::vector<int> idx(n2);
+    for (int i = 0; i < n2; ++i) idx[i] = i;
+    double* snap = nullptr;
+    if (run_core2_batched(round, tau2_, idx, 3, 2 * n2, &snap, 3, sel1)) {
+      const size_t pk = (size_t)p_ * K_;
+      const int F = (int)round.size();
+      for (int i = 0; i < n2; ++i)
+        for (int f = 0; f < F; ++f) {
+          const int k = round[f];
+          launch_loss(lane_of(k), folds_[k], snap + ((size_t)i * F + f) * pk, fold_scores(k) + i);
+        }
+    } else {
+      for (int k : round) enqueue_stage2(k, index1, 3);
+    }
   }
   flush();
   SPB_REQUIRE(rows != nullptr, "cv rows pointer is NULL");
@@ -1591,14 +1642,24 @@ void Engine::stage2_full(int index1, int index2) {
   if (!path) return;
   Lane& L = lane_of(-1);
   cudaStream_t s = L.res->stream;
-  double* tbuf = full_tempinv(index1);
   copy_pk(s, full_.R.get(), full_.Phi.get());                                 // :662
   zero_pk(s, full_.L1.get());                                                 // :663
+  // the whole path in one launch of the matrix-free kernel (one problem), unless a tempinv exists already
+  const int tag1 = ((int)tau1_.size() > 1) ? index1 : 0;
+  const bool have_tinv = cache_inverses_ && full_tinv_.get() != nullptr && full_tinv_index_ == tag1;
+  if (!have_tinv) {
+    std::vector<double> steps(path->begin(), path->begin() + upto);
+    std::vector<int> idx(upto);
+    for (int i = 0; i < upto; ++i) idx[i] = i;
+    if (run_core2_batched({-1}, steps, idx, 3, 2 * upto, nullptr, 3, sel1)) return;
+  }
+  double* tbuf = full_tempinv(index1);
   for (int i = 0; i < upto; ++i) run_core3(L, 3, -1, i, tbuf, (*path)[i], rho_full_, full_);
 }
 
 // ---- stage 3 (:682-692, worker :459-525) ---------------------------------------------------
-void Engine::enqueue_stage3_refit(int k, int index1, int index2) {
+// chain = false: only the start of the refit (copies); the caller runs the Core2 / Core3 calls batched
+void Engine::enqueue_stage3_refit(int k, int index1, int index2, bool chain) {
   FoldData& f = folds_[k];
   Lane& L = lane_of(k);
   cudaStream_t s = L.res->stream;
@@ -1613,13 +1674,15 @@ void Engine::enqueue_stage3_refit(int k, int index1, int index2) {
     if (n2 == 1) {
       drop_cached_inverses(f, index1);
       double* inv = cached_inverse(f, index1);
-      run_core2(L, 2, k, 0, sel1, f.rho, ch, inv, inv != nullptr);            // :475
+      if (chain) run_core2(L, 2, k, 0, sel1, f.rho, ch, inv, inv != nullptr); // :475
     } else {
-      SPB_REQUIRE(f.tinv.get() != nullptr, "stage 2 must run before stage 3 for every fold");
       copy_pk(s, ch.R.get(), ch.Phi.get());                                   // :478
       zero_pk(s, ch.L1.get());                                                // :479
-      for (int i = 0; i <= index2; ++i)                                       // :480-482
-        run_core3(L, 3, k, i, f.tinv.get(), tau2_[i], f.rho, ch);
+      if (chain) {
+        ensure_fold_tempinv(k, index1);
+        for (int i = 0; i <= index2; ++i)                                     // :480-482
+          run_core3(L, 3, k, i, f.tinv.get(), tau2_[i], f.rho, ch);
+      }
     }
   }
   L.dirty = true;
@@ -1647,8 +1710,36 @@ void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, 
     SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
   }
   gamma_out_.ensure((size_t)M_ * ng);
+  const int n2 = (int)tau2_.size();
+  const double sel1 = selected_tau1(index1);
+  const double max_tau2 = *std::max_element(tau2_.begin(), tau2_.end());
   for (const auto& round : lane_rounds(folds, nfolds)) {
-    for (int k : round) enqueue_stage3_refit(k, index1, index2);
+    // the refits (:473-482) of the round's folds in one launch of the batched matrix-free kernel when it applies
+    bool batched = false;
+    if (max_tau2 != 0.0 || sel1 != 0.0) {
+      if (n2 == 1) {
+        bool have_inverse = false;
+        for (int k : round) have_inverse |= (cached_inverse(folds_[k], index1) != nullptr);
+        batched = !have_inverse && sel1 != 0.0 && batch_eligible(round, 1, sel1, 8, 2);
+      } else {
+        bool have_tinv = false;
+        for (int k : round) have_tinv |= folds_[k].tinv_valid;
+        batched = !have_tinv && batch_eligible(round, index2 + 1, sel1, 2 * (index2 + 1), 3);
+      }
+    }
+    for (int k : round) enqueue_stage3_refit(k, index1, index2, !batched);
+    if (batched) {
+      bool ok;
+      if (n2 == 1) {
+        ok = run_core2_batched(round, {sel1}, {0}, 2, 8, nullptr);
+      } else {
+        std::vector<double> path(tau2_.begin(), tau2_.begin() + index2 + 1);
+        std::vector<int> idx(index2 + 1);
+        for (int i = 0; i <= index2; ++i) idx[i] = i;
+        ok = run_core2_batched(round, path, idx, 3, 2 * (index2 + 1), nullptr, 3, sel1);
+      }
+      SPB_REQUIRE(ok, "internal: the batched refit was refused after batch_eligible() accepted it");
+    }
     for (int k : round) {
       // eigen step, water filling and the covariance losses follow the refit on the fold's own stream: no host
       // synchronisation per fold (round 1 synchronised twice per fold around a host Jacobi solve)

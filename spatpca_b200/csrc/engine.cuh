@@ -110,6 +110,7 @@ struct FoldData {
   DevBuf<double> Phi0, L20;       // Phi_cv / Lambd2_cv slices of the reference (:569)
   DevBuf<double> tinv;            // tempinv_cv slice (p x p), allocated in stage 2
   int tinv_index = -1;            // tau1 index `tinv` was built for (reused across K)
+  bool tinv_valid = false;        // `tinv` holds that tempinv (false while the tau2 paths run matrix-free)
   std::vector<DevBuf<double>> inv_cache;   // stage-1 inverses by tau1 index (kept when memory allows)
   std::vector<char> inv_valid;
   std::vector<double> sv;         // singular values of Ytr
@@ -271,14 +272,19 @@ class Engine {
   void run_core3(Lane& L, int kind, int fold, int idx, const double* tinv, double tau2, double rho, ChainState& st);
   // fold-batched matrix-free Core2 (batched_cg.cu) for `folds` (each on its own lane) along `taus`: returns false
   // (nothing enqueued) when the shape / policy does not allow it.  snap: Phi after every step, or nullptr.
+  // mode 3: spatpcaCore3 along the tau2 values `taus` at `fixed_tau1` (R and Lambda1 of the chains carried as well).
   bool run_core2_batched(const std::vector<int>& folds, const std::vector<double>& taus, const std::vector<int>& idx,
-                         int kind, int expected_iters, double** snap_out);
+                         int kind, int expected_iters, double** snap_out, int mode = 2, double fixed_tau1 = 0.0);
+  // the checks of run_core2_batched without side effects: would this batch run matrix-free?
+  bool batch_eligible(const std::vector<int>& folds, int nsteps, double tau1_max, int expected_iters, int mode);
+  bool core3_matrix_free(int fold, double tau1, double rho, int expected_iters, double pass_scale = 1.0);
+  void ensure_fold_tempinv(int k, int index1);   // the fold's tempinv (:397) on its lane, unless already there
   void ensure_batch_buffers(int F, int nsteps);
   void launch_loss(Lane& L, const FoldData& f, const double* Phi, double* out_dev);
   std::vector<std::vector<int>> lane_rounds(const int* folds, int nfolds) const;
   void enqueue_stage1(int k, int step);
   void enqueue_stage2(int k, int index1, int step);
-  void enqueue_stage3_refit(int k, int index1, int index2);
+  void enqueue_stage3_refit(int k, int index1, int index2, bool chain = true);
   double* full_tempinv(int index1);              // tempinv of the full-data fit, built on first request
   void flush_lane(Lane& L);                      // sync the lane, move its call stats to the host log
   void flush();                                  // every lane + the sticky error flag
@@ -307,6 +313,7 @@ class Engine {
   cudaStream_t batch_stream_ = nullptr;          // stream of the batches enqueued since the last flush
   bool snap_in_use_ = false;
   int bcg_mode_ = 0;                             // SPB_BATCH: 0 = auto, 2 = never batch the folds
+  int core3_mode_ = 0;                           // SPB_CORE3: 0 = auto (matrix-free tau2 paths when the policy allows), 2 = always tempinv
   DevBuf<double> lmax_vec_, lmax_out_;           // power iteration: 2 p-vectors, norms
   double lmax_ = -1.0;                           // < 0: not read back yet
   bool lmax_enqueued_ = false;

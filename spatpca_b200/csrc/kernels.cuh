@@ -156,6 +156,10 @@ struct BatchedCore2Call {
   double* Phi[8];            // per problem, p x K (ld p): warm start in, last iterate out
   double* C[8];
   double* L2[8];
+  int mode = 2;              // 2: spatpcaCore2 / 2p, one step per tau1 value; 3: spatpcaCore3, one step per tau2 value
+  double* R[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};    // mode 3
+  double* L1[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // mode 3
+  const double* tau2 = nullptr;   // host, nsteps values (mode 3; tau1[] then repeats the fixed tau1)
   int nsteps;                // grid values solved one after the other, state carried (the tau1 path, :329-332)
   const double* tau1;        // host, nsteps values
   int maxit;

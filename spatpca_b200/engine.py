@@ -403,6 +403,35 @@ def core2_batched(omega, Y, nk, fold_ids, rho, tau1, Phi0, C0, L20, maxit, tol, 
     return out
 
 
+def core3_batched(omega, Y, nk, fold_ids, rho, tau1, tau2, Phi0, R0, C0, L10, L20, maxit, tol, cg_tol=0.0, snapshots=True):
+    """F matrix-free spatpcaCore3 problems in lock-step along a tau2 path at one tau1 (spb_core3_batched).
+    Returns dict(Phi, R, C, L1, L2: lists of F (p x K) arrays; iters: nsteps x F; snap; passes)."""
+    lib = _lib.load()
+    om, Ym, nkf = fmat(omega), fmat(Y), fvec(nk)
+    n, p = Ym.shape
+    F = len(Phi0)
+    K = np.asarray(Phi0[0]).shape[1]
+    pack = lambda xs: np.ascontiguousarray(np.concatenate([np.asfortranarray(x).ravel(order="F") for x in xs]))
+    Ph, Rm, Cm, L1, L2 = pack(Phi0), pack(R0), pack(C0), pack(L10), pack(L20)
+    t2 = fvec(tau2)
+    ns = len(t2)
+    fid = np.ascontiguousarray(np.asarray(fold_ids, dtype=np.int32))
+    rh = fvec(rho)
+    it = np.zeros(ns * F, dtype=np.int32)
+    snap = np.zeros(ns * F * p * K) if snapshots else None
+    ps = C.c_int(0)
+    check(lib.spb_core3_batched(ptr(om), ptr(Ym), ptr(nkf), p, n, K, F, fid.ctypes.data_as(C.POINTER(C.c_int)), ptr(rh),
+                                float(tau1), ptr(t2), ns, int(maxit), float(tol), float(cg_tol), ptr(Ph), ptr(Rm), ptr(Cm),
+                                ptr(L1), ptr(L2), it.ctypes.data_as(C.POINTER(C.c_int)), ptr(snap) if snapshots else None,
+                                C.byref(ps)))
+    unpack = lambda v: [v[f * p * K:(f + 1) * p * K].reshape((p, K), order="F") for f in range(F)]
+    out = dict(Phi=unpack(Ph), R=unpack(Rm), C=unpack(Cm), L1=unpack(L1), L2=unpack(L2), iters=it.reshape(ns, F),
+               passes=ps.value)
+    if snapshots:
+        out["snap"] = snap.reshape(ns, F, K, p).transpose(0, 1, 3, 2)
+    return out
+
+
 def default_blocks(p):
     return check(_lib.load().spb_default_blocks(int(p)))
 

@@ -390,6 +390,55 @@ def test_core2_batched_path_vs_oracle(sp, p, K, M, n):
     assert got["passes"] > 0
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("p,K,M,n", [(640, 3, 4, 40), (1500, 5, 5, 60), (2300, 2, 1, 30)])
+def test_core3_batched_path_vs_oracle(sp, p, K, M, n):
+    """spatpcaCore3 along a tau2 path for all folds in one launch of the matrix-free kernel (CG solves with
+    2 tau1 Omega - 2 Ytr'Ytr + 2 rho I instead of the tempinv product of :247) against the oracle's core3 with its
+    explicit inv_sympd: identical iteration counts per (step, fold), every snapshot of Phi and the final
+    (R, C, Lambda1, Lambda2) to 1e-10."""
+    from spatpca_b200 import engine as eng
+    if not eng.core2_batched_supported(p, n, K, M):
+        pytest.skip("shape not supported by the batched kernel on this device")
+    rng = np.random.default_rng(17 * p + K)
+    x = rng.uniform(0, 1, size=(p, 2))
+    Om = ref.thin_plate_spline_matrix(x)
+    Om[np.diag_indices(p)] += 1e-8
+    load = np.linalg.qr(rng.normal(size=(p, K)))[0]
+    Y = (rng.normal(size=(n, K)) * np.linspace(30, 10, K)) @ load.T + rng.normal(size=(n, p))
+    nk = rng.permutation(np.resize(np.arange(1, M + 1), n)).astype(float)
+    tau1 = 0.05
+    tau2 = np.array([0.0, 1e-3, 1e-2, 0.1, 1.0])
+    fold_ids = list(range(1, M + 1)) if M > 1 else [0]
+    starts, rhos, want = [], [], []
+    for k in range(M):
+        Ytr = Y[nk != fold_ids[k]] if fold_ids[k] else Y
+        _, rho, Phi0, L20 = ref.pca_init(Ytr, K)
+        G = np.asfortranarray(Ytr.T @ Ytr)
+        Phi, Cc, L2 = ref.core2(G, Phi0, Phi0, L20, Om, tau1, rho, 100, 1e-4)          # :392-393
+        starts.append((Phi, Phi.copy(), Cc, np.zeros_like(Phi), L2))                  # :394 R = Phi, :390 Lambda1 = 0
+        rhos.append(rho)
+        tinv = ref.core3_tempinv(Om, G, tau1, rho)
+        R, L1 = Phi.copy(), np.zeros_like(Phi)
+        snaps, its = [], []
+        for t in tau2:
+            tr = ref.Trace()
+            Phi, R, Cc, L1, L2 = ref.core3(tinv, Phi, R, Cc, L1, L2, t, rho, 100, 1e-4, tr)
+            snaps.append(Phi)
+            its.append(tr.calls[0][3])
+        want.append(dict(snaps=snaps, its=its, R=R, C=Cc, L1=L1, L2=L2))
+    got = eng.core3_batched(Om, Y, nk, fold_ids, rhos, tau1, tau2, *[[s[i] for s in starts] for i in range(5)], 100, 1e-4)
+    assert got["iters"].tolist() == np.array([w["its"] for w in want]).T.tolist()
+    rel = lambda a, b: np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+    for k in range(M):
+        for i in range(len(tau2)):
+            assert rel(got["snap"][i, k], want[k]["snaps"][i]) <= 1e-10, (k, i)
+        for name in ("R", "C", "L1", "L2"):
+            scale = max(np.max(np.abs(want[k][name])), 1e-12)
+            assert np.max(np.abs(got[name][k] - want[k][name])) / scale <= 1e-9, (k, name)
+    assert got["passes"] > 0
+
+
 @pytest.mark.parametrize("p,nc", [(64, 3), (1003, 25), (2500, 32), (4100, 12), (777, 17), (10000, 25)])
 def test_dmma_stream_vs_numpy(sp, p, nc):
     """U = A V on the TMA + DMMA stream (csrc/tma_dmma.cuh) against NumPy: swizzled tiles, fragment permutations,
