@@ -116,7 +116,12 @@ DeviceCtx& DeviceCtx::get() {
   if (it != ctxs.end()) return *it->second;
   std::unique_ptr<DeviceCtx> c(new DeviceCtx());
   c->device = dev;
-  SPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  // highest priority: the host-synchronous SVD starts (many small kernels) run on this stream while the Omega build
+  // keeps every SM busy with GEMM waves on a lowest-priority stream; without the priorities each small kernel waits
+  // for a whole GEMM grid to be dispatched (measured at p = 10 000: 38 ms per fold start instead of 9 ms)
+  int prio_least = 0, prio_greatest = 0;
+  SPB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  SPB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
   SPB_CUBLAS(cublasCreate(&c->blas));
   SPB_CUBLAS(cublasSetStream(c->blas, c->stream));
   SPB_CUBLAS(cublasSetPointerMode(c->blas, CUBLAS_POINTER_MODE_HOST));
@@ -139,7 +144,9 @@ OmegaRes::~OmegaRes() {
 OmegaRes& DeviceCtx::omega() {
   if (!omega_res) {
     std::unique_ptr<OmegaRes> r(new OmegaRes());
-    SPB_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    int prio_least = 0, prio_greatest = 0;
+    SPB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    SPB_CUDA(cudaStreamCreateWithPriority(&r->stream, cudaStreamNonBlocking, prio_least));
     SPB_CUBLAS(cublasCreate(&r->blas));
     SPB_CUBLAS(cublasSetStream(r->blas, r->stream));
     SPB_CUBLAS(cublasSetPointerMode(r->blas, CUBLAS_POINTER_MODE_HOST));
@@ -697,13 +704,18 @@ bool Engine::use_cg(double c_omega, double rho, double gram_top, int expected_it
   if (!(kappa < 1e6)) return false;
   const double sq = std::sqrt(kappa);
   const double rate = (sq - 1.0) / (sq + 1.0);
-  const double steps = rate <= 1e-12 ? 1.0 : std::ceil(std::log(5e-16) / std::log(rate));
-  // cost model in units of one p x p matrix pass (measured on B200, profiles/): a block factorisation costs
-  // ~65 + 0.0085 p passes and each ADMM iteration on it ~2.4; a CG solve costs its steps + 3 passes
+  const double cold = rate <= 1e-12 ? 1.0 : std::ceil(std::log(0.05 * cg_tol_) / std::log(rate));
+  // Cost model in units of one p x p matrix pass, calibrated on B200 at p = 10 000 (profiles/r02_notes.md): a block
+  // factorisation costs ~65 + 0.0085 p passes and each ADMM iteration on it ~2.4.  A CG solve from the PCA start takes
+  // ~0.7 of the cold-start bound; every later solve of the chain is warm-started by the previous iterate and takes
+  // about a quarter of it (measured: 19 / 10 / 7 passes per ADMM iteration for the cold Core2 call, a tau2 path and a
+  // tau1 path), plus one pass for the residual now and then (it is recycled between solves on the same matrix).
   const double factor_cost = 65.0 + 0.0085 * p_ + 2.4 * expected_iters;
+  const double warm = 0.25 * cold + 1.0;
+  const double cg_cost = 0.7 * cold + (expected_iters - 1) * warm + 0.25 * expected_iters + 1.0;
   // pass_scale: cost of a pass per problem relative to a single-problem pass (the fold-batched DMMA stream serves F
   // problems with one pass that takes ~2.1 single passes)
-  return expected_iters * (steps + 3.0) * pass_scale < factor_cost;
+  return cg_cost * pass_scale < factor_cost;
 }
 
 bool Engine::core2_matrix_free(int fold, double tau1, double rho, int expected_iters, double pass_scale) {
@@ -1314,6 +1326,9 @@ void Engine::flush() {
           log_.push_back(b.kind); log_.push_back(b.folds[f]); log_.push_back(b.idx[i]); log_.push_back(it);
           iters_sum += it;
         }
+      if (trace_on())
+        fprintf(stderr, "[spb batch] kind %d: %d problems x %d steps, %lld ADMM iterations, %d matrix passes\n", b.kind, F, ns,
+                iters_sum, passes);
       stats_.n_cg_calls += F * ns;
       stats_.cg_passes += passes;
       stats_.admm_bytes += passes * (pp8 + 16.0 * (double)b.n * (double)p_) + (double)iters_sum * (b.kind == 3 ? 9.0 : 5.0) * pk8;
@@ -1488,7 +1503,7 @@ void Engine::stage1_full(int index1) {
   // early, so that it overlaps with the folds' stage 2 -- unless stage2_full() will run matrix-free
   const int path_len = tau2_.size() > 1 ? (int)tau2_.size() : (int)l2_.size();
   if (cache_inverses_ && stage2_needs_tempinv &&
-      !batch_eligible({-1}, std::min(path_len, 64), selected_tau1(index1), 2 * path_len, 3))
+      !batch_eligible({-1}, std::min(path_len, 64), selected_tau1(index1), path_len + 2, 3))
     full_tempinv(index1);
 }
 
@@ -1578,7 +1593,7 @@ void Engine::stage2_folds(const int* folds, int nfolds, int index1, double* rows
     std::vector<int> idx(n2);
     for (int i = 0; i < n2; ++i) idx[i] = i;
     double* snap = nullptr;
-    if (run_core2_batched(round, tau2_, idx, 3, 2 * n2, &snap, 3, sel1)) {
+    if (run_core2_batched(round, tau2_, idx, 3, n2 + 2, &snap, 3, sel1)) {
       const size_t pk = (size_t)p_ * K_;
       const int F = (int)round.size();
       for (int i = 0; i < n2; ++i)
@@ -1651,7 +1666,7 @@ void Engine::stage2_full(int index1, int index2) {
     std::vector<double> steps(path->begin(), path->begin() + upto);
     std::vector<int> idx(upto);
     for (int i = 0; i < upto; ++i) idx[i] = i;
-    if (run_core2_batched({-1}, steps, idx, 3, 2 * upto, nullptr, 3, sel1)) return;
+    if (run_core2_batched({-1}, steps, idx, 3, upto + 2, nullptr, 3, sel1)) return;
   }
   double* tbuf = full_tempinv(index1);
   for (int i = 0; i < upto; ++i) run_core3(L, 3, -1, i, tbuf, (*path)[i], rho_full_, full_);
@@ -1724,7 +1739,7 @@ void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, 
       } else {
         bool have_tinv = false;
         for (int k : round) have_tinv |= folds_[k].tinv_valid;
-        batched = !have_tinv && batch_eligible(round, index2 + 1, sel1, 2 * (index2 + 1), 3);
+        batched = !have_tinv && batch_eligible(round, index2 + 1, sel1, index2 + 3, 3);
       }
     }
     for (int k : round) enqueue_stage3_refit(k, index1, index2, !batched);
@@ -1736,7 +1751,7 @@ void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, 
         std::vector<double> path(tau2_.begin(), tau2_.begin() + index2 + 1);
         std::vector<int> idx(index2 + 1);
         for (int i = 0; i <= index2; ++i) idx[i] = i;
-        ok = run_core2_batched(round, path, idx, 3, 2 * (index2 + 1), nullptr, 3, sel1);
+        ok = run_core2_batched(round, path, idx, 3, index2 + 3, nullptr, 3, sel1);
       }
       SPB_REQUIRE(ok, "internal: the batched refit was refused after batch_eligible() accepted it");
     }

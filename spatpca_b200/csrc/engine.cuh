@@ -318,7 +318,7 @@ class Engine {
   double lmax_ = -1.0;                           // < 0: not read back yet
   bool lmax_enqueued_ = false;
   int cg_mode_ = 0;                              // SPB_CORE2: 0 = auto, 1 = always matrix-free (K <= 8), 2 = never
-  double cg_tol_ = 1e-14;                        // SPB_CG_TOL
+  double cg_tol_ = 1e-12;                        // SPB_CG_TOL: relative residual of the CG solves (CV scores move by ~1e-13 at C4, the parity bar is 1e-9)
   std::vector<double> nk_;
   DevBuf<double> omega_u_;                       // symmatu(Omega) + 1e-8 I
   DevBuf<double> omega_diag_raw_;                // diagonal before the ridge (for get_omega)

@@ -316,9 +316,9 @@ bool omega_int8_enabled() {
 // contracts the error by the size of that residual.  The rows of X0 (left operand of the correction) are sliced from
 // a transposed copy parked in Xout (x0_symmetric: X0 itself).
 static void refine_cols_int8(OmegaRes& R, OmegaTemps& T, int q, size_t ldq, int c0, int nc, const double* X0,
-                             double* Xout, int S, bool x0_symmetric) {
+                             double* Xout, int S, bool x0_symmetric, bool x0_lu_accurate) {
   if (nc <= 0) return;
-  const int Sc = ozaki_env_slices("SPB_OZAKI_CORR_SLICES", x0_symmetric ? 8 : 6, 2, 16);
+  const int Sc = ozaki_env_slices("SPB_OZAKI_CORR_SLICES", x0_lu_accurate ? 6 : 8, 2, 16);
   const int Sm = std::max(S, Sc);
   const OzakiGeom g = ozaki_geom(q, nc);
   cudaStream_t s = R.stream;
@@ -399,10 +399,15 @@ bool omega_build_ok(OmegaTemps& tmp, double* resid_out) {
   return true;
 }
 
-// The SPD route to X0 (omega_x0_spd) is opt-in (SPB_OMEGA_X0=spd).  Measured on B200 against an extended-precision
-// ground truth (p = 4000) and at p = 10 000: its X0 costs 49 ms instead of the LU's 149 ms, but it starts further from
-// the inverse (|I - A X0| 3e-5 .. 5e-4 against 1e-7), one Newton-Schulz step leaves 4.6e-10 in Omega where the LU start
-// reaches 1e-11, and the second step it needs (67 ms) eats most of the gain.
+// Which start?  Measured on B200 at p = 10 000 (q = 10 003), checked against an extended-precision ground truth at
+// p = 4000 (tools/omega_truth.py):
+//   LU (cuSOLVER getrf + getrs on I)   149 ms, |I - A X0| ~ 1e-7: ONE Newton-Schulz step (63 ms) -> 1e-11 in Omega;
+//   SPD route (omega_x0_spd)            49 ms, |I - A X0| 3e-5 .. 5e-4: one step leaves 4.6e-10, TWO steps (9 planes
+//                                       for the first residual, 8 for the corrections: 141 ms) agree with the LU
+//                                       result to 1e-11; with 7 / 6 planes they do not (4e-9).
+// 233 ms against 212 ms: the SPD route saves 20 ms, hidden under the fold SVD starts anyway, and depends on plane
+// counts that were tuned at two sizes.  The LU start is the default; SPB_OMEGA_X0=spd selects the other (finish_omega()
+// repeats the build with the LU when the SPD route reports a non-positive pivot or starts too far off).
 bool omega_x0_spd_enabled(int p, int d) {
   static const bool spd = [] { const char* e = std::getenv("SPB_OMEGA_X0"); return e && std::string(e) == "spd"; }();
   return spd && omega_int8_enabled() && p >= 64 && p > 4 * (d + 1);
@@ -464,12 +469,11 @@ void Engine::build_omega_refined(OmegaRes& R, int* flag, const double* x_dev, in
   if (int8) {
     launch_tps_fill(x_dev, p, d, A, ldq, 1e-8, true, s);       // A again (the LU overwrote it)
     for (int step = 0; step < nsteps; ++step) {
-      if (step > 0) {                                          // the iterate moves back into X0's buffer
-        std::swap(X0, C2);
-        launch_symmatu_inplace(X0, q, ldq, 0.0, s);
-      }
+      // the iterate moves back into X0's buffer AS IT IS: mirroring its upper triangle would put its asymmetry (the
+      // size of its forward error, ~1e-9) into the next residual as A * 1e-9 |X| ~ 1, and the step would not contract
+      if (step > 0) std::swap(X0, C2);
       refine_cols_int8(R, tmp, q, ldq, 0, q, X0, C2, refine_planes(step, nsteps),     // C1 = I - A X0, C2 = X0 + X0 C1
-                       tmp.used_spd || step > 0);
+                       tmp.used_spd && step == 0, !tmp.used_spd);
       record_residual(tmp, s, C1, ldq, q, p, step, mxX);
     }
   } else {
@@ -592,11 +596,11 @@ bool Engine::omega_refine_cols(int c0, int c1) {
   const double one = 1.0, zero = 0.0, mone = -1.0;
   const dim3 gfull(ceil_div(q, 128), ceil_div(q, 8));
   clock_.begin(PH_OMEGA, s);
-  const bool x0_symmetric = !int8 || omega_x0_is_spd_ || T.col_step > 0;
+  const bool x0_symmetric = !int8 || (omega_x0_is_spd_ && T.col_step == 0);      // see build_omega_refined
   if (x0_symmetric) launch_symmatu_inplace(X0, q, ldq, 0.0, s);
   if (int8) {
     launch_tps_fill(dX_.get(), p_, d_, A, ldq, 1e-8, true, s);
-    refine_cols_int8(R, T, q, ldq, c0, nc, X0, C2, refine_planes(T.col_step, nsteps), x0_symmetric);
+    refine_cols_int8(R, T, q, ldq, c0, nc, X0, C2, refine_planes(T.col_step, nsteps), x0_symmetric, !omega_x0_is_spd_);
     ++T.col_step;
     clock_.end(s);
     SPB_CUDA(cudaGetLastError());
