@@ -440,15 +440,26 @@ void Engine::cv_loss(cudaStream_t s, const double* Yva, int m, int p, const doub
   launch_residual_sumsq(Yva, m, p, Phi, K, W, scratch, out_dev, s);
 }
 
-void GammaWork::ensure(int p, int K, int n_tr, int ng) {
+void GammaWork::ensure(int p, int K, int n_tr, int n_va, int ng, bool tiles) {
+  const int rows = std::max(n_tr, n_va);
   W.ensure((size_t)n_tr * K);
-  scr.ensure(yphi_scratch_doubles(n_tr, p, K));
+  scr.ensure(yphi_scratch_doubles(rows, p, std::max(K, std::min(n_va, SPB_MAX_K))));
   H.ensure((size_t)K * K);
   Q.ensure((size_t)K * K);
   B.ensure((size_t)p * K);
   lam.ensure((size_t)ng * K);
   err.ensure((size_t)ng);
-  gscr.ensure(gamma_scratch_doubles(p));
+  if (tiles) {
+    gscr.ensure(gamma_scratch_doubles(p));
+  } else {
+    Yvt.ensure((size_t)p * n_va);
+    Gv.ensure((size_t)n_va * n_va);
+    Wv.ensure((size_t)n_va * K);
+    Cv.ensure((size_t)K * K);
+    BtB.ensure((size_t)K * K);
+    cst.ensure(2);
+    red.ensure(1024);
+  }
 }
 
 void Engine::gamma_losses_async(cudaStream_t s, GammaWork& w, const double* Phi, int p, int K, const double* Ytr, int n_tr,
@@ -456,16 +467,35 @@ void Engine::gamma_losses_async(cudaStream_t s, GammaWork& w, const double* Phi,
   // stage-3 body for one fold (:489-523), entirely on stream `s`: H = Phi' S_tr Phi through W = Ytr Phi, its
   // eigen-decomposition + water filling in a one-warp kernel (no host round trip), B = Phi Q, then the covariance
   // losses of all gammas without ever forming a p x p matrix.
-  w.ensure(p, K, n_tr, ng);
+  // SPB_GAMMA_LOSS=tiles evaluates the p x p residual tile by tile (round 1 / 2a: 5.2 ms per fold at p = 10 000,
+  // FMA-bound); the default expands the norm into O(K^2) statistics (launch_gamma_combine: ~0.1 ms).
+  static const bool tiles = [] { const char* e = std::getenv("SPB_GAMMA_LOSS"); return e && std::string(e) == "tiles"; }();
+  const bool use_tiles = tiles || n_va == 0;
+  w.ensure(p, K, n_tr, n_va, ng, use_tiles);
   launch_yphi(Ytr, n_tr, p, Phi, K, w.W.get(), w.scr.get(), s);
   launch_small_gram(w.W.get(), n_tr, K, 1.0 / (double)n_tr, w.H.get(), s);
   launch_gamma_eigen(w.H.get(), K, tv, p, gamma_dev, ng, w.Q.get(), w.lam.get(), w.err.get(), nullptr, s);
   launch_small_rmul(Phi, p, K, w.Q.get(), w.B.get(), s);
-  for (int g0 = 0; g0 < ng; g0 += kGammaBatch) {
-    const int nb = std::min(kGammaBatch, ng - g0);
-    launch_gamma_loss(Yva, n_va, p, w.B.get(), K, w.lam.get() + (size_t)g0 * K, w.err.get() + g0, nb, w.gscr.get(),
-                      out_dev + g0, s);
+  if (use_tiles) {
+    for (int g0 = 0; g0 < ng; g0 += kGammaBatch) {
+      const int nb = std::min(kGammaBatch, ng - g0);
+      launch_gamma_loss(Yva, n_va, p, w.B.get(), K, w.lam.get() + (size_t)g0 * K, w.err.get() + g0, nb, w.gscr.get(),
+                        out_dev + g0, s);
+    }
+    return;
   }
+  // Gv = Yva Yva' / m in column chunks of <= SPB_MAX_K (the W = Y Phi kernel with Phi = a block of Yva')
+  launch_transpose(Yva, n_va, p, w.Yvt.get(), s);                               // p x n_va
+  for (int c0 = 0; c0 < n_va; c0 += SPB_MAX_K) {
+    const int nc = std::min(SPB_MAX_K, n_va - c0);
+    launch_yphi(Yva, n_va, p, w.Yvt.get() + (size_t)c0 * p, nc, w.Gv.get() + (size_t)c0 * n_va, w.scr.get(), s);
+  }
+  launch_sumsq(w.Gv.get(), (size_t)n_va * n_va, w.red.get(), w.cst.get(), s);                 // m^2 |S_va|_F^2
+  launch_sumsq(Yva, (size_t)n_va * p, w.red.get() + 512, w.cst.get() + 1, s);                 // m tr(S_va)
+  launch_yphi(Yva, n_va, p, w.B.get(), K, w.Wv.get(), w.scr.get(), s);
+  launch_small_gram(w.Wv.get(), n_va, K, 1.0 / (double)n_va, w.Cv.get(), s);                  // B' S_va B
+  launch_small_gram(w.B.get(), p, K, 1.0, w.BtB.get(), s);
+  launch_gamma_combine(w.cst.get(), w.Cv.get(), w.BtB.get(), w.lam.get(), w.err.get(), ng, K, p, n_va, out_dev, s);
 }
 
 void Engine::gamma_losses(DeviceCtx& ctx, cudaStream_t s, const double* Phi, int p, int K, const double* Ytr,

@@ -121,7 +121,8 @@ struct FoldData {
 // device temporaries of one stage-3 evaluation (kept per lane so that the work can stay asynchronous)
 struct GammaWork {
   DevBuf<double> W, scr, H, Q, B, lam, err, gscr;
-  void ensure(int p, int K, int n_tr, int ng);
+  DevBuf<double> Yvt, Gv, Wv, Cv, BtB, cst, red;      // low-rank form of the loss: Yva', Yva Yva' / m, Yva B, ...
+  void ensure(int p, int K, int n_tr, int n_va, int ng, bool tiles);
 };
 
 struct CallRec { int kind, fold, idx, slot, n_tr; };

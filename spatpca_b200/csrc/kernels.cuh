@@ -192,6 +192,8 @@ void launch_gamma_eigen(const double* H, int K, double tv, int p, const double* 
 // out[g] = || Yva'Yva / m - B diag(lam_g) B' - err_g I ||_F^2
 constexpr int kGammaBatch = 16;
 size_t gamma_scratch_doubles(int p);
+void launch_gamma_combine(const double* cst, const double* Cv, const double* BtB, const double* lam, const double* err,
+                          int ng, int K, int p, int m, double* out, cudaStream_t s);
 void launch_gamma_loss(const double* Yva, int m, int p, const double* B, int K,
                        const double* lam_dev /* ng x K, row g contiguous */,
                        const double* err_dev /* ng */, int ng, double* scratch, double* out,

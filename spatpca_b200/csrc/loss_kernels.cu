@@ -428,6 +428,44 @@ void launch_small_gram(const double* W, int m, int K, double alpha, double* H, c
   SPB_CUDA(cudaGetLastError());
 }
 
+namespace {
+// out[g] = |S_va - B diag(lam_g) B' - err_g I|_F^2 from O(K^2) sufficient statistics (see launch_gamma_combine)
+__global__ void gamma_combine_kernel(const double* __restrict__ cst, const double* __restrict__ Cv,
+                                     const double* __restrict__ BtB, const double* __restrict__ lam,
+                                     const double* __restrict__ errv, int ng, int K, int p, double inv_m,
+                                     double* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  const double s2 = cst[0] * inv_m * inv_m;       // |S_va|_F^2 = |Yva Yva'|_F^2 / m^2
+  const double trS = cst[1] * inv_m;              // tr(S_va) = |Yva|_F^2 / m
+  const double e = errv[g];
+  const double* l = lam + (size_t)g * K;
+  double quad = 0.0, cross = 0.0, trB = 0.0;
+  for (int a = 0; a < K; ++a) {
+    for (int b = 0; b < K; ++b) {
+      const double t = BtB[(size_t)b * K + a];
+      quad = fma(l[a] * l[b], t * t, quad);       // |B L B'|_F^2 = sum_ab l_a l_b (B'B)_ab^2
+    }
+    cross = fma(l[a], Cv[(size_t)a * K + a], cross);      // <S_va, B L B'> = sum_a l_a (B' S_va B)_aa
+    trB = fma(l[a], BtB[(size_t)a * K + a], trB);         // tr(B L B')
+  }
+  out[g] = ((s2 + quad) + e * e * (double)p) - 2.0 * cross - 2.0 * e * trS + 2.0 * e * trB;
+}
+}  // namespace
+
+// The stage-3 loss (:521-523) without its p x p residual:
+//   |S - B L B' - e I|_F^2 = |S|_F^2 + |B L B'|_F^2 + e^2 p - 2 <S, B L B'> - 2 e tr S + 2 e tr(B L B'),
+// every term a function of the m x m Gram matrix Yva Yva', of Wv = Yva B (m x K) and of B'B (K x K): O(p m^2)
+// work instead of O(p^2 (m + n_gamma K)).  No cancellation to speak of: the loss is 0.1 .. 1.0 of |S|_F^2 on every
+// configuration measured (S is a rank-m sample covariance with noise, the fit has rank K), and the parity tests
+// compare with the oracle's tile-by-tile evaluation.
+void launch_gamma_combine(const double* cst, const double* Cv, const double* BtB, const double* lam, const double* err,
+                          int ng, int K, int p, int m, double* out, cudaStream_t s) {
+  gamma_combine_kernel<<<ceil_div(ng, 64), 64, 0, s>>>(cst, Cv, BtB, lam, err, ng, K, p, 1.0 / (double)m, out);
+  count_launch();
+  SPB_CUDA(cudaGetLastError());
+}
+
 size_t gamma_scratch_doubles(int p) {
   size_t nt = ceil_div(p, kGT);
   return (size_t)kGammaBatch * (nt * (nt + 1) / 2);
