@@ -597,6 +597,7 @@ void Engine::reset_k(int K) {
   for (auto& f : folds_) SPB_REQUIRE(K <= std::min(f.n_tr, p_), "K must not exceed min(training rows, p)");
   flush();
   K_ = K;
+  pend_core2p_ = -1; pend_path_ = false;
   if (!cache_inverses_) for (auto& f : folds_) f.tinv_valid = false;
   alloc_k_state();
   full_ready_ = false;                          // prepare() re-derives the full-data start for the new K
@@ -672,6 +673,7 @@ void Engine::upload(const double* sxy, const double* Y, const double* nk) {
   full_ready_ = false;
   full_svd_done_ = false;
   full_inv2_index_ = full_tinv_index_ = -1;
+  pend_core2p_ = -1; pend_path_ = false; my_stage1_folds_ = 0;
   for (auto& L : lanes_) L->gram_owner = -2;
 }
 
@@ -1148,7 +1150,8 @@ bool Engine::batch_eligible(const std::vector<int>& folds, int ns, double tau1_m
 }
 
 bool Engine::run_core2_batched(const std::vector<int>& folds, const std::vector<double>& taus, const std::vector<int>& idx,
-                               int kind, int expected_iters, double** snap_out, int mode, double fixed_tau1) {
+                               int kind, int expected_iters, double** snap_out, int mode, double fixed_tau1,
+                               const std::vector<int>* kinds, const std::vector<int>* idx_override) {
   const int F = (int)folds.size(), ns = (int)taus.size();
   if (ns < 1) return false;
   const double tmax = mode == 3 ? fixed_tau1 : *std::max_element(taus.begin(), taus.end());
@@ -1203,6 +1206,8 @@ bool Engine::run_core2_batched(const std::vector<int>& folds, const std::vector<
   }
   BatchRec rec;
   rec.kind = kind; rec.folds = folds; rec.idx = idx; rec.it_off = bcg_it_used_; rec.st_off = bcg_st_used_; rec.n = n_;
+  if (kinds) rec.kinds = *kinds;
+  if (idx_override) rec.idx_override = *idx_override;
   batch_pending_.push_back(rec);
   bcg_it_used_ += (size_t)ns * F;
   bcg_st_used_ += 2;
@@ -1353,7 +1358,9 @@ void Engine::flush() {
       for (int i = 0; i < ns; ++i)
         for (int f = 0; f < F; ++f) {
           const int it = its[b.it_off + (size_t)i * F + f];
-          log_.push_back(b.kind); log_.push_back(b.folds[f]); log_.push_back(b.idx[i]); log_.push_back(it);
+          const int kd = b.kinds.empty() ? b.kind : b.kinds[f];
+          const int ix = (!b.idx_override.empty() && b.idx_override[f] >= 0) ? b.idx_override[f] : b.idx[i];
+          log_.push_back(kd); log_.push_back(b.folds[f]); log_.push_back(ix); log_.push_back(it);
           iters_sum += it;
         }
       if (trace_on())
@@ -1465,6 +1472,7 @@ void Engine::stage1_folds(const int* folds, int nfolds, double* rows) {
   SPB_REQUIRE(folds != nullptr && nfolds >= 0, "invalid fold list");
   for (int f = 0; f < nfolds; ++f) SPB_REQUIRE(folds[f] >= 0 && folds[f] < M_, "fold index out of range");
   const int n1 = (int)tau1_.size();
+  my_stage1_folds_ = nfolds;
   for (int f = 0; f < nfolds; ++f) fold_prepare(folds[f]);                    // SVD starts (host-synchronous)
   for (const auto& round : lane_rounds(folds, nfolds)) {                      // tau1 paths, concurrent lanes
     for (int k : round) enqueue_stage1(k, 0);
@@ -1517,6 +1525,14 @@ void Engine::stage1_full(int index1) {
       double* buf = nullptr;
       bool have = false;
       const bool kept = cache_inverses_ && full_inv2_index_ == index1;
+      if (!kept && my_stage1_folds_ > 0 && tau2_.size() > 1 && batch_eligible({-1}, 1, tau1_[index1], 8, 2)) {
+        pend_core2p_ = index1;               // rides with the folds' cold Core2 batch of stage 2 (same tau1)
+        const bool stage2_needs = tau2_.size() > 1 || tau2_[0] > 0.0;
+        const int plen = tau2_.size() > 1 ? (int)tau2_.size() : (int)l2_.size();
+        if (cache_inverses_ && stage2_needs && !batch_eligible({-1}, std::min(plen, 64), selected_tau1(index1), plen + 2, 3))
+          full_tempinv(index1);
+        return;
+      }
       if (cache_inverses_ && (kept || !core2_matrix_free(-1, tau1_[index1], rho_full_, 8))) {
         full_inv2_.ensure(ld_ * (size_t)p_);
         buf = full_inv2_.get();
@@ -1613,8 +1629,16 @@ void Engine::stage2_folds(const int* folds, int nfolds, int index1, double* rows
     if (sel1 != 0.0) {
       bool have_inverse = false;
       for (int k : round) have_inverse |= (cached_inverse(folds_[k], index1) != nullptr);
-      if (!have_inverse) batched = run_core2_batched(round, {sel1}, {0}, 2, 8, nullptr);   // :392-393, all folds at once
+      if (!have_inverse && pend_core2p_ == index1 && (int)tau1_.size() > 1 && tau1_[index1] == sel1) {
+        // the deferred full-data Core2p (:598-599) as one more problem of this launch
+        std::vector<int> with_full(round), kinds(round.size(), 2), ixo(round.size(), -1);
+        with_full.push_back(-1); kinds.push_back(20); ixo.push_back(index1);
+        batched = run_core2_batched(with_full, {sel1}, {0}, 2, 8, nullptr, 2, 0.0, &kinds, &ixo);
+        if (batched) pend_core2p_ = -1;
+      }
+      if (!batched && !have_inverse) batched = run_core2_batched(round, {sel1}, {0}, 2, 8, nullptr);   // :392-393, all folds at once
     }
+    if (pend_core2p_ >= 0) run_pending_full();
     if (!batched)
       for (int k : round) enqueue_stage2(k, index1, 1);
     for (int k : round) enqueue_stage2(k, index1, 2);
@@ -1685,6 +1709,21 @@ void Engine::stage2_full(int index1, int index2) {
     path = &l2_; upto = (int)l2_.size();                                      // :672-678
   }
   if (!path) return;
+  if (pend_core2p_ >= 0) run_pending_full();                                  // (not consumed by a stage-2 batch)
+  // the tau2 path can ride with the folds' refit batch of stage 3 (same tau1, same tau2 values up to index2)
+  if (n2 > 1 && my_stage1_folds_ > 0 && batch_eligible({-1}, upto, sel1, upto + 2, 3)) {
+    const int tag1 = ((int)tau1_.size() > 1) ? index1 : 0;
+    const bool have_tinv = cache_inverses_ && full_tinv_.get() != nullptr && full_tinv_index_ == tag1;
+    if (!have_tinv) {
+      pend_path_ = true; pend_path_i1_ = index1; pend_path_upto_ = upto;
+      return;
+    }
+  }
+  run_full_path(index1, *path, upto);
+}
+
+void Engine::run_full_path(int index1, const std::vector<double>& path, int upto) {
+  const double sel1 = selected_tau1(index1);
   Lane& L = lane_of(-1);
   cudaStream_t s = L.res->stream;
   copy_pk(s, full_.R.get(), full_.Phi.get());                                 // :662
@@ -1693,13 +1732,25 @@ void Engine::stage2_full(int index1, int index2) {
   const int tag1 = ((int)tau1_.size() > 1) ? index1 : 0;
   const bool have_tinv = cache_inverses_ && full_tinv_.get() != nullptr && full_tinv_index_ == tag1;
   if (!have_tinv) {
-    std::vector<double> steps(path->begin(), path->begin() + upto);
+    std::vector<double> steps(path.begin(), path.begin() + upto);
     std::vector<int> idx(upto);
     for (int i = 0; i < upto; ++i) idx[i] = i;
     if (run_core2_batched({-1}, steps, idx, 3, upto + 2, nullptr, 3, sel1)) return;
   }
   double* tbuf = full_tempinv(index1);
-  for (int i = 0; i < upto; ++i) run_core3(L, 3, -1, i, tbuf, (*path)[i], rho_full_, full_);
+  for (int i = 0; i < upto; ++i) run_core3(L, 3, -1, i, tbuf, path[i], rho_full_, full_);
+}
+
+void Engine::run_pending_full() {
+  if (pend_core2p_ >= 0) {
+    const int i1 = pend_core2p_;
+    pend_core2p_ = -1;
+    run_core2(lane_of(-1), 20, -1, i1, tau1_[i1], rho_full_, full_, nullptr, false);
+  }
+  if (pend_path_) {
+    pend_path_ = false;
+    run_full_path(pend_path_i1_, tau2_, pend_path_upto_);
+  }
 }
 
 // ---- stage 3 (:682-692, worker :459-525) ---------------------------------------------------
@@ -1758,6 +1809,7 @@ void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, 
   const int n2 = (int)tau2_.size();
   const double sel1 = selected_tau1(index1);
   const double max_tau2 = *std::max_element(tau2_.begin(), tau2_.end());
+  if (pend_core2p_ >= 0) run_pending_full();
   for (const auto& round : lane_rounds(folds, nfolds)) {
     // the refits (:473-482) of the round's folds in one launch of the batched matrix-free kernel when it applies
     bool batched = false;
@@ -1781,7 +1833,20 @@ void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, 
         std::vector<double> path(tau2_.begin(), tau2_.begin() + index2 + 1);
         std::vector<int> idx(index2 + 1);
         for (int i = 0; i <= index2; ++i) idx[i] = i;
-        ok = run_core2_batched(round, path, idx, 3, index2 + 3, nullptr, 3, sel1);
+        ok = false;
+        if (pend_path_ && pend_path_i1_ == index1 && pend_path_upto_ == index2 + 1) {
+          std::vector<int> with_full(round);
+          with_full.push_back(-1);
+          if (batch_eligible(with_full, index2 + 1, sel1, index2 + 3, 3)) {
+            cudaStream_t sf = lane_of(-1).res->stream;
+            copy_pk(sf, full_.R.get(), full_.Phi.get());                      // :662
+            zero_pk(sf, full_.L1.get());                                      // :663
+            ok = run_core2_batched(with_full, path, idx, 3, index2 + 3, nullptr, 3, sel1);
+            SPB_REQUIRE(ok, "internal: the batched refit was refused after batch_eligible() accepted it");
+            pend_path_ = false;
+          }
+        }
+        if (!ok) ok = run_core2_batched(round, path, idx, 3, index2 + 3, nullptr, 3, sel1);
       }
       SPB_REQUIRE(ok, "internal: the batched refit was refused after batch_eligible() accepted it");
     }
@@ -1797,6 +1862,7 @@ void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, 
       L.dirty = true;
     }
   }
+  run_pending_full();                       // (a full-data path that found no batch to ride with)
   flush();
   for (int f = 0; f < nfolds; ++f)
     SPB_CUDA(cudaMemcpy(rows + (size_t)f * ng, gamma_out_.get() + (size_t)folds[f] * ng, sizeof(double) * ng,
@@ -1807,6 +1873,7 @@ void Engine::stage3_folds(const int* folds, int nfolds, int index1, int index2, 
 void Engine::get_eigenfn(double* out) {
   SPB_REQUIRE(out != nullptr, "NULL output");
   auto t0 = std::chrono::steady_clock::now();
+  run_pending_full();
   flush();
   SPB_CUDA(cudaMemcpy(out, full_.Phi.get(), sizeof(double) * (size_t)p_ * K_, cudaMemcpyDeviceToHost));
   stats_.bytes_d2h += (long long)sizeof(double) * p_ * K_;
@@ -1814,6 +1881,7 @@ void Engine::get_eigenfn(double* out) {
 }
 
 void Engine::get_stats(spb_cv_stats* st) {
+  run_pending_full();
   flush();
   double ms[PH_COUNT], sum[PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
   clock_.collect(ms);

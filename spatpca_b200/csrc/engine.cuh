@@ -132,6 +132,8 @@ struct BatchRec {
   int kind;                        // call-log kind of its calls (2 or 20)
   std::vector<int> folds;          // problem f -> fold (-1: full data)
   std::vector<int> idx;            // step -> grid index reported in the call log
+  std::vector<int> kinds;          // per problem, when they differ (a full-data Core2p riding with the folds' Core2)
+  std::vector<int> idx_override;   // per problem: grid index of its (single) step, or -1
   size_t it_off, st_off;           // offsets into bcg_iters_ / bcg_status_
   int n;                           // rows of Y seen by the kernel (for the byte accounting)
 };
@@ -275,7 +277,17 @@ class Engine {
   // (nothing enqueued) when the shape / policy does not allow it.  snap: Phi after every step, or nullptr.
   // mode 3: spatpcaCore3 along the tau2 values `taus` at `fixed_tau1` (R and Lambda1 of the chains carried as well).
   bool run_core2_batched(const std::vector<int>& folds, const std::vector<double>& taus, const std::vector<int>& idx,
-                         int kind, int expected_iters, double** snap_out, int mode = 2, double fixed_tau1 = 0.0);
+                         int kind, int expected_iters, double** snap_out, int mode = 2, double fixed_tau1 = 0.0,
+                         const std::vector<int>* kinds = nullptr, const std::vector<int>* idx_override = nullptr);
+  // Full-data work that can ride with the folds' next batch (the padded columns of the DMMA tiles are free): the
+  // Core2p call of stage1_full() joins stage 2's cold Core2 batch, the tau2 path of stage2_full() joins stage 3's
+  // refit batch.  run_pending_full() runs whatever is still pending on its own.
+  int pend_core2p_ = -1;           // tau1 index of a deferred Core2p (:598-599), or -1
+  bool pend_path_ = false;         // deferred tau2 path of the full-data fit (:662-666)
+  int pend_path_i1_ = 0, pend_path_upto_ = 0;
+  int my_stage1_folds_ = 0;        // folds this engine ran in stage 1 (0: a dedicated full-fit rank, nothing to ride with)
+  void run_pending_full();
+  void run_full_path(int index1, const std::vector<double>& path, int upto);
   // the checks of run_core2_batched without side effects: would this batch run matrix-free?
   bool batch_eligible(const std::vector<int>& folds, int nsteps, double tau1_max, int expected_iters, int mode);
   bool core3_matrix_free(int fold, double tau1, double rho, int expected_iters, double pass_scale = 1.0);
