@@ -388,6 +388,7 @@ bool omega_build_ok(OmegaTemps& tmp, double* resid_out = nullptr);
 int omega_refine_steps(bool spd_start);
 bool omega_int8_enabled();
 
+
 // ---- ozaki_int8.cu: extended-precision products on the INT8 tensor cores ----
 struct OzakiGeom {
   size_t kq = 0;      // contraction length of one digit plane (q rounded up to 128)

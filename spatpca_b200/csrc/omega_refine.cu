@@ -116,6 +116,73 @@ __global__ void __launch_bounds__(128) unit_cols_kernel(double* __restrict__ C, 
   }
 }
 
+// SPB_OMEGA_SPDINV=schur: the SPD route inverts its block with the recursive Schur-complement inverse (round 2a)
+bool omega_spd_schur() {
+  static const bool v = [] { const char* e = std::getenv("SPB_OMEGA_SPDINV"); return e && std::string(e) == "schur"; }();
+  return v;
+}
+
+// strictly upper triangle of the leading n x n block <- 0 (a lower-triangular factor that DGEMM may read as dense)
+__global__ void __launch_bounds__(128) zero_strict_upper_kernel(double* __restrict__ A, size_t ld, int n) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int j0 = blockIdx.y * 8;
+  if (i >= n) return;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = j0 + jj;
+    if (j >= n) break;
+    if (i < j) A[(size_t)j * ld + i] = 0.0;
+  }
+}
+
+// V = L^-1 in place for a lower-triangular L (n x n, its strict upper triangle stored as zeros): recursive,
+//   [L11 0; L21 L22]^-1 = [V11 0; -V22 L21 V11  V22],
+// every flop in a cuBLAS DGEMM that reads the triangular blocks as dense (2/3 n^3 flop instead of 1/3, at the DGEMM
+// rate instead of cuSOLVER's trtri rate); 512-row leaves by TRSM on an identity.  T: scratch of >= n^2 / 4 + 512^2.
+void trtri_lower_gemm(cublasHandle_t blas, cudaStream_t s, double* L, int n, size_t ld, double* T) {
+  const double one = 1.0, zero = 0.0, mone = -1.0;
+  if (n <= 512) {
+    launch_set_identity(T, n, n, (size_t)n, s);
+    SPB_CUBLAS(cublasDtrsm(blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, n, n, &one, L,
+                           (int)ld, T, n));
+    SPB_CUDA(cudaMemcpy2DAsync(L, ld * sizeof(double), T, (size_t)n * sizeof(double), (size_t)n * sizeof(double), n,
+                               cudaMemcpyDeviceToDevice, s));
+    return;
+  }
+  const int h = (int)(((size_t)(n / 2) + 63) / 64 * 64);
+  const int r = n - h;
+  double* L21 = L + h;
+  double* L22 = L + (size_t)h * ld + h;
+  trtri_lower_gemm(blas, s, L, h, ld, T);
+  trtri_lower_gemm(blas, s, L22, r, ld, T);
+  SPB_CUBLAS(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, r, h, h, &one, L21, (int)ld, L, (int)ld, &zero, T, r));       // L21 V11
+  SPB_CUBLAS(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, r, h, r, &mone, L22, (int)ld, T, r, &zero, L21, (int)ld));    // -V22 (.)
+}
+
+// B (n x n, SPD, upper triangle valid) -> B^-1 (full storage) through its Cholesky factor: B = L L', V = L^-1,
+// B^-1 = V'V.  Backward stable where the recursive Schur-complement inverse (spd_inverse_recursive) is not: for the
+// rotated TPS block (cond ~1e8) the start X0 built from it has |I - A X0| = 3e-8 at p = 10 000 instead of 5e-4
+// (measured), so ONE Newton-Schulz step is enough.  potrf: cuSOLVER; everything else GEMM-rate.
+// C: n x n scratch (ldc), T: scratch of >= n^2 / 4 + 512^2 doubles.
+void spd_inverse_cholesky(OmegaRes& R, int* flag, double* B, int n, size_t ld, double* C, size_t ldc, double* T) {
+  cudaStream_t s = R.stream;
+  launch_symmatu_inplace(B, n, ld, 0.0, s);                                   // potrf reads the lower triangle
+  int lw = 0;
+  SPB_CUSOLVER(cusolverDnDpotrf_bufferSize(R.solver, CUBLAS_FILL_MODE_LOWER, n, B, (int)ld, &lw));
+  R.work.ensure((size_t)lw);
+  SPB_CUSOLVER(cusolverDnDpotrf(R.solver, CUBLAS_FILL_MODE_LOWER, n, B, (int)ld, R.work.get(), lw, R.info.get()));
+  launch_check_info(R.info.get(), flag, SPB_ERR_NOT_POSDEF, s);
+  zero_strict_upper_kernel<<<dim3(ceil_div(n, 128), ceil_div(n, 8)), 128, 0, s>>>(B, ld, n);
+  count_launch();
+  trtri_lower_gemm(R.blas, s, B, n, ld, T);
+  SPB_CUDA(cudaMemset2DAsync(C, ldc * sizeof(double), 0, (size_t)n * sizeof(double), n, s));
+  gemm_upper_tn(R.blas, n, n, 1.0, B, ld, B, ld, C, ldc);                     // upper(V'V)
+  SPB_CUDA(cudaMemcpy2DAsync(B, ld * sizeof(double), C, ldc * sizeof(double), (size_t)n * sizeof(double), n,
+                             cudaMemcpyDeviceToDevice, s));
+  launch_symmatu_inplace(B, n, ld, 0.0, s);
+  SPB_CUDA(cudaGetLastError());
+}
+
 // ---- X0 through the symmetric positive definite part of the bordered system ---------------------------------
 // v = Householder vector j of a geqrf-factored p x m matrix: zeros above row j, 1 at row j, the stored tail below
 __global__ void hh_vector_kernel(const double* __restrict__ V, size_t ldv, int p, int j, double* __restrict__ v) {
@@ -252,7 +319,9 @@ void omega_x0_spd(OmegaRes& R, const double* x_dev, int p, int d, double* Pbuf, 
   SPB_CUSOLVER(cusolverDnDgeqrf_bufferSize(R.solver, p, m, Tm, (int)ldq, &lw1));
   SPB_CUSOLVER(cusolverDnDormqr_bufferSize(R.solver, CUBLAS_SIDE_LEFT, CUBLAS_OP_N, p, m, m, Tm, (int)ldq, tau, Mrot, (int)ldq,
                                            &lw2));
-  R.work.ensure((size_t)std::max(lw1, lw2));
+  int lw3 = 0;                               // potrf of the rotated block: sized here so that the workspace never moves
+  SPB_CUSOLVER(cusolverDnDpotrf_bufferSize(R.solver, CUBLAS_FILL_MODE_LOWER, pm, Pbuf + (size_t)m * ldq + m, (int)ldq, &lw3));
+  R.work.ensure((size_t)std::max(std::max(lw1, lw2), lw3));
   SPB_CUSOLVER(cusolverDnDgeqrf(R.solver, p, m, Tm, (int)ldq, tau, R.work.get(), lw1, R.info.get()));
   // 2. P <- Q'(E + eps I)Q on the upper triangle: reflectors 0 .. m-1
   auto two_sided = [&](int j) {
@@ -265,7 +334,10 @@ void omega_x0_spd(OmegaRes& R, const double* x_dev, int p, int d, double* Pbuf, 
   for (int j = 0; j < m; ++j) two_sided(j);
   // 3. B^-1 in place (B = rows / columns m .. p-1), GEMM-rate recursive SPD inverse
   double* B = Pbuf + (size_t)m * ldq + m;
-  {
+  // SPB_OMEGA_SPDINV = schur: the round-2a recursive Schur-complement inverse (35 ms, but a start 1e4 times further off)
+  if (!omega_spd_schur()) {
+    spd_inverse_cholesky(R, flag, B, pm, ldq, X0, ldq, inv_ws);               // X0 is free until step 7
+  } else {
     Exec ex{s, R.blas, flag, nullptr};
     spd_inverse_recursive(ex, B, pm, ldq, inv_ws);
   }
@@ -356,7 +428,7 @@ int omega_refine_steps(bool spd_start) {
     const char* e = std::getenv("SPB_OMEGA_STEPS");
     return e ? std::min(4, std::max(1, std::atoi(e))) : 0;
   }();
-  return n > 0 ? n : (spd_start ? 2 : 1);
+  return n > 0 ? n : ((spd_start && omega_spd_schur()) ? 2 : 1);
 }
 static int refine_planes(int step, int nsteps) {
   const int S = ozaki_env_slices("SPB_OZAKI_SLICES", 12, 4, 16);
@@ -393,24 +465,28 @@ bool omega_build_ok(OmegaTemps& tmp, double* resid_out) {
     if (hf[0] != 0) return false;
   }
   if (tmp.resid.get() != nullptr && tmp.used_spd) {
-    // the SPD start must be close enough for its two steps (measured: 5e-4 at p = 10 000)
-    if (!(r[0] < 5e-3)) return false;
+    // the start must be close enough for its step(s): 2.3e-8 (Cholesky inverse) / 4.9e-4 (Schur inverse) at p = 10 000
+    if (!(r[0] < (omega_spd_schur() ? 5e-3 : 1e-5))) return false;
   }
   return true;
 }
 
 // Which start?  Measured on B200 at p = 10 000 (q = 10 003), checked against an extended-precision ground truth at
-// p = 4000 (tools/omega_truth.py):
-//   LU (cuSOLVER getrf + getrs on I)   149 ms, |I - A X0| ~ 1e-7: ONE Newton-Schulz step (63 ms) -> 1e-11 in Omega;
-//   SPD route (omega_x0_spd)            49 ms, |I - A X0| 3e-5 .. 5e-4: one step leaves 4.6e-10, TWO steps (9 planes
-//                                       for the first residual, 8 for the corrections: 141 ms) agree with the LU
-//                                       result to 1e-11; with 7 / 6 planes they do not (4e-9).
-// 233 ms against 212 ms: the SPD route saves 20 ms, hidden under the fold SVD starts anyway, and depends on plane
-// counts that were tuned at two sizes.  The LU start is the default; SPB_OMEGA_X0=spd selects the other (finish_omega()
-// repeats the build with the LU when the SPD route reports a non-positive pivot or starts too far off).
+// p = 4000 (tools/omega_truth.py) and against each other:
+//   LU (cuSOLVER getrf + getrs on I)             149 ms, |I - A X0| = 1.2e-7 -> one Newton-Schulz step -> 1e-11 in Omega
+//   SPD route, Cholesky inverse (default)          80 ms, |I - A X0| = 2.3e-8 -> one step, 4e-12 from the LU result
+//   SPD route, recursive Schur-complement inverse  49 ms, |I - A X0| = 4.9e-4 -> needs two steps (141 ms) and tuned
+//                                                  plane counts; kept as SPB_OMEGA_SPDINV=schur
+// The SPD route is taken from p = 2048 on (below that the LU is as fast); finish_omega() / spb_tps_matrix() repeat the
+// build with the LU when the Cholesky factorisation reports a non-positive pivot (one-dimensional sites at cond ~1e11)
+// or the start is further off than 1e-5.  SPB_OMEGA_X0 = lu | spd forces one.
 bool omega_x0_spd_enabled(int p, int d) {
-  static const bool spd = [] { const char* e = std::getenv("SPB_OMEGA_X0"); return e && std::string(e) == "spd"; }();
-  return spd && omega_int8_enabled() && p >= 64 && p > 4 * (d + 1);
+  static const int forced = [] {
+    const char* e = std::getenv("SPB_OMEGA_X0");
+    return !e ? 0 : (std::string(e) == "spd" ? 1 : (std::string(e) == "lu" ? 2 : 0));
+  }();
+  if (forced == 2 || !omega_int8_enabled() || p < 64 || p <= 4 * (d + 1)) return false;
+  return forced == 1 || p >= 2048;
 }
 
 double omega_refined_flops(int p) {          // X0 1 (SPD inverse; LU + solve: 2.7) + residual 6 + correction 1 + product 1
@@ -473,7 +549,7 @@ void Engine::build_omega_refined(OmegaRes& R, int* flag, const double* x_dev, in
       // size of its forward error, ~1e-9) into the next residual as A * 1e-9 |X| ~ 1, and the step would not contract
       if (step > 0) std::swap(X0, C2);
       refine_cols_int8(R, tmp, q, ldq, 0, q, X0, C2, refine_planes(step, nsteps),     // C1 = I - A X0, C2 = X0 + X0 C1
-                       tmp.used_spd && step == 0, !tmp.used_spd);
+                       tmp.used_spd && step == 0, !(tmp.used_spd && omega_spd_schur()));
       record_residual(tmp, s, C1, ldq, q, p, step, mxX);
     }
   } else {
@@ -600,7 +676,7 @@ bool Engine::omega_refine_cols(int c0, int c1) {
   if (x0_symmetric) launch_symmatu_inplace(X0, q, ldq, 0.0, s);
   if (int8) {
     launch_tps_fill(dX_.get(), p_, d_, A, ldq, 1e-8, true, s);
-    refine_cols_int8(R, T, q, ldq, c0, nc, X0, C2, refine_planes(T.col_step, nsteps), x0_symmetric, !omega_x0_is_spd_);
+    refine_cols_int8(R, T, q, ldq, c0, nc, X0, C2, refine_planes(T.col_step, nsteps), x0_symmetric, !(omega_x0_is_spd_ && omega_spd_schur()));
     ++T.col_step;
     clock_.end(s);
     SPB_CUDA(cudaGetLastError());
