@@ -403,7 +403,12 @@ void ozaki_slice(cudaStream_t s, const double* M, size_t ld, int rows, int cols,
 void ozaki_product(cublasHandle_t blas, cudaStream_t s, const OzakiGeom& g, const int8_t* left, int Sa,
                    const int8_t* right, int Sb, int S, int m, int n, int* C, double* acc, size_t lda, const int* ea,
                    const int* eb, int mode, int col0, double coef, const double* base, size_t ldb, double* out,
-                   size_t ldo, const int* bad);      // host check after the build has been waited for (SPD route held, residual small)
+                   size_t ldo, const int* bad);
+// the same for a symmetric result of which only the upper triangle is used: column strips, rows above the strip's end only
+void ozaki_product_upper(cublasHandle_t blas, cudaStream_t s, const OzakiGeom& g, const int8_t* left, int Sa,
+                         const int8_t* right, int Sb, int S, int m, int n, int* C, double* acc, size_t lda, const int* ea,
+                         const int* eb, int mode, int col0, double coef, const double* base, size_t ldb, double* out,
+                         size_t ldo, const int* bad, int strip);
 
 // small host helpers (host_math.cpp-like, defined in engine.cu)
 double arma_accumulate(const double* x, int n);

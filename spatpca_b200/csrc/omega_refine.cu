@@ -135,10 +135,17 @@ __global__ void __launch_bounds__(128) zero_strict_upper_kernel(double* __restri
   }
 }
 
+// Strip width of the triangular-aware products below: a product with a triangular operand is cut into strips of
+// kTriStrip rows / columns, and every strip only runs over the part of the contraction range where the triangular
+// operand is non-zero (plain cuBLAS DGEMMs on sub-blocks, pointer arithmetic only).  10 strips at p = 10 000:
+// 0.55 of the dense flop count instead of 1 (the ideal, 0.5, needs infinitely thin strips).
+constexpr int kTriStrip = 1024;
+
 // V = L^-1 in place for a lower-triangular L (n x n, its strict upper triangle stored as zeros): recursive,
 //   [L11 0; L21 L22]^-1 = [V11 0; -V22 L21 V11  V22],
-// every flop in a cuBLAS DGEMM that reads the triangular blocks as dense (2/3 n^3 flop instead of 1/3, at the DGEMM
-// rate instead of cuSOLVER's trtri rate); 512-row leaves by TRSM on an identity.  T: scratch of >= n^2 / 4 + 512^2.
+// every flop in a cuBLAS DGEMM at the DGEMM rate (instead of cuSOLVER's trtri rate); both products have a triangular
+// operand and are cut into strips (see kTriStrip); 512-row leaves by TRSM on an identity.
+// T: scratch of >= n^2 / 4 + 512^2.
 void trtri_lower_gemm(cublasHandle_t blas, cudaStream_t s, double* L, int n, size_t ld, double* T) {
   const double one = 1.0, zero = 0.0, mone = -1.0;
   if (n <= 512) {
@@ -155,8 +162,31 @@ void trtri_lower_gemm(cublasHandle_t blas, cudaStream_t s, double* L, int n, siz
   double* L22 = L + (size_t)h * ld + h;
   trtri_lower_gemm(blas, s, L, h, ld, T);
   trtri_lower_gemm(blas, s, L22, r, ld, T);
-  SPB_CUBLAS(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, r, h, h, &one, L21, (int)ld, L, (int)ld, &zero, T, r));       // L21 V11
-  SPB_CUBLAS(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, r, h, r, &mone, L22, (int)ld, T, r, &zero, L21, (int)ld));    // -V22 (.)
+  // T = L21 V11 (r x h): column strip [j0, j0 + nb) of the lower-triangular V11 is zero above row j0
+  for (int j0 = 0; j0 < h; j0 += kTriStrip) {
+    const int nb = std::min(kTriStrip, h - j0);
+    SPB_CUBLAS(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, r, nb, h - j0, &one, L21 + (size_t)j0 * ld, (int)ld,
+                           L + (size_t)j0 * ld + j0, (int)ld, &zero, T + (size_t)j0 * r, r));
+  }
+  // V21 = -V22 T (r x h): row strip [i0, i0 + nb) of the lower-triangular V22 is zero right of column i0 + nb
+  for (int i0 = 0; i0 < r; i0 += kTriStrip) {
+    const int nb = std::min(kTriStrip, r - i0);
+    SPB_CUBLAS(cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, nb, h, i0 + nb, &mone, L22 + i0, (int)ld, T, r, &zero,
+                           L21 + i0, (int)ld));
+  }
+}
+
+// upper(C) = V'V for a lower-triangular V (n x n, strict upper triangle stored as zeros).  Column strip [j0, j0 + nb)
+// of C needs the rows 0 .. j0 + nb - 1 (on / above the diagonal block) and, because V[k, j] = 0 for k < j, only the
+// contraction range k >= j0: 0.44 n^3 flop in 10 strips instead of the n^3 of a product that treats V as dense.
+// The part of C below the diagonal blocks is not written.
+void vtv_upper_strips(cublasHandle_t blas, const double* V, int n, size_t ld, double* C, size_t ldc) {
+  const double one = 1.0, zero = 0.0;
+  for (int j0 = 0; j0 < n; j0 += kTriStrip) {
+    const int nb = std::min(kTriStrip, n - j0);
+    SPB_CUBLAS(cublasDgemm(blas, CUBLAS_OP_T, CUBLAS_OP_N, j0 + nb, nb, n - j0, &one, V + j0, (int)ld,
+                           V + (size_t)j0 * ld + j0, (int)ld, &zero, C + (size_t)j0 * ldc, (int)ldc));
+  }
 }
 
 // B (n x n, SPD, upper triangle valid) -> B^-1 (full storage) through its Cholesky factor: B = L L', V = L^-1,
@@ -176,7 +206,7 @@ void spd_inverse_cholesky(OmegaRes& R, int* flag, double* B, int n, size_t ld, d
   count_launch();
   trtri_lower_gemm(R.blas, s, B, n, ld, T);
   SPB_CUDA(cudaMemset2DAsync(C, ldc * sizeof(double), 0, (size_t)n * sizeof(double), n, s));
-  gemm_upper_tn(R.blas, n, n, 1.0, B, ld, B, ld, C, ldc);                     // upper(V'V)
+  vtv_upper_strips(R.blas, B, n, ld, C, ldc);                                 // upper(V'V)
   SPB_CUDA(cudaMemcpy2DAsync(B, ld * sizeof(double), C, ldc * sizeof(double), (size_t)n * sizeof(double), n,
                              cudaMemcpyDeviceToDevice, s));
   launch_symmatu_inplace(B, n, ld, 0.0, s);
@@ -387,8 +417,11 @@ bool omega_int8_enabled() {
 // forward errors and lifts the residual to ~cond * eps * sqrt(q) (0.1 at p = 10 000, measured) -- and the step only
 // contracts the error by the size of that residual.  The rows of X0 (left operand of the correction) are sliced from
 // a transposed copy parked in Xout (x0_symmetric: X0 itself).
+// upper_result: only the part of Xout on / above the diagonal is read afterwards (the one-piece build mirrors the upper
+// triangle of its last iterate): the correction then runs in column strips over the rows above each strip's end.
+constexpr int kOzakiStrip = 2048;
 static void refine_cols_int8(OmegaRes& R, OmegaTemps& T, int q, size_t ldq, int c0, int nc, const double* X0,
-                             double* Xout, int S, bool x0_symmetric, bool x0_lu_accurate) {
+                             double* Xout, int S, bool x0_symmetric, bool x0_lu_accurate, bool upper_result = false) {
   if (nc <= 0) return;
   const int Sc = ozaki_env_slices("SPB_OZAKI_CORR_SLICES", x0_lu_accurate ? 6 : 8, 2, 16);
   const int Sm = std::max(S, Sc);
@@ -416,8 +449,13 @@ static void refine_cols_int8(OmegaRes& R, OmegaTemps& T, int q, size_t ldq, int 
   }
   ozaki_slice(s, X0rows, ldq, q, q, g.mp, Sc, false, left, g.kq, ea, bad);        // rows of X0
   ozaki_slice(s, C1, ldq, q, nc, g.np, Sc, true, right, g.kq, eb, bad);
-  ozaki_product(R.blas, s, g, left, Sc, right, Sc, Sc, q, nc, T.oz_c.get(), acc, ldq, ea, eb, 1, c0, 1.0, X0 + o, ldq,
-                Xout + o, ldq, bad);
+  if (upper_result && c0 == 0 && nc == q) {
+    ozaki_product_upper(R.blas, s, g, left, Sc, right, Sc, Sc, q, nc, T.oz_c.get(), acc, ldq, ea, eb, 1, c0, 1.0, X0 + o, ldq,
+                        Xout + o, ldq, bad, kOzakiStrip);
+  } else {
+    ozaki_product(R.blas, s, g, left, Sc, right, Sc, Sc, q, nc, T.oz_c.get(), acc, ldq, ea, eb, 1, c0, 1.0, X0 + o, ldq,
+                  Xout + o, ldq, bad);
+  }
 }
 
 // Newton-Schulz steps of the build: ONE.  The step takes the forward error E0 of X0 to E0 A E0; a second step cannot
@@ -548,8 +586,9 @@ void Engine::build_omega_refined(OmegaRes& R, int* flag, const double* x_dev, in
       // the iterate moves back into X0's buffer AS IT IS: mirroring its upper triangle would put its asymmetry (the
       // size of its forward error, ~1e-9) into the next residual as A * 1e-9 |X| ~ 1, and the step would not contract
       if (step > 0) std::swap(X0, C2);
+      // the last iterate is only read through its upper triangle (mirrored below)
       refine_cols_int8(R, tmp, q, ldq, 0, q, X0, C2, refine_planes(step, nsteps),     // C1 = I - A X0, C2 = X0 + X0 C1
-                       tmp.used_spd && step == 0, !(tmp.used_spd && omega_spd_schur()));
+                       tmp.used_spd && step == 0, !(tmp.used_spd && omega_spd_schur()), step + 1 == nsteps);
       record_residual(tmp, s, C1, ldq, q, p, step, mxX);
     }
   } else {
@@ -594,8 +633,9 @@ void Engine::build_omega_refined(OmegaRes& R, int* flag, const double* x_dev, in
     const OzakiGeom g = ozaki_geom(p, p);
     ozaki_slice(s, C2, ldq, p, p, g.mp, Sp, false, tmp.oz_left.get(), g.kq, tmp.oz_ea.get(), tmp.oz_bad.get());
     ozaki_slice(s, C2, ldq, p, p, g.np, Sp, true, tmp.oz_right.get(), g.kq, tmp.oz_eb.get(), tmp.oz_bad.get());
-    ozaki_product(R.blas, s, g, tmp.oz_left.get(), Sp, tmp.oz_right.get(), Sp, Sp, p, p, tmp.oz_c.get(), S2, ldq,
-                  tmp.oz_ea.get(), tmp.oz_eb.get(), 1, 0, -1e-8, C2, ldq, omega_dev, ld, tmp.oz_bad.get());
+    // Omega is symmetric and only its upper triangle is read (symmatu, here or in prepare()): upper strips
+    ozaki_product_upper(R.blas, s, g, tmp.oz_left.get(), Sp, tmp.oz_right.get(), Sp, Sp, p, p, tmp.oz_c.get(), S2, ldq,
+                        tmp.oz_ea.get(), tmp.oz_eb.get(), 1, 0, -1e-8, C2, ldq, omega_dev, ld, tmp.oz_bad.get(), kOzakiStrip);
   } else {
     SPB_CUDA(cudaMemcpy2DAsync(omega_dev, ld * sizeof(double), C2, ldq * sizeof(double), (size_t)p * sizeof(double), p,
                                cudaMemcpyDeviceToDevice, s));

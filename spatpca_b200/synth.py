@@ -83,6 +83,9 @@ _CASES = {
                tau2=_log_grid(1.0, 400.0, 10), seed=2024),
     "C5": dict(x=lambda s: _uniform(40000, 3, s), n=500, K=8, M=5, tau1=_log_grid(1e-6, 1.0, 7),
                tau2=_log_grid(1.0, 400.0, 7), seed=2024),
+    # smallest irregular case whose Core2 / Core3 calls take the matrix-free (fold-batched) path (p >= 2048)
+    "irregular2d_2304": dict(x=lambda s: _uniform(2304, 2, s), n=100, K=3, M=5, tau1=_log_grid(1e-5, 1.0, 4),
+                             tau2=_log_grid(1.0, 400.0, 3), seed=77),
     # mid-size irregular case used by the slower parity test
     "irregular2d_1500": dict(x=lambda s: _uniform(1500, 2, s), n=200, K=5, M=5, tau1=_log_grid(1e-6, 1.0, 9),
                              tau2=_log_grid(1.0, 400.0, 9), seed=2024),

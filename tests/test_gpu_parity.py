@@ -755,6 +755,59 @@ def test_sharded_two_engines_match_single(sp):
         e.close()
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_matrix_free_worlds(sp, world):
+    """Fold sharding on a case whose ADMM calls take the fold-batched matrix-free kernel (p >= 2048), emulated with one
+    engine per rank that owns work: world = 2 / 3 batch different numbers of folds per launch, world = 8 has single-fold
+    ranks, idle ranks and a full-data fit on a rank WITHOUT folds (its Core2p / tau2 path has no fold batch to ride
+    with).  Batches of different width sum in different orders, so the comparison with the single-engine job is to
+    the parity tolerances, with identical selections and identical per-rank iteration totals."""
+    from spatpca_b200 import distributed as D
+    case = make_case("irregular2d_2304")
+    single = _run_cv(sp, case)
+    assert single["stats"]["n_cg_calls"] > 0            # the case must exercise the matrix-free path
+    M = case["M"]
+    mine = [[k for k in range(M) if D.fold_owner(k, world) == r] for r in range(world)]
+    full = D.full_fit_owner(M, world)
+    engines = {}
+    for r in range(world):
+        if not mine[r] and r != full:
+            continue                                     # a rank without work only takes part in the collectives
+        e = sp.Engine(case["x"].shape[0], case["x"].shape[1], case["Y"].shape[0], M, case["K"], case["tau1"],
+                      case["tau2"], case["gamma"], 100, 1e-4, case["l2"])
+        e.upload(case["x"], case["Y"], case["nk"])
+        e.prepare()
+        engines[r] = e
+
+    def gather(stage, width, *idx):
+        cv = np.zeros((M, width))
+        for r, e in engines.items():
+            if mine[r]:
+                for k, row in getattr(e, stage)(mine[r], *idx).items():
+                    cv[k] = row
+        return cv
+
+    try:
+        i1, s1 = sp.select_index(gather("stage1_folds", len(case["tau1"])))
+        engines[full].stage1_full(i1)
+        i2, s2 = sp.select_index(gather("stage2_folds", len(case["tau2"]), i1))
+        engines[full].stage2_full(i1, i2)
+        i3, s3 = sp.select_index(gather("stage3_folds", len(case["gamma"]), i1, i2))
+        phi = engines[full].get_eigenfn()
+        iters = sum(int(e.stats()["admm_iters"]) for e in engines.values())
+    finally:
+        for e in engines.values():
+            e.close()
+    assert case["tau1"][i1] == single["selected_tau1"]
+    assert case["tau2"][i2] == single["selected_tau2"]
+    assert case["gamma"][i3] == single["selected_gamma"]
+    np.testing.assert_allclose(s1, single["cv_score_tau1"], rtol=CV_RTOL)
+    np.testing.assert_allclose(s2, single["cv_score_tau2"], rtol=CV_RTOL)
+    np.testing.assert_allclose(s3, single["cv_score_gamma"], rtol=CV_RTOL)
+    assert eig_err(phi, single["estimated_eigenfn"]) <= EIG_RTOL
+    assert iters == int(single["stats"]["admm_iters"])
+
+
 def test_cv_forced_iterations(sp):
     """thr = 0: every ADMM call runs exactly maxit iterations (the deterministic-denominator mode of
     SURVEY.md section 8d); iterates still match the oracle."""
