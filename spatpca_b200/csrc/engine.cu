@@ -12,6 +12,7 @@
 #include <map>
 #include <mutex>
 #include <numeric>
+#include <thread>
 
 namespace spb {
 
@@ -114,6 +115,13 @@ DeviceCtx& DeviceCtx::get() {
   SPB_CUDA(cudaGetDevice(&dev));
   auto it = ctxs.find(dev);
   if (it != ctxs.end()) return *it->second;
+  std::unique_ptr<DeviceCtx> c = create(dev, true);
+  DeviceCtx& ref = *c;
+  ctxs[dev] = std::move(c);
+  return ref;
+}
+
+std::unique_ptr<DeviceCtx> DeviceCtx::create(int dev, bool with_blas) {
   std::unique_ptr<DeviceCtx> c(new DeviceCtx());
   c->device = dev;
   // highest priority: the host-synchronous SVD starts (many small kernels) run on this stream while the Omega build
@@ -122,17 +130,24 @@ DeviceCtx& DeviceCtx::get() {
   int prio_least = 0, prio_greatest = 0;
   SPB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
   SPB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
-  SPB_CUBLAS(cublasCreate(&c->blas));
-  SPB_CUBLAS(cublasSetStream(c->blas, c->stream));
-  SPB_CUBLAS(cublasSetPointerMode(c->blas, CUBLAS_POINTER_MODE_HOST));
+  if (with_blas) {
+    SPB_CUBLAS(cublasCreate(&c->blas));
+    SPB_CUBLAS(cublasSetStream(c->blas, c->stream));
+    SPB_CUBLAS(cublasSetPointerMode(c->blas, CUBLAS_POINTER_MODE_HOST));
+  }
   SPB_CUSOLVER(cusolverDnCreate(&c->solver));
   SPB_CUSOLVER(cusolverDnSetStream(c->solver, c->stream));
   c->info.alloc(4);
   c->flag.alloc(1);
   SPB_CUDA(cudaMemsetAsync(c->flag.get(), 0, sizeof(int), c->stream));
-  DeviceCtx& ref = *c;
-  ctxs[dev] = std::move(c);
-  return ref;
+  return c;
+}
+
+// i-th pooled context for a host worker thread (own high-priority stream, cuSOLVER handle, workspace, error flag);
+// created on the owning thread, kept for the life of this context
+DeviceCtx& DeviceCtx::worker(int i) {
+  while ((int)worker_pool.size() <= i) worker_pool.push_back(create(device, false));
+  return *worker_pool[i];
 }
 
 OmegaRes::~OmegaRes() {
@@ -606,6 +621,7 @@ void Engine::reset_k(int K) {
   std::memset(&stats_, 0, sizeof(stats_));
   stats_.bytes_h2d = h2d;
   clock_.reset();
+  prologue_wall_ms_ = 0.0;
   for (auto& L : lanes_) L->clock.reset();
   launches_at_start_ = g_launch_count;
   t_created = std::chrono::steady_clock::now();
@@ -997,8 +1013,18 @@ void Engine::fold_prepare(int k) {
   if (f.prepared) return;
   trace(ctx_, "fold_prepare: enter");
   Scoped sc(clock_, PH_PROLOGUE, ctx_.stream);
-  cudaStream_t s = ctx_.stream;
+  fold_prepare_on(ctx_, k);
+  trace(ctx_, "fold_prepare: done");
+}
+
+// The start of one fold (:318-326) on the stream / cuSOLVER handle of `c`: safe to run for DIFFERENT folds from
+// different host threads (each with its own context): it touches only folds_[k], read-only engine state and the
+// (mutex-protected) caching allocator.
+void Engine::fold_prepare_on(DeviceCtx& c, int k) {
+  FoldData& f = folds_[k];
+  cudaStream_t s = c.stream;
   DevBuf<int> rows((size_t)n_);
+  DevBuf<double> scratch(512 + 8);
   f.Ytr.alloc((size_t)f.n_tr * p_);
   SPB_CUDA(cudaMemcpyAsync(rows.get(), f.rows_tr.data(), sizeof(int) * f.n_tr, cudaMemcpyHostToDevice, s));
   launch_gather_rows(dY_.get(), n_, p_, rows.get(), f.n_tr, f.Ytr.get(), s);
@@ -1014,17 +1040,62 @@ void Engine::fold_prepare(int k) {
   f.L20.alloc((size_t)p_ * K_);
   f.kcap = std::min(std::min(f.n_tr, p_), SPB_MAX_K);
   f.V.alloc((size_t)p_ * f.kcap);
-  svd_right(ctx_, f.Ytr.get(), f.n_tr, p_, f.kcap, f.sv, f.V.get());          // :321
+  svd_right(c, f.Ytr.get(), f.n_tr, p_, f.kcap, f.sv, f.V.get());             // :321
   f.rho = 10.0 * (f.sv[0] * f.sv[0]);                                         // :322
   // trace(Ytr'Ytr) / n_tr (:489, :491)
-  double* out = loss_out_.get() + (size_t)M_ * max_grid_;
-  launch_sumsq(f.Ytr.get(), (size_t)f.n_tr * p_, prep_scratch_.get(), out, s);
+  double* out = scratch.get() + 512;
+  launch_sumsq(f.Ytr.get(), (size_t)f.n_tr * p_, scratch.get(), out, s);
   double ss = 0.0;
   SPB_CUDA(cudaMemcpyAsync(&ss, out, sizeof(double), cudaMemcpyDeviceToHost, s));
   SPB_CUDA(cudaStreamSynchronize(s));
   f.tv = ss / (double)f.n_tr;
   f.prepared = true;
-  trace(ctx_, "fold_prepare: done");
+}
+
+// The starts of several folds at once.  One start is ~270 dependent small launches (transpose, Householder QR of the
+// p x n_tr block, one-sided Jacobi SVD of its triangular factor with a host read per sweep, back-transformation) and
+// is latency-bound: ~9 ms alone, ~23 ms while the Omega build fills the SMs with GEMM waves -- 5 folds one after the
+// other took as long as the whole Omega build (141 of 152 ms at p = 10 000) and slowed it by their SM share.  cuSOLVER's
+// gesvdj synchronises with the host inside the call, so the overlap needs host threads: one per fold, each with a
+// pooled worker context.  Same kernels on the same inputs as the serial path: bitwise identical starts.
+// SPB_PROLOGUE_THREADS=0 keeps the serial path.
+void Engine::prepare_folds(const int* folds, int nfolds) {
+  std::vector<int> todo;
+  for (int i = 0; i < nfolds; ++i)
+    if (!folds_[folds[i]].prepared && std::find(todo.begin(), todo.end(), folds[i]) == todo.end()) todo.push_back(folds[i]);
+  static const bool threaded = [] { const char* e = std::getenv("SPB_PROLOGUE_THREADS"); return !(e && e[0] == '0'); }();
+  if (todo.size() < 2 || !threaded) {
+    for (int k : todo) fold_prepare(k);
+    return;
+  }
+  NvtxRange nvtx_range("spb::prepare_folds (SVD starts of all folds, one host thread each)");
+  trace(ctx_, "prepare_folds: enter");
+  const int nt = (int)todo.size();
+  std::vector<DeviceCtx*> res;
+  for (int i = 0; i < nt; ++i) res.push_back(&ctx_.worker(i));                // created on this thread
+  SPB_CUDA(cudaStreamSynchronize(ctx_.stream));                               // Y was uploaded on the main stream
+  std::vector<std::exception_ptr> errs((size_t)nt);
+  std::vector<long long> launches((size_t)nt, 0);
+  const int dev = ctx_.device;
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> workers;
+  for (int i = 0; i < nt; ++i) {
+    workers.emplace_back([this, i, dev, &todo, &res, &errs, &launches] {
+      try {
+        SPB_CUDA(cudaSetDevice(dev));
+        fold_prepare_on(*res[i], todo[i]);
+      } catch (...) {
+        errs[i] = std::current_exception();
+      }
+      launches[i] = g_launch_count;                                           // thread-local counter of this worker
+    });
+  }
+  for (auto& w : workers) w.join();
+  for (int i = 0; i < nt; ++i) g_launch_count += launches[i];
+  prologue_wall_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  for (int i = 0; i < nt; ++i)
+    if (errs[i]) std::rethrow_exception(errs[i]);
+  trace(ctx_, "prepare_folds: done");
 }
 
 void Engine::ensure_gram(Lane& L, int k) {
@@ -1473,7 +1544,7 @@ void Engine::stage1_folds(const int* folds, int nfolds, double* rows) {
   for (int f = 0; f < nfolds; ++f) SPB_REQUIRE(folds[f] >= 0 && folds[f] < M_, "fold index out of range");
   const int n1 = (int)tau1_.size();
   my_stage1_folds_ = nfolds;
-  for (int f = 0; f < nfolds; ++f) fold_prepare(folds[f]);                    // SVD starts (host-synchronous)
+  prepare_folds(folds, nfolds);                                               // SVD starts, one host thread per fold
   for (const auto& round : lane_rounds(folds, nfolds)) {                      // tau1 paths, concurrent lanes
     for (int k : round) enqueue_stage1(k, 0);
     bool batched = false;
@@ -1892,7 +1963,7 @@ void Engine::get_stats(spb_cv_stats* st) {
   }
   // per-phase STREAM time summed over lanes: with concurrent lanes the sum exceeds the wall time
   stats_.ms_omega = sum[PH_OMEGA];
-  stats_.ms_prologue = sum[PH_PROLOGUE];
+  stats_.ms_prologue = sum[PH_PROLOGUE] + prologue_wall_ms_;     // threaded fold starts: host wall time of the group
   stats_.ms_inverse = sum[PH_INVERSE];
   stats_.ms_admm = sum[PH_ADMM];
   stats_.ms_cv_loss = sum[PH_CVLOSS];

@@ -71,6 +71,9 @@ struct DeviceCtx {
   Exec exec() { return Exec{stream, blas, flag.get(), &inv_work}; }
 
   static DeviceCtx& get();        // context of the calling thread's current device
+  static std::unique_ptr<DeviceCtx> create(int dev, bool with_blas);
+  std::vector<std::unique_ptr<DeviceCtx>> worker_pool;
+  DeviceCtx& worker(int i);       // i-th pooled context for a host worker thread (created on first use)
   void sync_and_check();          // stream sync + translate the sticky flag into an Error
   double* work(size_t doubles) { solver_work.ensure(doubles); return solver_work.get(); }
   ~DeviceCtx();
@@ -257,6 +260,9 @@ class Engine {
 
  private:
   void fold_prepare(int k);
+  void fold_prepare_on(DeviceCtx& c, int k);
+  void prepare_folds(const int* folds, int nfolds);
+  double prologue_wall_ms_ = 0.0;   // host wall time of the threaded fold starts (added to ms_prologue)
   Lane& lane_of(int fold);                       // fold < 0: the full-data lane
   void ensure_gram(Lane& L, int k);              // k = -1: full data
   void init_lambda(cudaStream_t s, const double* Phi, const std::vector<double>& sv, double rho, double* L2);

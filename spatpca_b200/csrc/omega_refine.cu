@@ -423,7 +423,10 @@ constexpr int kOzakiStrip = 2048;
 static void refine_cols_int8(OmegaRes& R, OmegaTemps& T, int q, size_t ldq, int c0, int nc, const double* X0,
                              double* Xout, int S, bool x0_symmetric, bool x0_lu_accurate, bool upper_result = false) {
   if (nc <= 0) return;
-  const int Sc = ozaki_env_slices("SPB_OZAKI_CORR_SLICES", x0_lu_accurate ? 6 : 8, 2, 16);
+  // correction planes: the step's |I - A X0| is at most 1e-5 (omega_build_ok), so 5 planes (2^-33 of the term sizes)
+  // leave < 1e-15 |X0|; measured at p = 10 000 (tools/omega_planes_probe.py): 6 -> 5 -> 4 planes move Omega by
+  // 0 / 3e-15 / 1e-14, while one residual plane less (12 -> 11) moves it by 1e-12 and one product plane less by 3e-11
+  const int Sc = ozaki_env_slices("SPB_OZAKI_CORR_SLICES", x0_lu_accurate ? 5 : 8, 2, 16);
   const int Sm = std::max(S, Sc);
   const OzakiGeom g = ozaki_geom(q, nc);
   cudaStream_t s = R.stream;
