@@ -134,7 +134,7 @@ def run_job_resident(sp, case, coll=None):
     t0 = time.perf_counter()
     if coll is None:
         coll = D.Collective()
-    D.prepare_sharded(eng, coll)           # Omega shared by the ranks (column blocks over NCCL), SVD start
+    D.prepare_sharded(eng, coll, D.my_folds(M, coll))   # Omega shared by the ranks (column blocks over NCCL), SVD starts
     res = D.run_sharded(eng, sp.select_index, coll, M, len(case["tau1"]), len(case["tau2"]), len(case["gamma"]),
                         case["tau1"], case["tau2"], case["gamma"],
                         share_inverses=os.environ.get("SPB_SHARE_INVERSES", "1") != "0")

@@ -230,6 +230,11 @@ SPB_API int spb_engine_sync(spb_engine* e);
  * are device memory; call omega_sync before handing them to a collective.  spb_engine_prepare() afterwards
  * only adds the full-data SVD start.                                          */
 SPB_API int spb_engine_omega_begin(spb_engine* e, int* needed);
+/* The SVD starts (svd_econ of src/RcppSpatPCA.cpp:563 for the full data, :321 for each listed fold) ahead of
+ * spb_engine_prepare() / stage1_folds(): called right after omega_begin(), they run under the replicated first
+ * stage of the column-split Omega build instead of after it.  Optional: prepare() and stage1_folds() do whatever
+ * has not been done yet.                                                                               */
+SPB_API int spb_engine_prepare_starts(spb_engine* e, const int* folds, int nfolds);
 SPB_API int spb_engine_omega_solve_cols(spb_engine* e, int c0, int c1);
 SPB_API int spb_engine_omega_product_cols(spb_engine* e, int c0, int c1);
 /* Refined build (the default, csrc/omega_refine.cu): between the exchange of buffer 0 (X0 = A^-1 columns) and

@@ -86,6 +86,7 @@ SIGNATURES = {
     "spb_engine_stage3_folds": (C.c_int, [_vp, _ip, C.c_int, C.c_int, C.c_int, _dp]),
     "spb_engine_can_share_inverses": (C.c_int, [_vp]),
     "spb_engine_prepare_fold": (C.c_int, [_vp, C.c_int]),
+    "spb_engine_prepare_starts": (C.c_int, [_vp, C.POINTER(C.c_int), C.c_int]),
     "spb_engine_inverse_buffer": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]),
     "spb_engine_build_inverse": (C.c_int, [_vp, C.c_int, C.c_int]),
     "spb_engine_mark_inverse": (C.c_int, [_vp, C.c_int, C.c_int]),

@@ -301,6 +301,9 @@ int spb_engine_can_share_inverses(spb_engine* e) {
   return rc == SPB_OK ? v : rc;
 }
 int spb_engine_prepare_fold(spb_engine* e, int k) { SPB_ENGINE_CALL(e->impl->prepare_fold(k)); }
+int spb_engine_prepare_starts(spb_engine* e, const int* folds, int nfolds) {
+  SPB_ENGINE_CALL(e->impl->prepare_starts(folds, nfolds));
+}
 int spb_engine_inverse_buffer(spb_engine* e, int k, int i, void** dev_ptr, long long* bytes) {
   SPB_ENGINE_CALL(SPB_REQUIRE(dev_ptr != nullptr, "NULL output"); *dev_ptr = e->impl->inverse_buffer(k, i, bytes));
 }

@@ -841,14 +841,7 @@ void Engine::prepare() {
     }
     omega_ready_ = true;
   }
-  if (!full_svd_done_) {
-    Scoped sc(clock_, PH_PROLOGUE, s);
-    kcap_full_ = std::min(std::min(n_, p_), SPB_MAX_K);
-    Vfull_.alloc((size_t)p_ * kcap_full_);
-    svd_right(ctx_, dY_.get(), n_, p_, kcap_full_, sv_full_, Vfull_.get());   // :563
-    rho_full_ = 10.0 * (sv_full_[0] * sv_full_[0]);                           // :564
-    full_svd_done_ = true;
-  }
+  full_svd_start();
   if (!full_ready_) {
     copy_pk(s, full_.Phi.get(), Vfull_.get());                                // :565 (first K columns)
     copy_pk(s, full_.C.get(), full_.Phi.get());                               // :566
@@ -857,6 +850,29 @@ void Engine::prepare() {
   }
   ctx_.sync_and_check();            // the lanes read Omega and the full-data start from other streams
   trace(ctx_, "prepare: done");
+}
+
+void Engine::full_svd_start() {
+  if (full_svd_done_) return;
+  Scoped sc(clock_, PH_PROLOGUE, ctx_.stream);
+  kcap_full_ = std::min(std::min(n_, p_), SPB_MAX_K);
+  Vfull_.alloc((size_t)p_ * kcap_full_);
+  svd_right(ctx_, dY_.get(), n_, p_, kcap_full_, sv_full_, Vfull_.get());     // :563
+  rho_full_ = 10.0 * (sv_full_[0] * sv_full_[0]);                             // :564
+  full_svd_done_ = true;
+}
+
+// The SVD starts of the full data and of the given folds ahead of prepare() / stage1_folds().  The column-split Omega
+// build of a multi-GPU job is driven from the host (synchronise + exchange between its phases), so nothing can hide
+// under it unless the caller asks for it: distributed.prepare_sharded() calls this right after omega_begin(), and
+// the starts (~25 ms + ~20 ms, latency-bound) then run under the replicated X0 stage instead of after the build.
+void Engine::prepare_starts(const int* folds, int nfolds) {
+  SPB_REQUIRE(dY_.get() != nullptr, "upload() must be called before prepare_starts()");
+  SPB_REQUIRE(nfolds == 0 || folds != nullptr, "invalid fold list");
+  for (int f = 0; f < nfolds; ++f) SPB_REQUIRE(folds[f] >= 0 && folds[f] < M_, "fold index out of range");
+  SPB_CUDA(cudaStreamSynchronize(ctx_.stream));
+  full_svd_start();
+  prepare_folds(folds, nfolds);
 }
 
 void Engine::wait_omega(Lane& L) {
@@ -925,6 +941,7 @@ bool Engine::omega_begin() {
 void Engine::omega_solve_cols(int c0, int c1) {
   SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
   SPB_REQUIRE(c0 >= 0 && c0 <= c1 && c1 <= p_, "column range out of bounds");
+  omega_x0_resolve();
   OmegaRes& R = ctx_.omega();
   const int q = p_ + d_ + 1;
   const size_t ldq = padded_ld(q);
@@ -940,6 +957,7 @@ void Engine::omega_solve_cols(int c0, int c1) {
 void Engine::omega_product_cols(int c0, int c1) {
   SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
   SPB_REQUIRE(c0 >= 0 && c0 <= c1 && c1 <= p_, "column range out of bounds");
+  omega_x0_resolve();
   if (omega_refine_enabled()) { omega_product_cols_refined(c0, c1); return; }
   OmegaRes& R = ctx_.omega();
   cudaStream_t s = R.stream;
@@ -965,6 +983,7 @@ void* Engine::omega_buffer(int which, int c0, int c1, long long* bytes) {
   SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
   SPB_REQUIRE(c0 >= 0 && c0 <= c1 && c1 <= p_, "column range out of bounds");
   SPB_REQUIRE(which >= 0 && which <= 2, "which must be 0 (X0 / Lp), 1 (Omega) or 2 (refined X1)");
+  omega_x0_resolve();
   const size_t ldq = padded_ld(p_ + d_ + 1);
   if (which == 0 || which == 2) {
     const bool refined = omega_refine_enabled();
@@ -978,7 +997,10 @@ void* Engine::omega_buffer(int which, int c0, int c1, long long* bytes) {
   return omega_u_.get() + (size_t)c0 * ld_;
 }
 
-void Engine::omega_stream_sync() { SPB_CUDA(cudaStreamSynchronize(ctx_.omega().stream)); }
+void Engine::omega_stream_sync() {
+  omega_x0_resolve();
+  SPB_CUDA(cudaStreamSynchronize(ctx_.omega().stream));
+}
 
 void Engine::omega_finish() {
   SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");

@@ -190,6 +190,7 @@ class Engine {
   // home GPU.  Require the stage-1 inverse cache (memory permitting).
   bool can_share_inverses();      // false when stage 1 runs matrix-free (there is no inverse to share)
   void prepare_fold(int k) { fold_prepare(k); }
+  void prepare_starts(const int* folds, int nfolds);   // full-data + fold SVD starts ahead of prepare()
   void* inverse_buffer(int k, int i, long long* bytes);   // device buffer of inverse (k, tau1[i]), allocated on demand
   void build_inverse(int k, int i);                        // enqueue on fold k's lane
   void mark_inverse(int k, int i);                         // the buffer was filled from outside (peer copy)
@@ -261,6 +262,10 @@ class Engine {
  private:
   void fold_prepare(int k);
   void fold_prepare_on(DeviceCtx& c, int k);
+  void full_svd_start();
+  void omega_lu_factor();
+  void omega_x0_resolve();
+  bool omega_x0_check_pending_ = false;   // column build: the SPD route's flag has not been read yet
   void prepare_folds(const int* folds, int nfolds);
   double prologue_wall_ms_ = 0.0;   // host wall time of the threaded fold starts (added to ms_prologue)
   Lane& lane_of(int fold);                       // fold < 0: the full-data lane

@@ -671,22 +671,13 @@ bool Engine::omega_begin_refined() {
   omega_x0_is_spd_ = omega_x0_spd_enabled(p_, d_);
   if (omega_x0_is_spd_) {
     // X0 is built whole on every rank (p^3 flop at GEMM rate, deterministic: the ranks hold identical copies, so the
-    // first exchange is not needed); only the refinement and the final product are split by columns
+    // first exchange is not needed); only the refinement and the final product are split by columns.  Enqueued only:
+    // whether the SPD route held is read by omega_x0_resolve() at the next omega_* call, so that the caller can run
+    // the SVD starts (prepare_starts) under it.
     omega_x0_spd(R, dX_.get(), p_, d_, T.L.get(), T.Bm.get(), T.C1.get(), T);
-    int hf[4] = {0, 0, 0, 0};
-    SPB_CUDA(cudaStreamSynchronize(s));
-    SPB_CUDA(cudaMemcpy(hf, T.spdflag.get(), sizeof(hf), cudaMemcpyDeviceToHost));
-    if (hf[0] != 0) omega_x0_is_spd_ = false;                  // not positive definite in FP64: the LU route below
-  }
-  if (!omega_x0_is_spd_) {
-    launch_tps_fill(dX_.get(), p_, d_, T.L.get(), ldq, 1e-8, true, s);
-    launch_set_identity(T.Bm.get(), q, q, ldq, s);
-    int lwork = 0;
-    SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(R.solver, q, q, T.L.get(), (int)ldq, &lwork));
-    R.ipiv.ensure(q);
-    R.work.ensure((size_t)lwork);
-    SPB_CUSOLVER(cusolverDnDgetrf(R.solver, q, q, T.L.get(), (int)ldq, R.work.get(), R.ipiv.get(), R.info.get()));
-    launch_check_info(R.info.get(), ctx_.flag.get(), SPB_ERR_SINGULAR, s);
+    omega_x0_check_pending_ = true;
+  } else {
+    omega_lu_factor();
   }
   clock_.end(s);
   stats_.p3_flops += omega_refined_flops(p_);
@@ -694,10 +685,46 @@ bool Engine::omega_begin_refined() {
   return true;
 }
 
+// LU of the bordered system for the column-split build (the start when the SPD route is off or broke down)
+void Engine::omega_lu_factor() {
+  OmegaRes& R = ctx_.omega();
+  cudaStream_t s = R.stream;
+  OmegaTemps& T = *omega_tmp_;
+  const int q = p_ + d_ + 1;
+  const size_t ldq = padded_ld(q);
+  launch_tps_fill(dX_.get(), p_, d_, T.L.get(), ldq, 1e-8, true, s);
+  launch_set_identity(T.Bm.get(), q, q, ldq, s);
+  int lwork = 0;
+  SPB_CUSOLVER(cusolverDnDgetrf_bufferSize(R.solver, q, q, T.L.get(), (int)ldq, &lwork));
+  R.ipiv.ensure(q);
+  R.work.ensure((size_t)lwork);
+  SPB_CUSOLVER(cusolverDnDgetrf(R.solver, q, q, T.L.get(), (int)ldq, R.work.get(), R.ipiv.get(), R.info.get()));
+  launch_check_info(R.info.get(), ctx_.flag.get(), SPB_ERR_SINGULAR, s);
+}
+
+// Waits for the X0 enqueued by omega_begin_refined() and falls back to the LU when the Cholesky factorisation of the
+// rotated block reported a non-positive pivot (not positive definite in FP64).  Every rank sees the same flag: the
+// build is deterministic and replicated.
+void Engine::omega_x0_resolve() {
+  if (!omega_x0_check_pending_) return;
+  omega_x0_check_pending_ = false;
+  OmegaRes& R = ctx_.omega();
+  int hf[4] = {0, 0, 0, 0};
+  SPB_CUDA(cudaStreamSynchronize(R.stream));
+  SPB_CUDA(cudaMemcpy(hf, omega_tmp_->spdflag.get(), sizeof(hf), cudaMemcpyDeviceToHost));
+  if (hf[0] != 0) {
+    omega_x0_is_spd_ = false;
+    clock_.begin(PH_OMEGA, R.stream);
+    omega_lu_factor();
+    clock_.end(R.stream);
+  }
+}
+
 bool Engine::omega_refine_cols(int c0, int c1) {
   SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
   SPB_REQUIRE(c0 >= 0 && c0 <= c1 && c1 <= p_, "column range out of bounds");
   if (!omega_refine_enabled()) return false;
+  omega_x0_resolve();
   OmegaRes& R = ctx_.omega();
   cudaStream_t s = R.stream;
   const int q = p_ + d_ + 1;
@@ -764,7 +791,8 @@ void Engine::omega_product_cols_refined(int c0, int c1) {
   cudaStream_t s = R.stream;
   const int q = p_ + d_ + 1;
   const size_t ldq = padded_ld(q);
-  double* X1 = omega_tmp_->C2.get();
+  OmegaTemps& T = *omega_tmp_;
+  double* X1 = T.C2.get();
   clock_.begin(PH_OMEGA, s);
   launch_symmatu_inplace(X1, q, ldq, 0.0, s);
   if (c1 > c0) {
@@ -772,10 +800,31 @@ void Engine::omega_product_cols_refined(int c0, int c1) {
     const double one = 1.0, eps = 1e-8, meps = -1e-8;
     double* out = omega_u_.get() + (size_t)c0 * ld_;
     // rows 0 .. c1-1 of these columns cover the upper triangle, which is all that is used downstream
-    SPB_CUDA(cudaMemcpy2DAsync(out, ld_ * sizeof(double), X1 + (size_t)c0 * ldq, ldq * sizeof(double),
-                               (size_t)c1 * sizeof(double), nc, cudaMemcpyDeviceToDevice, s));
-    SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_T, CUBLAS_OP_N, c1, nc, p_, &meps, X1, (int)ldq, X1 + (size_t)c0 * ldq,
-                           (int)ldq, &one, out, (int)ld_));                                   // - eps Lp Lp
+    if (omega_int8_enabled()) {
+      // Lp - eps Lp Lp on INT8 digit planes, as in the one-piece build: rows [0, c1) of Lp (its columns: Lp is
+      // symmetric after the mirror above) against this rank's columns
+      const int Sp = ozaki_env_slices("SPB_OZAKI_PROD_SLICES", 7, 3, 16);
+      OzakiGeom g = ozaki_geom(p_, nc);
+      g.mp = (int)(((size_t)c1 + 15) / 16 * 16);
+      T.oz_left.ensure((size_t)Sp * g.kq * g.mp);
+      T.oz_right.ensure((size_t)Sp * g.kq * g.np);
+      T.oz_c.ensure((size_t)g.mp * g.np);
+      T.oz_ea.ensure(g.mp);
+      T.oz_eb.ensure(g.np);
+      T.oz_bad.ensure(1);
+      SPB_CUDA(cudaMemsetAsync(T.oz_bad.get(), 0, sizeof(int), s));
+      ozaki_slice(s, X1, ldq, p_, c1, g.mp, Sp, false, T.oz_left.get(), g.kq, T.oz_ea.get(), T.oz_bad.get());
+      ozaki_slice(s, X1 + (size_t)c0 * ldq, ldq, p_, nc, g.np, Sp, true, T.oz_right.get(), g.kq, T.oz_eb.get(),
+                  T.oz_bad.get());
+      ozaki_product(R.blas, s, g, T.oz_left.get(), Sp, T.oz_right.get(), Sp, Sp, c1, nc, T.oz_c.get(),
+                    T.T1.get() + (size_t)c0 * ldq, ldq, T.oz_ea.get(), T.oz_eb.get(), 1, 0, -1e-8, X1 + (size_t)c0 * ldq, ldq,
+                    out, ld_, T.oz_bad.get());
+    } else {
+      SPB_CUDA(cudaMemcpy2DAsync(out, ld_ * sizeof(double), X1 + (size_t)c0 * ldq, ldq * sizeof(double),
+                                 (size_t)c1 * sizeof(double), nc, cudaMemcpyDeviceToDevice, s));
+      SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_T, CUBLAS_OP_N, c1, nc, p_, &meps, X1, (int)ldq, X1 + (size_t)c0 * ldq,
+                             (int)ldq, &one, out, (int)ld_));                                   // - eps Lp Lp
+    }
     SPB_CUBLAS(cublasDgemm(R.blas, CUBLAS_OP_N, CUBLAS_OP_T, c1, nc, d_ + 1, &eps, X1 + (size_t)p_ * ldq, (int)ldq,
                            X1 + (size_t)p_ * ldq + c0, (int)ldq, &one, out, (int)ld_));       // + eps M M'
   }

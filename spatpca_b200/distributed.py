@@ -27,6 +27,11 @@ def full_fit_owner(M: int, world: int) -> int:
     return max(r for r in range(world) if loads[r] == best)
 
 
+def my_folds(M: int, coll) -> list:
+    """The folds of the calling rank."""
+    return [k for k in range(M) if fold_owner(k, coll.world) == coll.rank]
+
+
 def plan_inverse_jobs(M: int, n_tau1: int, world: int):
     """Owner rank of every stage-1 inverse job (fold k, tau1 index i), i = 1..n_tau1-1.
 
@@ -151,12 +156,18 @@ def omega_columns(p: int, world: int):
     return [(min(p, r * step), min(p, (r + 1) * step)) for r in range(world)]
 
 
-def prepare_sharded(engine, coll: Collective):
+def prepare_sharded(engine, coll: Collective, folds=None):
     """`engine.prepare()` with thinPlateSplineMatrix (:58-76) shared by the ranks: the LU of the bordered
     system is replicated, the solves, the residual / correction products of the refinement and the final
     product are split by columns, and the column blocks travel by NCCL broadcast (3 x 8 p^2 bytes in total).
-    With one rank, or an engine without the column API, this is `engine.prepare()`."""
+    With one rank, or an engine without the column API, this is `engine.prepare()`.
+
+    `folds`: this rank's folds.  The build is driven from the host (sync + exchange between its phases), so the SVD
+    starts of the full data and of these folds are run right after omega_begin() has enqueued the replicated first
+    stage (X0): they hide under it instead of following the build."""
     if coll.world > 1 and hasattr(engine, "omega_begin") and engine.omega_begin():
+        if folds is not None and hasattr(engine, "prepare_starts"):
+            engine.prepare_starts(list(folds))
         cols = omega_columns(engine.p, coll.world)
         c0, c1 = cols[coll.rank]
         engine.omega_solve_cols(c0, c1)

@@ -206,6 +206,11 @@ class Engine:
     def prepare_fold(self, k):
         check(self._lib.spb_engine_prepare_fold(self._h, int(k)))
 
+    def prepare_starts(self, folds):
+        """SVD starts of the full data and of `folds` ahead of prepare() (they then hide under the Omega build)."""
+        f = self._folds(folds)
+        check(self._lib.spb_engine_prepare_starts(self._h, f.ctypes.data_as(C.POINTER(C.c_int)), len(f)))
+
     def inverse_buffer(self, k, i):
         """(device pointer, bytes) of the buffer that holds / will hold inverse (fold k, tau1[i])."""
         p = C.c_void_p()

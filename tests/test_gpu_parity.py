@@ -627,11 +627,14 @@ def test_error_paths(sp):
 # ---------------------------------------------------------------------------------------------
 # determinism, sharding, larger sizes
 # ---------------------------------------------------------------------------------------------
-def test_omega_column_blocks_match_single_build(sp):
+@pytest.mark.parametrize("name", ["irregular2d_small", "irregular2d_2304"])
+def test_omega_column_blocks_match_single_build(sp, name):
     """The multi-GPU Omega build (column blocks of Lp and of Lp'(E Lp)) against the one-piece build: the same
-    LU, the same right-hand sides, only the GEMM / solve calls are split by columns."""
+    start, the same right-hand sides, only the GEMM / solve calls are split by columns.  p = 300 takes the LU start,
+    p = 2304 the replicated SPD / Cholesky start with the INT8 refinement and product; the SVD starts asked for right
+    after omega_begin() (prepare_starts) run under the enqueued first stage."""
     from spatpca_b200 import distributed as D
-    case = make_case("irregular2d_small")
+    case = make_case(name)
     p = case["x"].shape[0]
     whole = sp.thinPlateSplineMatrix(case["x"])
     e = sp.Engine(p, case["x"].shape[1], case["Y"].shape[0], case["M"], case["K"], case["tau1"], case["tau2"],
@@ -639,6 +642,7 @@ def test_omega_column_blocks_match_single_build(sp):
     try:
         e.upload(case["x"], case["Y"], case["nk"])
         assert e.omega_begin()
+        e.prepare_starts([0, 2])
         cols = D.omega_columns(p, 3)
         for c0, c1 in cols:
             e.omega_solve_cols(c0, c1)

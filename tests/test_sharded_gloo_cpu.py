@@ -69,6 +69,11 @@ class OracleBackedEngine:
         assert bool((self.om == 2.0 * self.torch.arange(self.p, dtype=self.torch.float64)).all())
         self.asked.append(("omega_finish",))
 
+    def prepare_starts(self, folds):
+        # the SVD starts hide under the replicated first stage: asked for right after omega_begin(), before any solve
+        assert not any(a[0] == "omega_solve" for a in self.asked)
+        self.asked.append(("starts", tuple(folds)))
+
     def prepare(self):
         assert ("omega_finish",) in self.asked
         self.asked.append(("prepare",))
@@ -153,7 +158,7 @@ def _worker(rank, world, port, out_dir):
 
     eng = OracleBackedEngine(case, want)
     coll = D.TorchCollective()
-    D.prepare_sharded(eng, coll)
+    D.prepare_sharded(eng, coll, D.my_folds(case["M"], coll))
     got = D.run_sharded(eng, select_index, coll, case["M"], len(case["tau1"]), len(case["tau2"]),
                         len(case["gamma"]), case["tau1"], case["tau2"], case["gamma"])
     ok = True
@@ -167,6 +172,7 @@ def _worker(rank, world, port, out_dir):
     ok &= my_folds == [k for k in range(case["M"]) if D.fold_owner(k, world) == rank]
     did_full = any(a[0] == "f1" for a in eng.asked)
     ok &= did_full == (rank == D.full_fit_owner(case["M"], world))
+    ok &= ("starts", tuple(k for k in range(case["M"]) if D.fold_owner(k, world) == rank)) in eng.asked
     # Omega: this rank solved and multiplied exactly its own column block, then prepare() ran
     c0, c1 = D.omega_columns(eng.p, world)[rank]
     ok &= ("omega_solve", c0, c1) in eng.asked and ("omega_product", c0, c1) in eng.asked
