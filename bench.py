@@ -516,8 +516,10 @@ def main():
             "path_factor_frac_of_dgemm": fac_flops(m_path) / (fac2_ms * 1e-3) / 1e12 / dgemm_tf,
             "job": {"p3_flops": float(stats.get("p3_flops", 0.0)), "n_factorisations": int(stats["n_inverses"]),
                     "ms_omega": float(stats["ms_omega"]), "ms_factorisations_summed": float(stats["ms_inverse"]),
-                    "omega_frac_of_dgemm": ((2.0 / 3 + 5.0) * p3 / (float(stats["ms_omega"]) * 1e-3) / 1e12 / dgemm_tf)
-                    if stats["ms_omega"] > 0 else None}}
+                    "omega_note": "Omega build: FP64 Cholesky inverse of the rotated SPD block (potrf + GEMM-rate trtri + V'V, "
+                                  "~1.1 p^3 FP64 flop) + one Newton-Schulz step and the final product on INT8 digit planes "
+                                  "(78 + 15 + 28 plane products of 2 p^3 integer operations, upper strips); no single FP64 "
+                                  "rate describes it, so only its stream time is reported"}}
 
     # ---- forced-iteration mode (SURVEY 8d mode ii: thr = 0, every ADMM call runs exactly maxit iterations): the
     # deterministic-denominator figure of BASELINE.json's "ADMM iters/s"; HBM floor = peak / (8 p^2 + 72 p K) ----
