@@ -102,6 +102,13 @@ void cached_free(void* ptr, size_t bytes) {
 // ---------------------------------------------------------------------------------------
 // DeviceCtx
 // ---------------------------------------------------------------------------------------
+// SPB_PRIO=swap: the Omega build on the highest-priority stream and the SVD starts on the lowest (experiment: with the
+// fold starts running concurrently on host threads they have slack, the Omega build is the critical path)
+static bool prio_swapped() {
+  static const bool v = [] { const char* e = std::getenv("SPB_PRIO"); return e && std::string(e) == "swap"; }();
+  return v;
+}
+
 DeviceCtx& DeviceCtx::get() {
   static thread_local std::map<int, std::unique_ptr<DeviceCtx>> ctxs;
   int count = 0;
@@ -129,7 +136,7 @@ std::unique_ptr<DeviceCtx> DeviceCtx::create(int dev, bool with_blas) {
   // for a whole GEMM grid to be dispatched (measured at p = 10 000: 38 ms per fold start instead of 9 ms)
   int prio_least = 0, prio_greatest = 0;
   SPB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-  SPB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
+  SPB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_swapped() ? prio_least : prio_greatest));
   if (with_blas) {
     SPB_CUBLAS(cublasCreate(&c->blas));
     SPB_CUBLAS(cublasSetStream(c->blas, c->stream));
@@ -161,7 +168,7 @@ OmegaRes& DeviceCtx::omega() {
     std::unique_ptr<OmegaRes> r(new OmegaRes());
     int prio_least = 0, prio_greatest = 0;
     SPB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-    SPB_CUDA(cudaStreamCreateWithPriority(&r->stream, cudaStreamNonBlocking, prio_least));
+    SPB_CUDA(cudaStreamCreateWithPriority(&r->stream, cudaStreamNonBlocking, prio_swapped() ? prio_greatest : prio_least));
     SPB_CUBLAS(cublasCreate(&r->blas));
     SPB_CUBLAS(cublasSetStream(r->blas, r->stream));
     SPB_CUBLAS(cublasSetPointerMode(r->blas, CUBLAS_POINTER_MODE_HOST));

@@ -717,6 +717,27 @@ def test_inverse_matches_cusolver_path(sp, monkeypatch):
     assert np.max(np.abs(pa - pb)) / np.max(np.abs(pb)) <= 1e-10
 
 
+def test_threaded_starts_match_serial(sp):
+    """The fold SVD starts on one host thread each (default) against the serial path (SPB_PROLOGUE_THREADS=0): the same
+    kernels on the same inputs, so the whole job must agree bit for bit.  The switch is read once per process, hence
+    the subprocesses."""
+    import subprocess, sys, os, json
+    code = (
+        "import sys, json, numpy as np; sys.path.insert(0, '.'); sys.path.insert(0, 'tests');"
+        "from synth import make_case; import spatpca_b200 as sp;"
+        "c = make_case('irregular2d_small');"
+        "r = sp.spatpcaCV(c['x'], c['Y'], c['M'], c['K'], c['tau1'], c['tau2'], c['gamma'], c['nk'], 100, 1e-4, c['l2']);"
+        "print(json.dumps({'s1': list(r['cv_score_tau1']), 's2': list(r['cv_score_tau2']), 's3': list(r['cv_score_gamma']),"
+        "'sel': [r['selected_tau1'], r['selected_tau2'], r['selected_gamma']], 'phi': r['estimated_eigenfn'].ravel().tolist()}))")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for threads in ("1", "0"):
+        env = dict(os.environ, SPB_PROLOGUE_THREADS=threads)
+        res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, check=True)
+        outs.append(json.loads(res.stdout.strip().splitlines()[-1]))
+    assert outs[0] == outs[1]
+
+
 def test_sharded_two_engines_match_single(sp):
     """Fold sharding as bench.py does under torchrun, emulated with two engines in one process: the
     per-fold rows, the selections and the final fit must equal the single-engine run bit for bit."""
