@@ -1011,6 +1011,7 @@ void Engine::omega_stream_sync() {
 
 void Engine::omega_finish() {
   SPB_REQUIRE(omega_cols_open_, "omega_begin() must be called first");
+  omega_x0_resolve();
   OmegaRes& R = ctx_.omega();
   cudaStream_t s = R.stream;
   clock_.begin(PH_OMEGA, s);
