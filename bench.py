@@ -103,7 +103,8 @@ def make_workload(name):
     from spatpca_b200.synth import make_case
     c = make_case(name)
     cfg = {
-        "workload": f"{name}: 2-D irregular locations p={c['x'].shape[0]}, n={c['Y'].shape[0]}, K={c['K']}, "
+        "workload": f"{name}: {c['x'].shape[1]}-D {'irregular' if name in ('C3', 'C4', 'C5') else 'grid'} locations "
+                    f"p={c['x'].shape[0]}, n={c['Y'].shape[0]}, K={c['K']}, "
                     f"M={c['M']}-fold CV, tau1 x tau2 x gamma = {len(c['tau1'])} x {len(c['tau2'])} x {len(c['gamma'])}, "
                     "maxit=100, thr=1e-4 (SURVEY.md section 8d generator, seed 2024)",
         "p": int(c["x"].shape[0]), "n": int(c["Y"].shape[0]), "K": int(c["K"]), "M": int(c["M"]),
