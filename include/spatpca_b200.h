@@ -330,6 +330,12 @@ SPB_API int spb_default_path_blocks(int p);
  * first / one-past-last row that becomes final in the phase, segments} (returns the phase count).        */
 SPB_API int spb_block_offsets(int p, int blocks, int* off, int cap);
 SPB_API int spb_admm_phase_plan(int p, int K, int blocks, int* plan8, int cap);
+/* svd_econ(U, s, V, Y, "right") as the engine runs it for the ADMM starts (src/RcppSpatPCA.cpp:321, :563) and as
+ * setGamma() needs it (R/helper.R:207-217: d[1]^2 / nrow of the fold-1 training block): Householder QR of the long
+ * side, one-sided Jacobi SVD of the triangular factor, back-transformation, all on the device.
+ *   Y : m x p;  sv_out : min(m, p) singular values, descending;  V_out : p x K leading right singular vectors
+ *   (may be NULL).  Signs of the vectors are arbitrary, as in LAPACK.                                        */
+SPB_API int spb_svd_right(const double* Y, int m, int p, int K, double* sv_out, double* V_out);
 /* pow(norm(Yva * (I - Phi Phi'), "fro"), 2)   (:327, :331, :400)            */
 SPB_API int spb_cv_loss(const double* Yva, int n_va, int p, const double* Phi, int K, double* loss);
 /* stage-3 losses of one fold for all gammas (:489-523)                      */

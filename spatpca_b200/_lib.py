@@ -125,6 +125,7 @@ SIGNATURES = {
     "spb_default_path_blocks": (C.c_int, [C.c_int]),
     "spb_block_offsets": (C.c_int, [C.c_int, C.c_int, _ip, C.c_int]),
     "spb_admm_phase_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, C.c_int]),
+    "spb_svd_right": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, _dp, _dp]),
     "spb_cv_loss": (C.c_int, [_dp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
     "spb_gamma_loss": (C.c_int, [_dp, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp]),
     "spb_bench_admm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),

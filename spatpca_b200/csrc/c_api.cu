@@ -833,6 +833,25 @@ int spb_cv_loss(const double* Yva, int n_va, int p, const double* Phi, int K, do
   });
 }
 
+int spb_svd_right(const double* Y, int m, int p, int K, double* sv_out, double* V_out) {
+  return guarded([&] {
+    SPB_REQUIRE(Y && sv_out && m >= 1 && p >= 1, "invalid argument");
+    const int r = m < p ? m : p;
+    SPB_REQUIRE(K >= 1 && K <= r, "K must be in 1 .. min(m, p)");
+    DeviceCtx& ctx = DeviceCtx::get();
+    cudaStream_t s = ctx.stream;
+    DevBuf<double> dY((size_t)m * p), dV((size_t)p * K);
+    SPB_CUDA(cudaMemcpyAsync(dY.get(), Y, sizeof(double) * (size_t)m * p, cudaMemcpyHostToDevice, s));
+    std::vector<double> sv;
+    Engine::svd_right(ctx, dY.get(), m, p, K, sv, dV.get());          // synchronises the stream, checks the flag
+    for (int i = 0; i < r; ++i) sv_out[i] = sv[i];
+    if (V_out) {
+      SPB_CUDA(cudaMemcpyAsync(V_out, dV.get(), sizeof(double) * (size_t)p * K, cudaMemcpyDeviceToHost, s));
+      ctx.sync_and_check();
+    }
+  });
+}
+
 int spb_gamma_loss(const double* Phi, int p, int K, const double* Ytr, int n_tr, const double* Yva, int n_va,
                    const double* gamma, int n_gamma, double* out) {
   return guarded([&] {

@@ -460,6 +460,18 @@ def admm_phase_plan(p, K, blocks=0):
     return [dict(zip(keys, (int(v) for v in buf[8 * f:8 * f + 8]))) for f in range(n)]
 
 
+def svd_right(Y, K):
+    """Singular values and the K leading right singular vectors of Y (m x p) from the device SVD start
+    (src/RcppSpatPCA.cpp:321, :563; the quantity setGamma needs, R/helper.R:207-217)."""
+    lib = _lib.load()
+    Ym = fmat(Y)
+    m, p = Ym.shape
+    sv = np.zeros(min(m, p))
+    V = np.zeros((p, int(K)), order="F")
+    check(lib.spb_svd_right(ptr(Ym), m, p, int(K), ptr(sv), ptr(V)))
+    return sv, V
+
+
 def cv_loss(Yva, Phi):
     lib = _lib.load()
     Y, P = fmat(Yva), fmat(Phi)

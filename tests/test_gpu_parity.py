@@ -162,6 +162,24 @@ def test_tps_matrix_vs_oracle(sp, d, p):
     assert np.array_equal(got, got.T)          # the refined product is exactly symmetric
 
 
+@pytest.mark.parametrize("m,p,K", [(40, 300, 3), (160, 2304, 5), (200, 200, 8), (30, 20, 4)])
+def test_svd_start_vs_lapack(sp, m, p, K):
+    """The device SVD start (QR of the long side + one-sided Jacobi + back-transformation; src/RcppSpatPCA.cpp:321, :563)
+    against LAPACK: all singular values to 1e-12 of the largest, the K leading right singular vectors to 1e-10 up to
+    sign, and setGamma's maximum d[1]^2 / nrow (R/helper.R:207-217) to 1e-12."""
+    from spatpca_b200 import engine as eng
+    rng = np.random.default_rng(m * 1000 + p)
+    r = min(m, p)
+    load = np.linalg.qr(rng.normal(size=(p, r)))[0]
+    Y = (rng.normal(size=(m, r)) * np.linspace(30.0, 1.0, r)) @ load.T + 0.1 * rng.normal(size=(m, p))
+    sv, V = eng.svd_right(Y, K)
+    _, want_s, want_vt = np.linalg.svd(Y, full_matrices=False)
+    assert np.max(np.abs(sv - want_s)) <= 1e-12 * want_s[0]
+    assert eig_err(V, want_vt[:K].T) <= 1e-10
+    assert abs(sv[0] ** 2 / m - want_s[0] ** 2 / m) <= 1e-12 * want_s[0] ** 2 / m
+    assert np.max(np.abs(V.T @ V - np.eye(K))) <= 1e-12
+
+
 @pytest.mark.parametrize("d", [1, 2, 3])
 def test_eigen_function_vs_oracle(sp, d):
     rng = np.random.default_rng(40 + d)
