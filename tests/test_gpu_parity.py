@@ -419,6 +419,40 @@ def test_core2_batched_path_vs_oracle(sp, p, K, M, n):
     assert got["passes"] > 0
 
 
+def test_core2p_rides_with_the_folds(sp):
+    """spatpcaCore2p (src/RcppSpatPCA.cpp:187-222: the full-data fit at the selected tau1, :598-599) in the SAME launch
+    as the folds' spatpcaCore2 calls -- fold id 0 = all rows -- as stage 2 of the engine runs it: against the oracle's
+    core2 on the full Gram matrix and on each fold's, identical iteration counts, Phi to 1e-10."""
+    from spatpca_b200 import engine as eng
+    p, K, M, n = 2100, 3, 3, 60
+    if not eng.core2_batched_supported(p, n, K, M + 1):
+        pytest.skip("shape not supported by the batched kernel on this device")
+    rng = np.random.default_rng(99)
+    x = rng.uniform(0, 1, size=(p, 2))
+    Om = ref.thin_plate_spline_matrix(x)
+    Om[np.diag_indices(p)] += 1e-8
+    load = np.linalg.qr(rng.normal(size=(p, K)))[0]
+    Y = (rng.normal(size=(n, K)) * np.linspace(30, 10, K)) @ load.T + rng.normal(size=(n, p))
+    nk = rng.permutation(np.resize(np.arange(1, M + 1), n)).astype(float)
+    tau1 = np.array([0.05])
+    ids = [0] + list(range(1, M + 1))
+    starts, rhos, want, want_it = [], [], [], []
+    for fid in ids:
+        Ytr = Y if fid == 0 else Y[nk != fid]
+        _, rho, Phi0, L20 = ref.pca_init(Ytr, K)
+        starts.append((Phi0, L20))
+        rhos.append(rho)
+        tr = ref.Trace()
+        Phi, _, _ = ref.core2(np.asfortranarray(Ytr.T @ Ytr), Phi0, Phi0, L20, Om, tau1[0], rho, 100, 1e-4, tr)
+        want.append(Phi)
+        want_it.append(tr.calls[0][3])
+    got = eng.core2_batched(Om, Y, nk, ids, rhos, tau1, [s[0] for s in starts], [s[0] for s in starts],
+                            [s[1] for s in starts], 100, 1e-4)
+    assert got["iters"].tolist() == [want_it]
+    for f in range(len(ids)):
+        assert np.max(np.abs(got["snap"][0, f] - want[f])) / np.max(np.abs(want[f])) <= 1e-10, f
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("p,K,M,n", [(640, 3, 4, 40), (1500, 5, 5, 60), (2300, 2, 1, 30)])
 def test_core3_batched_path_vs_oracle(sp, p, K, M, n):
