@@ -679,12 +679,16 @@ def test_error_paths(sp):
     with pytest.raises(SpatpcaError):                            # K larger than the training block
         sp.spatpcaCV(x, Y, 5, 9, [0, 1.0], [0.0], [0.0], np.resize(np.arange(1, 6), 10), 10, 1e-4, [1.0])
     # duplicate 2-D sites: 0 * log(0) = NaN in the reference too (:29); the LU then fails or yields NaN
-    xd = np.vstack([x, x[:1]])
-    try:
-        om = sp.thinPlateSplineMatrix(xd)
-        assert not np.all(np.isfinite(om))
-    except SpatpcaError:
-        pass
+    # ... at a size that takes the LU start (p = 21) and at one that takes the SPD / Cholesky start with the INT8
+    # refinement (p = 2301: the digit-plane kernels poison their output on a non-finite operand, the fallback LU
+    # reports a singular matrix -- "inv(): matrix is singular", as Armadillo would)
+    for xs in (x, np.random.default_rng(0).uniform(size=(2300, 2))):
+        xd = np.vstack([xs, xs[:1]])
+        try:
+            om = sp.thinPlateSplineMatrix(xd)
+            assert not np.all(np.isfinite(om))
+        except SpatpcaError:
+            pass
 
 
 # ---------------------------------------------------------------------------------------------
